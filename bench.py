@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py - rows/sec of the tabular-DNN train step (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg1|cfg2|cfg0] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one mini-batch: load -> forward -> loss -> backward -> gradient mean
+over ranks (NCCL) -> optimizer update.  `value` times steps whose mini-batches are already resident in HBM
+(sb_trainer_step_resident_async, CUDA events on the trainer's stream, max over ranks); `e2e` times the same step
+through the public C-ABI call with HOST (pinned) buffers, H2D of the batch and D2H of the loss inside the timed
+region.  Weak scaling: every rank owns its own `batch` rows per step.  PyTorch is used for plumbing only
+(rendezvous, barrier, max-reduce, events); all compute is libshifu_b200.so.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SEED = 20260921
+# BASELINE.json configs.  Activation: relu (ModelConfig ActivationFunc); loss: the reference's MSE-on-sigmoid
+# (res/ssgd_monitor.py:129) - same cost as the sigmoid-CE variant.
+CONFIGS = {
+    "cfg0": dict(F=200, hidden=[100, 50], batch=100, optimizer="adadelta", lr=1.0, n_batches=90),
+    "cfg1": dict(F=1000, hidden=[512, 256, 128], batch=4096, optimizer="adam", lr=0.001, n_batches=64),
+    "cfg2": dict(F=2000, hidden=[1024, 512, 256], batch=8192, optimizer="momentum", lr=0.01, n_batches=32),
+}
+OPT_ID = {"adadelta": 0, "adam": 1, "sgd": 2, "momentum": 3}
+
+
+def flops_per_row(F, hidden):
+    """F_train = 6*sum(W) - 2*W_1; hidden-GEMM share drops the out=1 layer (6*h_L)."""
+    dims = [F] + list(hidden) + [1]
+    sw = sum(a * b for a, b in zip(dims[:-1], dims[1:]))
+    f_train = 6 * sw - 2 * dims[0] * dims[1]
+    return f_train, f_train - 6 * hidden[-1], 2 * sw
+
+
+def synth_dataset(cfg, rank, n_batches=None):
+    """X~N(0,1) clipped +-4 fp32 row-major, y~Bernoulli(0.2), w=1; per-rank seed."""
+    nb = n_batches or cfg["n_batches"]
+    rows = nb * cfg["batch"]
+    rng = np.random.default_rng(SEED + 1000 * rank)
+    X = rng.standard_normal((rows, cfg["F"]), dtype=np.float32)
+    np.clip(X, -4, 4, out=X)
+    y = (rng.random(rows, dtype=np.float32) < 0.2).astype(np.float32)
+    w = np.ones(rows, np.float32)
+    return X, y, w
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.lines:
+            if not (t0 - 0.05 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except Exception:
+                continue
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, cfg, rank, world):
+    """`--impl reference`: the reference-equivalent CPU worker (oracle port on torch-CPU, all host threads) on the same
+    config / metric.  TF 1.x + Python 2 cannot be installed here, so the oracle port IS the CPU arm (kind "port").
+    Under torchrun only rank 0 works."""
+    if rank != 0:
+        return
+    import torch
+    from oracle import shifu_oracle as so
+    from oracle.torch_cpu_worker import TorchCpuWorker
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    net = so.NetDesc(cfg["F"], cfg["hidden"], [so.ACT_RELU] * len(cfg["hidden"]))
+    params = so.xavier_init(net, SEED % 100000)
+    opt = so.OptConfig(kind=OPT_ID[cfg["optimizer"]], lr=cfg["lr"])
+    nb = min(4, cfg["n_batches"])
+    X, y, w = synth_dataset(cfg, 0, nb)
+    B = cfg["batch"]
+    tb = [(torch.from_numpy(X[i * B:(i + 1) * B]), torch.from_numpy(y[i * B:(i + 1) * B].reshape(-1, 1)),
+           torch.from_numpy(w[i * B:(i + 1) * B].reshape(-1, 1))) for i in range(nb)]
+    wk = TorchCpuWorker(net, params, opt)
+    for i in range(args.warmup):
+        wk.step(*tb[i % nb])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        wk.step(*tb[i % nb])
+    el = time.perf_counter() - t0
+    val = args.steps * B / el
+    out = {
+        "impl": "reference", "metric": "rows/sec tabular-DNN train", "value": val, "unit": "rows/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_block(args.config, cfg, 1),
+        "cpu_baseline": {"value": val, "unit": "rows/s", "cores": threads, "kind": "port",
+                         "sample": "%d steps of %s (batch %d) on torch-CPU fp32, batch loop only" % (args.steps, args.config, B)},
+        "e2e": {"value": val, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+def config_block(name, cfg, world):
+    return {"workload": "%s: %d cols x %d rows/GPU/step, MLP %s relu, %s, MSE-on-sigmoid loss" %
+                        (name, cfg["F"], cfg["batch"], cfg["hidden"], cfg["optimizer"]),
+            "global_batch": cfg["batch"] * world, "rows_per_gpu": cfg["batch"], "parallelism": "dp%d" % world,
+            "resident_set": "%d batches (%.0f MB fp32 per GPU) cycled, larger than the 126 MB L2" %
+                            (cfg["n_batches"], cfg["n_batches"] * cfg["batch"] * cfg["F"] * 4 / 1e6)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--config", default="cfg1", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default: min(steps, 50))")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, cfg, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import shifu_tensorflow_b200 as sb
+
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        buf = torch.zeros(sb.capi.SB_NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(sb.capi.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, 0)
+        nccl_id = bytes(buf.cpu().numpy().tobytes())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        tns = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tns, op=dist.ReduceOp.MAX)
+        return float(tns.item())
+
+    B, F, hidden = cfg["batch"], cfg["F"], cfg["hidden"]
+    prec = sb.PREC_BF16 if args.precision == "bf16" else sb.PREC_FP32
+    desc = sb.make_desc(F, hidden, [sb.ACT_RELU] * len(hidden), loss=sb.LOSS_MSE, optimizer=OPT_ID[cfg["optimizer"]],
+                        learning_rate=cfg["lr"], max_batch=B, precision=prec)
+    t = sb.Trainer(desc, device=local_rank, nccl_id=nccl_id, rank=rank, world=world)
+    t.init_xavier(SEED)  # same seed on every rank -> identical replicas
+    X, y, w = synth_dataset(cfg, rank)
+    t.load_dataset(X, y, w)
+    nb = cfg["n_batches"]
+    stream = torch.cuda.ExternalStream(t.stream, device=torch.device("cuda", local_rank))
+
+    # ---------------- device-resident leg (value) ----------------
+    for i in range(args.warmup):
+        t.step_resident_async((i % nb) * B, B)
+    t.sync()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    wall0 = time.perf_counter()
+    ev0.record(stream)
+    for i in range(args.steps):
+        t.step_resident_async(((args.warmup + i) % nb) * B, B)
+    ev1.record(stream)
+    t.sync()
+    barrier()
+    wall1 = time.perf_counter()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    clk = clocks.stop(wall0, wall1) if rank == 0 else None
+    last_loss = t.last_loss()
+    value = world * B * args.steps / (ms / 1e3)
+
+    # ---------------- per-kernel times for the roofline (live CUDA events, un-graphed steps) ----------------
+    prof = {}
+    n_prof = 5
+    for i in range(n_prof + 1):
+        rec = t.profile_step((i % nb) * B, B)
+        if i == 0:
+            continue  # first un-graphed step pays lazy module loading
+        for name, v in rec:
+            prof[name] = prof.get(name, 0.0) + v / n_prof
+    f_train, f_gemm, _ = flops_per_row(F, hidden)
+    gemm_ms = sum(v for k, v in prof.items() if k.startswith("gemm_"))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    peak_src = "measured burst (MEASURED_PEAKS.json bf16_tflops)" if peaks else "fallback 1.59 PF (B200_PROFILING.md)"
+    ach_tf = (B * f_gemm / (gemm_ms / 1e3)) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                "traffic": None, "kernel": "gemm_tc_kernel (all hidden-layer fwd/dA/dW GEMMs of one step)",
+                "flops_per_launch_set": B * f_gemm, "kernel_ms_per_step": gemm_ms, "peak_source": peak_src,
+                "step_fraction_of_peak": (value / world * f_train / 1e12) / peak_tf,
+                "kernels_ms": {k: round(v, 5) for k, v in prof.items()}}
+
+    # ---------------- end-to-end leg: host (pinned) buffers through sb_trainer_step ----------------
+    e2e_steps = args.e2e_steps or min(args.steps, 50)
+    n_pin = 4
+    pin = []
+    for i in range(n_pin):
+        px = torch.empty((B, F), dtype=torch.float32).pin_memory()
+        py = torch.empty(B, dtype=torch.float32).pin_memory()
+        pw = torch.empty(B, dtype=torch.float32).pin_memory()
+        px.numpy()[:] = X[i * B:(i + 1) * B]; py.numpy()[:] = y[i * B:(i + 1) * B]; pw.numpy()[:] = w[i * B:(i + 1) * B]
+        pin.append((px.numpy(), py.numpy(), pw.numpy()))
+    for i in range(3):
+        t.step(*pin[i % n_pin])
+    barrier()
+    e0 = time.perf_counter()
+    for i in range(e2e_steps):
+        loss_h = t.step(*pin[i % n_pin])  # synchronous: H2D batch, step, D2H loss
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - e0)
+    e2e = {"value": world * B * e2e_steps / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": B * (F + 2) * 4,
+           "d2h_bytes_per_step": 16, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "timer": "host wall clock around synchronous sb_trainer_step calls (pinned host buffers), max over ranks"}
+
+    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import shifu_oracle as so
+        from oracle.torch_cpu_worker import time_train
+        net = so.NetDesc(F, hidden, [so.ACT_RELU] * len(hidden))
+        nbc = min(4, nb)
+        batches = [(X[i * B:(i + 1) * B], y[i * B:(i + 1) * B], w[i * B:(i + 1) * B]) for i in range(nbc)]
+        r = time_train(net, so.xavier_init(net, 1), so.OptConfig(kind=OPT_ID[cfg["optimizer"]], lr=cfg["lr"]), batches,
+                       min_seconds=10.0, max_steps=400, threads=os.cpu_count())
+        cpu = {"value": r["rows_per_sec"], "unit": "rows/s", "cores": r["cores"], "kind": "port",
+               "sample": "%d steps (%.1f s) of %s on torch-CPU fp32 = reference-equivalent worker loop (TF-1.x absent)" %
+                         (r["steps"], r["seconds"], args.config)}
+
+    if rank == 0:
+        out = {
+            "metric": "rows/sec tabular-DNN train", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if prec == sb.PREC_BF16 else "f32", "data": "synthetic",
+            "config": config_block(args.config, cfg, world),
+            "clocks": clk, "e2e": e2e, "gpu_launches": t.kernels_per_step(B) * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "last_loss": last_loss,
+        }
+        print(json.dumps(out), flush=True)
+    t.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,384 @@
+"""ctypes binding of include/shifu_b200.h (the C-ABI a JNI shim binds the same way).
+
+No compute lives here: every call forwards to libshifu_b200.so.  If the library has not been built the
+import fails loudly - there is no Python / CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libshifu_b200.so")
+
+SB_MAX_HIDDEN = 32
+SB_NCCL_ID_BYTES = 128
+ACT_SIGMOID, ACT_TANH, ACT_RELU, ACT_LEAKYRELU, ACT_NONE = 0, 1, 2, 3, -1
+LOSS_MSE, LOSS_SIGMOID_CE = 0, 1
+OPT_ADADELTA, OPT_ADAM, OPT_SGD, OPT_MOMENTUM = 0, 1, 2, 3
+PREC_FP32, PREC_BF16 = 0, 1
+SB_OK, SB_ERR_INVALID, SB_ERR_CUDA, SB_ERR_NCCL, SB_ERR_IO, SB_ERR_STATE, SB_ERR_FORMAT = 0, -1, -2, -3, -4, -5, -6
+
+
+class NetDesc(C.Structure):
+    _fields_ = [
+        ("n_features", C.c_int32), ("n_hidden", C.c_int32),
+        ("hidden", C.c_int32 * SB_MAX_HIDDEN), ("acts", C.c_int32 * SB_MAX_HIDDEN),
+        ("loss", C.c_int32), ("optimizer", C.c_int32),
+        ("learning_rate", C.c_float), ("rho", C.c_float), ("epsilon", C.c_float),
+        ("beta1", C.c_float), ("beta2", C.c_float), ("momentum", C.c_float),
+        ("max_batch", C.c_int32), ("precision", C.c_int32),
+    ]
+
+
+def make_desc(n_features: int, hidden: Sequence[int], acts: Sequence[int], loss: int = LOSS_MSE,
+              optimizer: int = OPT_ADADELTA, learning_rate: float = 0.001, rho: float = 0.95, epsilon: float = 1e-8,
+              beta1: float = 0.9, beta2: float = 0.999, momentum: float = 0.9, max_batch: int = 128,
+              precision: int = PREC_FP32) -> NetDesc:
+    if len(hidden) != len(acts):
+        raise ValueError("hidden and acts must have the same length")
+    if len(hidden) > SB_MAX_HIDDEN:
+        raise ValueError("at most %d hidden layers" % SB_MAX_HIDDEN)
+    d = NetDesc()
+    d.n_features, d.n_hidden = int(n_features), len(hidden)
+    for i, (h, a) in enumerate(zip(hidden, acts)):
+        d.hidden[i], d.acts[i] = int(h), int(a)
+    d.loss, d.optimizer = int(loss), int(optimizer)
+    d.learning_rate, d.rho, d.epsilon = learning_rate, rho, epsilon
+    d.beta1, d.beta2, d.momentum = beta1, beta2, momentum
+    d.max_batch, d.precision = int(max_batch), int(precision)
+    return d
+
+
+class ShifuB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("[%d] %s" % (code, msg))
+        self.code = code
+
+
+_lib = None
+
+# name -> (restype, argtypes); the single source of truth for tests/test_capi_symbols.py
+_P = C.POINTER
+_f32p, _f64p, _vp, _cp = _P(C.c_float), _P(C.c_double), C.c_void_p, C.c_char_p
+PROTOTYPES = {
+    "sb_version": (C.c_char_p, []),
+    "sb_last_error": (C.c_char_p, []),
+    "sb_device_count": (C.c_int, []),
+    "sb_host_alloc": (C.c_int, [_P(_vp), C.c_uint64]),
+    "sb_host_free": (C.c_int, [_vp]),
+    "sb_nccl_unique_id": (C.c_int, [_vp]),
+    "sb_trainer_create": (C.c_int, [_P(NetDesc), C.c_int, _vp, C.c_int, C.c_int, _P(_vp)]),
+    "sb_trainer_destroy": (C.c_int, [_vp]),
+    "sb_trainer_param_count": (C.c_int64, [_vp]),
+    "sb_trainer_set_params": (C.c_int, [_vp, _f32p, C.c_int64]),
+    "sb_trainer_get_params": (C.c_int, [_vp, _f32p, C.c_int64]),
+    "sb_trainer_init_xavier": (C.c_int, [_vp, C.c_uint64]),
+    "sb_trainer_get_grads": (C.c_int, [_vp, _f32p, C.c_int64]),
+    "sb_trainer_step": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_int32, _f32p]),
+    "sb_trainer_accumulate": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_int32, _f32p]),
+    "sb_trainer_apply_accumulated": (C.c_int, [_vp]),
+    "sb_trainer_load_dataset": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_int64]),
+    "sb_trainer_step_resident": (C.c_int, [_vp, C.c_int64, C.c_int32, _f32p]),
+    "sb_trainer_step_resident_async": (C.c_int, [_vp, C.c_int64, C.c_int32]),
+    "sb_trainer_accumulate_resident": (C.c_int, [_vp, C.c_int64, C.c_int32, _f32p]),
+    "sb_trainer_last_loss": (C.c_int, [_vp, _f32p]),
+    "sb_trainer_sync": (C.c_int, [_vp]),
+    "sb_trainer_stream": (C.c_void_p, [_vp]),
+    "sb_trainer_kernels_per_step": (C.c_int, [_vp, C.c_int32]),
+    "sb_trainer_profile_step": (C.c_int, [_vp, C.c_int64, C.c_int32, C.c_char_p, C.c_int32, _f32p, C.c_int32, _P(C.c_int32)]),
+    "sb_trainer_eval_loss": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_int64, _f32p]),
+    "sb_trainer_predict": (C.c_int, [_vp, _f32p, C.c_int64, _f32p]),
+    "sb_trainer_save_checkpoint": (C.c_int, [_vp, _cp]),
+    "sb_trainer_load_checkpoint": (C.c_int, [_vp, _cp]),
+    "sb_trainer_global_step": (C.c_int64, [_vp]),
+    "sb_trainer_export_savedmodel": (C.c_int, [_vp, _cp]),
+    "sb_model_load": (C.c_int, [_cp, _cp, _cp, _cp, C.c_int, C.c_int, _P(_vp)]),
+    "sb_model_create": (C.c_int, [_P(NetDesc), _f32p, C.c_int64, C.c_int, _P(_vp)]),
+    "sb_model_destroy": (C.c_int, [_vp]),
+    "sb_model_n_features": (C.c_int32, [_vp]),
+    "sb_model_n_layers": (C.c_int32, [_vp]),
+    "sb_model_score": (C.c_int, [_vp, _f32p, C.c_int64, _f32p]),
+    "sb_model_score_row_f64": (C.c_int, [_vp, _f64p, C.c_int32, _f64p]),
+    "sb_model_score_device": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
+    "sb_model_sync": (C.c_int, [_vp]),
+    "sb_model_stream": (C.c_void_p, [_vp]),
+    "sb_savedmodel_write": (C.c_int, [_cp, _P(NetDesc), _f32p, C.c_int64]),
+    "sb_savedmodel_read": (C.c_int, [_cp, _cp, _cp, _cp, _P(NetDesc), _P(C.c_int32), _f32p, C.c_int64, _P(C.c_int64)]),
+    "sb_debug_gemm_bf16": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
+}
+
+
+def lib():
+    """Load libshifu_b200.so (once).  Raises ImportError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libshifu_b200.so is missing (%s). Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `python shifu-tensorflow_b200/build.py`. There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+def check(status: int) -> None:
+    if status != SB_OK:
+        raise ShifuB200Error(status, lib().sb_last_error().decode("utf-8", "replace"))
+
+
+def _f32(a, shape=None) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None and a.shape != shape:
+        a = a.reshape(shape)
+    return a
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(_f32p)
+
+
+class Trainer:
+    """Owns one sb_trainer_t.  X is [rows, n_features] float32, y / w are [rows] (or [rows,1])."""
+
+    def __init__(self, desc: NetDesc, device: int = 0, nccl_id: Optional[bytes] = None, rank: int = 0, world: int = 1):
+        self._h = C.c_void_p()
+        self.desc = desc
+        idbuf = None
+        if nccl_id is not None:
+            if len(nccl_id) != SB_NCCL_ID_BYTES:
+                raise ValueError("nccl_id must be %d bytes" % SB_NCCL_ID_BYTES)
+            idbuf = C.create_string_buffer(bytes(nccl_id), SB_NCCL_ID_BYTES)
+        check(lib().sb_trainer_create(C.byref(desc), device, C.cast(idbuf, _vp) if idbuf is not None else None,
+                                      rank, world, C.byref(self._h)))
+        self.n_params = int(lib().sb_trainer_param_count(self._h))
+        self.n_features = int(desc.n_features)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().sb_trainer_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- parameters ----
+    def set_params(self, flat):
+        flat = _f32(flat).reshape(-1)
+        check(lib().sb_trainer_set_params(self._h, _ptr(flat), flat.size))
+
+    def get_params(self) -> np.ndarray:
+        out = np.empty(self.n_params, np.float32)
+        check(lib().sb_trainer_get_params(self._h, _ptr(out), out.size))
+        return out
+
+    def get_grads(self) -> np.ndarray:
+        out = np.empty(self.n_params, np.float32)
+        check(lib().sb_trainer_get_grads(self._h, _ptr(out), out.size))
+        return out
+
+    def init_xavier(self, seed: int):
+        check(lib().sb_trainer_init_xavier(self._h, seed))
+
+    # ---- steps ----
+    def _xyw(self, X, y, w):
+        X = _f32(X)
+        rows = X.shape[0]
+        if X.ndim != 2 or X.shape[1] != self.n_features:
+            raise ValueError("X must be [rows, %d]" % self.n_features)
+        y = _f32(y).reshape(-1)
+        w = None if w is None else _f32(w).reshape(-1)
+        if y.size != rows or (w is not None and w.size != rows):
+            raise ValueError("y / w length must equal rows")
+        return X, y, w, rows
+
+    def step(self, X, y, w=None) -> float:
+        X, y, w, rows = self._xyw(X, y, w)
+        loss = C.c_float()
+        check(lib().sb_trainer_step(self._h, _ptr(X), _ptr(y), _ptr(w), rows, C.byref(loss)))
+        return float(loss.value)
+
+    def accumulate(self, X, y, w=None) -> float:
+        X, y, w, rows = self._xyw(X, y, w)
+        loss = C.c_float()
+        check(lib().sb_trainer_accumulate(self._h, _ptr(X), _ptr(y), _ptr(w), rows, C.byref(loss)))
+        return float(loss.value)
+
+    def apply_accumulated(self):
+        check(lib().sb_trainer_apply_accumulated(self._h))
+
+    def load_dataset(self, X, y, w=None):
+        X, y, w, rows = self._xyw(X, y, w)
+        check(lib().sb_trainer_load_dataset(self._h, _ptr(X), _ptr(y), _ptr(w), rows))
+        self.dataset_rows = rows
+
+    def step_resident(self, row_offset: int, rows: int) -> float:
+        loss = C.c_float()
+        check(lib().sb_trainer_step_resident(self._h, row_offset, rows, C.byref(loss)))
+        return float(loss.value)
+
+    def step_resident_async(self, row_offset: int, rows: int):
+        check(lib().sb_trainer_step_resident_async(self._h, row_offset, rows))
+
+    def accumulate_resident(self, row_offset: int, rows: int) -> float:
+        loss = C.c_float()
+        check(lib().sb_trainer_accumulate_resident(self._h, row_offset, rows, C.byref(loss)))
+        return float(loss.value)
+
+    def last_loss(self) -> float:
+        loss = C.c_float()
+        check(lib().sb_trainer_last_loss(self._h, C.byref(loss)))
+        return float(loss.value)
+
+    def sync(self):
+        check(lib().sb_trainer_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().sb_trainer_stream(self._h) or 0)
+
+    def kernels_per_step(self, rows: int) -> int:
+        n = lib().sb_trainer_kernels_per_step(self._h, rows)
+        if n < 0:
+            check(n)
+        return n
+
+    def profile_step(self, row_offset: int, rows: int):
+        """-> [(kernel name, milliseconds)] for one real (un-graphed) step over resident rows"""
+        names = C.create_string_buffer(4096)
+        ms = (C.c_float * 256)()
+        n = C.c_int32(0)
+        check(lib().sb_trainer_profile_step(self._h, row_offset, rows, names, 4096, ms, 256, C.byref(n)))
+        nm = names.value.decode().split("\n") if n.value else []
+        return [(nm[i], float(ms[i])) for i in range(n.value)]
+
+    def eval_loss(self, X, y, w=None) -> float:
+        X, y, w, rows = self._xyw(X, y, w)
+        loss = C.c_float()
+        check(lib().sb_trainer_eval_loss(self._h, _ptr(X), _ptr(y), _ptr(w), rows, C.byref(loss)))
+        return float(loss.value)
+
+    def predict(self, X) -> np.ndarray:
+        X = _f32(X)
+        out = np.empty(X.shape[0], np.float32)
+        check(lib().sb_trainer_predict(self._h, _ptr(X), X.shape[0], _ptr(out)))
+        return out
+
+    @property
+    def global_step(self) -> int:
+        return int(lib().sb_trainer_global_step(self._h))
+
+    def save_checkpoint(self, path: str):
+        check(lib().sb_trainer_save_checkpoint(self._h, path.encode()))
+
+    def load_checkpoint(self, path: str):
+        check(lib().sb_trainer_load_checkpoint(self._h, path.encode()))
+
+    def export_savedmodel(self, export_dir: str):
+        check(lib().sb_trainer_export_savedmodel(self._h, export_dir.encode()))
+
+
+class Model:
+    """Owns one sb_model_t (batched scorer)."""
+
+    def __init__(self, handle):
+        self._h = handle
+        self.n_features = int(lib().sb_model_n_features(self._h))
+
+    @classmethod
+    def load(cls, saved_model_dir: str, input_name: str, output_name: str, tag: str = "serve", device: int = 0,
+             precision: int = PREC_FP32) -> "Model":
+        h = C.c_void_p()
+        enc = lambda s: None if s is None else s.encode()
+        check(lib().sb_model_load(enc(saved_model_dir), enc(input_name), enc(output_name), enc(tag), device, precision,
+                                  C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def create(cls, desc: NetDesc, flat_params, device: int = 0) -> "Model":
+        h = C.c_void_p()
+        flat = _f32(flat_params).reshape(-1)
+        check(lib().sb_model_create(C.byref(desc), _ptr(flat), flat.size, device, C.byref(h)))
+        return cls(h)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().sb_model_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def score(self, X) -> np.ndarray:
+        X = _f32(X)
+        if X.ndim != 2 or X.shape[1] != self.n_features:
+            raise ValueError("X must be [rows, %d]" % self.n_features)
+        out = np.empty(X.shape[0], np.float32)
+        check(lib().sb_model_score(self._h, _ptr(X), X.shape[0], _ptr(out)))
+        return out
+
+    def score_row_f64(self, row) -> float:
+        row = np.ascontiguousarray(row, dtype=np.float64).reshape(-1)
+        out = C.c_double()
+        check(lib().sb_model_score_row_f64(self._h, row.ctypes.data_as(_f64p), row.size, C.byref(out)))
+        return float(out.value)
+
+    def score_device(self, dX_ptr: int, rows: int, dOut_ptr: int):
+        check(lib().sb_model_score_device(self._h, C.c_void_p(dX_ptr), rows, C.c_void_p(dOut_ptr)))
+
+    def sync(self):
+        check(lib().sb_model_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(lib().sb_model_stream(self._h) or 0)
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(SB_NCCL_ID_BYTES)
+    check(lib().sb_nccl_unique_id(C.cast(buf, _vp)))
+    return buf.raw
+
+
+def device_count() -> int:
+    return int(lib().sb_device_count())
+
+
+def savedmodel_write(export_dir: str, desc: NetDesc, flat_params) -> None:
+    flat = _f32(flat_params).reshape(-1)
+    check(lib().sb_savedmodel_write(export_dir.encode(), C.byref(desc), _ptr(flat), flat.size))
+
+
+def savedmodel_read(saved_model_dir: str, input_name: str, output_name: str, tag: str = "serve"):
+    """-> (n_features, hidden list, acts list, out_act, flat params)"""
+    d = NetDesc()
+    out_act = C.c_int32(0)
+    n = C.c_int64(0)
+    args = (saved_model_dir.encode(), input_name.encode(), output_name.encode(), tag.encode())
+    check(lib().sb_savedmodel_read(*args, C.byref(d), C.byref(out_act), None, 0, C.byref(n)))
+    flat = np.empty(n.value, np.float32)
+    check(lib().sb_savedmodel_read(*args, C.byref(d), C.byref(out_act), _ptr(flat), flat.size, C.byref(n)))
+    return int(d.n_features), [int(d.hidden[i]) for i in range(d.n_hidden)], [int(d.acts[i]) for i in range(d.n_hidden)], \
+        int(out_act.value), flat
+
+
+def debug_gemm_bf16(A: np.ndarray, B: np.ndarray, split_k: int = 1, device: int = 0) -> np.ndarray:
+    """D[M,N] = bf16(A)[M,K] . bf16(B)[N,K]^T through the tcgen05 kernel."""
+    A, B = _f32(A), _f32(B)
+    M, K = A.shape
+    N, K2 = B.shape
+    assert K == K2
+    D = np.zeros((M, N), np.float32)
+    check(lib().sb_debug_gemm_bf16(_ptr(A), _ptr(B), _ptr(D), M, N, K, split_k, device))
+    return D

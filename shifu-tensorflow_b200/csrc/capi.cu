@@ -1,0 +1,702 @@
+// extern "C" surface of libshifu_b200.so: trainer, scorer, rendezvous, test hooks.
+// See include/shifu_b200.h for the contract and the reference call each entry point replaces.
+#include <math.h>
+#include <string.h>
+#include <memory>
+#include <random>
+#include "net.cuh"
+#include "savedmodel.h"
+
+using namespace sb;
+
+// ================================================================================================
+// trainer
+// ================================================================================================
+enum { G_STEP = 0, G_ACC = 1, G_KINDS = 2 };
+
+struct sb_trainer {
+  Net net;
+  sb_net_desc desc;
+  OptHyper hyper;
+  float lr = 0.f;
+  int rank = 0, world = 1;
+  NcclComm comm = nullptr;
+  float *grad = nullptr, *s1 = nullptr, *s2 = nullptr, *acc = nullptr;
+  int n_acc = 0;
+  float grad_out_scale = 1.f;  // what sb_trainer_get_grads multiplies the raw buffer by
+  long long global_step = 0;
+  float* h_scal = nullptr;  // pinned [SCAL_COUNT]
+  // HBM-resident training set
+  float *dsX = nullptr, *dsY = nullptr, *dsW = nullptr;
+  long long ds_rows = 0;
+  std::map<std::pair<int, int>, cudaGraphExec_t> graphs;  // (rows, kind) -> captured step
+  std::map<int, int> kernels_per_step;
+};
+
+static float lr_for_step(const sb_trainer* t, long long step /*1-based*/) {
+  if (t->hyper.kind == SB_OPT_ADAM) {
+    const double b1 = t->hyper.beta1, b2 = t->hyper.beta2;
+    return static_cast<float>(t->lr * sqrt(1.0 - pow(b2, static_cast<double>(step))) / (1.0 - pow(b1, static_cast<double>(step))));
+  }
+  return t->lr;
+}
+
+static int enqueue_allreduce(sb_trainer* t, float* buf) {
+  if (t->world <= 1) return SB_OK;
+  NcclApi* api = nccl_api();
+  SB_CHECK(api && t->comm, SB_ERR_NCCL, "NCCL communicator missing");
+  int r = api->AllReduce(buf, buf, static_cast<size_t>(t->net.n_params), NCCL_FLOAT32, NCCL_SUM, t->comm, t->net.stream);
+  SB_CHECK(r == 0, SB_ERR_NCCL, "ncclAllReduce failed: %s", api->GetErrorString(r));
+  return SB_OK;
+}
+
+static int enqueue_optimizer(sb_trainer* t, const float* g) {
+  Net& n = t->net;
+  optimizer_kernel<<<n.n_work, 256, 0, n.stream>>>(n.work, n.desc, t->hyper, n.theta, g, t->s1, t->s2);
+  SB_CUDA(cudaGetLastError());
+  n.mark("optimizer");
+  return SB_OK;
+}
+
+// the body of one step as a sequence of stream operations (captured into a CUDA graph)
+static int enqueue_step_body(sb_trainer* t, int rows, int kind) {
+  Net& n = t->net;
+  SB_CUDA(cudaMemsetAsync(t->grad, 0, sizeof(float) * n.n_params, n.stream));
+  SB_CUDA(cudaMemsetAsync(n.scal, 0, sizeof(float) * SCAL_COUNT, n.stream));
+  SB_TRY(n.enqueue_load(rows));
+  SB_TRY(n.enqueue_hidden_forward(rows));
+  SB_TRY(n.enqueue_out(rows, true, true, nullptr, t->grad));
+  SB_TRY(n.enqueue_backward(rows, t->grad));
+  if (kind == G_STEP) {
+    SB_TRY(enqueue_allreduce(t, t->grad));
+    if (t->world > 1 && n.profiling) { n.mark("allreduce"); --n.launches; }
+    SB_TRY(enqueue_optimizer(t, t->grad));
+  } else {
+    const long long np = n.n_params;
+    axpy_kernel<<<static_cast<unsigned>((np + 255) / 256), 256, 0, n.stream>>>(t->acc, t->grad, np);
+    SB_CUDA(cudaGetLastError());
+    n.mark("accumulate");
+  }
+  return SB_OK;
+}
+
+static int get_graph(sb_trainer* t, int rows, int kind, cudaGraphExec_t* out) {
+  auto key = std::make_pair(rows, kind);
+  auto it = t->graphs.find(key);
+  if (it != t->graphs.end()) { *out = it->second; return SB_OK; }
+  Net& n = t->net;
+  n.launches = 0;
+  cudaGraph_t g = nullptr;
+  SB_CUDA(cudaStreamBeginCapture(n.stream, cudaStreamCaptureModeThreadLocal));
+  int s = enqueue_step_body(t, rows, kind);
+  cudaError_t e = cudaStreamEndCapture(n.stream, &g);
+  if (s != SB_OK) { if (g) cudaGraphDestroy(g); return s; }
+  SB_CHECK(e == cudaSuccess, SB_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+  cudaGraphExec_t ge = nullptr;
+  SB_CUDA(cudaGraphInstantiate(&ge, g, 0));
+  cudaGraphDestroy(g);
+  t->graphs[key] = ge;
+  if (kind == G_STEP) t->kernels_per_step[rows] = n.launches + 1;  // + set_batch_kernel
+  *out = ge;
+  return SB_OK;
+}
+
+// X, y, w are DEVICE pointers here
+static int run_step(sb_trainer* t, const float* X, const float* y, const float* w, int rows, int kind) {
+  Net& n = t->net;
+  SB_CHECK(rows > 0 && rows <= n.max_batch, SB_ERR_INVALID, "rows=%d outside (0, max_batch=%d]", rows, n.max_batch);
+  SB_CUDA(cudaSetDevice(n.device));
+  cudaGraphExec_t ge;
+  SB_TRY(get_graph(t, rows, kind, &ge));
+  float lr_t = t->lr, gscale = 1.f / static_cast<float>(t->world);
+  if (kind == G_STEP) {
+    ++t->global_step;
+    lr_t = lr_for_step(t, t->global_step);
+  }
+  set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, X, y, w ? w : n.ones, lr_t, gscale);
+  SB_CUDA(cudaGetLastError());
+  SB_CUDA(cudaGraphLaunch(ge, n.stream));
+  SB_CUDA(cudaMemcpyAsync(t->h_scal, n.scal, sizeof(float) * SCAL_COUNT, cudaMemcpyDeviceToHost, n.stream));
+  if (kind == G_ACC) ++t->n_acc;
+  t->grad_out_scale = (kind == G_STEP) ? gscale : 1.f;
+  return SB_OK;
+}
+
+static int finish_loss(sb_trainer* t, float* loss_out) {
+  SB_CUDA(cudaStreamSynchronize(t->net.stream));
+  if (loss_out) {
+    const float nnz = t->h_scal[SCAL_NNZ];
+    *loss_out = nnz > 0.f ? t->h_scal[SCAL_LOSS_SUM] / nnz : 0.f;
+  }
+  return SB_OK;
+}
+
+static int stage_host_batch(sb_trainer* t, const float* X, const float* y, const float* w, int rows) {
+  Net& n = t->net;
+  SB_CHECK(X && y, SB_ERR_INVALID, "X and y must not be null");
+  SB_CHECK(rows > 0 && rows <= n.max_batch, SB_ERR_INVALID, "rows=%d outside (0, max_batch=%d]", rows, n.max_batch);
+  SB_CUDA(cudaSetDevice(n.device));
+  SB_CUDA(cudaMemcpyAsync(n.stX, X, sizeof(float) * rows * static_cast<size_t>(n.F), cudaMemcpyHostToDevice, n.stream));
+  SB_CUDA(cudaMemcpyAsync(n.stY, y, sizeof(float) * rows, cudaMemcpyHostToDevice, n.stream));
+  if (w) SB_CUDA(cudaMemcpyAsync(n.stW, w, sizeof(float) * rows, cudaMemcpyHostToDevice, n.stream));
+  return SB_OK;
+}
+
+extern "C" {
+
+const char* sb_version(void) { return "shifu_b200 0.1 (sm_100a)"; }
+const char* sb_last_error(void) { return last_error_ref().c_str(); }
+
+int sb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return set_error(SB_ERR_CUDA, "cudaGetDeviceCount failed");
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+  }
+  return ok;
+}
+
+int sb_host_alloc(void** ptr, uint64_t bytes) {
+  SB_CHECK(ptr, SB_ERR_INVALID, "ptr is null");
+  SB_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocDefault));
+  return SB_OK;
+}
+int sb_host_free(void* ptr) {
+  SB_CUDA(cudaFreeHost(ptr));
+  return SB_OK;
+}
+
+int sb_nccl_unique_id(void* out128) {
+  SB_CHECK(out128, SB_ERR_INVALID, "out is null");
+  NcclApi* api = nccl_api();
+  SB_CHECK(api, SB_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  NcclUniqueId id;
+  int r = api->GetUniqueId(&id);
+  SB_CHECK(r == 0, SB_ERR_NCCL, "ncclGetUniqueId failed: %s", api->GetErrorString(r));
+  memcpy(out128, &id, sizeof(id));
+  return SB_OK;
+}
+
+int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, int rank, int world, sb_trainer_t** out) {
+  SB_CHECK(out, SB_ERR_INVALID, "out is null");
+  *out = nullptr;
+  SB_TRY(validate_desc(desc));
+  SB_CHECK(world >= 1 && rank >= 0 && rank < world, SB_ERR_INVALID, "bad rank/world %d/%d", rank, world);
+  SB_CHECK(world == 1 || nccl_id != nullptr, SB_ERR_INVALID, "nccl_id required when world > 1");
+  std::unique_ptr<sb_trainer> t(new sb_trainer());
+  t->desc = *desc;
+  t->rank = rank; t->world = world;
+  t->lr = desc->learning_rate;
+  t->hyper.kind = desc->optimizer;
+  t->hyper.rho = desc->rho; t->hyper.eps = desc->epsilon;
+  t->hyper.beta1 = desc->beta1; t->hyper.beta2 = desc->beta2; t->hyper.momentum = desc->momentum;
+  int s = t->net.init(desc, device, true);
+  if (s != SB_OK) { t->net.destroy(); return s; }
+  Net& n = t->net;
+  if ((s = n.dalloc(&t->grad, n.n_params)) || (s = n.dalloc(&t->s1, n.n_params)) || (s = n.dalloc(&t->s2, n.n_params)) ||
+      (s = n.dalloc(&t->acc, n.n_params))) { n.destroy(); return s; }
+  if (cudaHostAlloc(reinterpret_cast<void**>(&t->h_scal), sizeof(float) * SCAL_COUNT, cudaHostAllocDefault) != cudaSuccess) {
+    n.destroy();
+    return set_error(SB_ERR_CUDA, "cudaHostAlloc failed");
+  }
+  memset(t->h_scal, 0, sizeof(float) * SCAL_COUNT);
+  if (world > 1) {
+    NcclApi* api = nccl_api();
+    if (!api) { n.destroy(); return set_error(SB_ERR_NCCL, "libnccl.so.2 could not be loaded"); }
+    NcclUniqueId id;
+    memcpy(&id, nccl_id, sizeof(id));
+    int r = api->CommInitRank(&t->comm, world, id, rank);
+    if (r != 0) { n.destroy(); return set_error(SB_ERR_NCCL, "ncclCommInitRank failed: %s", api->GetErrorString(r)); }
+  }
+  SB_CUDA(cudaStreamSynchronize(n.stream));
+  *out = t.release();
+  return SB_OK;
+}
+
+int sb_trainer_destroy(sb_trainer_t* t) {
+  if (!t) return SB_OK;
+  cudaSetDevice(t->net.device);
+  if (t->net.stream) cudaStreamSynchronize(t->net.stream);
+  for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);
+  if (t->comm) { NcclApi* api = nccl_api(); if (api) api->CommDestroy(t->comm); }
+  if (t->dsX) cudaFree(t->dsX);
+  if (t->dsY) cudaFree(t->dsY);
+  if (t->dsW) cudaFree(t->dsW);
+  if (t->h_scal) cudaFreeHost(t->h_scal);
+  t->net.destroy();
+  delete t;
+  return SB_OK;
+}
+
+int64_t sb_trainer_param_count(const sb_trainer_t* t) { return t ? t->net.n_params : 0; }
+
+int sb_trainer_set_params(sb_trainer_t* t, const float* flat, int64_t n) {
+  SB_CHECK(t && flat, SB_ERR_INVALID, "null argument");
+  SB_CHECK(n == t->net.n_params, SB_ERR_INVALID, "expected %lld params, got %lld", (long long)t->net.n_params, (long long)n);
+  SB_CUDA(cudaSetDevice(t->net.device));
+  SB_CUDA(cudaMemcpyAsync(t->net.theta, flat, sizeof(float) * n, cudaMemcpyHostToDevice, t->net.stream));
+  SB_TRY(t->net.refresh_shadows());
+  SB_CUDA(cudaStreamSynchronize(t->net.stream));
+  return SB_OK;
+}
+
+int sb_trainer_get_params(sb_trainer_t* t, float* flat, int64_t n) {
+  SB_CHECK(t && flat, SB_ERR_INVALID, "null argument");
+  SB_CHECK(n == t->net.n_params, SB_ERR_INVALID, "expected %lld params, got %lld", (long long)t->net.n_params, (long long)n);
+  SB_CUDA(cudaSetDevice(t->net.device));
+  SB_CUDA(cudaMemcpyAsync(flat, t->net.theta, sizeof(float) * n, cudaMemcpyDeviceToHost, t->net.stream));
+  SB_CUDA(cudaStreamSynchronize(t->net.stream));
+  return SB_OK;
+}
+
+int sb_trainer_init_xavier(sb_trainer_t* t, uint64_t seed) {
+  SB_CHECK(t, SB_ERR_INVALID, "null trainer");
+  // xavier_initializer() (uniform) on weights and biases, res/ssgd_monitor.py:59-68
+  std::vector<float> flat(static_cast<size_t>(t->net.n_params));
+  std::mt19937_64 rng(seed);
+  for (const Layer& ly : t->net.layers) {
+    const double lw = sqrt(6.0 / (ly.in + ly.out)), lb = sqrt(3.0 / ly.out);
+    std::uniform_real_distribution<double> uw(-lw, lw), ub(-lb, lb);
+    for (long long i = 0; i < static_cast<long long>(ly.in) * ly.out; ++i) flat[ly.w_off + i] = static_cast<float>(uw(rng));
+    for (int i = 0; i < ly.out; ++i) flat[ly.b_off + i] = static_cast<float>(ub(rng));
+  }
+  return sb_trainer_set_params(t, flat.data(), t->net.n_params);
+}
+
+int sb_trainer_get_grads(sb_trainer_t* t, float* flat, int64_t n) {
+  SB_CHECK(t && flat, SB_ERR_INVALID, "null argument");
+  SB_CHECK(n == t->net.n_params, SB_ERR_INVALID, "expected %lld grads, got %lld", (long long)t->net.n_params, (long long)n);
+  SB_CUDA(cudaSetDevice(t->net.device));
+  SB_CUDA(cudaMemcpyAsync(flat, t->grad, sizeof(float) * n, cudaMemcpyDeviceToHost, t->net.stream));
+  SB_CUDA(cudaStreamSynchronize(t->net.stream));
+  const float gs = t->grad_out_scale;
+  if (gs != 1.f) for (int64_t i = 0; i < n; ++i) flat[i] *= gs;
+  return SB_OK;
+}
+
+int sb_trainer_step(sb_trainer_t* t, const float* X, const float* y, const float* w, int32_t rows, float* loss_out) {
+  SB_CHECK(t, SB_ERR_INVALID, "null trainer");
+  SB_TRY(stage_host_batch(t, X, y, w, rows));
+  SB_TRY(run_step(t, t->net.stX, t->net.stY, w ? t->net.stW : nullptr, rows, G_STEP));
+  return finish_loss(t, loss_out);
+}
+
+int sb_trainer_accumulate(sb_trainer_t* t, const float* X, const float* y, const float* w, int32_t rows, float* loss_out) {
+  SB_CHECK(t, SB_ERR_INVALID, "null trainer");
+  SB_TRY(stage_host_batch(t, X, y, w, rows));
+  SB_TRY(run_step(t, t->net.stX, t->net.stY, w ? t->net.stW : nullptr, rows, G_ACC));
+  return finish_loss(t, loss_out);
+}
+
+int sb_trainer_apply_accumulated(sb_trainer_t* t) {
+  SB_CHECK(t, SB_ERR_INVALID, "null trainer");
+  SB_CHECK(t->n_acc > 0, SB_ERR_STATE, "no accumulated gradients");
+  Net& n = t->net;
+  SB_CUDA(cudaSetDevice(n.device));
+  ++t->global_step;
+  const float gscale = 1.f / (static_cast<float>(t->world) * static_cast<float>(t->n_acc));
+  set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, nullptr, nullptr, nullptr, lr_for_step(t, t->global_step), gscale);
+  SB_CUDA(cudaGetLastError());
+  SB_TRY(enqueue_allreduce(t, t->acc));
+  SB_TRY(enqueue_optimizer(t, t->acc));
+  // keep the applied mean gradient readable through sb_trainer_get_grads, then clear the accumulator
+  SB_CUDA(cudaMemcpyAsync(t->grad, t->acc, sizeof(float) * n.n_params, cudaMemcpyDeviceToDevice, n.stream));
+  const long long np = n.n_params;
+  scale_kernel<<<static_cast<unsigned>((np + 255) / 256), 256, 0, n.stream>>>(t->grad, n.desc, np);
+  SB_CUDA(cudaGetLastError());
+  t->grad_out_scale = 1.f;  // scale_kernel already applied 1/(world * n_acc)
+  SB_CUDA(cudaMemsetAsync(t->acc, 0, sizeof(float) * np, n.stream));
+  SB_CUDA(cudaStreamSynchronize(n.stream));
+  t->n_acc = 0;
+  return SB_OK;
+}
+
+int sb_trainer_load_dataset(sb_trainer_t* t, const float* X, const float* y, const float* w, int64_t n_rows) {
+  SB_CHECK(t && X && y, SB_ERR_INVALID, "null argument");
+  SB_CHECK(n_rows > 0, SB_ERR_INVALID, "n_rows must be > 0");
+  Net& n = t->net;
+  SB_CUDA(cudaSetDevice(n.device));
+  SB_CUDA(cudaStreamSynchronize(n.stream));
+  if (t->dsX) { cudaFree(t->dsX); cudaFree(t->dsY); cudaFree(t->dsW); t->dsX = t->dsY = t->dsW = nullptr; }
+  SB_CUDA(cudaMalloc(&t->dsX, sizeof(float) * n_rows * n.F));
+  SB_CUDA(cudaMalloc(&t->dsY, sizeof(float) * n_rows));
+  SB_CUDA(cudaMalloc(&t->dsW, sizeof(float) * n_rows));
+  SB_CUDA(cudaMemcpyAsync(t->dsX, X, sizeof(float) * n_rows * n.F, cudaMemcpyHostToDevice, n.stream));
+  SB_CUDA(cudaMemcpyAsync(t->dsY, y, sizeof(float) * n_rows, cudaMemcpyHostToDevice, n.stream));
+  if (w) {
+    SB_CUDA(cudaMemcpyAsync(t->dsW, w, sizeof(float) * n_rows, cudaMemcpyHostToDevice, n.stream));
+  } else {
+    fill_kernel<<<static_cast<unsigned>((n_rows + 255) / 256), 256, 0, n.stream>>>(t->dsW, 1.f, n_rows);
+    SB_CUDA(cudaGetLastError());
+  }
+  SB_CUDA(cudaStreamSynchronize(n.stream));
+  t->ds_rows = n_rows;
+  return SB_OK;
+}
+
+static int resident_step(sb_trainer_t* t, int64_t row_offset, int32_t rows, int kind) {
+  SB_CHECK(t, SB_ERR_INVALID, "null trainer");
+  SB_CHECK(t->dsX, SB_ERR_STATE, "no resident dataset loaded");
+  SB_CHECK(row_offset >= 0 && rows > 0 && row_offset + rows <= t->ds_rows, SB_ERR_INVALID,
+           "rows [%lld, %lld) outside the resident set of %lld rows", (long long)row_offset, (long long)(row_offset + rows),
+           (long long)t->ds_rows);
+  return run_step(t, t->dsX + row_offset * t->net.F, t->dsY + row_offset, t->dsW + row_offset, rows, kind);
+}
+
+int sb_trainer_step_resident(sb_trainer_t* t, int64_t row_offset, int32_t rows, float* loss_out) {
+  SB_TRY(resident_step(t, row_offset, rows, G_STEP));
+  return finish_loss(t, loss_out);
+}
+int sb_trainer_step_resident_async(sb_trainer_t* t, int64_t row_offset, int32_t rows) {
+  return resident_step(t, row_offset, rows, G_STEP);
+}
+int sb_trainer_accumulate_resident(sb_trainer_t* t, int64_t row_offset, int32_t rows, float* loss_out) {
+  SB_TRY(resident_step(t, row_offset, rows, G_ACC));
+  return finish_loss(t, loss_out);
+}
+int sb_trainer_last_loss(sb_trainer_t* t, float* loss_out) {
+  SB_CHECK(t && loss_out, SB_ERR_INVALID, "null argument");
+  return finish_loss(t, loss_out);
+}
+int sb_trainer_sync(sb_trainer_t* t) {
+  SB_CHECK(t, SB_ERR_INVALID, "null trainer");
+  SB_CUDA(cudaStreamSynchronize(t->net.stream));
+  return SB_OK;
+}
+void* sb_trainer_stream(sb_trainer_t* t) { return t ? reinterpret_cast<void*>(t->net.stream) : nullptr; }
+
+int sb_trainer_kernels_per_step(sb_trainer_t* t, int32_t rows) {
+  SB_CHECK(t, SB_ERR_INVALID, "null trainer");
+  cudaGraphExec_t ge;
+  SB_TRY(get_graph(t, rows, G_STEP, &ge));
+  return t->kernels_per_step[rows];
+}
+
+// One un-captured step over resident rows with a CUDA event after every launch.
+// ms[i] = device time between the end of launch i-1 (or the start marker) and the end of launch i.
+int sb_trainer_profile_step(sb_trainer_t* t, int64_t row_offset, int32_t rows, char* names, int32_t names_cap, float* ms,
+                            int32_t cap, int32_t* n_out) {
+  SB_CHECK(t && ms && n_out, SB_ERR_INVALID, "null argument");
+  SB_CHECK(t->dsX, SB_ERR_STATE, "no resident dataset loaded");
+  SB_CHECK(row_offset >= 0 && rows > 0 && rows <= t->net.max_batch && row_offset + rows <= t->ds_rows, SB_ERR_INVALID, "bad row range");
+  Net& n = t->net;
+  SB_CUDA(cudaSetDevice(n.device));
+  ++t->global_step;
+  const float gscale = 1.f / static_cast<float>(t->world);
+  set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, t->dsX + row_offset * n.F, t->dsY + row_offset, t->dsW + row_offset,
+                                           lr_for_step(t, t->global_step), gscale);
+  n.profiling = true;
+  n.prof_events.clear(); n.prof_names.clear();
+  n.launches = 0;
+  // the two memsets of the step body run before the start marker so they are not charged to load_batch
+  int s = SB_OK;
+  {
+    SB_CUDA(cudaMemsetAsync(t->grad, 0, sizeof(float) * n.n_params, n.stream));
+    SB_CUDA(cudaMemsetAsync(n.scal, 0, sizeof(float) * SCAL_COUNT, n.stream));
+    n.mark("start"); --n.launches;
+    s = n.enqueue_load(rows);
+    if (s == SB_OK) s = n.enqueue_hidden_forward(rows);
+    if (s == SB_OK) s = n.enqueue_out(rows, true, true, nullptr, t->grad);
+    if (s == SB_OK) s = n.enqueue_backward(rows, t->grad);
+    if (s == SB_OK) s = enqueue_allreduce(t, t->grad);
+    if (s == SB_OK && t->world > 1) { n.mark("allreduce"); --n.launches; }
+    if (s == SB_OK) s = enqueue_optimizer(t, t->grad);
+  }
+  n.profiling = false;
+  cudaError_t e = cudaStreamSynchronize(n.stream);
+  int cnt = 0;
+  std::string joined;
+  if (s == SB_OK && e == cudaSuccess) {
+    for (size_t i = 1; i < n.prof_events.size(); ++i) {
+      float v = 0.f;
+      cudaEventElapsedTime(&v, n.prof_events[i - 1], n.prof_events[i]);
+      if (cnt < cap) ms[cnt] = v;
+      if (!joined.empty()) joined += "\n";
+      joined += n.prof_names[i];
+      ++cnt;
+    }
+  }
+  for (cudaEvent_t ev : n.prof_events) cudaEventDestroy(ev);
+  n.prof_events.clear(); n.prof_names.clear();
+  SB_TRY(s);
+  SB_CHECK(e == cudaSuccess, SB_ERR_CUDA, "profile step failed: %s", cudaGetErrorString(e));
+  t->grad_out_scale = gscale;
+  *n_out = cnt;
+  if (names && names_cap > 0) { strncpy(names, joined.c_str(), names_cap - 1); names[names_cap - 1] = 0; }
+  return SB_OK;
+}
+
+// forward (+ optional loss) over any number of host rows, in max_batch chunks
+static int forward_chunks(Net& n, const float* X, const float* y, const float* w, int64_t rows, bool do_loss,
+                          float* out, double* loss_sum, double* nnz) {
+  SB_CUDA(cudaSetDevice(n.device));
+  float h[SCAL_COUNT];
+  for (int64_t r0 = 0; r0 < rows; r0 += n.max_batch) {
+    const int c = static_cast<int>(rows - r0 < n.max_batch ? rows - r0 : n.max_batch);
+    SB_CUDA(cudaMemcpyAsync(n.stX, X + r0 * n.F, sizeof(float) * c * static_cast<size_t>(n.F), cudaMemcpyHostToDevice, n.stream));
+    if (do_loss) {
+      SB_CUDA(cudaMemcpyAsync(n.stY, y + r0, sizeof(float) * c, cudaMemcpyHostToDevice, n.stream));
+      if (w) SB_CUDA(cudaMemcpyAsync(n.stW, w + r0, sizeof(float) * c, cudaMemcpyHostToDevice, n.stream));
+    }
+    set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, n.stX, n.stY, (do_loss && w) ? n.stW : n.ones, 0.f, 1.f);
+    SB_CUDA(cudaMemsetAsync(n.scal, 0, sizeof(float) * SCAL_COUNT, n.stream));
+    SB_TRY(n.enqueue_load(c));
+    SB_TRY(n.enqueue_hidden_forward(c));
+    SB_TRY(n.enqueue_out(c, do_loss, false, n.yhat, nullptr));
+    if (out) SB_CUDA(cudaMemcpyAsync(out + r0, n.yhat, sizeof(float) * c, cudaMemcpyDeviceToHost, n.stream));
+    if (do_loss) SB_CUDA(cudaMemcpyAsync(h, n.scal, sizeof(h), cudaMemcpyDeviceToHost, n.stream));
+    SB_CUDA(cudaStreamSynchronize(n.stream));
+    if (do_loss) { *loss_sum += h[SCAL_LOSS_SUM]; *nnz += h[SCAL_NNZ]; }
+  }
+  return SB_OK;
+}
+
+int sb_trainer_eval_loss(sb_trainer_t* t, const float* X, const float* y, const float* w, int64_t rows, float* loss_out) {
+  SB_CHECK(t && X && y && loss_out, SB_ERR_INVALID, "null argument");
+  SB_CHECK(rows > 0, SB_ERR_INVALID, "rows must be > 0");
+  double ls = 0, nz = 0;
+  SB_TRY(forward_chunks(t->net, X, y, w, rows, true, nullptr, &ls, &nz));
+  *loss_out = nz > 0 ? static_cast<float>(ls / nz) : 0.f;
+  return SB_OK;
+}
+
+int sb_trainer_predict(sb_trainer_t* t, const float* X, int64_t rows, float* out) {
+  SB_CHECK(t && X && out, SB_ERR_INVALID, "null argument");
+  SB_CHECK(rows > 0, SB_ERR_INVALID, "rows must be > 0");
+  double ls = 0, nz = 0;
+  return forward_chunks(t->net, X, nullptr, nullptr, rows, false, out, &ls, &nz);
+}
+
+// ---- checkpoint: flat blob {magic, version, n_params, global_step, optimizer, theta, s1, s2} ----
+static const uint64_t CKPT_MAGIC = 0x5348494655423230ull;  // "SHIFUB20"
+
+int sb_trainer_save_checkpoint(sb_trainer_t* t, const char* path) {
+  SB_CHECK(t && path, SB_ERR_INVALID, "null argument");
+  Net& n = t->net;
+  SB_CUDA(cudaSetDevice(n.device));
+  std::vector<float> buf(static_cast<size_t>(n.n_params) * 3);
+  SB_CUDA(cudaMemcpyAsync(buf.data(), n.theta, sizeof(float) * n.n_params, cudaMemcpyDeviceToHost, n.stream));
+  SB_CUDA(cudaMemcpyAsync(buf.data() + n.n_params, t->s1, sizeof(float) * n.n_params, cudaMemcpyDeviceToHost, n.stream));
+  SB_CUDA(cudaMemcpyAsync(buf.data() + 2 * n.n_params, t->s2, sizeof(float) * n.n_params, cudaMemcpyDeviceToHost, n.stream));
+  SB_CUDA(cudaStreamSynchronize(n.stream));
+  std::string tmp = std::string(path) + ".tmp";
+  FILE* f = fopen(tmp.c_str(), "wb");
+  SB_CHECK(f, SB_ERR_IO, "cannot open %s for writing", tmp.c_str());
+  uint64_t hdr[5] = {CKPT_MAGIC, 1, static_cast<uint64_t>(n.n_params), static_cast<uint64_t>(t->global_step),
+                     static_cast<uint64_t>(t->hyper.kind)};
+  bool ok = fwrite(hdr, sizeof(hdr), 1, f) == 1 && fwrite(buf.data(), sizeof(float), buf.size(), f) == buf.size();
+  ok = (fclose(f) == 0) && ok;
+  SB_CHECK(ok, SB_ERR_IO, "short write to %s", tmp.c_str());
+  SB_CHECK(rename(tmp.c_str(), path) == 0, SB_ERR_IO, "rename to %s failed", path);
+  return SB_OK;
+}
+
+int sb_trainer_load_checkpoint(sb_trainer_t* t, const char* path) {
+  SB_CHECK(t && path, SB_ERR_INVALID, "null argument");
+  Net& n = t->net;
+  FILE* f = fopen(path, "rb");
+  SB_CHECK(f, SB_ERR_IO, "cannot open %s", path);
+  uint64_t hdr[5];
+  std::vector<float> buf(static_cast<size_t>(n.n_params) * 3);
+  bool ok = fread(hdr, sizeof(hdr), 1, f) == 1;
+  ok = ok && hdr[0] == CKPT_MAGIC && hdr[2] == static_cast<uint64_t>(n.n_params);
+  ok = ok && fread(buf.data(), sizeof(float), buf.size(), f) == buf.size();
+  fclose(f);
+  SB_CHECK(ok, SB_ERR_FORMAT, "%s is not a checkpoint of this network", path);
+  SB_CUDA(cudaSetDevice(n.device));
+  SB_CUDA(cudaMemcpyAsync(n.theta, buf.data(), sizeof(float) * n.n_params, cudaMemcpyHostToDevice, n.stream));
+  SB_CUDA(cudaMemcpyAsync(t->s1, buf.data() + n.n_params, sizeof(float) * n.n_params, cudaMemcpyHostToDevice, n.stream));
+  SB_CUDA(cudaMemcpyAsync(t->s2, buf.data() + 2 * n.n_params, sizeof(float) * n.n_params, cudaMemcpyHostToDevice, n.stream));
+  SB_TRY(n.refresh_shadows());
+  SB_CUDA(cudaStreamSynchronize(n.stream));
+  t->global_step = static_cast<long long>(hdr[3]);
+  return SB_OK;
+}
+
+int64_t sb_trainer_global_step(const sb_trainer_t* t) { return t ? t->global_step : 0; }
+
+int sb_trainer_export_savedmodel(sb_trainer_t* t, const char* export_dir) {
+  SB_CHECK(t && export_dir, SB_ERR_INVALID, "null argument");
+  std::vector<float> flat(static_cast<size_t>(t->net.n_params));
+  SB_TRY(sb_trainer_get_params(t, flat.data(), t->net.n_params));
+  return sb_savedmodel_write(export_dir, &t->desc, flat.data(), t->net.n_params);
+}
+
+// ================================================================================================
+// scorer
+// ================================================================================================
+}  // extern "C"
+
+struct sb_model {
+  Net net;
+  sb_net_desc desc;
+  std::mutex mu;
+};
+
+static const int MODEL_CHUNK_ROWS = 16384;
+
+static int model_from_desc(sb_net_desc d, const float* flat, int64_t n, int device, sb_model_t** out) {
+  d.max_batch = MODEL_CHUNK_ROWS;
+  std::unique_ptr<sb_model> m(new sb_model());
+  m->desc = d;
+  int s = m->net.init(&d, device, false);
+  if (s != SB_OK) { m->net.destroy(); return s; }
+  if (n != m->net.n_params) {
+    m->net.destroy();
+    return set_error(SB_ERR_INVALID, "expected %lld params, got %lld", (long long)m->net.n_params, (long long)n);
+  }
+  Net& net = m->net;
+  SB_CUDA(cudaMemcpyAsync(net.theta, flat, sizeof(float) * n, cudaMemcpyHostToDevice, net.stream));
+  SB_TRY(net.refresh_shadows());
+  SB_CUDA(cudaStreamSynchronize(net.stream));
+  *out = m.release();
+  return SB_OK;
+}
+
+extern "C" {
+
+int sb_model_create(const sb_net_desc* desc, const float* flat_params, int64_t n, int device, sb_model_t** out) {
+  SB_CHECK(out && flat_params, SB_ERR_INVALID, "null argument");
+  *out = nullptr;
+  sb_net_desc d = *desc;
+  if (d.max_batch <= 0) d.max_batch = 1;
+  SB_TRY(validate_desc(&d));
+  return model_from_desc(d, flat_params, n, device, out);
+}
+
+int sb_model_load(const char* saved_model_dir, const char* input_name, const char* output_name, const char* tag,
+                  int device, int precision, sb_model_t** out) {
+  SB_CHECK(out, SB_ERR_INVALID, "out is null");
+  *out = nullptr;
+  // the null checks mirror TensorflowModel.init (TensorflowModel.java:147-166)
+  SB_CHECK(saved_model_dir && saved_model_dir[0], SB_ERR_INVALID, "Model path is null");
+  SB_CHECK(input_name && input_name[0], SB_ERR_INVALID, "Input names is null");
+  SB_CHECK(output_name && output_name[0], SB_ERR_INVALID, "Output names is null");
+  SB_CHECK(tag && tag[0], SB_ERR_INVALID, "Tags is null");
+  sb_net_desc d;
+  memset(&d, 0, sizeof(d));
+  int32_t out_act = SB_ACT_SIGMOID;
+  int64_t np = 0;
+  SB_TRY(sb_savedmodel_read(saved_model_dir, input_name, output_name, tag, &d, &out_act, nullptr, 0, &np));
+  SB_CHECK(out_act == SB_ACT_SIGMOID, SB_ERR_FORMAT, "output layer must be a sigmoid unit");
+  std::vector<float> flat(static_cast<size_t>(np));
+  SB_TRY(sb_savedmodel_read(saved_model_dir, input_name, output_name, tag, &d, &out_act, flat.data(), np, &np));
+  d.precision = precision;
+  d.max_batch = 1;
+  return model_from_desc(d, flat.data(), np, device, out);
+}
+
+int sb_model_destroy(sb_model_t* m) {
+  if (!m) return SB_OK;
+  cudaSetDevice(m->net.device);
+  m->net.destroy();
+  delete m;
+  return SB_OK;
+}
+
+int32_t sb_model_n_features(const sb_model_t* m) { return m ? m->net.F : 0; }
+int32_t sb_model_n_layers(const sb_model_t* m) { return m ? m->net.L + 1 : 0; }
+
+int sb_model_score(sb_model_t* m, const float* X, int64_t rows, float* out) {
+  SB_CHECK(m, SB_ERR_STATE, "TF model not initialized.");
+  SB_CHECK(X && out, SB_ERR_INVALID, "null argument");
+  if (rows <= 0) return SB_OK;
+  std::lock_guard<std::mutex> lk(m->mu);
+  double a = 0, b = 0;
+  return forward_chunks(m->net, X, nullptr, nullptr, rows, false, out, &a, &b);
+}
+
+int sb_model_score_row_f64(sb_model_t* m, const double* row, int32_t n, double* out) {
+  SB_CHECK(m, SB_ERR_STATE, "TF model not initialized.");
+  SB_CHECK(row && out, SB_ERR_INVALID, "null argument");
+  SB_CHECK(n == m->net.F, SB_ERR_INVALID, "expected %d features, got %d", m->net.F, n);
+  std::vector<float> f(static_cast<size_t>(n));
+  for (int i = 0; i < n; ++i) f[i] = static_cast<float>(row[i]);  // TensorflowModel.java:64-68
+  float r = 0.f;
+  SB_TRY(sb_model_score(m, f.data(), 1, &r));
+  *out = static_cast<double>(r);
+  return SB_OK;
+}
+
+int sb_model_score_device(sb_model_t* m, const float* dX, int64_t rows, float* dOut) {
+  SB_CHECK(m, SB_ERR_STATE, "TF model not initialized.");
+  SB_CHECK(dX && dOut, SB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(m->mu);
+  Net& n = m->net;
+  SB_CUDA(cudaSetDevice(n.device));
+  for (int64_t r0 = 0; r0 < rows; r0 += n.max_batch) {
+    const int c = static_cast<int>(rows - r0 < n.max_batch ? rows - r0 : n.max_batch);
+    set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, dX + r0 * n.F, nullptr, n.ones, 0.f, 1.f);
+    SB_TRY(n.enqueue_load(c));
+    SB_TRY(n.enqueue_hidden_forward(c));
+    SB_TRY(n.enqueue_out(c, false, false, dOut + r0, nullptr));
+  }
+  return SB_OK;
+}
+
+int sb_model_sync(sb_model_t* m) {
+  SB_CHECK(m, SB_ERR_STATE, "TF model not initialized.");
+  SB_CUDA(cudaStreamSynchronize(m->net.stream));
+  return SB_OK;
+}
+void* sb_model_stream(sb_model_t* m) { return m ? reinterpret_cast<void*>(m->net.stream) : nullptr; }
+
+// ================================================================================================
+// kernel-level test hook
+// ================================================================================================
+int sb_debug_gemm_bf16(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k, int device) {
+  SB_CHECK(A && B && D && M > 0 && N > 0 && K > 0, SB_ERR_INVALID, "bad argument");
+  int n_dev = 0;
+  SB_CHECK(cudaGetDeviceCount(&n_dev) == cudaSuccess && n_dev > 0, SB_ERR_CUDA, "no CUDA device available");
+  cudaDeviceProp prop;
+  SB_CUDA(cudaGetDeviceProperties(&prop, device));
+  SB_CHECK(prop.major == 10, SB_ERR_CUDA, "device is sm_%d%d, need sm_100", prop.major, prop.minor);
+  SB_CUDA(cudaSetDevice(device));
+  const int ldk = round_up(K, 8);
+  float *dA32 = nullptr, *dB32 = nullptr, *dD = nullptr;
+  __nv_bfloat16 *dA = nullptr, *dB = nullptr;
+  SB_CUDA(cudaMalloc(&dA32, sizeof(float) * M * K));
+  SB_CUDA(cudaMalloc(&dB32, sizeof(float) * N * K));
+  SB_CUDA(cudaMalloc(&dD, sizeof(float) * M * N));
+  SB_CUDA(cudaMalloc(&dA, sizeof(__nv_bfloat16) * M * ldk));
+  SB_CUDA(cudaMalloc(&dB, sizeof(__nv_bfloat16) * N * ldk));
+  SB_CUDA(cudaMemset(dA, 0, sizeof(__nv_bfloat16) * M * ldk));
+  SB_CUDA(cudaMemset(dB, 0, sizeof(__nv_bfloat16) * N * ldk));
+  SB_CUDA(cudaMemset(dD, 0, sizeof(float) * M * N));
+  SB_CUDA(cudaMemcpy(dA32, A, sizeof(float) * M * K, cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMemcpy(dB32, B, sizeof(float) * N * K, cudaMemcpyHostToDevice));
+  cast_bf16_kernel<<<static_cast<unsigned>((static_cast<long long>(M) * K + 255) / 256), 256>>>(dA32, M, K, dA, ldk);
+  cast_bf16_kernel<<<static_cast<unsigned>((static_cast<long long>(N) * K + 255) / 256), 256>>>(dB32, N, K, dB, ldk);
+  const int bn = N <= 64 ? 64 : 128;
+  CUtensorMap ta, tb;
+  int s = make_tmap_bf16(&ta, dA, M, K, ldk, 128);
+  if (s == SB_OK) s = make_tmap_bf16(&tb, dB, N, K, ldk, bn);
+  if (s == SB_OK) {
+    GemmTcParams p = {};
+    p.M = M; p.N = N; p.K = K;
+    const int total_kb = (K + 63) / 64;
+    int want = split_k < 1 ? 1 : (split_k > total_kb ? total_kb : split_k);
+    p.kb_per_split = (total_kb + want - 1) / want;
+    p.split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+    p.accum = dD; p.ld_acc = N;
+    const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
+    const int n_work = tiles * p.split_k;
+    const int grid = n_work < prop.multiProcessorCount ? n_work : prop.multiProcessorCount;
+    if (bn == 64) {
+      cudaFuncSetAttribute(gemm_tc_kernel<64, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmTcCfg<64>::SMEM_BYTES);
+      gemm_tc_kernel<64, EPI_F32><<<grid, 192, GemmTcCfg<64>::SMEM_BYTES>>>(ta, tb, p);
+    } else {
+      cudaFuncSetAttribute(gemm_tc_kernel<128, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmTcCfg<128>::SMEM_BYTES);
+      gemm_tc_kernel<128, EPI_F32><<<grid, 192, GemmTcCfg<128>::SMEM_BYTES>>>(ta, tb, p);
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) s = set_error(SB_ERR_CUDA, "gemm_tc_kernel failed: %s", cudaGetErrorString(e));
+    else if (cudaMemcpy(D, dD, sizeof(float) * M * N, cudaMemcpyDeviceToHost) != cudaSuccess) s = set_error(SB_ERR_CUDA, "D2H failed");
+  }
+  cudaFree(dA32); cudaFree(dB32); cudaFree(dD); cudaFree(dA); cudaFree(dB);
+  return s;
+}
+
+}  // extern "C"

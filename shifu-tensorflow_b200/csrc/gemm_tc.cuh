@@ -1,0 +1,310 @@
+// tcgen05 / TMEM / TMA dense-layer GEMM for sm_100a with fused epilogues.
+//
+//   D[M,N] = A[M,K] * B[N,K]^T        A, B bf16, K-major (K contiguous), fp32 accumulation in TMEM
+//
+// This one kernel covers every dense contraction of the tabular-DNN step (the TF ops behind
+// nn_layer, res/ssgd_monitor.py:57-71, and their gradients built by opt.minimize, :142):
+//   EPI_FWD : Z = A_{l-1} W_l        + bias, activation, write A_l (bf16) and A_l^T          (MatMul+Add+act)
+//   EPI_DA  : dA = dZ_l W_l^T        * act'(A_{l-1}), write dZ_{l-1}, dZ_{l-1}^T, column sums -> db_{l-1}
+//   EPI_DW  : dW_l = A_{l-1}^T dZ_l  split-K over the batch, fp32 red.add into the flat gradient
+//   EPI_F32 : plain fp32 store (kernel-level parity test hook)
+//
+// Structure (one persistent CTA per SM, 192 threads):
+//   warp 0     : TMA producer   - cp.async.bulk.tensor 128B-swizzled tiles into a STAGES-deep smem ring
+//   warp 1     : MMA issuer     - one thread issues tcgen05.mma (128 x BN x 16), commits to mbarriers
+//   warps 2..5 : epilogue       - tcgen05.ld the accumulator (double-buffered in TMEM) and apply the epilogue
+// M/N/K tails need no special code on the load side: TMA zero-fills out-of-bounds box elements.
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace sb {
+
+enum { EPI_FWD = 0, EPI_DA = 1, EPI_DW = 2, EPI_F32 = 3 };
+
+struct GemmTcParams {
+  int M, N, K;
+  int kb_per_split;  // k-blocks (of 64) per split
+  int split_k;       // number of splits actually used (all non-empty)
+  // EPI_FWD
+  const float* bias;  // [N]
+  int act;            // FWD: activation applied; DA: activation whose derivative is applied
+  __nv_bfloat16* out;   // [M, ld_out] row-major (FWD, DA)
+  int ld_out;
+  __nv_bfloat16* outT;  // [N, ld_outT] transposed copy, nullable (FWD, DA)
+  int ld_outT;
+  // EPI_DA
+  const __nv_bfloat16* aux;  // activation output A_{l-1} [M, ld_aux]
+  int ld_aux;
+  float* colsum;  // [N] fp32, atomically accumulated (bias gradient), nullable
+  // EPI_DW / EPI_F32
+  float* accum;  // [M, ld_acc] fp32
+  int ld_acc;
+  int acc_vec4;  // 1 if 16-byte aligned rows -> red.global.add.v4.f32
+};
+
+template <int BN>
+struct GemmTcCfg {
+  static constexpr int BM = 128;
+  static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int THREADS = 192;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
+  using Cfg = GemmTcCfg<BN>;
+  constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
+  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem base slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto smem_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
+  auto smem_b = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + Cfg::A_BYTES; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  const int tiles_m = (p.M + BM - 1) / BM;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int n_tiles = tiles_m * tiles_n;
+  const int n_work = n_tiles * p.split_k;
+  const int total_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+        const int tile = w % n_tiles, ks = w / n_tiles;
+        const int tm = tile / tiles_n, tn = tile % tiles_n;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          tma_load_2d(smem_a(stage), &tmA, full_bar(stage), kb * BK, tm * BM);
+          tma_load_2d(smem_b(stage), &tmB, full_bar(stage), kb * BK, tn * BN);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+        const int ks = w / n_tiles;
+        const int kb0 = ks * p.kb_per_split;
+        const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
+          tcgen05_fence_after();
+          const uint64_t da = make_kmajor_sw128_desc(smem_a(stage));
+          const uint64_t db = make_kmajor_sw128_desc(smem_b(stage));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
+            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ================= epilogue warps (2..5) =================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int it = 0;
+    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+      const int tile = w % n_tiles;
+      const int tm = tile / tiles_n, tn = tile % tiles_n;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const int row = tm * BM + quarter * 32 + lane;  // output row owned by this thread
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = tn * BN + c * 32;
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, raw);
+        tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        if (col0 >= p.N) continue;  // whole chunk out of range (warp-uniform)
+
+        if constexpr (EPI == EPI_FWD) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int cc = col0 + j;
+            const float b = (cc < p.N) ? __ldg(p.bias + cc) : 0.f;
+            v[j] = act_apply(v[j] + b, p.act);
+          }
+        } else if constexpr (EPI == EPI_DA) {
+          // multiply by act'(A_{l-1}[row, col]) read as bf16 (64 B per thread per chunk)
+          uint4 a4[4];
+          if (row_ok) {
+            const uint4* ap = reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(row) * p.ld_aux + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a4[q] = (col0 + q * 8 < p.ld_aux) ? __ldg(ap + q) : make_uint4(0, 0, 0, 0);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a4[q] = make_uint4(0, 0, 0, 0);
+          }
+          const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(a4);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float g = act_grad_from_out(__bfloat162float(ah[j]), p.act);
+            v[j] = (row_ok && col0 + j < p.N) ? v[j] * g : 0.f;
+          }
+        }
+
+        if constexpr (EPI == EPI_FWD || EPI == EPI_DA) {
+          if (row_ok) {
+            // row-major bf16: 4 x 16 B per thread
+            __nv_bfloat16* op = p.out + static_cast<size_t>(row) * p.ld_out + col0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (col0 + q * 8 < p.ld_out) {
+                uint4 o;
+                o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+                o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+                o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+                o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+                *reinterpret_cast<uint4*>(op + q * 8) = o;
+              }
+            }
+            // transposed bf16: consecutive lanes = consecutive rows -> 64 B contiguous per column
+            if (p.outT != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (col0 + j < p.N) p.outT[static_cast<size_t>(col0 + j) * p.ld_outT + row] = __float2bfloat16_rn(v[j]);
+              }
+            }
+          }
+          if constexpr (EPI == EPI_DA) {
+            if (p.colsum != nullptr) {
+              // bias gradient: per-column sum over this warp's 32 rows, one atomic per column per warp
+              const float s = warp_colsum_32x32(v, lane);
+              if (col0 + lane < p.N) red_add_f32(p.colsum + col0 + lane, s);
+            }
+          }
+        } else if constexpr (EPI == EPI_DW) {
+          if (row_ok) {
+            float* gp = p.accum + static_cast<size_t>(row) * p.ld_acc + col0;
+            if (p.acc_vec4 && col0 + 32 <= p.N) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) red_add_v4_f32(gp + q * 4, v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) red_add_f32(gp + j, v[j]);
+            }
+          }
+        } else {  // EPI_F32
+          if (row_ok) {
+            float* gp = p.accum + static_cast<size_t>(row) * p.ld_acc + col0;
+            if (p.split_k == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) gp[j] = v[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) red_add_f32(gp + j, v[j]);
+            }
+          }
+        }
+      }
+      // release the accumulator back to the MMA warp
+      tcgen05_fence_before();
+      mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode_tiled();
+
+// Tensor map of a row-major bf16 matrix [rows, cols] with leading dimension ld (elements):
+// box = 64 columns x box_rows rows, 128-byte swizzle.  cols/rows are the LOGICAL extents (TMA
+// zero-fills beyond them), ld*2 must be a multiple of 16 bytes.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int cols, int ld, int box_rows);
+
+int pick_split_k(int M, int N, int K, int BN, int num_sms, int* kb_per_split);
+
+template <int BN, int EPI>
+int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmTcParams p, int num_sms, cudaStream_t st) {
+  using Cfg = GemmTcCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+    attr_done = true;
+  }
+  const int tiles = ((p.M + 127) / 128) * ((p.N + BN - 1) / BN);
+  const int n_work = tiles * p.split_k;
+  const int grid = n_work < num_sms ? n_work : num_sms;
+  gemm_tc_kernel<BN, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
+  SB_CUDA(cudaGetLastError());
+  return SB_OK;
+}
+
+}  // namespace sb

@@ -1,0 +1,368 @@
+// Net: device state + kernel sequencing for the tabular-DNN forward / backward.
+// Mirrors generate_from_modelconf + model (res/ssgd_monitor.py:91-144) as a list of fused launches.
+#include <stdarg.h>
+#include <string.h>
+#include "net.cuh"
+
+namespace sb {
+
+std::string& last_error_ref() {
+  thread_local std::string e;
+  return e;
+}
+int set_error(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+
+PFN_encodeTiled get_encode_tiled() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int cols, int ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode_tiled();
+  SB_CHECK(enc != nullptr, SB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
+  SB_CHECK(rows > 0 && cols > 0 && (ld % 8) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0, SB_ERR_INVALID,
+           "tensor map: bad geometry rows=%d cols=%d ld=%d", rows, cols, ld);
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstr[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {64u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SB_CHECK(r == CUDA_SUCCESS, SB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d cols=%d ld=%d box_rows=%d",
+           static_cast<int>(r), rows, cols, ld, box_rows);
+  return SB_OK;
+}
+
+int pick_split_k(int M, int N, int K, int BN, int num_sms, int* kb_per_split) {
+  const int tiles = ((M + 127) / 128) * ((N + BN - 1) / BN);
+  const int total_kb = (K + 63) / 64;
+  int want = num_sms / (tiles > 0 ? tiles : 1);
+  if (want < 1) want = 1;
+  int cap = total_kb / 2;
+  if (cap < 1) cap = 1;
+  if (want > cap) want = cap;
+  const int kb_per = (total_kb + want - 1) / want;
+  *kb_per_split = kb_per;
+  return (total_kb + kb_per - 1) / kb_per;
+}
+
+int validate_desc(const sb_net_desc* d) {
+  SB_CHECK(d != nullptr, SB_ERR_INVALID, "net desc is null");
+  SB_CHECK(d->n_features > 0, SB_ERR_INVALID, "n_features must be > 0 (got %d)", d->n_features);
+  SB_CHECK(d->n_hidden >= 1 && d->n_hidden <= SB_MAX_HIDDEN, SB_ERR_INVALID, "n_hidden must be in [1,%d] (got %d)",
+           SB_MAX_HIDDEN, d->n_hidden);
+  for (int l = 0; l < d->n_hidden; ++l) {
+    SB_CHECK(d->hidden[l] > 0, SB_ERR_INVALID, "hidden[%d] must be > 0", l);
+    SB_CHECK(d->acts[l] >= SB_ACT_NONE && d->acts[l] <= SB_ACT_LEAKYRELU, SB_ERR_INVALID, "acts[%d] invalid", l);
+  }
+  SB_CHECK(d->max_batch > 0, SB_ERR_INVALID, "max_batch must be > 0");
+  SB_CHECK(d->precision == SB_PREC_FP32 || d->precision == SB_PREC_BF16, SB_ERR_INVALID, "precision invalid");
+  SB_CHECK(d->loss == SB_LOSS_MSE || d->loss == SB_LOSS_SIGMOID_CE, SB_ERR_INVALID, "loss invalid");
+  SB_CHECK(d->optimizer >= SB_OPT_ADADELTA && d->optimizer <= SB_OPT_MOMENTUM, SB_ERR_INVALID, "optimizer invalid");
+  return SB_OK;
+}
+
+static int check_device(int device, int* num_sms) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  SB_CHECK(e == cudaSuccess && n > 0, SB_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+           cudaGetErrorString(e));
+  SB_CHECK(device >= 0 && device < n, SB_ERR_INVALID, "device %d out of range [0,%d)", device, n);
+  cudaDeviceProp prop;
+  SB_CUDA(cudaGetDeviceProperties(&prop, device));
+  SB_CHECK(prop.major == 10, SB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+           prop.major, prop.minor);
+  *num_sms = prop.multiProcessorCount;
+  return SB_OK;
+}
+
+int Net::init(const sb_net_desc* d, int device_, bool training_) {
+  SB_TRY(validate_desc(d));
+  SB_TRY(check_device(device_, &num_sms));
+  device = device_;
+  training = training_;
+  SB_CUDA(cudaSetDevice(device));
+  SB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  F = d->n_features;
+  L = d->n_hidden;
+  precision = d->precision;
+  loss = d->loss;
+  max_batch = d->max_batch;
+  ldB = round_up(max_batch, 8);
+  ldF = round_up(F, 8);
+  layers.resize(L + 1);
+  long long off = 0;
+  int prev = F;
+  for (int l = 0; l <= L; ++l) {
+    Layer& ly = layers[l];
+    ly.in = prev;
+    ly.out = (l < L) ? d->hidden[l] : 1;
+    ly.act = (l < L) ? d->acts[l] : SB_ACT_SIGMOID;
+    ly.w_off = off; off += static_cast<long long>(ly.in) * ly.out;
+    ly.b_off = off; off += ly.out;
+    ly.ld_in = round_up(ly.in, 8);
+    ly.ld_out = round_up(ly.out, 8);
+    prev = ly.out;
+  }
+  n_params = off;
+  SB_TRY(dalloc(&theta, n_params));
+  SB_TRY(dalloc(&scal, SCAL_COUNT));
+  SB_TRY(dalloc(&desc, 1));
+  SB_TRY(dalloc(&yhat, max_batch));
+  SB_TRY(dalloc(&ones, max_batch));
+  SB_TRY(dalloc(&stX, static_cast<size_t>(max_batch) * F));
+  SB_TRY(dalloc(&stY, max_batch));
+  SB_TRY(dalloc(&stW, max_batch));
+  fill_kernel<<<(max_batch + 255) / 256, 256, 0, stream>>>(ones, 1.f, max_batch);
+
+  const bool bf = precision == SB_PREC_BF16;
+  if (bf) {
+    SB_TRY(dalloc(&Xb, static_cast<size_t>(max_batch) * ldF));
+    if (training) SB_TRY(dalloc(&XbT, static_cast<size_t>(F) * ldB));
+    A.assign(L, nullptr); AT.assign(L, nullptr); dZ.assign(L, nullptr); dZT.assign(L, nullptr);
+    for (int l = 0; l < L; ++l) {
+      Layer& ly = layers[l];
+      SB_TRY(dalloc(&ly.Wt, static_cast<size_t>(ly.out) * ly.ld_in));
+      if (training && l > 0) SB_TRY(dalloc(&ly.Wn, static_cast<size_t>(ly.in) * ly.ld_out));
+      SB_TRY(dalloc(&A[l], static_cast<size_t>(max_batch) * ly.ld_out));
+      if (training) {
+        if (l < L - 1) SB_TRY(dalloc(&AT[l], static_cast<size_t>(ly.out) * ldB));
+        SB_TRY(dalloc(&dZ[l], static_cast<size_t>(max_batch) * ly.ld_out));
+        SB_TRY(dalloc(&dZT[l], static_cast<size_t>(ly.out) * ldB));
+      }
+    }
+  } else {
+    SB_TRY(dalloc(&Xf, static_cast<size_t>(max_batch) * F));
+    Af.assign(L, nullptr); dZf.assign(L, nullptr);
+    for (int l = 0; l < L; ++l) {
+      SB_TRY(dalloc(&Af[l], static_cast<size_t>(max_batch) * layers[l].out));
+      if (training) SB_TRY(dalloc(&dZf[l], static_cast<size_t>(max_batch) * layers[l].out));
+    }
+  }
+
+  // optimizer / shadow-refresh work table
+  std::vector<OptWork> wk;
+  auto add_plain = [&](long long o, long long n) {
+    for (long long s = 0; s < n; s += 1024) {
+      OptWork w = {};
+      w.off = o + s; w.kind = 0; w.count = static_cast<int>(n - s < 1024 ? n - s : 1024);
+      wk.push_back(w);
+    }
+  };
+  for (int l = 0; l <= L; ++l) {
+    Layer& ly = layers[l];
+    if (bf && l < L) {
+      for (int ti = 0; ti < (ly.in + 31) / 32; ++ti)
+        for (int to = 0; to < (ly.out + 31) / 32; ++to) {
+          OptWork w = {};
+          w.off = ly.w_off; w.kind = 1; w.in_dim = ly.in; w.out_dim = ly.out; w.ti = ti; w.to = to;
+          w.Wt = ly.Wt; w.ld_in = ly.ld_in; w.Wn = ly.Wn; w.ld_out = ly.ld_out;
+          wk.push_back(w);
+        }
+      add_plain(ly.b_off, ly.out);
+    } else {
+      add_plain(ly.w_off, static_cast<long long>(ly.in) * ly.out + ly.out);
+    }
+  }
+  n_work = static_cast<int>(wk.size());
+  SB_TRY(dalloc(&work, wk.size()));
+  SB_CUDA(cudaMemcpyAsync(work, wk.data(), wk.size() * sizeof(OptWork), cudaMemcpyHostToDevice, stream));
+  SB_CUDA(cudaStreamSynchronize(stream));
+
+  // opt in to > 48 KB dynamic shared memory once, outside of any stream capture
+  if (bf) {
+#define SB_ATTR(BN, EPI) \
+  SB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmTcCfg<BN>::SMEM_BYTES))
+    SB_ATTR(64, EPI_FWD); SB_ATTR(128, EPI_FWD);
+    SB_ATTR(64, EPI_DA);  SB_ATTR(128, EPI_DA);
+    SB_ATTR(64, EPI_DW);  SB_ATTR(128, EPI_DW);
+#undef SB_ATTR
+  }
+  return SB_OK;
+}
+
+void Net::destroy() {
+  if (stream) cudaStreamSynchronize(stream);
+  for (void* p : allocs) cudaFree(p);
+  allocs.clear();
+  if (stream) cudaStreamDestroy(stream);
+  stream = nullptr;
+}
+
+int Net::refresh_shadows() {
+  if (precision != SB_PREC_BF16) return SB_OK;
+  shadow_refresh_kernel<<<n_work, 256, 0, stream>>>(work, theta);
+  SB_CUDA(cudaGetLastError());
+  return SB_OK;
+}
+
+int Net::enqueue_load(int rows) {
+  dim3 grid((F + 31) / 32, (rows + 31) / 32);
+  if (precision == SB_PREC_BF16)
+    load_batch_kernel<true><<<grid, 256, 0, stream>>>(desc, rows, F, Xb, ldF, XbT, ldB, nullptr, scal);
+  else
+    load_batch_kernel<false><<<grid, 256, 0, stream>>>(desc, rows, F, nullptr, 0, nullptr, 0, Xf, scal);
+  SB_CUDA(cudaGetLastError());
+  mark("load_batch");
+  return SB_OK;
+}
+
+template <int EPI>
+static int launch_tc_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmTcParams& p, int num_sms, cudaStream_t st) {
+  using namespace sb;
+  const int tiles = ((p.M + 127) / 128) * ((p.N + bn - 1) / bn);
+  const int n_work = tiles * p.split_k;
+  const int grid = n_work < num_sms ? n_work : num_sms;
+  if (bn == 64)
+    gemm_tc_kernel<64, EPI><<<grid, 192, GemmTcCfg<64>::SMEM_BYTES, st>>>(a, b, p);
+  else
+    gemm_tc_kernel<128, EPI><<<grid, 192, GemmTcCfg<128>::SMEM_BYTES, st>>>(a, b, p);
+  SB_CUDA(cudaGetLastError());
+  return SB_OK;
+}
+
+static inline int pick_bn(int N) { return N <= 64 ? 64 : 128; }
+
+int Net::enqueue_hidden_forward(int rows) {
+  for (int l = 0; l < L; ++l) {
+    Layer& ly = layers[l];
+    if (precision == SB_PREC_BF16) {
+      const int bn = pick_bn(ly.out);
+      CUtensorMap ta, tb;
+      const __nv_bfloat16* src = (l == 0) ? Xb : A[l - 1];
+      SB_TRY(make_tmap_bf16(&ta, src, rows, ly.in, ly.ld_in, 128));
+      SB_TRY(make_tmap_bf16(&tb, ly.Wt, ly.out, ly.in, ly.ld_in, bn));
+      GemmTcParams p = {};
+      p.M = rows; p.N = ly.out; p.K = ly.in;
+      p.split_k = 1; p.kb_per_split = (ly.in + 63) / 64;
+      p.bias = theta + ly.b_off; p.act = ly.act;
+      p.out = A[l]; p.ld_out = ly.ld_out;
+      p.outT = (training && l < L - 1) ? AT[l] : nullptr; p.ld_outT = ldB;
+      SB_TRY(launch_tc_bn<EPI_FWD>(bn, ta, tb, p, num_sms, stream));
+    } else {
+      GemmF32Params p = {};
+      p.M = rows; p.N = ly.out; p.K = ly.in;
+      p.A = (l == 0) ? Xf : Af[l - 1]; p.sAm = ly.in; p.sAk = 1;
+      p.B = theta + ly.w_off; p.sBk = ly.out; p.sBn = 1;
+      p.bias = theta + ly.b_off; p.act = ly.act;
+      p.out = Af[l]; p.ld_out = ly.out;
+      SB_TRY(launch_gemm_f32<EPI_FWD>(p, 1, stream));
+    }
+    mark("gemm_fwd");
+  }
+  return SB_OK;
+}
+
+int Net::enqueue_out(int rows, bool do_loss, bool do_bwd, float* yhat_dst, float* grad) {
+  Layer& hl = layers[L - 1];
+  Layer& ol = layers[L];
+  OutLayerParams p = {};
+  p.rows = rows; p.H = hl.out;
+  p.wo = theta + ol.w_off; p.bo = theta + ol.b_off;
+  p.desc = desc; p.scal = scal; p.loss = loss; p.act = hl.act;
+  p.do_bwd = do_bwd ? 1 : 0; p.do_loss = do_loss ? 1 : 0;
+  p.yhat = yhat_dst;
+  if (do_bwd) {
+    p.g_wo = grad + ol.w_off; p.g_bo = grad + ol.b_off; p.g_bL = grad + hl.b_off;
+  }
+  const int grid = (rows + 31) / 32;
+  if (precision == SB_PREC_BF16) {
+    p.A = A[L - 1]; p.ldA = hl.ld_out;
+    if (do_bwd) { p.dZ = dZ[L - 1]; p.ld_dZ = hl.ld_out; p.dZT = dZT[L - 1]; p.ld_dZT = ldB; }
+    out_layer_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p);
+  } else {
+    p.A = Af[L - 1]; p.ldA = hl.out;
+    if (do_bwd) { p.dZ = dZf[L - 1]; p.ld_dZ = hl.out; p.dZT = nullptr; }
+    out_layer_kernel<float><<<grid, 256, 0, stream>>>(p);
+  }
+  SB_CUDA(cudaGetLastError());
+  mark("out_layer");
+  return SB_OK;
+}
+
+int Net::enqueue_backward(int rows, float* grad) {
+  for (int l = L - 1; l >= 0; --l) {
+    Layer& ly = layers[l];
+    if (precision == SB_PREC_BF16) {
+      // dW_l[in,out] += A_{l-1}^T[in, rows] * dZ_l^T[out, rows]^T   (reduction over the batch, split-K)
+      {
+        const int bn = pick_bn(ly.out);
+        CUtensorMap ta, tb;
+        const __nv_bfloat16* aT = (l == 0) ? XbT : AT[l - 1];
+        SB_TRY(make_tmap_bf16(&ta, aT, ly.in, rows, ldB, 128));
+        SB_TRY(make_tmap_bf16(&tb, dZT[l], ly.out, rows, ldB, bn));
+        GemmTcParams p = {};
+        p.M = ly.in; p.N = ly.out; p.K = rows;
+        p.split_k = pick_split_k(p.M, p.N, p.K, bn, num_sms, &p.kb_per_split);
+        p.accum = grad + ly.w_off; p.ld_acc = ly.out;
+        p.acc_vec4 = (ly.out % 4 == 0 && ly.w_off % 4 == 0) ? 1 : 0;
+        SB_TRY(launch_tc_bn<EPI_DW>(bn, ta, tb, p, num_sms, stream));
+        mark("gemm_dw");
+      }
+      if (l > 0) {
+        // dZ_{l-1}[rows,in] = (dZ_l[rows,out] * W_l[in,out]^T) .* act'(A_{l-1})
+        Layer& pl = layers[l - 1];
+        const int bn = pick_bn(ly.in);
+        CUtensorMap ta, tb;
+        SB_TRY(make_tmap_bf16(&ta, dZ[l], rows, ly.out, ly.ld_out, 128));
+        SB_TRY(make_tmap_bf16(&tb, ly.Wn, ly.in, ly.out, ly.ld_out, bn));
+        GemmTcParams p = {};
+        p.M = rows; p.N = ly.in; p.K = ly.out;
+        p.split_k = 1; p.kb_per_split = (ly.out + 63) / 64;
+        p.act = pl.act;
+        p.aux = A[l - 1]; p.ld_aux = pl.ld_out;
+        p.out = dZ[l - 1]; p.ld_out = pl.ld_out;
+        p.outT = dZT[l - 1]; p.ld_outT = ldB;
+        p.colsum = grad + pl.b_off;
+        SB_TRY(launch_tc_bn<EPI_DA>(bn, ta, tb, p, num_sms, stream));
+        mark("gemm_da");
+      }
+    } else {
+      {
+        GemmF32Params p = {};
+        p.M = ly.in; p.N = ly.out; p.K = rows;
+        p.A = (l == 0) ? Xf : Af[l - 1]; p.sAm = 1; p.sAk = ly.in;
+        p.B = dZf[l]; p.sBk = ly.out; p.sBn = 1;
+        p.accum = grad + ly.w_off; p.ld_acc = ly.out;
+        const int tiles = ((p.M + 63) / 64) * ((p.N + 63) / 64);
+        int split = (2 * num_sms) / (tiles > 0 ? tiles : 1);
+        const int cap = (rows + 63) / 64;
+        if (split > cap) split = cap;
+        SB_TRY(launch_gemm_f32<EPI_DW>(p, split, stream));
+        mark("gemm_dw");
+      }
+      if (l > 0) {
+        Layer& pl = layers[l - 1];
+        GemmF32Params p = {};
+        p.M = rows; p.N = ly.in; p.K = ly.out;
+        p.A = dZf[l]; p.sAm = ly.out; p.sAk = 1;
+        p.B = theta + ly.w_off; p.sBk = 1; p.sBn = ly.out;
+        p.act = pl.act;
+        p.aux = Af[l - 1]; p.ld_aux = pl.out;
+        p.out = dZf[l - 1]; p.ld_out = pl.out;
+        p.colsum = grad + pl.b_off;
+        SB_TRY(launch_gemm_f32<EPI_DA>(p, 1, stream));
+        mark("gemm_da");
+      }
+    }
+  }
+  return SB_OK;
+}
+
+}  // namespace sb

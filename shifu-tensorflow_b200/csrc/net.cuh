@@ -1,0 +1,81 @@
+// Device-side network state shared by the trainer and the scorer: parameters, bf16 shadow weights,
+// activation workspace, and the enqueue_* routines that put the step's kernels on a stream.
+#pragma once
+#include <vector>
+#include <map>
+#include <mutex>
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "gemm_f32.cuh"
+#include "kernels.cuh"
+#include "nccl_dyn.h"
+
+namespace sb {
+
+struct Layer {
+  int in, out, act;
+  long long w_off, b_off;              // offsets into the flat parameter vector
+  __nv_bfloat16 *Wt = nullptr, *Wn = nullptr;  // bf16 shadows: W^T [out, ld_in], W [in, ld_out]
+  int ld_in = 0, ld_out = 0;
+};
+
+struct Net {
+  int device = 0, num_sms = 148;
+  cudaStream_t stream = nullptr;
+  int F = 0, L = 0;             // features, hidden layers
+  std::vector<Layer> layers;    // L hidden + 1 output (out = 1)
+  long long n_params = 0;
+  int precision = SB_PREC_FP32, loss = SB_LOSS_MSE;
+  int max_batch = 0, ldB = 0, ldF = 0;
+  bool training = false;
+
+  float* theta = nullptr;
+  // bf16 workspace
+  __nv_bfloat16 *Xb = nullptr, *XbT = nullptr;
+  std::vector<__nv_bfloat16*> A, AT, dZ, dZT;
+  // fp32 workspace
+  float* Xf = nullptr;
+  std::vector<float*> Af, dZf;
+  float *yhat = nullptr, *scal = nullptr, *ones = nullptr;
+  BatchDesc* desc = nullptr;
+  float *stX = nullptr, *stY = nullptr, *stW = nullptr;  // H2D staging (device)
+  OptWork* work = nullptr;
+  int n_work = 0;
+  int launches = 0;  // kernels enqueued since last reset (for gpu_launches accounting)
+  // optional per-launch CUDA-event timing (sb_trainer_profile_step): one event after every launch
+  bool profiling = false;
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<std::string> prof_names;
+  void mark(const char* name) {
+    ++launches;
+    if (!profiling) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, stream);
+    prof_events.push_back(e);
+    prof_names.push_back(name);
+  }
+
+  std::vector<void*> allocs;
+  template <typename T> int dalloc(T** p, size_t n) {
+    void* q = nullptr;
+    SB_CUDA(cudaMalloc(&q, n * sizeof(T) + 256));
+    SB_CUDA(cudaMemsetAsync(q, 0, n * sizeof(T) + 256, stream));
+    allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return SB_OK;
+  }
+
+  int init(const sb_net_desc* d, int device_, bool training_);
+  void destroy();
+  int refresh_shadows();
+  // forward through the hidden layers (A_0 = current batch -> A_L)
+  int enqueue_load(int rows);
+  int enqueue_hidden_forward(int rows);
+  int enqueue_out(int rows, bool do_loss, bool do_bwd, float* yhat_dst, float* grad);
+  int enqueue_backward(int rows, float* grad);
+};
+
+int validate_desc(const sb_net_desc* d);
+
+}  // namespace sb

@@ -1,0 +1,46 @@
+"""Kernel-level parity of the tcgen05 GEMM (gemm_tc.cuh) through the C-ABI test hook.
+
+Oracle: float64 matmul of the bf16-rounded operands (the kernel multiplies exact bf16 products and accumulates
+in fp32 in TMEM, so the only difference is fp32 summation order/rounding)."""
+import numpy as np
+import pytest
+
+from conftest import bf16_round
+
+SHAPES = [
+    # (M, N, K, split_k)
+    (128, 128, 64, 1),        # one tile, one k-block
+    (128, 64, 128, 1),        # BN = 64 path
+    (256, 256, 256, 1),       # several tiles
+    (100, 50, 200, 1),        # ragged M/N/K (cfg0 layer shapes): TMA zero fill + guarded stores
+    (4096, 512, 1000, 1),     # cfg1 layer-0 forward, K tail (1000 % 64 != 0)
+    (1000, 512, 4096, 4),     # cfg1 layer-0 dW as split-K over the batch
+    (512, 256, 4096, 16),     # deeper split
+    (130, 129, 72, 2),        # everything ragged + split
+    (8192, 1024, 2000, 1),    # cfg2 layer-0 forward (persistent: > 148 tiles, TMEM double buffering)
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M,N,K,split_k", SHAPES)
+def test_gemm_bf16_matches_fp64(sb, M, N, K, split_k):
+    rng = np.random.RandomState(M * 7 + N * 3 + K)
+    A = bf16_round(rng.standard_normal((M, K)).astype(np.float32))
+    B = bf16_round(rng.standard_normal((N, K)).astype(np.float32))
+    D = sb.capi.debug_gemm_bf16(A, B, split_k=split_k)
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    # fp32 accumulation over K terms of magnitude ~1: error ~ sqrt(K) * 2^-24 * |sum|-ish; 1e-3 absolute is generous
+    err = np.abs(D - ref).max()
+    scale = np.sqrt(K)
+    assert err <= 2e-5 * scale * 4, "max abs err %g (K=%d)" % (err, K)
+
+
+@pytest.mark.gpu
+def test_gemm_identity_exact(sb):
+    """A = I (128x128 padded into K=128), B arbitrary bf16: result must be exactly B^T."""
+    rng = np.random.RandomState(1)
+    K = 128
+    A = np.eye(128, K, dtype=np.float32)
+    B = bf16_round(rng.standard_normal((128, K)).astype(np.float32))
+    D = sb.capi.debug_gemm_bf16(A, B)
+    np.testing.assert_array_equal(D, B.T)

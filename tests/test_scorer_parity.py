@@ -1,0 +1,104 @@
+"""Parity of the batched scorer (sb_model_*) and of eval/predict against the oracle, through the C-ABI.
+Contract (BASELINE.json): eval scores within 1e-5 of the reference-equivalent CPU path (fp32 parity mode)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import shifu_oracle as so
+from util import make_pair
+
+GOLDEN_HEAD = os.path.join(os.path.dirname(__file__), "golden", "dummydl_head.npz")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,tol", [(0, 1e-5), (1, 2e-2)])
+def test_model_score_matches_oracle(sb, precision, tol):
+    net, params, cfg, desc = make_pair(sb, 200, [100, 50], [so.ACT_RELU, so.ACT_TANH], precision=precision)
+    X, _, _ = so.synth_batch(1000, 200, 3)
+    m = sb.Model.create(desc, so.flatten_params(params))
+    got = m.score(X)
+    want = so.score_rows(net, params, X.astype(np.float64))
+    assert np.abs(got - want).max() <= tol
+    # compute(MLData): one row of doubles (TensorflowModel.java:53-94)
+    r = m.score_row_f64(X[7].astype(np.float64))
+    assert abs(r - want[7]) <= tol
+    with pytest.raises(sb.ShifuB200Error):
+        m.score_row_f64(np.zeros(199))
+    m.close()
+
+
+@pytest.mark.gpu
+def test_model_score_many_chunks_and_ragged_tail(sb):
+    """more rows than one internal chunk (16384) and a ragged tail; every row must be scored exactly once"""
+    net, params, cfg, desc = make_pair(sb, 40, [24], [so.ACT_SIGMOID])
+    rows = 16384 * 2 + 77
+    X, _, _ = so.synth_batch(rows, 40, 9)
+    m = sb.Model.create(desc, so.flatten_params(params))
+    got = m.score(X)
+    want = so.score_rows(net, params, X.astype(np.float64))
+    assert np.abs(got - want).max() <= 1e-5
+    m.close()
+
+
+@pytest.mark.gpu
+def test_scorer_on_reference_fixture_weights(sb):
+    """kernels vs the REAL weights of the reference's SavedModel fixture (dummydl; first 3 + last layer, committed
+    as tests/golden/dummydl_head.npz by tests/golden/make_golden.py)."""
+    g = np.load(GOLDEN_HEAD)
+    hidden = [g["W0"].shape[1], g["W1"].shape[1], g["W2"].shape[1]]
+    flat = np.concatenate([np.concatenate([g["W%d" % i].ravel(), g["b%d" % i].ravel()]) for i in range(4)])
+    desc = sb.make_desc(1522, hidden, [so.ACT_RELU] * 3)
+    m = sb.Model.create(desc, flat)
+    assert np.abs(m.score(g["X"]) - g["Y"].ravel()).max() <= 1e-5
+    m.close()
+
+
+@pytest.mark.gpu
+def test_savedmodel_export_then_load_scores_identically(sb, tmp_path):
+    net, params, cfg, desc = make_pair(sb, 30, [16, 8], [so.ACT_LEAKYRELU, so.ACT_TANH], max_batch=64)
+    X, y, w = so.synth_batch(64, 30, 1, weights="mixed")
+    d = str(tmp_path / "final_model")
+    with sb.Trainer(desc) as t:
+        t.set_params(so.flatten_params(params))
+        t.step(X, y, w)
+        trained = t.get_params()
+        pred = t.predict(X)
+        t.export_savedmodel(d)
+    m = sb.Model.load(d, "shifu_input_0", "shifu_output_0", tag="serve")
+    got = m.score(X)
+    np.testing.assert_allclose(got, pred, atol=1e-7)
+    want = so.score_rows(net, so.unflatten_params(net, trained), X.astype(np.float64))
+    assert np.abs(got - want).max() <= 1e-5
+    m.close()
+
+
+@pytest.mark.gpu
+def test_eval_loss_is_one_big_batch(sb):
+    """validation pass (ssgd_monitor.py:281-284): the whole valid set in ONE sess.run, i.e. sum over all rows /
+    count of non-zero weights over all rows - also when it is processed in several max_batch chunks."""
+    net, params, cfg, desc = make_pair(sb, 25, [12], [so.ACT_TANH], max_batch=50)
+    X, y, w = so.synth_batch(173, 25, 4, weights="mixed")
+    ref = so.CleanTrainer(net, params, cfg)
+    with sb.Trainer(desc) as t:
+        t.set_params(so.flatten_params(params))
+        assert abs(t.eval_loss(X, y, w) - ref.eval_loss(X, y, w)) <= 1e-6
+        np.testing.assert_allclose(t.predict(X), so.score_rows(net, params, X.astype(np.float64)), atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_checkpoint_roundtrip_resumes_identically(sb, tmp_path):
+    net, params, cfg, desc = make_pair(sb, 20, [10], [so.ACT_RELU], optimizer=so.OPT_ADAM, max_batch=32)
+    batches = [so.synth_batch(32, 20, s, weights="mixed") for s in range(4)]
+    ck = str(tmp_path / "model.ckpt")
+    with sb.Trainer(desc) as a:
+        a.set_params(so.flatten_params(params))
+        a.step(*batches[0]); a.step(*batches[1])
+        a.save_checkpoint(ck)
+        a.step(*batches[2]); a.step(*batches[3])
+        want = a.get_params()
+    with sb.Trainer(desc) as b:
+        b.load_checkpoint(ck)
+        assert b.global_step == 2
+        b.step(*batches[2]); b.step(*batches[3])
+        np.testing.assert_array_equal(b.get_params(), want)

@@ -1,0 +1,155 @@
+"""Parity of the CUDA training step against the CPU oracle, through the C-ABI (sb_trainer_*).
+
+Tolerances (BASELINE.json north_star): per-step loss and gradients within 1e-4 absolute in fp32 parity mode.
+The bf16 performance mode is checked against the same oracle with a bf16-sized tolerance, stated per test."""
+import numpy as np
+import pytest
+
+from oracle import shifu_oracle as so
+from util import make_pair
+
+ACT_NAMES = {0: "sigmoid", 1: "tanh", 2: "relu", 3: "leakyrelu"}
+
+
+def _one_step(sb, n_features, hidden, acts, rows, loss, optimizer, precision, weights="mixed", seed=3, lr=0.05):
+    net, params, cfg, desc = make_pair(sb, n_features, hidden, acts, loss=loss, optimizer=optimizer, lr=lr,
+                                       max_batch=rows, precision=precision)
+    X, y, w = so.synth_batch(rows, n_features, seed, weights=weights)
+    ref = so.CleanTrainer(net, params, cfg, loss=loss)
+    ref_loss = ref.step([(X, y, w)])[0]
+    with sb.Trainer(desc) as t:
+        t.set_params(so.flatten_params(params))
+        got_loss = t.step(X, y, w)
+        return ref_loss, ref.last_grads, ref.theta, got_loss, t.get_grads(), t.get_params()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+@pytest.mark.parametrize("loss", [so.LOSS_MSE, so.LOSS_SIGMOID_CE])
+def test_fp32_step_cfg0_all_activations(sb, act, loss):
+    """cfg0: 200 cols, [100, 50], B=100 (the reference's hard-coded BATCH_SIZE, ssgd_monitor.py:33)."""
+    rl, rg, rt, gl, gg, gt = _one_step(sb, 200, [100, 50], [act, act], 100, loss, so.OPT_SGD, sb.PREC_FP32)
+    assert abs(gl - rl) <= 1e-4
+    assert np.abs(gg - rg).max() <= 1e-4
+    # in practice fp32 vs fp32 agrees far tighter than the contract; keep a regression guard too
+    assert np.abs(gg - rg).max() <= 5e-6 + 1e-4 * np.abs(rg).max()
+    assert np.abs(gt - rt).max() <= 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("optimizer", [so.OPT_ADADELTA, so.OPT_ADAM, so.OPT_SGD, so.OPT_MOMENTUM])
+def test_fp32_three_steps_each_optimizer(sb, optimizer):
+    net, params, cfg, desc = make_pair(sb, 64, [48, 24], [so.ACT_TANH, so.ACT_RELU], optimizer=optimizer, lr=0.05,
+                                       max_batch=96, precision=sb.PREC_FP32)
+    ref = so.CleanTrainer(net, params, cfg)
+    with sb.Trainer(desc) as t:
+        t.set_params(so.flatten_params(params))
+        for s in range(3):
+            X, y, w = so.synth_batch(96, 64, 100 + s, weights="mixed")
+            rl = ref.step([(X, y, w)])[0]
+            gl = t.step(X, y, w)
+            assert abs(gl - rl) <= 1e-4, "step %d" % s
+            assert np.abs(t.get_params() - ref.theta).max() <= 2e-5, "step %d" % s
+        assert t.global_step == 3
+
+
+@pytest.mark.gpu
+def test_fp32_ragged_shapes_and_zero_weights(sb):
+    """odd widths (not multiples of 4/8/32), rows not a multiple of 32, and an all-zero weight batch
+    (loss must be 0 and no update must happen: _safe_div in SUM_BY_NONZERO_WEIGHTS)."""
+    net, params, cfg, desc = make_pair(sb, 37, [19, 7], [so.ACT_LEAKYRELU, so.ACT_SIGMOID], optimizer=so.OPT_SGD,
+                                       max_batch=101, precision=sb.PREC_FP32)
+    X, y, w = so.synth_batch(101, 37, 5, weights="mixed")
+    ref = so.CleanTrainer(net, params, cfg)
+    rl = ref.step([(X, y, w)])[0]
+    with sb.Trainer(desc) as t:
+        flat0 = so.flatten_params(params)
+        t.set_params(flat0)
+        assert abs(t.step(X, y, w) - rl) <= 1e-5
+        assert np.abs(t.get_grads() - ref.last_grads).max() <= 1e-5
+        before = t.get_params()
+        assert t.step(X, y, np.zeros_like(w)) == 0.0
+        np.testing.assert_array_equal(t.get_grads(), np.zeros_like(before))
+        np.testing.assert_array_equal(t.get_params(), before)
+        # w = None means all ones
+        ref2 = so.CleanTrainer(net, so.unflatten_params(net, before.copy()), cfg)
+        rl2 = ref2.step([(X, y, np.ones_like(w))])[0]
+        assert abs(t.step(X, y, None) - rl2) <= 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg_name,F,hidden,rows", [("cfg0", 200, [100, 50], 100), ("cfg1", 1000, [512, 256, 128], 4096)])
+def test_bf16_step_against_oracle(sb, cfg_name, F, hidden, rows):
+    """bf16 operands / fp32 accumulate (tcgen05 path) against the fp32 oracle.  bf16 has 8 mantissa bits, so the
+    contract here is the bf16-sized one: loss within 2e-3 relative, gradients within 3% of the gradient's max
+    magnitude (and in practice within 1e-4 absolute, reported in DESIGN.md)."""
+    acts = [so.ACT_RELU] * len(hidden)
+    rl, rg, rt, gl, gg, gt = _one_step(sb, F, hidden, acts, rows, so.LOSS_MSE, so.OPT_SGD, sb.PREC_BF16, weights="ones")
+    assert abs(gl - rl) <= 2e-3 * max(1e-3, abs(rl))
+    gmax = np.abs(rg).max()
+    assert np.abs(gg - rg).max() <= 0.03 * gmax, (np.abs(gg - rg).max(), gmax)
+    # layer-wise direction check: cosine similarity of every gradient block > 0.999
+    net = so.NetDesc(F, hidden, acts)
+    for a, b in zip(so.unflatten_params(net, gg), so.unflatten_params(net, rg)):
+        a = a.ravel().astype(np.float64); b = b.ravel().astype(np.float64)
+        if np.linalg.norm(b) > 0:
+            assert a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-300) > 0.999
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_bf16_small_all_activations(sb, act):
+    rl, rg, rt, gl, gg, gt = _one_step(sb, 72, [40, 24], [act, act], 130, so.LOSS_SIGMOID_CE, so.OPT_ADAM, sb.PREC_BF16,
+                                       weights="mixed")
+    assert abs(gl - rl) <= 5e-3 * max(1e-3, abs(rl))
+    assert np.abs(gg - rg).max() <= 0.03 * np.abs(rg).max()
+
+
+@pytest.mark.gpu
+def test_resident_dataset_equals_host_steps(sb):
+    """sb_trainer_step_resident over an HBM-resident set must equal sb_trainer_step fed the same rows."""
+    net, params, cfg, desc = make_pair(sb, 50, [32, 16], [so.ACT_RELU, so.ACT_TANH], optimizer=so.OPT_MOMENTUM,
+                                       max_batch=64, precision=sb.PREC_FP32)
+    X, y, w = so.synth_batch(64 * 4 + 13, 50, 11, weights="mixed")
+    flat = so.flatten_params(params)
+    with sb.Trainer(desc) as a, sb.Trainer(desc) as b:
+        a.set_params(flat); b.set_params(flat)
+        b.load_dataset(X, y, w)
+        offs = [(0, 64), (64, 64), (128, 64), (192, 64), (256, 13)]
+        for off, n in offs:
+            la = a.step(X[off:off + n], y[off:off + n], w[off:off + n])
+            lb = b.step_resident(off, n)
+            assert abs(la - lb) <= 1e-6
+        assert np.abs(a.get_params() - b.get_params()).max() <= 1e-6
+        with pytest.raises(sb.ShifuB200Error):
+            b.step_resident(260, 64)      # runs past the end of the resident set
+        with pytest.raises(sb.ShifuB200Error):
+            a.step(X[:65], y[:65], w[:65])  # rows > max_batch
+
+
+@pytest.mark.gpu
+def test_epoch_sync_schedule_matches_syncreplicas_oracle(sb):
+    """Reference schedule (D3): mean of R mini-batch gradients, one Adadelta update per 'epoch'
+    (ssgd_monitor.py:136-141).  Oracle = the clean mean-of-batch-means; batches from np.array_split."""
+    n_rows, F = 1030, 30
+    net, params, cfg, desc = make_pair(sb, F, [20, 10], [so.ACT_TANH, so.ACT_TANH], optimizer=so.OPT_ADADELTA, lr=1.0,
+                                       max_batch=128, precision=sb.PREC_FP32)
+    X, y, w = so.synth_batch(n_rows, F, 21, weights="mixed")
+    batches = so.split_batches(n_rows, 100)
+    assert len(batches) == 10 and {len(b) for b in batches} == {103}
+    theta = so.flatten_params(params).astype(np.float32)
+    opt = so.Optimizer(cfg, theta.size)
+    with sb.Trainer(desc) as t:
+        t.set_params(theta)
+        for epoch in range(2):
+            P = so.unflatten_params(so.NetDesc(F, [20, 10], [1, 1]), theta)
+            gsum = np.zeros_like(theta)
+            for idx in batches:
+                L, g, _ = so.loss_and_grads(net, P, X[idx], y[idx], w[idx])
+                gsum += so.flatten_params(g)
+                gl = t.accumulate(X[idx], y[idx], w[idx])
+                assert abs(gl - L) <= 1e-5
+            theta = opt.apply(theta, gsum / np.float32(len(batches)))
+            t.apply_accumulated()
+            assert np.abs(t.get_grads() - gsum / len(batches)).max() <= 1e-5
+            assert np.abs(t.get_params() - theta).max() <= 1e-4
