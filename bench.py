@@ -102,6 +102,22 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads() -> int:
+    """threads the CPU arm may really use: affinity mask and cgroup quota, not the box's core count"""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(p))))
+    except Exception:
+        pass
+    return n
+
+
 def run_reference(args, cfg, rank, world):
     """`--impl reference`: the reference-equivalent CPU worker (oracle port on torch-CPU, all host threads) on the same
     config / metric.  TF 1.x + Python 2 cannot be installed here, so the oracle port IS the CPU arm (kind "port").
@@ -111,7 +127,7 @@ def run_reference(args, cfg, rank, world):
     import torch
     from oracle import shifu_oracle as so
     from oracle.torch_cpu_worker import TorchCpuWorker
-    threads = os.cpu_count() or 1
+    threads = host_threads()
     torch.set_num_threads(threads)
     net = so.NetDesc(cfg["F"], cfg["hidden"], [so.ACT_RELU] * len(cfg["hidden"]))
     params = so.xavier_init(net, SEED % 100000)
@@ -287,7 +303,7 @@ def main():
         nbc = min(4, nb)
         batches = [(X[i * B:(i + 1) * B], y[i * B:(i + 1) * B], w[i * B:(i + 1) * B]) for i in range(nbc)]
         r = time_train(net, so.xavier_init(net, 1), so.OptConfig(kind=OPT_ID[cfg["optimizer"]], lr=cfg["lr"]), batches,
-                       min_seconds=10.0, max_steps=400, threads=os.cpu_count())
+                       min_seconds=10.0, max_steps=400, threads=host_threads())
         cpu = {"value": r["rows_per_sec"], "unit": "rows/s", "cores": r["cores"], "kind": "port",
                "sample": "%d steps (%.1f s) of %s on torch-CPU fp32 = reference-equivalent worker loop (TF-1.x absent)" %
                          (r["steps"], r["seconds"], args.config)}

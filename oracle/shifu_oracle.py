@@ -434,3 +434,50 @@ def synth_batch(rows: int, n_features: int, seed: int, weights: str = "ones"):
     else:
         w = rng.choice(np.array([0.0, 1.0, 2.5], np.float32), size=(rows, 1)).astype(np.float32)
     return X, y, w
+
+
+# --------------------------------------------------------------------------
+# bf16 performance-mode emulation (checker for SB_PREC_BF16)
+# --------------------------------------------------------------------------
+def bf16_round(a: np.ndarray) -> np.ndarray:
+    """fp32 -> nearest-even bf16 -> fp32 (what __float2bfloat16_rn does)."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    u = a.view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32).reshape(a.shape)
+
+
+def loss_and_grads_bf16(net: NetDesc, params, X, y, w, loss=LOSS_MSE):
+    """The SAME math as loss_and_grads, with a bf16 rounding wherever the CUDA performance mode stores an
+    operand as bf16 (DESIGN.md 'precision modes'): X, hidden-layer W, every activation A_l and every dZ_l that is
+    fed to a tensor-core GEMM.  Accumulation stays in higher precision (fp64 here vs fp32 in TMEM), the output
+    layer uses fp32 w_o, and bias gradients / dw_o are summed from the un-rounded values exactly like the kernels
+    do.  Lets the tests check the tcgen05 path to ~1e-5 instead of the loose bf16-vs-fp32 bound."""
+    q = bf16_round
+    f64 = np.float64
+    L_hidden = len(net.acts)
+    A = [q(X).astype(f64)]
+    for l, act in enumerate(net.acts):
+        W, b = q(params[2 * l]).astype(f64), params[2 * l + 1].astype(f64)
+        A.append(q(act_forward((A[-1] @ W + b).astype(np.float32), act)).astype(f64))
+    Wo, bo = params[-2].astype(f64), params[-1].astype(f64)
+    z = (A[-1] @ Wo + bo).astype(np.float32)
+    yhat = _sigmoid(z)
+    Lv, n_nz = loss_value(z, yhat, y.astype(np.float32), w.astype(np.float32), loss)
+    grads = [np.zeros_like(p, dtype=np.float32) for p in params]
+    if n_nz == 0:
+        return Lv, grads, yhat
+    y64, w64, yh = y.astype(f64), w.astype(f64), yhat.astype(f64)
+    dz = (2 * w64 * (yh - y64) * yh * (1 - yh) / n_nz) if loss == LOSS_MSE else (w64 * (yh - y64) / n_nz)
+    dz = dz.astype(np.float32).astype(f64)
+    grads[-2] = (A[-1].T @ dz).astype(np.float32)
+    grads[-1] = dz.sum(axis=0).astype(np.float32)
+    g_un = (dz @ Wo.T) * act_grad_from_output(A[-1].astype(np.float32), net.acts[-1]).astype(f64)  # un-rounded dZ_L
+    for l in range(L_hidden - 1, -1, -1):
+        grads[2 * l + 1] = g_un.sum(axis=0).astype(np.float32)          # bias grad from un-rounded values
+        dZ = q(g_un.astype(np.float32)).astype(f64)                     # stored bf16 -> GEMM operand
+        grads[2 * l] = (A[l].T @ dZ).astype(np.float32)
+        if l > 0:
+            Wl = q(params[2 * l]).astype(f64)
+            g_un = (dZ @ Wl.T) * act_grad_from_output(A[l].astype(np.float32), net.acts[l - 1]).astype(f64)
+    return Lv, grads, yhat

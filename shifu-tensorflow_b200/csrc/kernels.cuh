@@ -52,11 +52,13 @@ load_batch_kernel(const BatchDesc* __restrict__ desc, int rows, int F, __nv_bflo
     }
   }
   if constexpr (BF16) {
-    __syncthreads();
+    if (XbT != nullptr) {  // the scorer needs no transposed copy (no dW GEMM)
+      __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int c = c0 + ty + 8 * i, r = r0 + tx;
-      if (c < F && r < rows) XbT[static_cast<size_t>(c) * ldB + r] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, r = r0 + tx;
+        if (c < F && r < rows) XbT[static_cast<size_t>(c) * ldB + r] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+      }
     }
   }
   if (blockIdx.x == 0 && blockIdx.y == 0) {

