@@ -190,6 +190,10 @@ int sb_savedmodel_read(const char* saved_model_dir, const char* input_name, cons
  * bf16 on the device; D fp32 host.  split_k >= 1. */
 int sb_debug_gemm_bf16(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K,
                        int32_t split_k, int device);
+/* same with explicit operand layouts: a_mn = 0: A is [M,K] (K-major), 1: A is [K,M] (MN-major); b_mn likewise for
+ * B ([N,K] or [K,N]).  Instantiated combinations: (0,0) dA GEMM, (0,1) forward GEMM, (1,1) dW GEMM. */
+int sb_debug_gemm_bf16_ex(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K,
+                          int32_t split_k, int32_t a_mn, int32_t b_mn, int device);
 
 #ifdef __cplusplus
 }

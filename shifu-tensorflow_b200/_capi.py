@@ -109,6 +109,7 @@ PROTOTYPES = {
     "sb_savedmodel_write": (C.c_int, [_cp, _P(NetDesc), _f32p, C.c_int64]),
     "sb_savedmodel_read": (C.c_int, [_cp, _cp, _cp, _cp, _P(NetDesc), _P(C.c_int32), _f32p, C.c_int64, _P(C.c_int64)]),
     "sb_debug_gemm_bf16": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
+    "sb_debug_gemm_bf16_ex": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
 }
 
 
@@ -373,12 +374,14 @@ def savedmodel_read(saved_model_dir: str, input_name: str, output_name: str, tag
         int(out_act.value), flat
 
 
-def debug_gemm_bf16(A: np.ndarray, B: np.ndarray, split_k: int = 1, device: int = 0) -> np.ndarray:
-    """D[M,N] = bf16(A)[M,K] . bf16(B)[N,K]^T through the tcgen05 kernel."""
+def debug_gemm_bf16(A: np.ndarray, B: np.ndarray, split_k: int = 1, device: int = 0, a_mn: bool = False,
+                    b_mn: bool = False) -> np.ndarray:
+    """D[M,N] = sum_k A(m,k) B(n,k) through the tcgen05 kernel (operands rounded to bf16 on the device).
+    A is [M,K] (K-major) or, with a_mn, [K,M] (MN-major); B is [N,K] or, with b_mn, [K,N]."""
     A, B = _f32(A), _f32(B)
-    M, K = A.shape
-    N, K2 = B.shape
+    (K, M) = A.shape if a_mn else A.shape[::-1]
+    (K2, N) = B.shape if b_mn else B.shape[::-1]
     assert K == K2
     D = np.zeros((M, N), np.float32)
-    check(lib().sb_debug_gemm_bf16(_ptr(A), _ptr(B), _ptr(D), M, N, K, split_k, device))
+    check(lib().sb_debug_gemm_bf16_ex(_ptr(A), _ptr(B), _ptr(D), M, N, K, split_k, int(a_mn), int(b_mn), device))
     return D

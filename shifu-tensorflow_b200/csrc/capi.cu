@@ -646,33 +646,39 @@ void* sb_model_stream(sb_model_t* m) { return m ? reinterpret_cast<void*>(m->net
 // ================================================================================================
 // kernel-level test hook
 // ================================================================================================
-int sb_debug_gemm_bf16(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k, int device) {
+int sb_debug_gemm_bf16_ex(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k,
+                          int32_t a_mn, int32_t b_mn, int device) {
   SB_CHECK(A && B && D && M > 0 && N > 0 && K > 0, SB_ERR_INVALID, "bad argument");
+  SB_CHECK((a_mn == 0 && b_mn == 0) || (a_mn == 0 && b_mn == 1) || (a_mn == 1 && b_mn == 1), SB_ERR_INVALID,
+           "layout combination not instantiated (use KK, KM or MM)");
   int n_dev = 0;
   SB_CHECK(cudaGetDeviceCount(&n_dev) == cudaSuccess && n_dev > 0, SB_ERR_CUDA, "no CUDA device available");
   cudaDeviceProp prop;
   SB_CUDA(cudaGetDeviceProperties(&prop, device));
   SB_CHECK(prop.major == 10, SB_ERR_CUDA, "device is sm_%d%d, need sm_100", prop.major, prop.minor);
   SB_CUDA(cudaSetDevice(device));
-  const int ldk = round_up(K, 8);
+  // stored shapes: K-major [R, K]; MN-major [K, R]
+  const int a_rows = a_mn ? K : M, a_cols = a_mn ? M : K;
+  const int b_rows = b_mn ? K : N, b_cols = b_mn ? N : K;
+  const int lda = round_up(a_cols, 8), ldb = round_up(b_cols, 8);
   float *dA32 = nullptr, *dB32 = nullptr, *dD = nullptr;
   __nv_bfloat16 *dA = nullptr, *dB = nullptr;
   SB_CUDA(cudaMalloc(&dA32, sizeof(float) * M * K));
   SB_CUDA(cudaMalloc(&dB32, sizeof(float) * N * K));
   SB_CUDA(cudaMalloc(&dD, sizeof(float) * M * N));
-  SB_CUDA(cudaMalloc(&dA, sizeof(__nv_bfloat16) * M * ldk));
-  SB_CUDA(cudaMalloc(&dB, sizeof(__nv_bfloat16) * N * ldk));
-  SB_CUDA(cudaMemset(dA, 0, sizeof(__nv_bfloat16) * M * ldk));
-  SB_CUDA(cudaMemset(dB, 0, sizeof(__nv_bfloat16) * N * ldk));
+  SB_CUDA(cudaMalloc(&dA, sizeof(__nv_bfloat16) * a_rows * lda));
+  SB_CUDA(cudaMalloc(&dB, sizeof(__nv_bfloat16) * b_rows * ldb));
+  SB_CUDA(cudaMemset(dA, 0, sizeof(__nv_bfloat16) * a_rows * lda));
+  SB_CUDA(cudaMemset(dB, 0, sizeof(__nv_bfloat16) * b_rows * ldb));
   SB_CUDA(cudaMemset(dD, 0, sizeof(float) * M * N));
   SB_CUDA(cudaMemcpy(dA32, A, sizeof(float) * M * K, cudaMemcpyHostToDevice));
   SB_CUDA(cudaMemcpy(dB32, B, sizeof(float) * N * K, cudaMemcpyHostToDevice));
-  cast_bf16_kernel<<<static_cast<unsigned>((static_cast<long long>(M) * K + 255) / 256), 256>>>(dA32, M, K, dA, ldk);
-  cast_bf16_kernel<<<static_cast<unsigned>((static_cast<long long>(N) * K + 255) / 256), 256>>>(dB32, N, K, dB, ldk);
+  cast_bf16_kernel<<<static_cast<unsigned>((static_cast<long long>(M) * K + 255) / 256), 256>>>(dA32, a_rows, a_cols, dA, lda);
+  cast_bf16_kernel<<<static_cast<unsigned>((static_cast<long long>(N) * K + 255) / 256), 256>>>(dB32, b_rows, b_cols, dB, ldb);
   const int bn = N <= 64 ? 64 : 128;
   CUtensorMap ta, tb;
-  int s = make_tmap_bf16(&ta, dA, M, K, ldk, 128);
-  if (s == SB_OK) s = make_tmap_bf16(&tb, dB, N, K, ldk, bn);
+  int s = make_tmap_bf16(&ta, dA, a_rows, a_cols, lda, a_mn ? 64 : 128);
+  if (s == SB_OK) s = make_tmap_bf16(&tb, dB, b_rows, b_cols, ldb, b_mn ? 64 : bn);
   if (s == SB_OK) {
     GemmTcParams p = {};
     p.M = M; p.N = N; p.K = K;
@@ -684,19 +690,32 @@ int sb_debug_gemm_bf16(const float* A, const float* B, float* D, int32_t M, int3
     const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
     const int n_work = tiles * p.split_k;
     const int grid = n_work < prop.multiProcessorCount ? n_work : prop.multiProcessorCount;
+#define SB_DBG_LAUNCH(BN, AMN, BMN)                                                                                   \
+  do {                                                                                                                \
+    cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI_F32, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                         GemmTcCfg<BN>::SMEM_BYTES);                                                                  \
+    gemm_tc_kernel<BN, EPI_F32, AMN, BMN><<<grid, GemmTcCfg<BN>::THREADS, GemmTcCfg<BN>::SMEM_BYTES>>>(ta, tb, p);    \
+  } while (0)
     if (bn == 64) {
-      cudaFuncSetAttribute(gemm_tc_kernel<64, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmTcCfg<64>::SMEM_BYTES);
-      gemm_tc_kernel<64, EPI_F32><<<grid, 192, GemmTcCfg<64>::SMEM_BYTES>>>(ta, tb, p);
+      if (!a_mn && !b_mn) SB_DBG_LAUNCH(64, false, false);
+      else if (!a_mn) SB_DBG_LAUNCH(64, false, true);
+      else SB_DBG_LAUNCH(64, true, true);
     } else {
-      cudaFuncSetAttribute(gemm_tc_kernel<128, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmTcCfg<128>::SMEM_BYTES);
-      gemm_tc_kernel<128, EPI_F32><<<grid, 192, GemmTcCfg<128>::SMEM_BYTES>>>(ta, tb, p);
+      if (!a_mn && !b_mn) SB_DBG_LAUNCH(128, false, false);
+      else if (!a_mn) SB_DBG_LAUNCH(128, false, true);
+      else SB_DBG_LAUNCH(128, true, true);
     }
+#undef SB_DBG_LAUNCH
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) s = set_error(SB_ERR_CUDA, "gemm_tc_kernel failed: %s", cudaGetErrorString(e));
     else if (cudaMemcpy(D, dD, sizeof(float) * M * N, cudaMemcpyDeviceToHost) != cudaSuccess) s = set_error(SB_ERR_CUDA, "D2H failed");
   }
   cudaFree(dA32); cudaFree(dB32); cudaFree(dD); cudaFree(dA); cudaFree(dB);
   return s;
+}
+
+int sb_debug_gemm_bf16(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k, int device) {
+  return sb_debug_gemm_bf16_ex(A, B, D, M, N, K, split_k, 0, 0, device);
 }
 
 }  // extern "C"

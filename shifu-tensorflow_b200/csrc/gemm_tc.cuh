@@ -1,18 +1,25 @@
 // tcgen05 / TMEM / TMA dense-layer GEMM for sm_100a with fused epilogues.
 //
-//   D[M,N] = A[M,K] * B[N,K]^T        A, B bf16, K-major (K contiguous), fp32 accumulation in TMEM
+//   D[M,N] = sum_k A(m,k) * B(n,k)      A, B bf16, fp32 accumulation in TMEM
 //
-// This one kernel covers every dense contraction of the tabular-DNN step (the TF ops behind
-// nn_layer, res/ssgd_monitor.py:57-71, and their gradients built by opt.minimize, :142):
-//   EPI_FWD : Z = A_{l-1} W_l        + bias, activation, write A_l (bf16) and A_l^T          (MatMul+Add+act)
-//   EPI_DA  : dA = dZ_l W_l^T        * act'(A_{l-1}), write dZ_{l-1}, dZ_{l-1}^T, column sums -> db_{l-1}
-//   EPI_DW  : dW_l = A_{l-1}^T dZ_l  split-K over the batch, fp32 red.add into the flat gradient
+// Each operand is consumed in the layout it already has in HBM - no transposed copies anywhere:
+//   K-major  : element (r,k) at r*ld + k   (row-major [M|N, K]);  TMA box 64(K) x rows, UMMA K-major descriptor
+//   MN-major : element (r,k) at k*ld + r   (row-major [K, M|N]);  TMA boxes 64(MN) x 64(K), UMMA MN-major descriptor
+//
+// One kernel covers every dense contraction of the tabular-DNN step (the TF ops behind nn_layer,
+// res/ssgd_monitor.py:57-71, and their gradients built by opt.minimize, :142):
+//   EPI_FWD : Z = A_{l-1} W_l        A K-major [rows,in], B = W_l [in,out] MN-major; +bias, activation -> A_l (bf16)
+//   EPI_DA  : dA = dZ_l W_l^T        A K-major [rows,out], B = W_l [in,out] K-major; *act'(A_{l-1}) -> dZ_{l-1},
+//                                    column sums -> db_{l-1}
+//   EPI_DW  : dW_l = A_{l-1}^T dZ_l  A = A_{l-1} [rows,in] MN-major, B = dZ_l [rows,out] MN-major; split-K over the
+//                                    batch, fp32 red.add into the flat gradient
 //   EPI_F32 : plain fp32 store (kernel-level parity test hook)
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (one persistent CTA per SM, 320 threads):
 //   warp 0     : TMA producer   - cp.async.bulk.tensor 128B-swizzled tiles into a STAGES-deep smem ring
 //   warp 1     : MMA issuer     - one thread issues tcgen05.mma (128 x BN x 16), commits to mbarriers
-//   warps 2..5 : epilogue       - tcgen05.ld the accumulator (double-buffered in TMEM) and apply the epilogue
+//   warps 2..9 : epilogue       - tcgen05.ld the accumulator (double-buffered in TMEM) and apply the epilogue;
+//                                 two warps per TMEM lane quarter, each taking every other 32-column chunk
 // M/N/K tails need no special code on the load side: TMA zero-fills out-of-bounds box elements.
 #pragma once
 #include <cuda.h>
@@ -30,10 +37,8 @@ struct GemmTcParams {
   // EPI_FWD
   const float* bias;  // [N]
   int act;            // FWD: activation applied; DA: activation whose derivative is applied
-  __nv_bfloat16* out;   // [M, ld_out] row-major (FWD, DA)
+  __nv_bfloat16* out;  // [M, ld_out] row-major (FWD, DA)
   int ld_out;
-  __nv_bfloat16* outT;  // [N, ld_outT] transposed copy, nullable (FWD, DA)
-  int ld_outT;
   // EPI_DA
   const __nv_bfloat16* aux;  // activation output A_{l-1} [M, ld_aux]
   int ld_aux;
@@ -54,11 +59,24 @@ struct GemmTcCfg {
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int THREADS = 192;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(192, 1)
+// ---- epilogue element functions, specialised per activation so the switch is hoisted out of the element loop
+template <int ACT>
+__device__ __forceinline__ void epi_fwd_chunk(float (&v)[32], const float (&b)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = act_apply(v[j] + b[j], ACT);
+}
+template <int ACT>
+__device__ __forceinline__ void epi_da_chunk(float (&v)[32], const __nv_bfloat16* ah) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] *= act_grad_from_out(__bfloat162float(ah[j]), ACT);
+}
+
+template <int BN, int EPI, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GemmTcCfg<BN>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
   using Cfg = GemmTcCfg<BN>;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
@@ -89,7 +107,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 128);
+      mbar_init(tempty_bar(a), 32 * Cfg::EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -119,8 +137,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
           mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-          tma_load_2d(smem_a(stage), &tmA, full_bar(stage), kb * BK, tm * BM);
-          tma_load_2d(smem_b(stage), &tmB, full_bar(stage), kb * BK, tn * BN);
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)  // 64(MN) x 64(K) boxes, 8 KB each, side by side along MN
+              tma_load_2d(smem_a(stage) + i * 8192, &tmA, full_bar(stage), tm * BM + i * 64, kb * BK);
+          } else {
+            tma_load_2d(smem_a(stage), &tmA, full_bar(stage), kb * BK, tm * BM);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_2d(smem_b(stage) + i * 8192, &tmB, full_bar(stage), tn * BN + i * 64, kb * BK);
+          } else {
+            tma_load_2d(smem_b(stage), &tmB, full_bar(stage), kb * BK, tn * BN);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -128,7 +158,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      // descriptor step for 16 elements along K: K-major = 32 B inside the swizzle row; MN-major = 16 rows of 128 B
+      constexpr uint32_t a_kstep = A_MN ? (2048u >> 4) : (32u >> 4);
+      constexpr uint32_t b_kstep = B_MN ? (2048u >> 4) : (32u >> 4);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -144,13 +177,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
           tcgen05_fence_after();
-          const uint64_t da = make_kmajor_sw128_desc(smem_a(stage));
-          const uint64_t db = make_kmajor_sw128_desc(smem_b(stage));
+          const uint64_t da = A_MN ? make_mnmajor_sw128_desc(smem_a(stage), 8192u) : make_kmajor_sw128_desc(smem_a(stage));
+          const uint64_t db = B_MN ? make_mnmajor_sw128_desc(smem_b(stage), 8192u) : make_kmajor_sw128_desc(smem_b(stage));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // advance 16 bf16 = 32 B along K inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem_d, da + a_kstep * k, db + b_kstep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -158,8 +189,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ================= epilogue warps (2..5) =================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ================= epilogue warps (2..9) =================
+    const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;    // which of the two warps sharing the quarter
     int it = 0;
     for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
       const int tile = w % n_tiles;
@@ -171,62 +203,75 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int row = tm * BM + quarter * 32 + lane;  // output row owned by this thread
       const bool row_ok = row < p.M;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = half; c < BN / 32; c += 2) {
         const int col0 = tn * BN + c * 32;
+        if (col0 >= p.N) break;  // whole chunk out of range (warp-uniform)
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, raw);
         tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (col0 >= p.N) continue;  // whole chunk out of range (warp-uniform)
+        const bool full = col0 + 32 <= p.N;  // warp-uniform fast path
 
         if constexpr (EPI == EPI_FWD) {
+          float b[32];
+          if (full && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0)) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int cc = col0 + j;
-            const float b = (cc < p.N) ? __ldg(p.bias + cc) : 0.f;
-            v[j] = act_apply(v[j] + b, p.act);
+            for (int q = 0; q < 8; ++q) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q);
+              b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) b[j] = (col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
+          }
+          switch (p.act) {
+            case SB_ACT_RELU: epi_fwd_chunk<SB_ACT_RELU>(v, b); break;
+            case SB_ACT_SIGMOID: epi_fwd_chunk<SB_ACT_SIGMOID>(v, b); break;
+            case SB_ACT_TANH: epi_fwd_chunk<SB_ACT_TANH>(v, b); break;
+            case SB_ACT_LEAKYRELU: epi_fwd_chunk<SB_ACT_LEAKYRELU>(v, b); break;
+            default: epi_fwd_chunk<SB_ACT_NONE>(v, b); break;
           }
         } else if constexpr (EPI == EPI_DA) {
           // multiply by act'(A_{l-1}[row, col]) read as bf16 (64 B per thread per chunk)
           uint4 a4[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) a4[q] = make_uint4(0, 0, 0, 0);
           if (row_ok) {
             const uint4* ap = reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(row) * p.ld_aux + col0);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) a4[q] = (col0 + q * 8 < p.ld_aux) ? __ldg(ap + q) : make_uint4(0, 0, 0, 0);
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) a4[q] = make_uint4(0, 0, 0, 0);
+            for (int q = 0; q < 4; ++q)
+              if (col0 + q * 8 < p.ld_aux) a4[q] = __ldg(ap + q);
           }
           const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(a4);
+          switch (p.act) {
+            case SB_ACT_RELU: epi_da_chunk<SB_ACT_RELU>(v, ah); break;
+            case SB_ACT_SIGMOID: epi_da_chunk<SB_ACT_SIGMOID>(v, ah); break;
+            case SB_ACT_TANH: epi_da_chunk<SB_ACT_TANH>(v, ah); break;
+            case SB_ACT_LEAKYRELU: epi_da_chunk<SB_ACT_LEAKYRELU>(v, ah); break;
+            default: break;
+          }
+          if (!row_ok || !full) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float g = act_grad_from_out(__bfloat162float(ah[j]), p.act);
-            v[j] = (row_ok && col0 + j < p.N) ? v[j] * g : 0.f;
+            for (int j = 0; j < 32; ++j)
+              if (!row_ok || col0 + j >= p.N) v[j] = 0.f;
           }
         }
 
         if constexpr (EPI == EPI_FWD || EPI == EPI_DA) {
           if (row_ok) {
-            // row-major bf16: 4 x 16 B per thread
+            // row-major bf16: 4 x 16 B per thread (ld_out is a multiple of 8, pad columns belong to the buffer)
             __nv_bfloat16* op = p.out + static_cast<size_t>(row) * p.ld_out + col0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              if (col0 + q * 8 < p.ld_out) {
+              if (full || col0 + q * 8 < p.ld_out) {
                 uint4 o;
                 o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
                 o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
                 o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
                 o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
                 *reinterpret_cast<uint4*>(op + q * 8) = o;
-              }
-            }
-            // transposed bf16: consecutive lanes = consecutive rows -> 64 B contiguous per column
-            if (p.outT != nullptr) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (col0 + j < p.N) p.outT[static_cast<size_t>(col0 + j) * p.ld_outT + row] = __float2bfloat16_rn(v[j]);
               }
             }
           }
@@ -240,7 +285,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else if constexpr (EPI == EPI_DW) {
           if (row_ok) {
             float* gp = p.accum + static_cast<size_t>(row) * p.ld_acc + col0;
-            if (p.acc_vec4 && col0 + 32 <= p.N) {
+            if (p.acc_vec4 && full) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) red_add_v4_f32(gp + q * 4, v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
             } else {
@@ -285,26 +330,10 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 PFN_encodeTiled get_encode_tiled();
 
 // Tensor map of a row-major bf16 matrix [rows, cols] with leading dimension ld (elements):
-// box = 64 columns x box_rows rows, 128-byte swizzle.  cols/rows are the LOGICAL extents (TMA
-// zero-fills beyond them), ld*2 must be a multiple of 16 bytes.
+// box = 64 columns x box_rows rows, 128-byte swizzle.  cols/rows are the LOGICAL extents (TMA zero-fills beyond
+// them), ld*2 must be a multiple of 16 bytes.  K-major operand: box_rows = 128 (A) or BN (B); MN-major: 64.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int cols, int ld, int box_rows);
 
 int pick_split_k(int M, int N, int K, int BN, int num_sms, int* kb_per_split);
-
-template <int BN, int EPI>
-int launch_gemm_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmTcParams p, int num_sms, cudaStream_t st) {
-  using Cfg = GemmTcCfg<BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    attr_done = true;
-  }
-  const int tiles = ((p.M + 127) / 128) * ((p.N + BN - 1) / BN);
-  const int n_work = tiles * p.split_k;
-  const int grid = n_work < num_sms ? n_work : num_sms;
-  gemm_tc_kernel<BN, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmB, p);
-  SB_CUDA(cudaGetLastError());
-  return SB_OK;
-}
 
 }  // namespace sb

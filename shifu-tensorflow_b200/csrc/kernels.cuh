@@ -25,54 +25,60 @@ static __global__ void set_batch_kernel(BatchDesc* d, const float* X, const floa
 enum { SCAL_LOSS_SUM = 0, SCAL_NNZ = 1, SCAL_COUNT = 4 };
 
 // ------------------------------------------------------------------------------------------------
-// K1 mini-batch load.  fp32 rows -> (bf16 mode) row-major bf16 [rows, ldF] AND transposed bf16
-// [F, ldB] (the K-major operand of the layer-0 dW GEMM); (fp32 mode) fp32 copy into the batch buffer.
-// 32x32 tiles through shared memory so both the read and both writes are coalesced.
-// Block (0,0) additionally counts the non-zero sample weights of the batch (n_nz of
+// K1 mini-batch load.  fp32 rows of the current batch -> the operand buffer of the layer-0 GEMMs:
+// (bf16 mode) row-major bf16 [rows, ldF] - the SAME buffer feeds the forward GEMM (K-major) and the dW
+// GEMM (MN-major), so no transposed copy exists; (fp32 mode) fp32 copy into the batch buffer.
+// HBM-bound: each thread moves 8 consecutive columns (2 x 16 B loads -> one 16 B store).
+// Block 0 additionally counts the non-zero sample weights of the batch (n_nz of
 // SUM_BY_NONZERO_WEIGHTS, res/ssgd_monitor.py:129).
 // ------------------------------------------------------------------------------------------------
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 load_batch_kernel(const BatchDesc* __restrict__ desc, int rows, int F, __nv_bfloat16* __restrict__ Xb, int ldF,
-                  __nv_bfloat16* __restrict__ XbT, int ldB, float* __restrict__ Xf, float* __restrict__ scal) {
-  __shared__ float tile[32][33];
+                  float* __restrict__ Xf, float* __restrict__ scal) {
   const float* __restrict__ X = desc->X;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = r0 + ty + 8 * i, c = c0 + tx;
-    float v = 0.f;
-    if (r < rows && c < F) v = __ldg(X + static_cast<size_t>(r) * F + c);
-    if constexpr (BF16) {
-      tile[ty + 8 * i][tx] = v;
-      if (r < rows && c < ldF) Xb[static_cast<size_t>(r) * ldF + c] = __float2bfloat16_rn(v);
+  const int groups = ldF >> 3;  // 8-column groups per row (ldF is a multiple of 8)
+  const long long total = static_cast<long long>(rows) * groups;
+  const bool vec = ((F & 7) == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+  for (long long u = blockIdx.x * 256ll + threadIdx.x; u < total; u += gridDim.x * 256ll) {
+    const int r = static_cast<int>(u / groups), c = static_cast<int>(u % groups) * 8;
+    float v[8];
+    if (vec) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(X + static_cast<size_t>(r) * F + c));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(X + static_cast<size_t>(r) * F + c + 4));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     } else {
-      if (r < rows && c < F) Xf[static_cast<size_t>(r) * F + c] = v;
-    }
-  }
-  if constexpr (BF16) {
-    if (XbT != nullptr) {  // the scorer needs no transposed copy (no dW GEMM)
-      __syncthreads();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int c = c0 + ty + 8 * i, r = r0 + tx;
-        if (c < F && r < rows) XbT[static_cast<size_t>(c) * ldB + r] = __float2bfloat16_rn(tile[tx][ty + 8 * i]);
+      for (int j = 0; j < 8; ++j) v[j] = (c + j < F) ? __ldg(X + static_cast<size_t>(r) * F + c + j) : 0.f;
+    }
+    if constexpr (BF16) {
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(Xb + static_cast<size_t>(r) * ldF + c) = o;
+    } else {
+      if (vec) {
+        *reinterpret_cast<float4*>(Xf + static_cast<size_t>(r) * F + c) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(Xf + static_cast<size_t>(r) * F + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c + j < F) Xf[static_cast<size_t>(r) * F + c + j] = v[j];
       }
     }
   }
-  if (blockIdx.x == 0 && blockIdx.y == 0) {
+  if (blockIdx.x == 0) {
     const float* __restrict__ w = desc->w;
     float cnt = 0.f;
     for (int i = threadIdx.x; i < rows; i += 256) cnt += (__ldg(w + i) != 0.f) ? 1.f : 0.f;
     cnt = warp_sum(cnt);
     __shared__ float part[8];
-    if (tx == 0) part[ty] = cnt;
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
     __syncthreads();
     if (threadIdx.x == 0) {
-      float s = 0.f;
-      for (int i = 0; i < 8; ++i) s += part[i];
-      scal[SCAL_NNZ] = s;
+      float t = 0.f;
+      for (int i = 0; i < 8; ++i) t += part[i];
+      scal[SCAL_NNZ] = t;
     }
   }
 }
@@ -80,7 +86,7 @@ load_batch_kernel(const BatchDesc* __restrict__ desc, int rows, int F, __nv_bflo
 // ------------------------------------------------------------------------------------------------
 // K3+K4 (+ output-layer backward): y_hat = sigmoid(A_L w_o + b_o); loss = sum w (y_hat-y)^2 / n_nz
 // (res/ssgd_monitor.py:121,129) or the sigmoid-CE variant; d z_hat; then the rank-1 backward
-//   dZ_L[r,j] = dz_r * w_o[j] * act'(A_L[r,j])     (row-major + transposed bf16 copies)
+//   dZ_L[r,j] = dz_r * w_o[j] * act'(A_L[r,j])     (row-major, bf16 or fp32)
 //   dw_o[j] += sum_r dz_r A_L[r,j],  db_o += sum_r dz_r,  db_L[j] += sum_r dZ_L[r,j]
 // out = 1 is GEMV-class: CUDA cores, one pass over A_L.  Each block owns 32 rows.
 // ------------------------------------------------------------------------------------------------
@@ -96,7 +102,6 @@ struct OutLayerParams {
   int do_loss;               // 0: scores only (no y / w access)
   float* yhat;               // nullable [rows]
   void* dZ; int ld_dZ;       // [rows, ld_dZ] bf16 or fp32
-  __nv_bfloat16* dZT; int ld_dZT;  // [H, ld_dZT] (bf16 mode only)
   float* g_wo; float* g_bo; float* g_bL;  // gradient slots (atomic accumulate)
 };
 
@@ -111,7 +116,6 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 out_layer_kernel(const OutLayerParams p) {
   __shared__ float dz_row[32];
-  __shared__ float tileT[128][33];  // [column in chunk][row] for the transposed write
   __shared__ float blk_red[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r0 = blockIdx.x * 32;
@@ -185,20 +189,10 @@ out_layer_kernel(const OutLayerParams p) {
         s_db += g;
         st_from_float<T>(dZ + static_cast<size_t>(r) * p.ld_dZ + j, g);
       }
-      if (p.dZT) tileT[cl][rl] = g;
     }
     if (j < p.H) {
       atomicAdd(p.g_wo + j, s_dw);
       atomicAdd(p.g_bL + j, s_db);
-    }
-    if (p.dZT) {
-      __syncthreads();
-      // transposed write: 32 consecutive rows of one column = 64 contiguous bytes
-      for (int q = warp; q < 128; q += 8) {
-        const int jj = c0 + q, r = r0 + lane;
-        if (jj < p.H && r < p.rows) p.dZT[static_cast<size_t>(jj) * p.ld_dZT + r] = __float2bfloat16_rn(tileT[q][lane]);
-      }
-      __syncthreads();
     }
   }
 }
@@ -207,8 +201,7 @@ out_layer_kernel(const OutLayerParams p) {
 // K7 fused multi-tensor optimizer over the flat parameter vector (TF 1.x kernel forms: ApplyAdadelta
 // res/ssgd_monitor.py:138, ApplyAdam res/ssgd.py:57, ApplyGradientDescent res/ssgd_monitor_bk.py:81,
 // ApplyMomentum).  Reads the (all-reduced) gradient once, updates fp32 master weights + state, and in
-// bf16 mode refreshes the two bf16 shadow copies the GEMMs consume: W^T [out, ld_in] (forward B operand)
-// and W [in, ld_out] (dA B operand), transposing 32x32 tiles through shared memory.
+// bf16 mode refreshes the bf16 shadow of every hidden-layer weight matrix in the same pass.
 // ------------------------------------------------------------------------------------------------
 struct OptHyper {
   int kind;
@@ -235,83 +228,54 @@ __device__ __forceinline__ float opt_update(const OptHyper& h, float lr_t, float
   }
 }
 
-// One work item per block: either a 32x32 tile of a hidden-layer weight matrix (with shadows) or a
-// 1024-element run of "plain" parameters (biases, output layer, or everything in fp32 mode).
+// One work item per block: a run of <= 1024 consecutive parameters.  Runs that lie inside a hidden-layer
+// weight matrix also refresh its bf16 shadow W [in, ld_out] (row-major, the layout both the forward GEMM
+// (MN-major B operand) and the dA GEMM (K-major B operand) consume).
 struct OptWork {
-  long long off;        // flat offset of the matrix / run
-  int kind;             // 0 = plain run, 1 = weight tile
-  int count;            // plain: elements in this run (<= 1024)
-  int in_dim, out_dim;  // tile: matrix dims
-  int ti, to;           // tile: tile row (in) / col (out) index
-  __nv_bfloat16* Wt; int ld_in;   // [out, ld_in]
-  __nv_bfloat16* Wn; int ld_out;  // [in, ld_out]
+  long long off;          // flat offset of the first element of the run
+  int count;              // elements in this run (<= 1024)
+  int out_dim;            // > 0: run lies in a weight matrix with this many columns
+  long long mat_off;      // flat offset of that matrix
+  __nv_bfloat16* Wn;      // shadow base (nullptr: no shadow)
+  int ld_out;
 };
 
 static __global__ void __launch_bounds__(256)
 optimizer_kernel(const OptWork* __restrict__ work, const BatchDesc* __restrict__ desc, OptHyper h,
                  float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ s1, float* __restrict__ s2) {
-  __shared__ float tile[32][33];
   const OptWork wk = work[blockIdx.x];
   const float lr_t = desc->lr_t, gs = desc->gscale;
-  if (wk.kind == 0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int e = threadIdx.x + 256 * i;
-      if (e < wk.count) {
-        const long long idx = wk.off + e;
-        float a = s1[idx], b = s2[idx];
-        const float t = opt_update(h, lr_t, theta[idx], grad[idx] * gs, a, b);
-        theta[idx] = t; s1[idx] = a; s2[idx] = b;
+  for (int i = 0; i < 4; ++i) {
+    const int e = threadIdx.x + 256 * i;
+    if (e < wk.count) {
+      const long long idx = wk.off + e;
+      float a = s1[idx], b = s2[idx];
+      const float t = opt_update(h, lr_t, theta[idx], grad[idx] * gs, a, b);
+      theta[idx] = t; s1[idx] = a; s2[idx] = b;
+      if (wk.Wn != nullptr) {
+        const long long m = idx - wk.mat_off;
+        const long long r = m / wk.out_dim;
+        wk.Wn[r * wk.ld_out + (m - r * wk.out_dim)] = __float2bfloat16_rn(t);
       }
     }
-    return;
-  }
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int i0 = wk.ti * 32, o0 = wk.to * 32;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int i = i0 + ty + 8 * k, o = o0 + tx;
-    float t = 0.f;
-    if (i < wk.in_dim && o < wk.out_dim) {
-      const long long idx = wk.off + static_cast<long long>(i) * wk.out_dim + o;
-      float a = s1[idx], b = s2[idx];
-      t = opt_update(h, lr_t, theta[idx], grad[idx] * gs, a, b);
-      theta[idx] = t; s1[idx] = a; s2[idx] = b;
-      if (wk.Wn) wk.Wn[static_cast<size_t>(i) * wk.ld_out + o] = __float2bfloat16_rn(t);
-    }
-    tile[ty + 8 * k][tx] = t;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int o = o0 + ty + 8 * k, i = i0 + tx;
-    if (i < wk.in_dim && o < wk.out_dim) wk.Wt[static_cast<size_t>(o) * wk.ld_in + i] = __float2bfloat16_rn(tile[tx][ty + 8 * k]);
   }
 }
 
 // Refresh the bf16 shadows from the fp32 master without touching state (after set_params / restore).
 static __global__ void __launch_bounds__(256)
 shadow_refresh_kernel(const OptWork* __restrict__ work, const float* __restrict__ theta) {
-  __shared__ float tile[32][33];
   const OptWork wk = work[blockIdx.x];
-  if (wk.kind == 0) return;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int i0 = wk.ti * 32, o0 = wk.to * 32;
+  if (wk.Wn == nullptr) return;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int i = i0 + ty + 8 * k, o = o0 + tx;
-    float t = 0.f;
-    if (i < wk.in_dim && o < wk.out_dim) {
-      t = theta[wk.off + static_cast<long long>(i) * wk.out_dim + o];
-      if (wk.Wn) wk.Wn[static_cast<size_t>(i) * wk.ld_out + o] = __float2bfloat16_rn(t);
+  for (int i = 0; i < 4; ++i) {
+    const int e = threadIdx.x + 256 * i;
+    if (e < wk.count) {
+      const long long idx = wk.off + e;
+      const long long m = idx - wk.mat_off;
+      const long long r = m / wk.out_dim;
+      wk.Wn[r * wk.ld_out + (m - r * wk.out_dim)] = __float2bfloat16_rn(theta[idx]);
     }
-    tile[ty + 8 * k][tx] = t;
-  }
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int o = o0 + ty + 8 * k, i = i0 + tx;
-    if (i < wk.in_dim && o < wk.out_dim) wk.Wt[static_cast<size_t>(o) * wk.ld_in + i] = __float2bfloat16_rn(tile[tx][ty + 8 * k]);
   }
 }
 

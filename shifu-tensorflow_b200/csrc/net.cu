@@ -134,18 +134,12 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
   const bool bf = precision == SB_PREC_BF16;
   if (bf) {
     SB_TRY(dalloc(&Xb, static_cast<size_t>(max_batch) * ldF));
-    if (training) SB_TRY(dalloc(&XbT, static_cast<size_t>(F) * ldB));
-    A.assign(L, nullptr); AT.assign(L, nullptr); dZ.assign(L, nullptr); dZT.assign(L, nullptr);
+    A.assign(L, nullptr); dZ.assign(L, nullptr);
     for (int l = 0; l < L; ++l) {
       Layer& ly = layers[l];
-      SB_TRY(dalloc(&ly.Wt, static_cast<size_t>(ly.out) * ly.ld_in));
-      if (training && l > 0) SB_TRY(dalloc(&ly.Wn, static_cast<size_t>(ly.in) * ly.ld_out));
+      SB_TRY(dalloc(&ly.Wn, static_cast<size_t>(ly.in) * ly.ld_out));
       SB_TRY(dalloc(&A[l], static_cast<size_t>(max_batch) * ly.ld_out));
-      if (training) {
-        if (l < L - 1) SB_TRY(dalloc(&AT[l], static_cast<size_t>(ly.out) * ldB));
-        SB_TRY(dalloc(&dZ[l], static_cast<size_t>(max_batch) * ly.ld_out));
-        SB_TRY(dalloc(&dZT[l], static_cast<size_t>(ly.out) * ldB));
-      }
+      if (training) SB_TRY(dalloc(&dZ[l], static_cast<size_t>(max_batch) * ly.ld_out));
     }
   } else {
     SB_TRY(dalloc(&Xf, static_cast<size_t>(max_batch) * F));
@@ -156,28 +150,23 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
     }
   }
 
-  // optimizer / shadow-refresh work table
+  // optimizer / shadow-refresh work table: runs of <= 1024 consecutive parameters
   std::vector<OptWork> wk;
-  auto add_plain = [&](long long o, long long n) {
+  auto add_runs = [&](long long o, long long n, const Layer* mat) {
     for (long long s = 0; s < n; s += 1024) {
       OptWork w = {};
-      w.off = o + s; w.kind = 0; w.count = static_cast<int>(n - s < 1024 ? n - s : 1024);
+      w.off = o + s; w.count = static_cast<int>(n - s < 1024 ? n - s : 1024);
+      if (mat) { w.out_dim = mat->out; w.mat_off = mat->w_off; w.Wn = mat->Wn; w.ld_out = mat->ld_out; }
       wk.push_back(w);
     }
   };
   for (int l = 0; l <= L; ++l) {
     Layer& ly = layers[l];
     if (bf && l < L) {
-      for (int ti = 0; ti < (ly.in + 31) / 32; ++ti)
-        for (int to = 0; to < (ly.out + 31) / 32; ++to) {
-          OptWork w = {};
-          w.off = ly.w_off; w.kind = 1; w.in_dim = ly.in; w.out_dim = ly.out; w.ti = ti; w.to = to;
-          w.Wt = ly.Wt; w.ld_in = ly.ld_in; w.Wn = ly.Wn; w.ld_out = ly.ld_out;
-          wk.push_back(w);
-        }
-      add_plain(ly.b_off, ly.out);
+      add_runs(ly.w_off, static_cast<long long>(ly.in) * ly.out, &ly);
+      add_runs(ly.b_off, ly.out, nullptr);
     } else {
-      add_plain(ly.w_off, static_cast<long long>(ly.in) * ly.out + ly.out);
+      add_runs(ly.w_off, static_cast<long long>(ly.in) * ly.out + ly.out, nullptr);
     }
   }
   n_work = static_cast<int>(wk.size());
@@ -187,11 +176,12 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
 
   // opt in to > 48 KB dynamic shared memory once, outside of any stream capture
   if (bf) {
-#define SB_ATTR(BN, EPI) \
-  SB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmTcCfg<BN>::SMEM_BYTES))
-    SB_ATTR(64, EPI_FWD); SB_ATTR(128, EPI_FWD);
-    SB_ATTR(64, EPI_DA);  SB_ATTR(128, EPI_DA);
-    SB_ATTR(64, EPI_DW);  SB_ATTR(128, EPI_DW);
+#define SB_ATTR(BN, EPI, AMN, BMN)                                                                              \
+  SB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                               GemmTcCfg<BN>::SMEM_BYTES))
+    SB_ATTR(64, EPI_FWD, false, true); SB_ATTR(128, EPI_FWD, false, true);
+    SB_ATTR(64, EPI_DA, false, false); SB_ATTR(128, EPI_DA, false, false);
+    SB_ATTR(64, EPI_DW, true, true);   SB_ATTR(128, EPI_DW, true, true);
 #undef SB_ATTR
   }
   return SB_OK;
@@ -213,26 +203,29 @@ int Net::refresh_shadows() {
 }
 
 int Net::enqueue_load(int rows) {
-  dim3 grid((F + 31) / 32, (rows + 31) / 32);
+  const long long units = static_cast<long long>(rows) * (ldF / 8);
+  long long blocks = (units + 255) / 256;
+  const long long cap = static_cast<long long>(num_sms) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
   if (precision == SB_PREC_BF16)
-    load_batch_kernel<true><<<grid, 256, 0, stream>>>(desc, rows, F, Xb, ldF, XbT, ldB, nullptr, scal);
+    load_batch_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(desc, rows, F, Xb, ldF, nullptr, scal);
   else
-    load_batch_kernel<false><<<grid, 256, 0, stream>>>(desc, rows, F, nullptr, 0, nullptr, 0, Xf, scal);
+    load_batch_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(desc, rows, F, nullptr, ldF, Xf, scal);
   SB_CUDA(cudaGetLastError());
   mark("load_batch");
   return SB_OK;
 }
 
-template <int EPI>
+template <int EPI, bool A_MN, bool B_MN>
 static int launch_tc_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmTcParams& p, int num_sms, cudaStream_t st) {
-  using namespace sb;
   const int tiles = ((p.M + 127) / 128) * ((p.N + bn - 1) / bn);
   const int n_work = tiles * p.split_k;
   const int grid = n_work < num_sms ? n_work : num_sms;
   if (bn == 64)
-    gemm_tc_kernel<64, EPI><<<grid, 192, GemmTcCfg<64>::SMEM_BYTES, st>>>(a, b, p);
+    gemm_tc_kernel<64, EPI, A_MN, B_MN><<<grid, GemmTcCfg<64>::THREADS, GemmTcCfg<64>::SMEM_BYTES, st>>>(a, b, p);
   else
-    gemm_tc_kernel<128, EPI><<<grid, 192, GemmTcCfg<128>::SMEM_BYTES, st>>>(a, b, p);
+    gemm_tc_kernel<128, EPI, A_MN, B_MN><<<grid, GemmTcCfg<128>::THREADS, GemmTcCfg<128>::SMEM_BYTES, st>>>(a, b, p);
   SB_CUDA(cudaGetLastError());
   return SB_OK;
 }
@@ -243,18 +236,18 @@ int Net::enqueue_hidden_forward(int rows) {
   for (int l = 0; l < L; ++l) {
     Layer& ly = layers[l];
     if (precision == SB_PREC_BF16) {
+      // Z = A_{l-1}[rows,in] (K-major) x W_l[in,out] (MN-major B operand: n contiguous)
       const int bn = pick_bn(ly.out);
       CUtensorMap ta, tb;
       const __nv_bfloat16* src = (l == 0) ? Xb : A[l - 1];
       SB_TRY(make_tmap_bf16(&ta, src, rows, ly.in, ly.ld_in, 128));
-      SB_TRY(make_tmap_bf16(&tb, ly.Wt, ly.out, ly.in, ly.ld_in, bn));
+      SB_TRY(make_tmap_bf16(&tb, ly.Wn, ly.in, ly.out, ly.ld_out, 64));
       GemmTcParams p = {};
       p.M = rows; p.N = ly.out; p.K = ly.in;
       p.split_k = 1; p.kb_per_split = (ly.in + 63) / 64;
       p.bias = theta + ly.b_off; p.act = ly.act;
       p.out = A[l]; p.ld_out = ly.ld_out;
-      p.outT = (training && l < L - 1) ? AT[l] : nullptr; p.ld_outT = ldB;
-      SB_TRY(launch_tc_bn<EPI_FWD>(bn, ta, tb, p, num_sms, stream));
+      SB_TRY((launch_tc_bn<EPI_FWD, false, true>(bn, ta, tb, p, num_sms, stream)));
     } else {
       GemmF32Params p = {};
       p.M = rows; p.N = ly.out; p.K = ly.in;
@@ -284,11 +277,11 @@ int Net::enqueue_out(int rows, bool do_loss, bool do_bwd, float* yhat_dst, float
   const int grid = (rows + 31) / 32;
   if (precision == SB_PREC_BF16) {
     p.A = A[L - 1]; p.ldA = hl.ld_out;
-    if (do_bwd) { p.dZ = dZ[L - 1]; p.ld_dZ = hl.ld_out; p.dZT = dZT[L - 1]; p.ld_dZT = ldB; }
+    if (do_bwd) { p.dZ = dZ[L - 1]; p.ld_dZ = hl.ld_out; }
     out_layer_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p);
   } else {
     p.A = Af[L - 1]; p.ldA = hl.out;
-    if (do_bwd) { p.dZ = dZf[L - 1]; p.ld_dZ = hl.out; p.dZT = nullptr; }
+    if (do_bwd) { p.dZ = dZf[L - 1]; p.ld_dZ = hl.out; }
     out_layer_kernel<float><<<grid, 256, 0, stream>>>(p);
   }
   SB_CUDA(cudaGetLastError());
@@ -300,23 +293,23 @@ int Net::enqueue_backward(int rows, float* grad) {
   for (int l = L - 1; l >= 0; --l) {
     Layer& ly = layers[l];
     if (precision == SB_PREC_BF16) {
-      // dW_l[in,out] += A_{l-1}^T[in, rows] * dZ_l^T[out, rows]^T   (reduction over the batch, split-K)
+      // dW_l[in,out] += sum_rows A_{l-1}[rows,in] (MN-major A) * dZ_l[rows,out] (MN-major B), split-K over rows
       {
         const int bn = pick_bn(ly.out);
         CUtensorMap ta, tb;
-        const __nv_bfloat16* aT = (l == 0) ? XbT : AT[l - 1];
-        SB_TRY(make_tmap_bf16(&ta, aT, ly.in, rows, ldB, 128));
-        SB_TRY(make_tmap_bf16(&tb, dZT[l], ly.out, rows, ldB, bn));
+        const __nv_bfloat16* ap = (l == 0) ? Xb : A[l - 1];
+        SB_TRY(make_tmap_bf16(&ta, ap, rows, ly.in, ly.ld_in, 64));
+        SB_TRY(make_tmap_bf16(&tb, dZ[l], rows, ly.out, ly.ld_out, 64));
         GemmTcParams p = {};
         p.M = ly.in; p.N = ly.out; p.K = rows;
         p.split_k = pick_split_k(p.M, p.N, p.K, bn, num_sms, &p.kb_per_split);
         p.accum = grad + ly.w_off; p.ld_acc = ly.out;
         p.acc_vec4 = (ly.out % 4 == 0 && ly.w_off % 4 == 0) ? 1 : 0;
-        SB_TRY(launch_tc_bn<EPI_DW>(bn, ta, tb, p, num_sms, stream));
+        SB_TRY((launch_tc_bn<EPI_DW, true, true>(bn, ta, tb, p, num_sms, stream)));
         mark("gemm_dw");
       }
       if (l > 0) {
-        // dZ_{l-1}[rows,in] = (dZ_l[rows,out] * W_l[in,out]^T) .* act'(A_{l-1})
+        // dZ_{l-1}[rows,in] = (dZ_l[rows,out] (K-major) x W_l[in,out] (K-major B: k = out contiguous)) .* act'(A_{l-1})
         Layer& pl = layers[l - 1];
         const int bn = pick_bn(ly.in);
         CUtensorMap ta, tb;
@@ -328,9 +321,8 @@ int Net::enqueue_backward(int rows, float* grad) {
         p.act = pl.act;
         p.aux = A[l - 1]; p.ld_aux = pl.ld_out;
         p.out = dZ[l - 1]; p.ld_out = pl.ld_out;
-        p.outT = dZT[l - 1]; p.ld_outT = ldB;
         p.colsum = grad + pl.b_off;
-        SB_TRY(launch_tc_bn<EPI_DA>(bn, ta, tb, p, num_sms, stream));
+        SB_TRY((launch_tc_bn<EPI_DA, false, false>(bn, ta, tb, p, num_sms, stream)));
         mark("gemm_da");
       }
     } else {

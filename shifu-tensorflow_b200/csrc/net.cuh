@@ -15,7 +15,7 @@ namespace sb {
 struct Layer {
   int in, out, act;
   long long w_off, b_off;              // offsets into the flat parameter vector
-  __nv_bfloat16 *Wt = nullptr, *Wn = nullptr;  // bf16 shadows: W^T [out, ld_in], W [in, ld_out]
+  __nv_bfloat16* Wn = nullptr;  // bf16 shadow of W [in, ld_out] (row-major like the fp32 master)
   int ld_in = 0, ld_out = 0;
 };
 
@@ -31,8 +31,8 @@ struct Net {
 
   float* theta = nullptr;
   // bf16 workspace
-  __nv_bfloat16 *Xb = nullptr, *XbT = nullptr;
-  std::vector<__nv_bfloat16*> A, AT, dZ, dZT;
+  __nv_bfloat16* Xb = nullptr;             // current batch as bf16 [rows, ldF]
+  std::vector<__nv_bfloat16*> A, dZ;       // A_l, dZ_l as bf16 [rows, ld_out_l]
   // fp32 workspace
   float* Xf = nullptr;
   std::vector<float*> Af, dZf;

@@ -21,13 +21,20 @@ SHAPES = [
 ]
 
 
+LAYOUTS = {"KK": (False, False),   # dA GEMM:      dZ_l [rows,out]  x  W_l [in,out] as B[N=in, K=out]
+           "KM": (False, True),    # forward GEMM: A_{l-1} [rows,in] x W_l [in,out] as B stored [K=in, N=out]
+           "MM": (True, True)}     # dW GEMM:      A_{l-1} [rows,in] and dZ_l [rows,out], both stored [K=rows, *]
+
+
 @pytest.mark.gpu
+@pytest.mark.parametrize("layout", sorted(LAYOUTS))
 @pytest.mark.parametrize("M,N,K,split_k", SHAPES)
-def test_gemm_bf16_matches_fp64(sb, M, N, K, split_k):
+def test_gemm_bf16_matches_fp64(sb, M, N, K, split_k, layout):
+    a_mn, b_mn = LAYOUTS[layout]
     rng = np.random.RandomState(M * 7 + N * 3 + K)
     A = bf16_round(rng.standard_normal((M, K)).astype(np.float32))
     B = bf16_round(rng.standard_normal((N, K)).astype(np.float32))
-    D = sb.capi.debug_gemm_bf16(A, B, split_k=split_k)
+    D = sb.capi.debug_gemm_bf16(A.T.copy() if a_mn else A, B.T.copy() if b_mn else B, split_k=split_k, a_mn=a_mn, b_mn=b_mn)
     ref = A.astype(np.float64) @ B.astype(np.float64).T
     # fp32 accumulation over K terms of magnitude ~1: error ~ sqrt(K) * 2^-24 * |sum|-ish; 1e-3 absolute is generous
     err = np.abs(D - ref).max()
@@ -36,11 +43,14 @@ def test_gemm_bf16_matches_fp64(sb, M, N, K, split_k):
 
 
 @pytest.mark.gpu
-def test_gemm_identity_exact(sb):
-    """A = I (128x128 padded into K=128), B arbitrary bf16: result must be exactly B^T."""
+@pytest.mark.parametrize("layout", sorted(LAYOUTS))
+def test_gemm_identity_exact(sb, layout):
+    """A = I, B arbitrary bf16: the result must be exactly B^T - any swizzle / descriptor / layout mistake shows up
+    as a permutation."""
+    a_mn, b_mn = LAYOUTS[layout]
     rng = np.random.RandomState(1)
     K = 128
     A = np.eye(128, K, dtype=np.float32)
     B = bf16_round(rng.standard_normal((128, K)).astype(np.float32))
-    D = sb.capi.debug_gemm_bf16(A, B)
+    D = sb.capi.debug_gemm_bf16(A.T.copy() if a_mn else A, B.T.copy() if b_mn else B, a_mn=a_mn, b_mn=b_mn)
     np.testing.assert_array_equal(D, B.T)
