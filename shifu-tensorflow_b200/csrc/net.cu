@@ -99,6 +99,12 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
   training = training_;
   SB_CUDA(cudaSetDevice(device));
   SB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  if (training_) {
+    SB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    ev_dz.resize(d->n_hidden);
+    for (auto& e : ev_dz) SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    SB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
   F = d->n_features;
   L = d->n_hidden;
   precision = d->precision;
@@ -191,6 +197,12 @@ void Net::destroy() {
   if (stream) cudaStreamSynchronize(stream);
   for (void* p : allocs) cudaFree(p);
   allocs.clear();
+  for (cudaEvent_t e : ev_dz) cudaEventDestroy(e);
+  ev_dz.clear();
+  if (ev_join) cudaEventDestroy(ev_join);
+  ev_join = nullptr;
+  if (side) cudaStreamDestroy(side);
+  side = nullptr;
   if (stream) cudaStreamDestroy(stream);
   stream = nullptr;
 }
@@ -290,6 +302,9 @@ int Net::enqueue_out(int rows, bool do_loss, bool do_bwd, float* yhat_dst, float
 }
 
 int Net::enqueue_backward(int rows, float* grad) {
+  // dW_l and dA_l both consume dZ_l and are independent of each other: the dW GEMMs go to the side stream and
+  // overlap the dA chain (they are each well under one wave at cfg1 sizes).  Not while profiling (clean times).
+  const bool fork = concurrent_bwd && !profiling && side != nullptr && precision == SB_PREC_BF16;
   for (int l = L - 1; l >= 0; --l) {
     Layer& ly = layers[l];
     if (precision == SB_PREC_BF16) {
@@ -305,7 +320,11 @@ int Net::enqueue_backward(int rows, float* grad) {
         p.split_k = pick_split_k(p.M, p.N, p.K, bn, num_sms, &p.kb_per_split);
         p.accum = grad + ly.w_off; p.ld_acc = ly.out;
         p.acc_vec4 = (ly.out % 4 == 0 && ly.w_off % 4 == 0) ? 1 : 0;
-        SB_TRY((launch_tc_bn<EPI_DW, true, true>(bn, ta, tb, p, num_sms, stream)));
+        if (fork) {
+          SB_CUDA(cudaEventRecord(ev_dz[l], stream));
+          SB_CUDA(cudaStreamWaitEvent(side, ev_dz[l], 0));
+        }
+        SB_TRY((launch_tc_bn<EPI_DW, true, true>(bn, ta, tb, p, num_sms, fork ? side : stream)));
         mark("gemm_dw");
       }
       if (l > 0) {
@@ -353,6 +372,10 @@ int Net::enqueue_backward(int rows, float* grad) {
         mark("gemm_da");
       }
     }
+  }
+  if (fork) {
+    SB_CUDA(cudaEventRecord(ev_join, side));
+    SB_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
   }
   return SB_OK;
 }

@@ -22,6 +22,10 @@ struct Layer {
 struct Net {
   int device = 0, num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;               // dW GEMMs run here, concurrently with the dA chain on `stream`
+  std::vector<cudaEvent_t> ev_dz;            // ev_dz[l]: dZ_l is complete on `stream`
+  cudaEvent_t ev_join = nullptr;
+  bool concurrent_bwd = true;
   int F = 0, L = 0;             // features, hidden layers
   std::vector<Layer> layers;    // L hidden + 1 output (out = 1)
   long long n_params = 0;
