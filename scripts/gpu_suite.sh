@@ -12,6 +12,7 @@ run() { # name, timeout, args...
 : > gpurun_out/suite.log
 run gemm_identity 180 tests/test_gemm_tc.py -k identity
 run gemm_shapes 300 tests/test_gemm_tc.py -k matches
+run gemm_tiles 300 tests/test_gemm_tc.py -k every_tile
 run trainer_fp32 300 tests/test_trainer_parity.py -k "fp32 or resident or epoch"
 run trainer_bf16 300 tests/test_trainer_parity.py -k bf16
 run scorer 300 tests/test_scorer_parity.py

@@ -110,6 +110,8 @@ PROTOTYPES = {
     "sb_savedmodel_read": (C.c_int, [_cp, _cp, _cp, _cp, _P(NetDesc), _P(C.c_int32), _f32p, C.c_int64, _P(C.c_int64)]),
     "sb_debug_gemm_bf16": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
     "sb_debug_gemm_bf16_ex": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
+    "sb_debug_gemm_bf16_cfg": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                         C.c_int32, C.c_int32, C.c_int]),
 }
 
 
@@ -375,7 +377,7 @@ def savedmodel_read(saved_model_dir: str, input_name: str, output_name: str, tag
 
 
 def debug_gemm_bf16(A: np.ndarray, B: np.ndarray, split_k: int = 1, device: int = 0, a_mn: bool = False,
-                    b_mn: bool = False) -> np.ndarray:
+                    b_mn: bool = False, cg: int = 0, bn: int = 0) -> np.ndarray:
     """D[M,N] = sum_k A(m,k) B(n,k) through the tcgen05 kernel (operands rounded to bf16 on the device).
     A is [M,K] (K-major) or, with a_mn, [K,M] (MN-major); B is [N,K] or, with b_mn, [K,N]."""
     A, B = _f32(A), _f32(B)
@@ -383,5 +385,5 @@ def debug_gemm_bf16(A: np.ndarray, B: np.ndarray, split_k: int = 1, device: int 
     (K2, N) = B.shape if b_mn else B.shape[::-1]
     assert K == K2
     D = np.zeros((M, N), np.float32)
-    check(lib().sb_debug_gemm_bf16_ex(_ptr(A), _ptr(B), _ptr(D), M, N, K, split_k, int(a_mn), int(b_mn), device))
+    check(lib().sb_debug_gemm_bf16_cfg(_ptr(A), _ptr(B), _ptr(D), M, N, K, split_k, int(a_mn), int(b_mn), cg, bn, device))
     return D

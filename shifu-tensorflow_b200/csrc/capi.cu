@@ -5,6 +5,7 @@
 #include <memory>
 #include <random>
 #include "net.cuh"
+#include "gemm_tc_launch.cuh"
 #include "savedmodel.h"
 
 using namespace sb;
@@ -646,8 +647,10 @@ void* sb_model_stream(sb_model_t* m) { return m ? reinterpret_cast<void*>(m->net
 // ================================================================================================
 // kernel-level test hook
 // ================================================================================================
-int sb_debug_gemm_bf16_ex(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k,
-                          int32_t a_mn, int32_t b_mn, int device) {
+int sb_debug_gemm_bf16_cfg(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k,
+                           int32_t a_mn, int32_t b_mn, int32_t cfg_cg, int32_t cfg_bn, int device) {
+  SB_CHECK(cfg_cg == 0 || ((cfg_cg == 1 && (cfg_bn == 64 || cfg_bn == 128)) || (cfg_cg == 2 && (cfg_bn == 128 || cfg_bn == 256))),
+           SB_ERR_INVALID, "tile configuration cg=%d bn=%d not instantiated", cfg_cg, cfg_bn);
   SB_CHECK(A && B && D && M > 0 && N > 0 && K > 0, SB_ERR_INVALID, "bad argument");
   SB_CHECK((a_mn == 0 && b_mn == 0) || (a_mn == 0 && b_mn == 1) || (a_mn == 1 && b_mn == 1), SB_ERR_INVALID,
            "layout combination not instantiated (use KK, KM or MM)");
@@ -675,37 +678,36 @@ int sb_debug_gemm_bf16_ex(const float* A, const float* B, float* D, int32_t M, i
   SB_CUDA(cudaMemcpy(dB32, B, sizeof(float) * N * K, cudaMemcpyHostToDevice));
   cast_bf16_kernel<<<static_cast<unsigned>((static_cast<long long>(M) * K + 255) / 256), 256>>>(dA32, a_rows, a_cols, dA, lda);
   cast_bf16_kernel<<<static_cast<unsigned>((static_cast<long long>(N) * K + 255) / 256), 256>>>(dB32, b_rows, b_cols, dB, ldb);
-  const int bn = N <= 64 ? 64 : 128;
+  GemmPlan pl = plan_gemm(M, N, K, prop.multiProcessorCount, false);
+  if (cfg_cg > 0) {  // explicit tile configuration requested by the test
+    pl.cg = cfg_cg; pl.bn = cfg_bn;
+    const int tiles = ((M + 128 * pl.cg - 1) / (128 * pl.cg)) * ((N + pl.bn - 1) / pl.bn);
+    pl.split_k = 1; pl.kb_per_split = (K + 63) / 64;
+    const int slots = prop.multiProcessorCount / pl.cg;
+    pl.grid = (tiles < slots ? tiles : slots) * pl.cg;
+  }
+  {
+    const int total_kb = (K + 63) / 64;
+    int want = split_k < 1 ? 1 : (split_k > total_kb ? total_kb : split_k);
+    pl.kb_per_split = (total_kb + want - 1) / want;
+    pl.split_k = (total_kb + pl.kb_per_split - 1) / pl.kb_per_split;
+    const int tiles = ((M + 128 * pl.cg - 1) / (128 * pl.cg)) * ((N + pl.bn - 1) / pl.bn);
+    const int slots = prop.multiProcessorCount / pl.cg;
+    const int work = tiles * pl.split_k;
+    pl.grid = (work < slots ? work : slots) * pl.cg;
+  }
   CUtensorMap ta, tb;
   int s = make_tmap_bf16(&ta, dA, a_rows, a_cols, lda, a_mn ? 64 : 128);
-  if (s == SB_OK) s = make_tmap_bf16(&tb, dB, b_rows, b_cols, ldb, b_mn ? 64 : bn);
+  if (s == SB_OK) s = make_tmap_bf16(&tb, dB, b_rows, b_cols, ldb, b_mn ? 64 : plan_box_rows_b(pl));
   if (s == SB_OK) {
     GemmTcParams p = {};
     p.M = M; p.N = N; p.K = K;
-    const int total_kb = (K + 63) / 64;
-    int want = split_k < 1 ? 1 : (split_k > total_kb ? total_kb : split_k);
-    p.kb_per_split = (total_kb + want - 1) / want;
-    p.split_k = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
     p.accum = dD; p.ld_acc = N;
-    const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
-    const int n_work = tiles * p.split_k;
-    const int grid = n_work < prop.multiProcessorCount ? n_work : prop.multiProcessorCount;
-#define SB_DBG_LAUNCH(BN, AMN, BMN)                                                                                   \
-  do {                                                                                                                \
-    cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI_F32, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
-                         GemmTcCfg<BN>::SMEM_BYTES);                                                                  \
-    gemm_tc_kernel<BN, EPI_F32, AMN, BMN><<<grid, GemmTcCfg<BN>::THREADS, GemmTcCfg<BN>::SMEM_BYTES>>>(ta, tb, p);    \
-  } while (0)
-    if (bn == 64) {
-      if (!a_mn && !b_mn) SB_DBG_LAUNCH(64, false, false);
-      else if (!a_mn) SB_DBG_LAUNCH(64, false, true);
-      else SB_DBG_LAUNCH(64, true, true);
-    } else {
-      if (!a_mn && !b_mn) SB_DBG_LAUNCH(128, false, false);
-      else if (!a_mn) SB_DBG_LAUNCH(128, false, true);
-      else SB_DBG_LAUNCH(128, true, true);
-    }
-#undef SB_DBG_LAUNCH
+    if (!a_mn && !b_mn) { s = set_gemm_tc_attrs<EPI_F32, false, false>(); if (s == SB_OK) s = launch_gemm_tc<EPI_F32, false, false>(pl, ta, tb, p, 0); }
+    else if (!a_mn) { s = set_gemm_tc_attrs<EPI_F32, false, true>(); if (s == SB_OK) s = launch_gemm_tc<EPI_F32, false, true>(pl, ta, tb, p, 0); }
+    else { s = set_gemm_tc_attrs<EPI_F32, true, true>(); if (s == SB_OK) s = launch_gemm_tc<EPI_F32, true, true>(pl, ta, tb, p, 0); }
+  }
+  if (s == SB_OK) {
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) s = set_error(SB_ERR_CUDA, "gemm_tc_kernel failed: %s", cudaGetErrorString(e));
     else if (cudaMemcpy(D, dD, sizeof(float) * M * N, cudaMemcpyDeviceToHost) != cudaSuccess) s = set_error(SB_ERR_CUDA, "D2H failed");
@@ -714,8 +716,12 @@ int sb_debug_gemm_bf16_ex(const float* A, const float* B, float* D, int32_t M, i
   return s;
 }
 
+int sb_debug_gemm_bf16_ex(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k,
+                          int32_t a_mn, int32_t b_mn, int device) {
+  return sb_debug_gemm_bf16_cfg(A, B, D, M, N, K, split_k, a_mn, b_mn, 0, 0, device);
+}
 int sb_debug_gemm_bf16(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k, int device) {
-  return sb_debug_gemm_bf16_ex(A, B, D, M, N, K, split_k, 0, 0, device);
+  return sb_debug_gemm_bf16_cfg(A, B, D, M, N, K, split_k, 0, 0, 0, 0, device);
 }
 
 }  // extern "C"

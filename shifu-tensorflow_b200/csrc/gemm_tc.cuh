@@ -15,9 +15,16 @@
 //                                    batch, fp32 red.add into the flat gradient
 //   EPI_F32 : plain fp32 store (kernel-level parity test hook)
 //
-// Structure (one persistent CTA per SM, 320 threads):
+// Two tile configurations (template CG):
+//   CG = 1 : one CTA owns a 128 x BN tile (tcgen05.mma.cta_group::1, M = 128)         - small / narrow problems
+//   CG = 2 : a CTA PAIR (cluster of 2 on one TPC) owns a 256 x BN tile: tcgen05.mma.cta_group::2 with M = 256.
+//            Each CTA stages its own 128 rows of A and HALF of the B tile, so every byte fetched from L2 feeds
+//            twice the MMA work of CG = 1 - the 128x128 single-CTA tile is L2->SM bandwidth bound at ~45 % of the
+//            tensor peak on this part (measured), the pair tile is not.
+//
+// Structure (persistent, one CTA per SM, 320 threads):
 //   warp 0     : TMA producer   - cp.async.bulk.tensor 128B-swizzled tiles into a STAGES-deep smem ring
-//   warp 1     : MMA issuer     - one thread issues tcgen05.mma (128 x BN x 16), commits to mbarriers
+//   warp 1     : MMA issuer     - one thread (of the leader CTA when CG = 2) issues tcgen05.mma, commits to mbarriers
 //   warps 2..9 : epilogue       - tcgen05.ld the accumulator (double-buffered in TMEM) and apply the epilogue;
 //                                 two warps per TMEM lane quarter, each taking every other 32-column chunk
 // M/N/K tails need no special code on the load side: TMA zero-fills out-of-bounds box elements.
@@ -49,14 +56,19 @@ struct GemmTcParams {
   int acc_vec4;  // 1 if 16-byte aligned rows -> red.global.add.v4.f32
 };
 
-template <int BN>
+template <int BN, int CG>
 struct GemmTcCfg {
-  static constexpr int BM = 128;
-  static constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+  static_assert(CG == 1 || CG == 2, "cta group");
+  static_assert(BN == 64 || BN == 128 || BN == 256, "tile N");
+  static_assert(CG == 1 || BN >= 128, "pair tiles need BN >= 128 (each CTA stages BN/2 >= 64 rows of B)");
+  static constexpr int BM = 128;        // rows of the tile owned by ONE CTA
+  static constexpr int TILE_M = BM * CG;  // rows of the (pair) tile
+  static constexpr int BK = 64;         // 64 bf16 = 128 B = one swizzle row
+  static constexpr int BN_CTA = BN / CG;  // B rows staged by one CTA
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = BN_CTA * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int EPI_WARPS = 8;
@@ -75,16 +87,17 @@ __device__ __forceinline__ void epi_da_chunk(float (&v)[32], const __nv_bfloat16
   for (int j = 0; j < 32; ++j) v[j] *= act_grad_from_out(__bfloat162float(ah[j]), ACT);
 }
 
-template <int BN, int EPI, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(GemmTcCfg<BN>::THREADS, 1)
+template <int BN, int EPI, bool A_MN, bool B_MN, int CG>
+__global__ void __launch_bounds__(GemmTcCfg<BN, CG>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
-  using Cfg = GemmTcCfg<BN>;
-  constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES;
+  using Cfg = GemmTcCfg<BN, CG>;
+  constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES, TILE_M = Cfg::TILE_M, BN_CTA = Cfg::BN_CTA;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
   const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
-  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem base slot
+  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem base slot.
+  // CG = 2: full[] and tmem_empty[] are only used in the leader CTA (rank 0); empty[] / tmem_full[] in both.
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -95,6 +108,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // CTA rank inside the pair
+  const bool leader = rank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -102,105 +117,126 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), CG);  // CG = 2: leader producer's arrive.expect_tx + peer producer's remote arrive
       mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 32 * Cfg::EPI_WARPS);
+      mbar_init(tempty_bar(a), Cfg::EPI_WARPS * CG);  // one arrival per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  if constexpr (CG == 2) cluster_sync_all();  // both CTAs alive before the pair-wide TMEM allocation
+  if (warp == 2) {
+    if constexpr (CG == 2) tmem_alloc_cg2<Cfg::TMEM_COLS>(tmem_slot);
+    else tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  const int tiles_m = (p.M + BM - 1) / BM;
+  const int tiles_m = (p.M + TILE_M - 1) / TILE_M;
   const int tiles_n = (p.N + BN - 1) / BN;
   const int n_tiles = tiles_m * tiles_n;
   const int n_work = n_tiles * p.split_k;
   const int total_kb = (p.K + BK - 1) / BK;
+  const int w_first = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;   // work items are per CTA (CG=1) or per pair (CG=2)
+  const int w_step = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
 
   if (warp == 0) {
-    // ================= TMA producer =================
+    // ================= TMA producer (every CTA) =================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+      for (int w = w_first; w < n_work; w += w_step) {
         const int tile = w % n_tiles, ks = w / n_tiles;
         const int tm = tile / tiles_n, tn = tile % tiles_n;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(total_kb, kb0 + p.kb_per_split);
+        const int m0 = tm * TILE_M + static_cast<int>(rank) * BM;      // this CTA's rows of A
+        const int n0 = tn * BN + static_cast<int>(rank) * BN_CTA;      // this CTA's share of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1);
-          mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t fb = full_bar(stage);
+          if (leader) mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES * CG);
+          auto load = [&](uint32_t dst, const CUtensorMap* tm_, int c0, int c1) {
+            if constexpr (CG == 2) tma_load_2d_cg2(dst, tm_, fb, c0, c1);
+            else tma_load_2d(dst, tm_, fb, c0, c1);
+          };
           if constexpr (A_MN) {
 #pragma unroll
             for (int i = 0; i < BM / 64; ++i)  // 64(MN) x 64(K) boxes, 8 KB each, side by side along MN
-              tma_load_2d(smem_a(stage) + i * 8192, &tmA, full_bar(stage), tm * BM + i * 64, kb * BK);
+              load(smem_a(stage) + i * 8192, &tmA, m0 + i * 64, kb * BK);
           } else {
-            tma_load_2d(smem_a(stage), &tmA, full_bar(stage), kb * BK, tm * BM);
+            load(smem_a(stage), &tmA, kb * BK, m0);
           }
           if constexpr (B_MN) {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              tma_load_2d(smem_b(stage) + i * 8192, &tmB, full_bar(stage), tn * BN + i * 64, kb * BK);
+            for (int i = 0; i < BN_CTA / 64; ++i)
+              load(smem_b(stage) + i * 8192, &tmB, n0 + i * 64, kb * BK);
           } else {
-            tma_load_2d(smem_b(stage), &tmB, full_bar(stage), kb * BK, tn * BN);
+            load(smem_b(stage), &tmB, kb * BK, n0);
+          }
+          if constexpr (CG == 2) {
+            if (!leader) mbar_arrive_cluster(fb, 0);  // second arrival on the leader's full barrier
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+    // ================= MMA issuer (leader CTA only when CG = 2) =================
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
       // descriptor step for 16 elements along K: K-major = 32 B inside the swizzle row; MN-major = 16 rows of 128 B
       constexpr uint32_t a_kstep = A_MN ? (2048u >> 4) : (32u >> 4);
       constexpr uint32_t b_kstep = B_MN ? (2048u >> 4) : (32u >> 4);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+      for (int w = w_first; w < n_work; w += w_step, ++it) {
         const int ks = w / n_tiles;
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(total_kb, kb0 + p.kb_per_split);
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue has drained this accumulator
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);  // epilogue(s) have drained this accumulator
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full_bar(stage), phase);  // TMA bytes have landed
+          mbar_wait(full_bar(stage), phase);  // TMA bytes of both CTAs have landed
           tcgen05_fence_after();
           const uint64_t da = A_MN ? make_mnmajor_sw128_desc(smem_a(stage), 8192u) : make_kmajor_sw128_desc(smem_a(stage));
           const uint64_t db = B_MN ? make_mnmajor_sw128_desc(smem_b(stage), 8192u) : make_kmajor_sw128_desc(smem_b(stage));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(tmem_d, da + a_kstep * k, db + b_kstep * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs have read it
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint32_t accumulate = (kb > kb0 || k > 0) ? 1u : 0u;
+            if constexpr (CG == 2) umma_bf16_cg2(tmem_d, da + a_kstep * k, db + b_kstep * k, idesc, accumulate);
+            else umma_bf16(tmem_d, da + a_kstep * k, db + b_kstep * k, idesc, accumulate);
+          }
+          // frees the smem slot (in both CTAs) once these MMAs have read it
+          if constexpr (CG == 2) umma_commit_cg2(empty_bar(stage)); else umma_commit(empty_bar(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(tfull_bar(acc));  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs)
+        if constexpr (CG == 2) umma_commit_cg2(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
       }
     }
   } else {
-    // ================= epilogue warps (2..9) =================
+    // ================= epilogue warps (2..9), every CTA: its own 128 rows x BN columns =================
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;    // which of the two warps sharing the quarter
     int it = 0;
-    for (int w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+    for (int w = w_first; w < n_work; w += w_step, ++it) {
       const int tile = w % n_tiles;
       const int tm = tile / tiles_n, tn = tile % tiles_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
-      const int row = tm * BM + quarter * 32 + lane;  // output row owned by this thread
+      const int row = tm * TILE_M + static_cast<int>(rank) * BM + quarter * 32 + lane;  // output row of this thread
       const bool row_ok = row < p.M;
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
@@ -309,17 +345,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-      // release the accumulator back to the MMA warp
+      // release the accumulator back to the MMA warp: one arrival per warp on the leader's barrier
       tcgen05_fence_before();
-      mbar_arrive(tempty_bar(acc));
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+        else mbar_arrive(tempty_bar(acc));
+      }
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if constexpr (CG == 2) tmem_dealloc_cg2<Cfg::TMEM_COLS>(tmem_base);
+    else tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -331,9 +372,23 @@ PFN_encodeTiled get_encode_tiled();
 
 // Tensor map of a row-major bf16 matrix [rows, cols] with leading dimension ld (elements):
 // box = 64 columns x box_rows rows, 128-byte swizzle.  cols/rows are the LOGICAL extents (TMA zero-fills beyond
-// them), ld*2 must be a multiple of 16 bytes.  K-major operand: box_rows = 128 (A) or BN (B); MN-major: 64.
+// them), ld*2 must be a multiple of 16 bytes.  K-major operand: box_rows = rows one CTA stages (128 for A,
+// BN / CG for B); MN-major operand: 64.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int cols, int ld, int box_rows);
 
-int pick_split_k(int M, int N, int K, int BN, int num_sms, int* kb_per_split);
+// Tile configuration chosen per problem.
+struct GemmPlan {
+  int cg;            // 1 or 2
+  int bn;            // 64 / 128 / 256
+  int split_k, kb_per_split;
+  int grid;          // CTAs to launch (a multiple of cg)
+};
+GemmPlan plan_gemm(int M, int N, int K, int num_sms, bool allow_split);
+
+// Launch with the plan's configuration.  EPI / operand layouts are compile-time.
+template <int EPI, bool A_MN, bool B_MN>
+int launch_gemm_tc(const GemmPlan& pl, const CUtensorMap& a, const CUtensorMap& b, GemmTcParams p, cudaStream_t st);
+template <int EPI, bool A_MN, bool B_MN>
+int set_gemm_tc_attrs();
 
 }  // namespace sb

@@ -2,7 +2,9 @@
 // Mirrors generate_from_modelconf + model (res/ssgd_monitor.py:91-144) as a list of fused launches.
 #include <stdarg.h>
 #include <string.h>
+#include <algorithm>
 #include "net.cuh"
+#include "gemm_tc_launch.cuh"
 
 namespace sb {
 
@@ -49,17 +51,44 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int cols, int l
   return SB_OK;
 }
 
-int pick_split_k(int M, int N, int K, int BN, int num_sms, int* kb_per_split) {
-  const int tiles = ((M + 127) / 128) * ((N + BN - 1) / BN);
+// Tile configuration by a small cost model (cycles), constants measured on B200 (DESIGN.md "GEMM plan"):
+//   - a CTA's tensor core retires a 128 x bn x 64 k-block in 2*bn cycles (8192 dense bf16 flop/cycle/SM)
+//   - TMA delivers ~46 B/cycle/SM from L2 when all SMs pull at once (32 KB k-block stages measured at ~707 cycles)
+//   - ~1500 cycles per tile of pipeline fill / accumulator hand-off, ~5 cycles per output column of epilogue
+GemmPlan plan_gemm(int M, int N, int K, int num_sms, bool allow_split) {
   const int total_kb = (K + 63) / 64;
-  int want = num_sms / (tiles > 0 ? tiles : 1);
-  if (want < 1) want = 1;
-  int cap = total_kb / 2;
-  if (cap < 1) cap = 1;
-  if (want > cap) want = cap;
-  const int kb_per = (total_kb + want - 1) / want;
-  *kb_per_split = kb_per;
-  return (total_kb + kb_per - 1) / kb_per;
+  GemmPlan best = {};
+  double best_cost = 1e30;
+  const int cands[4][2] = {{1, 64}, {1, 128}, {2, 128}, {2, 256}};
+  for (const auto& c : cands) {
+    const int cg = c[0], bn = c[1];
+    if (bn == 64 && N > 64) continue;
+    if (bn == 256 && N <= 128) continue;
+    if (cg == 2 && M <= 128) continue;
+    const int slots = num_sms / cg;
+    const int tiles = ((M + 128 * cg - 1) / (128 * cg)) * ((N + bn - 1) / bn);
+    int split = 1, kb_per = total_kb;
+    if (allow_split && tiles < slots) {
+      int want = slots / tiles;
+      int cap = total_kb / 2;
+      if (cap < 1) cap = 1;
+      if (want > cap) want = cap;
+      if (want < 1) want = 1;
+      kb_per = (total_kb + want - 1) / want;
+      split = (total_kb + kb_per - 1) / kb_per;
+    }
+    const int work = tiles * split;
+    const int waves = (work + slots - 1) / slots;
+    const double stage_bytes = 128.0 * 64 * 2 + (bn / cg) * 64.0 * 2;
+    const double kb_cost = std::max(2.0 * bn, stage_bytes / 46.0);
+    const double cost = waves * (kb_per * kb_cost + 1500.0 + 5.0 * bn);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best.cg = cg; best.bn = bn; best.split_k = split; best.kb_per_split = kb_per;
+      best.grid = (work < slots ? work : slots) * cg;
+    }
+  }
+  return best;
 }
 
 int validate_desc(const sb_net_desc* d) {
@@ -182,13 +211,9 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
 
   // opt in to > 48 KB dynamic shared memory once, outside of any stream capture
   if (bf) {
-#define SB_ATTR(BN, EPI, AMN, BMN)                                                                              \
-  SB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                               GemmTcCfg<BN>::SMEM_BYTES))
-    SB_ATTR(64, EPI_FWD, false, true); SB_ATTR(128, EPI_FWD, false, true);
-    SB_ATTR(64, EPI_DA, false, false); SB_ATTR(128, EPI_DA, false, false);
-    SB_ATTR(64, EPI_DW, true, true);   SB_ATTR(128, EPI_DW, true, true);
-#undef SB_ATTR
+    SB_TRY((set_gemm_tc_attrs<EPI_FWD, false, true>()));
+    SB_TRY((set_gemm_tc_attrs<EPI_DA, false, false>()));
+    SB_TRY((set_gemm_tc_attrs<EPI_DW, true, true>()));
   }
   return SB_OK;
 }
@@ -229,37 +254,21 @@ int Net::enqueue_load(int rows) {
   return SB_OK;
 }
 
-template <int EPI, bool A_MN, bool B_MN>
-static int launch_tc_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmTcParams& p, int num_sms, cudaStream_t st) {
-  const int tiles = ((p.M + 127) / 128) * ((p.N + bn - 1) / bn);
-  const int n_work = tiles * p.split_k;
-  const int grid = n_work < num_sms ? n_work : num_sms;
-  if (bn == 64)
-    gemm_tc_kernel<64, EPI, A_MN, B_MN><<<grid, GemmTcCfg<64>::THREADS, GemmTcCfg<64>::SMEM_BYTES, st>>>(a, b, p);
-  else
-    gemm_tc_kernel<128, EPI, A_MN, B_MN><<<grid, GemmTcCfg<128>::THREADS, GemmTcCfg<128>::SMEM_BYTES, st>>>(a, b, p);
-  SB_CUDA(cudaGetLastError());
-  return SB_OK;
-}
-
-static inline int pick_bn(int N) { return N <= 64 ? 64 : 128; }
-
 int Net::enqueue_hidden_forward(int rows) {
   for (int l = 0; l < L; ++l) {
     Layer& ly = layers[l];
     if (precision == SB_PREC_BF16) {
       // Z = A_{l-1}[rows,in] (K-major) x W_l[in,out] (MN-major B operand: n contiguous)
-      const int bn = pick_bn(ly.out);
+      const GemmPlan pl = plan_gemm(rows, ly.out, ly.in, num_sms, false);
       CUtensorMap ta, tb;
       const __nv_bfloat16* src = (l == 0) ? Xb : A[l - 1];
       SB_TRY(make_tmap_bf16(&ta, src, rows, ly.in, ly.ld_in, 128));
       SB_TRY(make_tmap_bf16(&tb, ly.Wn, ly.in, ly.out, ly.ld_out, 64));
       GemmTcParams p = {};
       p.M = rows; p.N = ly.out; p.K = ly.in;
-      p.split_k = 1; p.kb_per_split = (ly.in + 63) / 64;
       p.bias = theta + ly.b_off; p.act = ly.act;
       p.out = A[l]; p.ld_out = ly.ld_out;
-      SB_TRY((launch_tc_bn<EPI_FWD, false, true>(bn, ta, tb, p, num_sms, stream)));
+      SB_TRY((launch_gemm_tc<EPI_FWD, false, true>(pl, ta, tb, p, stream)));
     } else {
       GemmF32Params p = {};
       p.M = rows; p.N = ly.out; p.K = ly.in;
@@ -310,38 +319,36 @@ int Net::enqueue_backward(int rows, float* grad) {
     if (precision == SB_PREC_BF16) {
       // dW_l[in,out] += sum_rows A_{l-1}[rows,in] (MN-major A) * dZ_l[rows,out] (MN-major B), split-K over rows
       {
-        const int bn = pick_bn(ly.out);
+        const GemmPlan pl = plan_gemm(ly.in, ly.out, rows, num_sms, true);
         CUtensorMap ta, tb;
         const __nv_bfloat16* ap = (l == 0) ? Xb : A[l - 1];
         SB_TRY(make_tmap_bf16(&ta, ap, rows, ly.in, ly.ld_in, 64));
         SB_TRY(make_tmap_bf16(&tb, dZ[l], rows, ly.out, ly.ld_out, 64));
         GemmTcParams p = {};
         p.M = ly.in; p.N = ly.out; p.K = rows;
-        p.split_k = pick_split_k(p.M, p.N, p.K, bn, num_sms, &p.kb_per_split);
         p.accum = grad + ly.w_off; p.ld_acc = ly.out;
         p.acc_vec4 = (ly.out % 4 == 0 && ly.w_off % 4 == 0) ? 1 : 0;
         if (fork) {
           SB_CUDA(cudaEventRecord(ev_dz[l], stream));
           SB_CUDA(cudaStreamWaitEvent(side, ev_dz[l], 0));
         }
-        SB_TRY((launch_tc_bn<EPI_DW, true, true>(bn, ta, tb, p, num_sms, fork ? side : stream)));
+        SB_TRY((launch_gemm_tc<EPI_DW, true, true>(pl, ta, tb, p, fork ? side : stream)));
         mark("gemm_dw");
       }
       if (l > 0) {
         // dZ_{l-1}[rows,in] = (dZ_l[rows,out] (K-major) x W_l[in,out] (K-major B: k = out contiguous)) .* act'(A_{l-1})
         Layer& pl = layers[l - 1];
-        const int bn = pick_bn(ly.in);
+        const GemmPlan gp = plan_gemm(rows, ly.in, ly.out, num_sms, false);
         CUtensorMap ta, tb;
         SB_TRY(make_tmap_bf16(&ta, dZ[l], rows, ly.out, ly.ld_out, 128));
-        SB_TRY(make_tmap_bf16(&tb, ly.Wn, ly.in, ly.out, ly.ld_out, bn));
+        SB_TRY(make_tmap_bf16(&tb, ly.Wn, ly.in, ly.out, ly.ld_out, plan_box_rows_b(gp)));
         GemmTcParams p = {};
         p.M = rows; p.N = ly.in; p.K = ly.out;
-        p.split_k = 1; p.kb_per_split = (ly.out + 63) / 64;
         p.act = pl.act;
         p.aux = A[l - 1]; p.ld_aux = pl.ld_out;
         p.out = dZ[l - 1]; p.ld_out = pl.ld_out;
         p.colsum = grad + pl.b_off;
-        SB_TRY((launch_tc_bn<EPI_DA, false, false>(bn, ta, tb, p, num_sms, stream)));
+        SB_TRY((launch_gemm_tc<EPI_DA, false, false>(gp, ta, tb, p, stream)));
         mark("gemm_da");
       }
     } else {

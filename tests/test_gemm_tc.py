@@ -42,6 +42,40 @@ def test_gemm_bf16_matches_fp64(sb, M, N, K, split_k, layout):
     assert err <= 2e-5 * scale * 4, "max abs err %g (K=%d)" % (err, K)
 
 
+TILES = [(1, 64), (1, 128), (2, 128), (2, 256)]   # (cta_group, BN)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cg,bn", TILES)
+@pytest.mark.parametrize("layout", sorted(LAYOUTS))
+@pytest.mark.parametrize("M,N,K,split_k", [(300, 200, 136, 1), (1000, 512, 1024, 2), (2048, 1024, 512, 1)])
+def test_gemm_every_tile_configuration(sb, M, N, K, split_k, layout, cg, bn):
+    """each instantiated tile shape (single CTA 128xBN, CTA pair 256xBN with cta_group::2) on ragged and multi-wave
+    problems, forced through the debug hook (the planner would not pick every one of them at these sizes)"""
+    if bn == 64 and N > 64:
+        N = 64
+    a_mn, b_mn = LAYOUTS[layout]
+    rng = np.random.RandomState(M + N + K + cg * 7 + bn)
+    A = bf16_round(rng.standard_normal((M, K)).astype(np.float32))
+    B = bf16_round(rng.standard_normal((N, K)).astype(np.float32))
+    D = sb.capi.debug_gemm_bf16(A.T.copy() if a_mn else A, B.T.copy() if b_mn else B, split_k=split_k, a_mn=a_mn, b_mn=b_mn,
+                                cg=cg, bn=bn)
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    assert np.abs(D - ref).max() <= 8e-5 * np.sqrt(K)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cg,bn", TILES)
+def test_gemm_identity_exact_pair_tiles(sb, cg, bn):
+    """A = [I; I] (256 x 128), B arbitrary: D must be exactly [B^T; B^T] for every tile configuration"""
+    rng = np.random.RandomState(2)
+    n = 64 if bn == 64 else 256
+    A = np.vstack([np.eye(128, dtype=np.float32)] * 2)
+    B = bf16_round(rng.standard_normal((n, 128)).astype(np.float32))
+    D = sb.capi.debug_gemm_bf16(A, B, cg=cg, bn=bn)
+    np.testing.assert_array_equal(D, np.vstack([B.T, B.T]))
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("layout", sorted(LAYOUTS))
 def test_gemm_identity_exact(sb, layout):
