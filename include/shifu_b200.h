@@ -199,6 +199,12 @@ int sb_debug_gemm_bf16_ex(const float* A, const float* B, float* D, int32_t M, i
 int sb_debug_gemm_bf16_cfg(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K,
                            int32_t split_k, int32_t a_mn, int32_t b_mn, int32_t cfg_cg, int32_t cfg_bn, int device);
 
+/* micro-benchmark of one tile configuration: average device milliseconds per launch over `iters` back-to-back launches
+ * (CUDA events on the launching stream, operands L2-warm) */
+int sb_debug_gemm_bench(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k,
+                        int32_t a_mn, int32_t b_mn, int32_t cfg_cg, int32_t cfg_bn, int device, int32_t iters,
+                        float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,6 +110,8 @@ PROTOTYPES = {
     "sb_savedmodel_read": (C.c_int, [_cp, _cp, _cp, _cp, _P(NetDesc), _P(C.c_int32), _f32p, C.c_int64, _P(C.c_int64)]),
     "sb_debug_gemm_bf16": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
     "sb_debug_gemm_bf16_ex": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
+    "sb_debug_gemm_bench": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                      C.c_int32, C.c_int32, C.c_int, C.c_int32, _f32p]),
     "sb_debug_gemm_bf16_cfg": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_int32, C.c_int32, C.c_int]),
 }
@@ -387,3 +389,16 @@ def debug_gemm_bf16(A: np.ndarray, B: np.ndarray, split_k: int = 1, device: int 
     D = np.zeros((M, N), np.float32)
     check(lib().sb_debug_gemm_bf16_cfg(_ptr(A), _ptr(B), _ptr(D), M, N, K, split_k, int(a_mn), int(b_mn), cg, bn, device))
     return D
+
+
+def debug_gemm_bench(M: int, N: int, K: int, split_k: int = 1, a_mn: bool = False, b_mn: bool = False, cg: int = 0,
+                     bn: int = 0, iters: int = 50, device: int = 0) -> float:
+    """average device ms per launch of one tile configuration (random operands)"""
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((K, M) if a_mn else (M, K), dtype=np.float32)
+    B = rng.standard_normal((K, N) if b_mn else (N, K), dtype=np.float32)
+    D = np.zeros((M, N), np.float32)
+    ms = C.c_float()
+    check(lib().sb_debug_gemm_bench(_ptr(A), _ptr(B), _ptr(D), M, N, K, split_k, int(a_mn), int(b_mn), cg, bn, device,
+                                    iters, C.byref(ms)))
+    return float(ms.value)

@@ -647,8 +647,22 @@ void* sb_model_stream(sb_model_t* m) { return m ? reinterpret_cast<void*>(m->net
 // ================================================================================================
 // kernel-level test hook
 // ================================================================================================
+static int debug_gemm_impl(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k,
+                           int32_t a_mn, int32_t b_mn, int32_t cfg_cg, int32_t cfg_bn, int device, int iters, float* ms_out);
+
 int sb_debug_gemm_bf16_cfg(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k,
                            int32_t a_mn, int32_t b_mn, int32_t cfg_cg, int32_t cfg_bn, int device) {
+  return debug_gemm_impl(A, B, D, M, N, K, split_k, a_mn, b_mn, cfg_cg, cfg_bn, device, 0, nullptr);
+}
+int sb_debug_gemm_bench(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k,
+                        int32_t a_mn, int32_t b_mn, int32_t cfg_cg, int32_t cfg_bn, int device, int32_t iters, float* ms_out) {
+  SB_CHECK(iters > 0 && ms_out, SB_ERR_INVALID, "iters / ms_out");
+  return debug_gemm_impl(A, B, D, M, N, K, split_k, a_mn, b_mn, cfg_cg, cfg_bn, device, iters, ms_out);
+}
+}  // extern "C"
+
+static int debug_gemm_impl(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k,
+                           int32_t a_mn, int32_t b_mn, int32_t cfg_cg, int32_t cfg_bn, int device, int iters, float* ms_out) {
   SB_CHECK(cfg_cg == 0 || ((cfg_cg == 1 && (cfg_bn == 64 || cfg_bn == 128)) || (cfg_cg == 2 && (cfg_bn == 128 || cfg_bn == 256))),
            SB_ERR_INVALID, "tile configuration cg=%d bn=%d not instantiated", cfg_cg, cfg_bn);
   SB_CHECK(A && B && D && M > 0 && N > 0 && K > 0, SB_ERR_INVALID, "bad argument");
@@ -703,9 +717,30 @@ int sb_debug_gemm_bf16_cfg(const float* A, const float* B, float* D, int32_t M, 
     GemmTcParams p = {};
     p.M = M; p.N = N; p.K = K;
     p.accum = dD; p.ld_acc = N;
-    if (!a_mn && !b_mn) { s = set_gemm_tc_attrs<EPI_F32, false, false>(); if (s == SB_OK) s = launch_gemm_tc<EPI_F32, false, false>(pl, ta, tb, p, 0); }
-    else if (!a_mn) { s = set_gemm_tc_attrs<EPI_F32, false, true>(); if (s == SB_OK) s = launch_gemm_tc<EPI_F32, false, true>(pl, ta, tb, p, 0); }
-    else { s = set_gemm_tc_attrs<EPI_F32, true, true>(); if (s == SB_OK) s = launch_gemm_tc<EPI_F32, true, true>(pl, ta, tb, p, 0); }
+    auto launch = [&]() -> int {
+      if (!a_mn && !b_mn) return launch_gemm_tc<EPI_F32, false, false>(pl, ta, tb, p, 0);
+      if (!a_mn) return launch_gemm_tc<EPI_F32, false, true>(pl, ta, tb, p, 0);
+      return launch_gemm_tc<EPI_F32, true, true>(pl, ta, tb, p, 0);
+    };
+    if (!a_mn && !b_mn) s = set_gemm_tc_attrs<EPI_F32, false, false>();
+    else if (!a_mn) s = set_gemm_tc_attrs<EPI_F32, false, true>();
+    else s = set_gemm_tc_attrs<EPI_F32, true, true>();
+    if (s == SB_OK) s = launch();
+    if (s == SB_OK && iters > 0) {
+      cudaEvent_t e0, e1;
+      cudaEventCreate(&e0); cudaEventCreate(&e1);
+      for (int i = 0; i < 3 && s == SB_OK; ++i) s = launch();
+      cudaEventRecord(e0, 0);
+      for (int i = 0; i < iters && s == SB_OK; ++i) s = launch();
+      cudaEventRecord(e1, 0);
+      cudaEventSynchronize(e1);
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      *ms_out = ms / iters;
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+      cudaMemset(dD, 0, sizeof(float) * M * N);
+      if (s == SB_OK) s = launch();  // leave a clean single result in D
+    }
   }
   if (s == SB_OK) {
     cudaError_t e = cudaDeviceSynchronize();
@@ -715,6 +750,8 @@ int sb_debug_gemm_bf16_cfg(const float* A, const float* B, float* D, int32_t M, 
   cudaFree(dA32); cudaFree(dB32); cudaFree(dD); cudaFree(dA); cudaFree(dB);
   return s;
 }
+
+extern "C" {
 
 int sb_debug_gemm_bf16_ex(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k,
                           int32_t a_mn, int32_t b_mn, int device) {
