@@ -727,19 +727,39 @@ static int debug_gemm_impl(const float* A, const float* B, float* D, int32_t M, 
     else s = set_gemm_tc_attrs<EPI_F32, true, true>();
     if (s == SB_OK) s = launch();
     if (s == SB_OK && iters > 0) {
+      // benchmark with the REAL epilogue of the layout's use: KM -> forward (bias + relu -> bf16), KK -> dA
+      // (act' * , bf16 store, column sums), MM -> dW (fp32 red.add)
+      const int ldn = round_up(N, 8);
+      float *d_bias = nullptr, *d_colsum = nullptr;
+      __nv_bfloat16 *d_out = nullptr, *d_aux = nullptr;
+      cudaMalloc(&d_bias, sizeof(float) * N); cudaMemset(d_bias, 0, sizeof(float) * N);
+      cudaMalloc(&d_colsum, sizeof(float) * N); cudaMemset(d_colsum, 0, sizeof(float) * N);
+      cudaMalloc(&d_out, sizeof(__nv_bfloat16) * static_cast<size_t>(M) * ldn);
+      cudaMalloc(&d_aux, sizeof(__nv_bfloat16) * static_cast<size_t>(M) * ldn);
+      cudaMemset(d_aux, 0x3f, sizeof(__nv_bfloat16) * static_cast<size_t>(M) * ldn);
+      GemmTcParams q = p;
+      q.bias = d_bias; q.act = SB_ACT_RELU; q.out = d_out; q.ld_out = ldn; q.aux = d_aux; q.ld_aux = ldn; q.colsum = d_colsum;
+      q.acc_vec4 = (N % 4 == 0) ? 1 : 0;
+      auto real = [&]() -> int {
+        if (!a_mn && !b_mn) return launch_gemm_tc<EPI_DA, false, false>(pl, ta, tb, q, 0);
+        if (!a_mn) return launch_gemm_tc<EPI_FWD, false, true>(pl, ta, tb, q, 0);
+        return launch_gemm_tc<EPI_DW, true, true>(pl, ta, tb, q, 0);
+      };
+      if (!a_mn && !b_mn) s = set_gemm_tc_attrs<EPI_DA, false, false>();
+      else if (!a_mn) s = set_gemm_tc_attrs<EPI_FWD, false, true>();
+      else s = set_gemm_tc_attrs<EPI_DW, true, true>();
       cudaEvent_t e0, e1;
       cudaEventCreate(&e0); cudaEventCreate(&e1);
-      for (int i = 0; i < 3 && s == SB_OK; ++i) s = launch();
+      for (int i = 0; i < 3 && s == SB_OK; ++i) s = real();
       cudaEventRecord(e0, 0);
-      for (int i = 0; i < iters && s == SB_OK; ++i) s = launch();
+      for (int i = 0; i < iters && s == SB_OK; ++i) s = real();
       cudaEventRecord(e1, 0);
       cudaEventSynchronize(e1);
       float ms = 0.f;
       cudaEventElapsedTime(&ms, e0, e1);
       *ms_out = ms / iters;
       cudaEventDestroy(e0); cudaEventDestroy(e1);
-      cudaMemset(dD, 0, sizeof(float) * M * N);
-      if (s == SB_OK) s = launch();  // leave a clean single result in D
+      cudaFree(d_bias); cudaFree(d_colsum); cudaFree(d_out); cudaFree(d_aux);
     }
   }
   if (s == SB_OK) {
