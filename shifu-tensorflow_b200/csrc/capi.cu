@@ -53,6 +53,7 @@ static int enqueue_allreduce(sb_trainer* t, float* buf) {
 
 static int enqueue_optimizer(sb_trainer* t, const float* g) {
   Net& n = t->net;
+  // after the side-stream join (two predecessors): plain dependency, no PDL attribute
   optimizer_kernel<<<n.n_work, 256, 0, n.stream>>>(n.work, n.desc, t->hyper, n.theta, g, t->s1, t->s2);
   SB_CUDA(cudaGetLastError());
   n.mark("optimizer");
@@ -62,9 +63,7 @@ static int enqueue_optimizer(sb_trainer* t, const float* g) {
 // the body of one step as a sequence of stream operations (captured into a CUDA graph)
 static int enqueue_step_body(sb_trainer* t, int rows, int kind) {
   Net& n = t->net;
-  SB_CUDA(cudaMemsetAsync(t->grad, 0, sizeof(float) * n.n_params, n.stream));
-  SB_CUDA(cudaMemsetAsync(n.scal, 0, sizeof(float) * SCAL_COUNT, n.stream));
-  SB_TRY(n.enqueue_load(rows));
+  SB_TRY(n.enqueue_load(rows, t->grad, n.n_params));   // also clears the gradient buffer and the step scalars
   SB_TRY(n.enqueue_hidden_forward(rows));
   SB_TRY(n.enqueue_out(rows, true, true, nullptr, t->grad));
   SB_TRY(n.enqueue_backward(rows, t->grad));
@@ -394,10 +393,8 @@ int sb_trainer_profile_step(sb_trainer_t* t, int64_t row_offset, int32_t rows, c
   // the two memsets of the step body run before the start marker so they are not charged to load_batch
   int s = SB_OK;
   {
-    SB_CUDA(cudaMemsetAsync(t->grad, 0, sizeof(float) * n.n_params, n.stream));
-    SB_CUDA(cudaMemsetAsync(n.scal, 0, sizeof(float) * SCAL_COUNT, n.stream));
     n.mark("start"); --n.launches;
-    s = n.enqueue_load(rows);
+    s = n.enqueue_load(rows, t->grad, n.n_params);
     if (s == SB_OK) s = n.enqueue_hidden_forward(rows);
     if (s == SB_OK) s = n.enqueue_out(rows, true, true, nullptr, t->grad);
     if (s == SB_OK) s = n.enqueue_backward(rows, t->grad);
@@ -442,7 +439,6 @@ static int forward_chunks(Net& n, const float* X, const float* y, const float* w
       if (w) SB_CUDA(cudaMemcpyAsync(n.stW, w + r0, sizeof(float) * c, cudaMemcpyHostToDevice, n.stream));
     }
     set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, n.stX, n.stY, (do_loss && w) ? n.stW : n.ones, 0.f, 1.f);
-    SB_CUDA(cudaMemsetAsync(n.scal, 0, sizeof(float) * SCAL_COUNT, n.stream));
     SB_TRY(n.enqueue_load(c));
     SB_TRY(n.enqueue_hidden_forward(c));
     SB_TRY(n.enqueue_out(c, do_loss, false, n.yhat, nullptr));

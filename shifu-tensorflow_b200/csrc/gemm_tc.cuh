@@ -136,6 +136,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
+  // from here on global memory written by it is touched.
+  pdl_wait();
+  pdl_launch_dependents();
 
   const int tiles_m = (p.M + TILE_M - 1) / TILE_M;
   const int tiles_n = (p.N + BN - 1) / BN;
@@ -385,10 +389,6 @@ struct GemmPlan {
 };
 GemmPlan plan_gemm(int M, int N, int K, int num_sms, bool allow_split);
 
-// Launch with the plan's configuration.  EPI / operand layouts are compile-time.
-template <int EPI, bool A_MN, bool B_MN>
-int launch_gemm_tc(const GemmPlan& pl, const CUtensorMap& a, const CUtensorMap& b, GemmTcParams p, cudaStream_t st);
-template <int EPI, bool A_MN, bool B_MN>
-int set_gemm_tc_attrs();
+// launch_gemm_tc<EPI, A_MN, B_MN>(plan, tmA, tmB, params, stream, pdl) lives in gemm_tc_launch.cuh
 
 }  // namespace sb

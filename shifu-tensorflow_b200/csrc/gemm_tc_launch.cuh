@@ -5,19 +5,25 @@
 namespace sb {
 
 template <int BN, int EPI, bool A_MN, bool B_MN, int CG>
-static int launch_gemm_tc_one(const GemmPlan& pl, const CUtensorMap& a, const CUtensorMap& b, const GemmTcParams& p, cudaStream_t st) {
+static int launch_gemm_tc_one(const GemmPlan& pl, const CUtensorMap& a, const CUtensorMap& b, const GemmTcParams& p, cudaStream_t st,
+                              bool pdl) {
   using Cfg = GemmTcCfg<BN, CG>;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(pl.grid));
   cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   int na = 0;
   if (CG == 2) {
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    na = 1;
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
@@ -26,13 +32,13 @@ static int launch_gemm_tc_one(const GemmPlan& pl, const CUtensorMap& a, const CU
 }
 
 template <int EPI, bool A_MN, bool B_MN>
-int launch_gemm_tc(const GemmPlan& pl, const CUtensorMap& a, const CUtensorMap& b, GemmTcParams p, cudaStream_t st) {
+int launch_gemm_tc(const GemmPlan& pl, const CUtensorMap& a, const CUtensorMap& b, GemmTcParams p, cudaStream_t st, bool pdl = false) {
   p.split_k = pl.split_k;
   p.kb_per_split = pl.kb_per_split;
-  if (pl.cg == 1 && pl.bn == 64) return launch_gemm_tc_one<64, EPI, A_MN, B_MN, 1>(pl, a, b, p, st);
-  if (pl.cg == 1 && pl.bn == 128) return launch_gemm_tc_one<128, EPI, A_MN, B_MN, 1>(pl, a, b, p, st);
-  if (pl.cg == 2 && pl.bn == 128) return launch_gemm_tc_one<128, EPI, A_MN, B_MN, 2>(pl, a, b, p, st);
-  if (pl.cg == 2 && pl.bn == 256) return launch_gemm_tc_one<256, EPI, A_MN, B_MN, 2>(pl, a, b, p, st);
+  if (pl.cg == 1 && pl.bn == 64) return launch_gemm_tc_one<64, EPI, A_MN, B_MN, 1>(pl, a, b, p, st, pdl);
+  if (pl.cg == 1 && pl.bn == 128) return launch_gemm_tc_one<128, EPI, A_MN, B_MN, 1>(pl, a, b, p, st, pdl);
+  if (pl.cg == 2 && pl.bn == 128) return launch_gemm_tc_one<128, EPI, A_MN, B_MN, 2>(pl, a, b, p, st, pdl);
+  if (pl.cg == 2 && pl.bn == 256) return launch_gemm_tc_one<256, EPI, A_MN, B_MN, 2>(pl, a, b, p, st, pdl);
   return set_error(SB_ERR_INVALID, "no gemm_tc instantiation for cg=%d bn=%d", pl.cg, pl.bn);
 }
 

@@ -35,7 +35,11 @@ enum { SCAL_LOSS_SUM = 0, SCAL_NNZ = 1, SCAL_COUNT = 4 };
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 load_batch_kernel(const BatchDesc* __restrict__ desc, int rows, int F, __nv_bfloat16* __restrict__ Xb, int ldF,
-                  float* __restrict__ Xf, float* __restrict__ scal) {
+                  float* __restrict__ Xf, float* __restrict__ scal, float* __restrict__ zero_buf, long long zero_n) {
+  pdl_wait();
+  pdl_launch_dependents();
+  // the step's gradient buffer is accumulated with atomics: clear it here (replaces a memset node in the graph)
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < zero_n; i += gridDim.x * 256ll) zero_buf[i] = 0.f;
   const float* __restrict__ X = desc->X;
   const int groups = ldF >> 3;  // 8-column groups per row (ldF is a multiple of 8)
   const long long total = static_cast<long long>(rows) * groups;
@@ -79,6 +83,7 @@ load_batch_kernel(const BatchDesc* __restrict__ desc, int rows, int F, __nv_bflo
       float t = 0.f;
       for (int i = 0; i < 8; ++i) t += part[i];
       scal[SCAL_NNZ] = t;
+      scal[SCAL_LOSS_SUM] = 0.f;
     }
   }
 }
@@ -115,6 +120,8 @@ template <> __device__ __forceinline__ void st_from_float<__nv_bfloat16>(__nv_bf
 template <typename T>
 __global__ void __launch_bounds__(256)
 out_layer_kernel(const OutLayerParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float dz_row[32];
   __shared__ float blk_red[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -243,6 +250,8 @@ struct OptWork {
 static __global__ void __launch_bounds__(256)
 optimizer_kernel(const OptWork* __restrict__ work, const BatchDesc* __restrict__ desc, OptHyper h,
                  float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ s1, float* __restrict__ s2) {
+  pdl_wait();
+  pdl_launch_dependents();
   const OptWork wk = work[blockIdx.x];
   const float lr_t = desc->lr_t, gs = desc->gscale;
 #pragma unroll

@@ -1,6 +1,7 @@
 // Net: device state + kernel sequencing for the tabular-DNN forward / backward.
 // Mirrors generate_from_modelconf + model (res/ssgd_monitor.py:91-144) as a list of fused launches.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include "net.cuh"
@@ -51,44 +52,48 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int cols, int l
   return SB_OK;
 }
 
-// Tile configuration by a small cost model (cycles), constants measured on B200 (DESIGN.md "GEMM plan"):
-//   - a CTA's tensor core retires a 128 x bn x 64 k-block in 2*bn cycles (8192 dense bf16 flop/cycle/SM)
-//   - TMA delivers ~46 B/cycle/SM from L2 when all SMs pull at once (32 KB k-block stages measured at ~707 cycles)
-//   - ~1500 cycles per tile of pipeline fill / accumulator hand-off, ~5 cycles per output column of epilogue
+// Tile configuration, rules fitted to the on-device sweep in profiles/gemm_sweep_r01.txt (scripts/gemm_sweep.py):
+//   - the single-CTA 128x128 tile is L2->SM bandwidth bound (~46 B/cycle/SM with every SM pulling, i.e. ~45 % of the
+//     tensor peak); the CTA-pair 256x256 tile (cta_group::2) halves the bytes per flop and reaches ~64 %;
+//   - the pair tile only pays when there are enough pair tiles to fill the 74 SM pairs AND the K loop is deep
+//     enough (>= 8 k-blocks per tile) to amortise its larger fill / epilogue;
+//   - split-K (dW GEMMs, reduction over the batch): fill the machine but keep >= 8 k-blocks per split.
 GemmPlan plan_gemm(int M, int N, int K, int num_sms, bool allow_split) {
   const int total_kb = (K + 63) / 64;
-  GemmPlan best = {};
-  double best_cost = 1e30;
-  const int cands[4][2] = {{1, 64}, {1, 128}, {2, 128}, {2, 256}};
-  for (const auto& c : cands) {
-    const int cg = c[0], bn = c[1];
-    if (bn == 64 && N > 64) continue;
-    if (bn == 256 && N <= 128) continue;
-    if (cg == 2 && M <= 128) continue;
+  GemmPlan pl = {};
+  auto finish = [&](int cg, int bn, int want_split) {
     const int slots = num_sms / cg;
     const int tiles = ((M + 128 * cg - 1) / (128 * cg)) * ((N + bn - 1) / bn);
-    int split = 1, kb_per = total_kb;
-    if (allow_split && tiles < slots) {
-      int want = slots / tiles;
-      int cap = total_kb / 2;
-      if (cap < 1) cap = 1;
-      if (want > cap) want = cap;
-      if (want < 1) want = 1;
-      kb_per = (total_kb + want - 1) / want;
-      split = (total_kb + kb_per - 1) / kb_per;
-    }
-    const int work = tiles * split;
-    const int waves = (work + slots - 1) / slots;
-    const double stage_bytes = 128.0 * 64 * 2 + (bn / cg) * 64.0 * 2;
-    const double kb_cost = std::max(2.0 * bn, stage_bytes / 46.0);
-    const double cost = waves * (kb_per * kb_cost + 1500.0 + 5.0 * bn);
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best.cg = cg; best.bn = bn; best.split_k = split; best.kb_per_split = kb_per;
-      best.grid = (work < slots ? work : slots) * cg;
+    if (want_split < 1) want_split = 1;
+    if (want_split > total_kb) want_split = total_kb;
+    pl.cg = cg; pl.bn = bn;
+    pl.kb_per_split = (total_kb + want_split - 1) / want_split;
+    pl.split_k = (total_kb + pl.kb_per_split - 1) / pl.kb_per_split;
+    const int work = tiles * pl.split_k;
+    pl.grid = (work < slots ? work : slots) * cg;
+  };
+  const int pairs = num_sms / 2;
+  const int pair_tiles = ((M + 255) / 256) * ((N + 255) / 256);
+  if (N >= 512 && M >= 512) {
+    if (!allow_split) {
+      if (pair_tiles * 5 >= pairs * 4 && total_kb >= 8) { finish(2, 256, 1); return pl; }
+    } else {
+      int split = pairs / pair_tiles;
+      if (split < 1) split = 1;
+      if (pair_tiles * split * 5 >= pairs * 4 && total_kb / split >= 32) { finish(2, 256, split); return pl; }
     }
   }
-  return best;
+  const int bn = N <= 64 ? 64 : 128;
+  const int tiles = ((M + 127) / 128) * ((N + bn - 1) / bn);
+  int split = 1;
+  if (allow_split) {
+    split = num_sms / tiles;
+    const int cap = total_kb / 8;
+    if (split > cap) split = cap;
+    if (split < 1) split = 1;
+  }
+  finish(1, bn, split);
+  return pl;
 }
 
 int validate_desc(const sb_net_desc* d) {
@@ -126,6 +131,8 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
   SB_TRY(check_device(device_, &num_sms));
   device = device_;
   training = training_;
+  if (const char* e = getenv("SB_NO_PDL")) use_pdl = !(e[0] == '1');
+  if (const char* e = getenv("SB_NO_FORK")) concurrent_bwd = !(e[0] == '1');
   SB_CUDA(cudaSetDevice(device));
   SB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   if (training_) {
@@ -239,17 +246,19 @@ int Net::refresh_shadows() {
   return SB_OK;
 }
 
-int Net::enqueue_load(int rows) {
+int Net::enqueue_load(int rows, float* zero_buf, long long zero_n) {
   const long long units = static_cast<long long>(rows) * (ldF / 8);
   long long blocks = (units + 255) / 256;
   const long long cap = static_cast<long long>(num_sms) * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
+  // first kernel of the step: its stream predecessor is set_batch_kernel (a kernel), so PDL applies here too
   if (precision == SB_PREC_BF16)
-    load_batch_kernel<true><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(desc, rows, F, Xb, ldF, nullptr, scal);
+    SB_TRY(launch(load_batch_kernel<true>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, use_pdl,
+                  static_cast<const BatchDesc*>(desc), rows, F, Xb, ldF, static_cast<float*>(nullptr), scal, zero_buf, zero_n));
   else
-    load_batch_kernel<false><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(desc, rows, F, nullptr, ldF, Xf, scal);
-  SB_CUDA(cudaGetLastError());
+    SB_TRY(launch(load_batch_kernel<false>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, use_pdl,
+                  static_cast<const BatchDesc*>(desc), rows, F, static_cast<__nv_bfloat16*>(nullptr), ldF, Xf, scal, zero_buf, zero_n));
   mark("load_batch");
   return SB_OK;
 }
@@ -268,7 +277,7 @@ int Net::enqueue_hidden_forward(int rows) {
       p.M = rows; p.N = ly.out; p.K = ly.in;
       p.bias = theta + ly.b_off; p.act = ly.act;
       p.out = A[l]; p.ld_out = ly.ld_out;
-      SB_TRY((launch_gemm_tc<EPI_FWD, false, true>(pl, ta, tb, p, stream)));
+      SB_TRY((launch_gemm_tc<EPI_FWD, false, true>(pl, ta, tb, p, stream, use_pdl)));
     } else {
       GemmF32Params p = {};
       p.M = rows; p.N = ly.out; p.K = ly.in;
@@ -299,11 +308,11 @@ int Net::enqueue_out(int rows, bool do_loss, bool do_bwd, float* yhat_dst, float
   if (precision == SB_PREC_BF16) {
     p.A = A[L - 1]; p.ldA = hl.ld_out;
     if (do_bwd) { p.dZ = dZ[L - 1]; p.ld_dZ = hl.ld_out; }
-    out_layer_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(p);
+    SB_TRY(launch(out_layer_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, use_pdl, p));
   } else {
     p.A = Af[L - 1]; p.ldA = hl.out;
     if (do_bwd) { p.dZ = dZf[L - 1]; p.ld_dZ = hl.out; }
-    out_layer_kernel<float><<<grid, 256, 0, stream>>>(p);
+    SB_TRY(launch(out_layer_kernel<float>, dim3(grid), dim3(256), 0, stream, use_pdl, p));
   }
   SB_CUDA(cudaGetLastError());
   mark("out_layer");
@@ -332,7 +341,7 @@ int Net::enqueue_backward(int rows, float* grad) {
           SB_CUDA(cudaEventRecord(ev_dz[l], stream));
           SB_CUDA(cudaStreamWaitEvent(side, ev_dz[l], 0));
         }
-        SB_TRY((launch_gemm_tc<EPI_DW, true, true>(pl, ta, tb, p, fork ? side : stream)));
+        SB_TRY((launch_gemm_tc<EPI_DW, true, true>(pl, ta, tb, p, fork ? side : stream, use_pdl && !fork)));
         mark("gemm_dw");
       }
       if (l > 0) {
@@ -348,7 +357,7 @@ int Net::enqueue_backward(int rows, float* grad) {
         p.aux = A[l - 1]; p.ld_aux = pl.ld_out;
         p.out = dZ[l - 1]; p.ld_out = pl.ld_out;
         p.colsum = grad + pl.b_off;
-        SB_TRY((launch_gemm_tc<EPI_DA, false, false>(gp, ta, tb, p, stream)));
+        SB_TRY((launch_gemm_tc<EPI_DA, false, false>(gp, ta, tb, p, stream, use_pdl)));
         mark("gemm_da");
       }
     } else {

@@ -26,6 +26,7 @@ struct Net {
   std::vector<cudaEvent_t> ev_dz;            // ev_dz[l]: dZ_l is complete on `stream`
   cudaEvent_t ev_join = nullptr;
   bool concurrent_bwd = true;
+  bool use_pdl = true;                       // programmatic dependent launch along the main chain
   int F = 0, L = 0;             // features, hidden layers
   std::vector<Layer> layers;    // L hidden + 1 output (out = 1)
   long long n_params = 0;
@@ -61,6 +62,18 @@ struct Net {
   }
 
   std::vector<void*> allocs;
+  // cudaLaunchKernelEx wrapper: optional programmatic-stream-serialization attribute
+  template <typename... KArgs, typename... Args>
+  int launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+    SB_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+    return SB_OK;
+  }
   template <typename T> int dalloc(T** p, size_t n) {
     void* q = nullptr;
     SB_CUDA(cudaMalloc(&q, n * sizeof(T) + 256));
@@ -74,7 +87,7 @@ struct Net {
   void destroy();
   int refresh_shadows();
   // forward through the hidden layers (A_0 = current batch -> A_L)
-  int enqueue_load(int rows);
+  int enqueue_load(int rows, float* zero_buf = nullptr, long long zero_n = 0);
   int enqueue_hidden_forward(int rows);
   int enqueue_out(int rows, bool do_loss, bool do_bwd, float* yhat_dst, float* grad);
   int enqueue_backward(int rows, float* grad);
