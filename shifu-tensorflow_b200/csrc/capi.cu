@@ -1,6 +1,7 @@
 // extern "C" surface of libshifu_b200.so: trainer, scorer, rendezvous, test hooks.
 // See include/shifu_b200.h for the contract and the reference call each entry point replaces.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <memory>
 #include <random>
@@ -106,8 +107,9 @@ static int run_step(sb_trainer* t, const float* X, const float* y, const float* 
   Net& n = t->net;
   SB_CHECK(rows > 0 && rows <= n.max_batch, SB_ERR_INVALID, "rows=%d outside (0, max_batch=%d]", rows, n.max_batch);
   SB_CUDA(cudaSetDevice(n.device));
-  cudaGraphExec_t ge;
-  SB_TRY(get_graph(t, rows, kind, &ge));
+  static const bool no_graph = getenv("SB_NO_GRAPH") != nullptr;
+  cudaGraphExec_t ge = nullptr;
+  if (!no_graph) SB_TRY(get_graph(t, rows, kind, &ge));
   float lr_t = t->lr, gscale = 1.f / static_cast<float>(t->world);
   if (kind == G_STEP) {
     ++t->global_step;
@@ -115,7 +117,8 @@ static int run_step(sb_trainer* t, const float* X, const float* y, const float* 
   }
   set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, X, y, w ? w : n.ones, lr_t, gscale);
   SB_CUDA(cudaGetLastError());
-  SB_CUDA(cudaGraphLaunch(ge, n.stream));
+  if (no_graph) SB_TRY(enqueue_step_body(t, rows, kind));
+  else SB_CUDA(cudaGraphLaunch(ge, n.stream));
   SB_CUDA(cudaMemcpyAsync(t->h_scal, n.scal, sizeof(float) * SCAL_COUNT, cudaMemcpyDeviceToHost, n.stream));
   if (kind == G_ACC) ++t->n_acc;
   t->grad_out_scale = (kind == G_STEP) ? gscale : 1.f;
@@ -736,10 +739,11 @@ static int debug_gemm_impl(const float* A, const float* B, float* D, int32_t M, 
       GemmTcParams q = p;
       q.bias = d_bias; q.act = SB_ACT_RELU; q.out = d_out; q.ld_out = ldn; q.aux = d_aux; q.ld_aux = ldn; q.colsum = d_colsum;
       q.acc_vec4 = (N % 4 == 0) ? 1 : 0;
+      const bool bench_pdl = getenv("SB_BENCH_PDL") != nullptr;
       auto real = [&]() -> int {
-        if (!a_mn && !b_mn) return launch_gemm_tc<EPI_DA, false, false>(pl, ta, tb, q, 0);
-        if (!a_mn) return launch_gemm_tc<EPI_FWD, false, true>(pl, ta, tb, q, 0);
-        return launch_gemm_tc<EPI_DW, true, true>(pl, ta, tb, q, 0);
+        if (!a_mn && !b_mn) return launch_gemm_tc<EPI_DA, false, false>(pl, ta, tb, q, 0, bench_pdl);
+        if (!a_mn) return launch_gemm_tc<EPI_FWD, false, true>(pl, ta, tb, q, 0, bench_pdl);
+        return launch_gemm_tc<EPI_DW, true, true>(pl, ta, tb, q, 0, bench_pdl);
       };
       if (!a_mn && !b_mn) s = set_gemm_tc_attrs<EPI_DA, false, false>();
       else if (!a_mn) s = set_gemm_tc_attrs<EPI_FWD, false, true>();
@@ -755,6 +759,33 @@ static int debug_gemm_impl(const float* A, const float* B, float* D, int32_t M, 
       cudaEventElapsedTime(&ms, e0, e1);
       *ms_out = ms / iters;
       cudaEventDestroy(e0); cudaEventDestroy(e1);
+      if (getenv("SB_GEMM_TRACE")) {
+        // one more launch with %globaltimer stamps from CTA 0 (ns relative to kernel entry), and the host-visible
+        // launch-to-completion time of a single isolated launch
+        unsigned long long* d_tr = nullptr;
+        cudaMalloc(&d_tr, 16 * sizeof(unsigned long long));
+        cudaMemset(d_tr, 0, 16 * sizeof(unsigned long long));
+        q.trace = d_tr;
+        cudaDeviceSynchronize();
+        cudaEvent_t t0, t1;
+        cudaEventCreate(&t0); cudaEventCreate(&t1);
+        cudaEventRecord(t0, 0);
+        s = real();
+        cudaEventRecord(t1, 0);
+        cudaEventSynchronize(t1);
+        float one = 0.f;
+        cudaEventElapsedTime(&one, t0, t1);
+        unsigned long long h[16];
+        cudaMemcpy(h, d_tr, sizeof(h), cudaMemcpyDeviceToHost);
+        fprintf(stderr, "[trace] M=%d N=%d K=%d cg=%d bn=%d split=%d single-launch %.2f us | ns since entry:", M, N, K, pl.cg, pl.bn,
+                pl.split_k, one * 1e3f);
+        const char* nm[9] = {"entry", "setup", "deps", "tma0", "land0", "mma_done", "acc_ready", "epi_done", "exit"};
+        for (int i = 1; i < 9; ++i) fprintf(stderr, " %s=%lld", nm[i], (long long)(h[i] - h[0]));
+        fprintf(stderr, "\n");
+        cudaEventDestroy(t0); cudaEventDestroy(t1);
+        cudaFree(d_tr);
+        q.trace = nullptr;
+      }
       cudaFree(d_bias); cudaFree(d_colsum); cudaFree(d_out); cudaFree(d_aux);
     }
   }

@@ -54,6 +54,7 @@ struct GemmTcParams {
   float* accum;  // [M, ld_acc] fp32
   int ld_acc;
   int acc_vec4;  // 1 if 16-byte aligned rows -> red.global.add.v4.f32
+  unsigned long long* trace;  // debug: CTA 0 writes %globaltimer stamps of its pipeline milestones (nullable)
 };
 
 template <int BN, int CG>
@@ -108,6 +109,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  auto stamp = [&](int slot) { if (tracing) p.trace[slot] = globaltimer_ns(); };
+  if (threadIdx.x == 0) stamp(0);  // kernel entry
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // CTA rank inside the pair
   const bool leader = rank == 0;
 
@@ -138,8 +142,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail;
   // from here on global memory written by it is touched.
+  if (threadIdx.x == 0) stamp(1);  // setup done
   pdl_wait();
   pdl_launch_dependents();
+  if (threadIdx.x == 0) stamp(2);  // dependencies resolved
 
   const int tiles_m = (p.M + TILE_M - 1) / TILE_M;
   const int tiles_n = (p.N + BN - 1) / BN;
@@ -186,6 +192,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if constexpr (CG == 2) {
             if (!leader) mbar_arrive_cluster(fb, 0);  // second arrival on the leader's full barrier
           }
+          if (kb == kb0 && w == w_first) stamp(3);  // first TMA issued
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -212,6 +219,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);  // TMA bytes of both CTAs have landed
           tcgen05_fence_after();
+          if (kb == kb0 && w == w_first) stamp(4);  // first stage landed
           const uint64_t da = A_MN ? make_mnmajor_sw128_desc(smem_a(stage), 8192u) : make_kmajor_sw128_desc(smem_a(stage));
           const uint64_t db = B_MN ? make_mnmajor_sw128_desc(smem_b(stage), 8192u) : make_kmajor_sw128_desc(smem_b(stage));
 #pragma unroll
@@ -226,6 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         // accumulator complete -> epilogue (of both CTAs)
         if constexpr (CG == 2) umma_commit_cg2(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
+        if (w == w_first) stamp(5);  // all MMAs of the first tile issued
       }
     }
   } else {
@@ -240,6 +249,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
+      if (w == w_first && warp == 2 && lane == 0) stamp(6);  // first accumulator complete
       const int row = tm * TILE_M + static_cast<int>(rank) * BM + quarter * 32 + lane;  // output row of this thread
       const bool row_ok = row < p.M;
 #pragma unroll 1
@@ -356,11 +366,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if constexpr (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
         else mbar_arrive(tempty_bar(acc));
       }
+      if (w == w_first && warp == 2 && lane == 0) stamp(7);  // first tile's epilogue done
     }
   }
 
   tcgen05_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (threadIdx.x == 0) stamp(8);  // all roles finished
   if (warp == 2) {
     tcgen05_fence_after();
     if constexpr (CG == 2) tmem_dealloc_cg2<Cfg::TMEM_COLS>(tmem_base);
