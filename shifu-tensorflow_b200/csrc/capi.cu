@@ -43,19 +43,24 @@ static float lr_for_step(const sb_trainer* t, long long step /*1-based*/) {
   return t->lr;
 }
 
-static int enqueue_allreduce(sb_trainer* t, float* buf) {
+static int enqueue_allreduce(sb_trainer* t, float* buf, long long off = 0, long long count = -1, cudaStream_t st = nullptr) {
   if (t->world <= 1) return SB_OK;
   NcclApi* api = nccl_api();
   SB_CHECK(api && t->comm, SB_ERR_NCCL, "NCCL communicator missing");
-  int r = api->AllReduce(buf, buf, static_cast<size_t>(t->net.n_params), NCCL_FLOAT32, NCCL_SUM, t->comm, t->net.stream);
+  if (count < 0) count = t->net.n_params;
+  if (!st) st = t->net.stream;
+  int r = api->AllReduce(buf + off, buf + off, static_cast<size_t>(count), NCCL_FLOAT32, NCCL_SUM, t->comm, st);
   SB_CHECK(r == 0, SB_ERR_NCCL, "ncclAllReduce failed: %s", api->GetErrorString(r));
   return SB_OK;
 }
 
-static int enqueue_optimizer(sb_trainer* t, const float* g) {
+static int enqueue_optimizer(sb_trainer* t, const float* g, int w0 = 0, int w1 = -1, cudaStream_t st = nullptr) {
   Net& n = t->net;
-  // after the side-stream join (two predecessors): plain dependency, no PDL attribute
-  optimizer_kernel<<<n.n_work, 256, 0, n.stream>>>(n.work, n.desc, t->hyper, n.theta, g, t->s1, t->s2);
+  if (w1 < 0) w1 = n.n_work;
+  if (!st) st = n.stream;
+  if (w1 <= w0) return SB_OK;
+  // plain dependency, no PDL attribute (runs after a stream join / on the comm stream)
+  optimizer_kernel<<<w1 - w0, 256, 0, st>>>(n.work + w0, n.desc, t->hyper, n.theta, g, t->s1, t->s2);
   SB_CUDA(cudaGetLastError());
   n.mark("optimizer");
   return SB_OK;
@@ -67,8 +72,30 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind) {
   SB_TRY(n.enqueue_load(rows, t->grad, n.n_params));   // also clears the gradient buffer and the step scalars
   SB_TRY(n.enqueue_hidden_forward(rows));
   SB_TRY(n.enqueue_out(rows, true, true, nullptr, t->grad));
-  SB_TRY(n.enqueue_backward(rows, t->grad));
+  // Gradient exchange pipelined behind the backward pass: as soon as layer l's dW GEMM is enqueued (side stream), its
+  // flat segment [W_l, b_l] (+ the output layer for l = L-1) is all-reduced and its optimizer update applied on the
+  // comm stream while the remaining dA / dW GEMMs still run - the role SyncReplicasOptimizer's accumulator + apply
+  // play in the reference (res/ssgd_monitor.py:136-142), without the parameter server.
+  const bool pipelined = kind == G_STEP && n.concurrent_bwd && !n.profiling && n.side != nullptr && n.precision == SB_PREC_BF16;
+  if (pipelined) {
+    n.on_layer_grads = [t](int l, cudaStream_t cs, int phase) -> int {
+      Net& nn = t->net;
+      const int last = (l == nn.L - 1) ? nn.L : l;
+      if (phase == 0) {
+        const long long off = nn.layers[l].w_off;
+        const long long end = nn.layers[last].b_off + nn.layers[last].out;
+        return enqueue_allreduce(t, t->grad, off, end - off, cs);
+      }
+      return enqueue_optimizer(t, t->grad, nn.work_begin[l], nn.work_end[last], cs);
+    };
+  } else {
+    n.on_layer_grads = nullptr;
+  }
+  int bs = n.enqueue_backward(rows, t->grad);
+  n.on_layer_grads = nullptr;
+  SB_TRY(bs);
   if (kind == G_STEP) {
+    if (pipelined) return SB_OK;
     SB_TRY(enqueue_allreduce(t, t->grad));
     if (t->world > 1 && n.profiling) { n.mark("allreduce"); --n.launches; }
     SB_TRY(enqueue_optimizer(t, t->grad));

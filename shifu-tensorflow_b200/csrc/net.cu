@@ -140,6 +140,12 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
     ev_dz.resize(d->n_hidden);
     for (auto& e : ev_dz) SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     SB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    SB_CUDA(cudaStreamCreateWithFlags(&comm, cudaStreamNonBlocking));
+    ev_dw.resize(d->n_hidden);
+    for (auto& e : ev_dw) SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ev_da.resize(d->n_hidden);
+    for (auto& e : ev_da) SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    SB_CUDA(cudaEventCreateWithFlags(&ev_comm, cudaEventDisableTiming));
   }
   F = d->n_features;
   L = d->n_hidden;
@@ -202,14 +208,17 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
       wk.push_back(w);
     }
   };
+  work_begin.assign(L + 1, 0); work_end.assign(L + 1, 0);
   for (int l = 0; l <= L; ++l) {
     Layer& ly = layers[l];
+    work_begin[l] = static_cast<int>(wk.size());
     if (bf && l < L) {
       add_runs(ly.w_off, static_cast<long long>(ly.in) * ly.out, &ly);
       add_runs(ly.b_off, ly.out, nullptr);
     } else {
       add_runs(ly.w_off, static_cast<long long>(ly.in) * ly.out + ly.out, nullptr);
     }
+    work_end[l] = static_cast<int>(wk.size());
   }
   n_work = static_cast<int>(wk.size());
   SB_TRY(dalloc(&work, wk.size()));
@@ -233,6 +242,14 @@ void Net::destroy() {
   ev_dz.clear();
   if (ev_join) cudaEventDestroy(ev_join);
   ev_join = nullptr;
+  for (cudaEvent_t e : ev_dw) cudaEventDestroy(e);
+  ev_dw.clear();
+  for (cudaEvent_t e : ev_da) cudaEventDestroy(e);
+  ev_da.clear();
+  if (ev_comm) cudaEventDestroy(ev_comm);
+  ev_comm = nullptr;
+  if (comm) cudaStreamDestroy(comm);
+  comm = nullptr;
   if (side) cudaStreamDestroy(side);
   side = nullptr;
   if (stream) cudaStreamDestroy(stream);
@@ -343,6 +360,11 @@ int Net::enqueue_backward(int rows, float* grad) {
         }
         SB_TRY((launch_gemm_tc<EPI_DW, true, true>(pl, ta, tb, p, fork ? side : stream, use_pdl && !fork)));
         mark("gemm_dw");
+        if (fork && on_layer_grads) {
+          SB_CUDA(cudaEventRecord(ev_dw[l], side));
+          SB_CUDA(cudaStreamWaitEvent(comm, ev_dw[l], 0));
+          SB_TRY(on_layer_grads(l, comm, 0));
+        }
       }
       if (l > 0) {
         // dZ_{l-1}[rows,in] = (dZ_l[rows,out] (K-major) x W_l[in,out] (K-major B: k = out contiguous)) .* act'(A_{l-1})
@@ -359,6 +381,13 @@ int Net::enqueue_backward(int rows, float* grad) {
         p.colsum = grad + pl.b_off;
         SB_TRY((launch_gemm_tc<EPI_DA, false, false>(gp, ta, tb, p, stream, use_pdl)));
         mark("gemm_da");
+      }
+      if (fork && on_layer_grads) {
+        if (l > 0) {
+          SB_CUDA(cudaEventRecord(ev_da[l], stream));
+          SB_CUDA(cudaStreamWaitEvent(comm, ev_da[l], 0));
+        }
+        SB_TRY(on_layer_grads(l, comm, 1));
       }
     } else {
       {
@@ -392,6 +421,10 @@ int Net::enqueue_backward(int rows, float* grad) {
   if (fork) {
     SB_CUDA(cudaEventRecord(ev_join, side));
     SB_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
+    if (on_layer_grads) {
+      SB_CUDA(cudaEventRecord(ev_comm, comm));
+      SB_CUDA(cudaStreamWaitEvent(stream, ev_comm, 0));
+    }
   }
   return SB_OK;
 }

@@ -4,6 +4,7 @@
 #include <vector>
 #include <map>
 #include <mutex>
+#include <functional>
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_f32.cuh"
@@ -25,6 +26,16 @@ struct Net {
   cudaStream_t side = nullptr;               // dW GEMMs run here, concurrently with the dA chain on `stream`
   std::vector<cudaEvent_t> ev_dz;            // ev_dz[l]: dZ_l is complete on `stream`
   cudaEvent_t ev_join = nullptr;
+  cudaStream_t comm = nullptr;               // per-layer gradient all-reduce + optimizer, pipelined behind the dW GEMMs
+  std::vector<cudaEvent_t> ev_dw;            // ev_dw[l]: dW_l (and db_l) complete on `side`
+  cudaEvent_t ev_comm = nullptr;
+  // called (while enqueueing the backward pass) once the gradient segment of hidden layer l - and, for l = L-1, of
+  // the output layer that follows it in the flat layout - has been enqueued; work is expected on `comm`
+  // phase 0: dW_l enqueued (gradient segment complete) -> exchange; phase 1: dA_l enqueued too (W_l no longer read
+  // by this step) -> the optimizer may overwrite W_l and its bf16 shadow
+  std::function<int(int /*layer*/, cudaStream_t /*comm*/, int /*phase*/)> on_layer_grads;
+  std::vector<cudaEvent_t> ev_da;            // ev_da[l]: dA_l complete on `stream`
+  std::vector<int> work_begin, work_end;     // optimizer work-table range of layer l (0..L)
   bool concurrent_bwd = true;
   bool use_pdl = true;                       // programmatic dependent launch along the main chain
   int F = 0, L = 0;             // features, hidden layers
