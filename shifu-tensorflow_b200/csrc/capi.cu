@@ -78,15 +78,20 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind) {
   // play in the reference (res/ssgd_monitor.py:136-142), without the parameter server.
   const bool pipelined = kind == G_STEP && n.concurrent_bwd && !n.profiling && n.side != nullptr && n.precision == SB_PREC_BF16;
   if (pipelined) {
-    n.on_layer_grads = [t](int l, cudaStream_t cs, int phase) -> int {
+    n.on_layer_grads = [t](int l, cudaStream_t cs, int phase, long long e0, long long e1) -> int {
       Net& nn = t->net;
+      const Layer& ly = nn.layers[l];
       const int last = (l == nn.L - 1) ? nn.L : l;
+      const bool completes = e1 == static_cast<long long>(ly.in) * ly.out;  // this chunk also carries b_l (+ output layer)
       if (phase == 0) {
-        const long long off = nn.layers[l].w_off;
-        const long long end = nn.layers[last].b_off + nn.layers[last].out;
+        const long long off = ly.w_off + e0;
+        const long long end = completes ? nn.layers[last].b_off + nn.layers[last].out : ly.w_off + e1;
         return enqueue_allreduce(t, t->grad, off, end - off, cs);
       }
-      return enqueue_optimizer(t, t->grad, nn.work_begin[l], nn.work_end[last], cs);
+      // work-table runs are 1024 parameters each, chunk boundaries are multiples of 1024 (128 rows x out % 8 == 0)
+      const int w0 = nn.work_begin[l] + static_cast<int>(e0 / 1024);
+      const int w1 = completes ? nn.work_end[last] : nn.work_begin[l] + static_cast<int>(e1 / 1024);
+      return enqueue_optimizer(t, t->grad, w0, w1, cs);
     };
   } else {
     n.on_layer_grads = nullptr;
@@ -233,6 +238,19 @@ int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, 
   }
   memset(t->h_scal, 0, sizeof(float) * SCAL_COUNT);
   if (world > 1) {
+    // The GEMMs are persistent (one CTA per SM, ~200 KB smem each): an NCCL CTA that lands on an SM evicts a GEMM CTA
+    // into a second wave.  Keep NCCL to a few CTAs and leave those SMs out of the GEMM grids.
+    int nccl_ctas = 8;
+    if (const char* e = getenv("SB_NCCL_CTAS")) nccl_ctas = atoi(e);
+    if (nccl_ctas < 1) nccl_ctas = 1;
+    if (nccl_ctas > 32) nccl_ctas = 32;
+    char buf[16];
+    snprintf(buf, sizeof(buf), "%d", nccl_ctas);
+    setenv("NCCL_MAX_CTAS", buf, 0);
+    n.gemm_sms = n.num_sms - nccl_ctas;
+    n.gemm_sms -= n.gemm_sms & 1;  // CTA pairs
+    n.dw_chunk_bytes = 2500000;
+    if (const char* e = getenv("SB_DW_CHUNK_BYTES")) n.dw_chunk_bytes = atoll(e);
     NcclApi* api = nccl_api();
     if (!api) { n.destroy(); return set_error(SB_ERR_NCCL, "libnccl.so.2 could not be loaded"); }
     NcclUniqueId id;

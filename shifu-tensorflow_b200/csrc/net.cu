@@ -133,6 +133,7 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
   training = training_;
   if (const char* e = getenv("SB_NO_PDL")) use_pdl = !(e[0] == '1');
   if (const char* e = getenv("SB_NO_FORK")) concurrent_bwd = !(e[0] == '1');
+  gemm_sms = num_sms;
   SB_CUDA(cudaSetDevice(device));
   SB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   if (training_) {
@@ -285,7 +286,7 @@ int Net::enqueue_hidden_forward(int rows) {
     Layer& ly = layers[l];
     if (precision == SB_PREC_BF16) {
       // Z = A_{l-1}[rows,in] (K-major) x W_l[in,out] (MN-major B operand: n contiguous)
-      const GemmPlan pl = plan_gemm(rows, ly.out, ly.in, num_sms, false);
+      const GemmPlan pl = plan_gemm(rows, ly.out, ly.in, gemm_sms, false);
       CUtensorMap ta, tb;
       const __nv_bfloat16* src = (l == 0) ? Xb : A[l - 1];
       SB_TRY(make_tmap_bf16(&ta, src, rows, ly.in, ly.ld_in, 128));
@@ -343,33 +344,47 @@ int Net::enqueue_backward(int rows, float* grad) {
   for (int l = L - 1; l >= 0; --l) {
     Layer& ly = layers[l];
     if (precision == SB_PREC_BF16) {
-      // dW_l[in,out] += sum_rows A_{l-1}[rows,in] (MN-major A) * dZ_l[rows,out] (MN-major B), split-K over rows
+      // dW_l[in,out] += sum_rows A_{l-1}[rows,in] (MN-major A) * dZ_l[rows,out] (MN-major B), split-K over rows.
+      // With a gradient exchange behind it, a big layer is cut into row chunks of W_l (each a contiguous slice of the
+      // flat gradient) so that the all-reduce of chunk c overlaps the GEMM of chunk c+1.
       {
-        const GemmPlan pl = plan_gemm(ly.in, ly.out, rows, num_sms, true);
-        CUtensorMap ta, tb;
-        const __nv_bfloat16* ap = (l == 0) ? Xb : A[l - 1];
-        SB_TRY(make_tmap_bf16(&ta, ap, rows, ly.in, ly.ld_in, 64));
-        SB_TRY(make_tmap_bf16(&tb, dZ[l], rows, ly.out, ly.ld_out, 64));
-        GemmTcParams p = {};
-        p.M = ly.in; p.N = ly.out; p.K = rows;
-        p.accum = grad + ly.w_off; p.ld_acc = ly.out;
-        p.acc_vec4 = (ly.out % 4 == 0 && ly.w_off % 4 == 0) ? 1 : 0;
+        const long long wl_elems = static_cast<long long>(ly.in) * ly.out;
+        int n_chunks = 1;
+        if (fork && on_layer_grads && dw_chunk_bytes > 0 && (ly.out % 8) == 0 && wl_elems * 4 > 2 * dw_chunk_bytes) {
+          n_chunks = static_cast<int>((wl_elems * 4 + dw_chunk_bytes - 1) / dw_chunk_bytes);
+          if (n_chunks > 8) n_chunks = 8;
+        }
+        int chunk_rows = round_up((ly.in + n_chunks - 1) / n_chunks, 128);
         if (fork) {
           SB_CUDA(cudaEventRecord(ev_dz[l], stream));
           SB_CUDA(cudaStreamWaitEvent(side, ev_dz[l], 0));
         }
-        SB_TRY((launch_gemm_tc<EPI_DW, true, true>(pl, ta, tb, p, fork ? side : stream, use_pdl && !fork)));
-        mark("gemm_dw");
-        if (fork && on_layer_grads) {
-          SB_CUDA(cudaEventRecord(ev_dw[l], side));
-          SB_CUDA(cudaStreamWaitEvent(comm, ev_dw[l], 0));
-          SB_TRY(on_layer_grads(l, comm, 0));
+        const __nv_bfloat16* ap = (l == 0) ? Xb : A[l - 1];
+        for (int r0 = 0; r0 < ly.in; r0 += chunk_rows) {
+          const int r1 = (r0 + chunk_rows < ly.in) ? r0 + chunk_rows : ly.in;
+          const GemmPlan pl = plan_gemm(r1 - r0, ly.out, rows, gemm_sms, true);
+          CUtensorMap ta, tb;
+          SB_TRY(make_tmap_bf16(&ta, ap + r0, rows, r1 - r0, ly.ld_in, 64));
+          SB_TRY(make_tmap_bf16(&tb, dZ[l], rows, ly.out, ly.ld_out, 64));
+          GemmTcParams p = {};
+          p.M = r1 - r0; p.N = ly.out; p.K = rows;
+          p.accum = grad + ly.w_off + static_cast<long long>(r0) * ly.out; p.ld_acc = ly.out;
+          p.acc_vec4 = (ly.out % 4 == 0 && ly.w_off % 4 == 0) ? 1 : 0;
+          SB_TRY((launch_gemm_tc<EPI_DW, true, true>(pl, ta, tb, p, fork ? side : stream, use_pdl && !fork)));
+          mark("gemm_dw");
+          if (fork && on_layer_grads) {
+            const long long e0 = static_cast<long long>(r0) * ly.out, e1 = static_cast<long long>(r1) * ly.out;
+            SB_CUDA(cudaEventRecord(ev_dw[l], side));
+            SB_CUDA(cudaStreamWaitEvent(comm, ev_dw[l], 0));
+            SB_TRY(on_layer_grads(l, comm, 0, e0, e1));
+            if (l == 0) SB_TRY(on_layer_grads(l, comm, 1, e0, e1));  // no dA_0: W_0 is free to be updated
+          }
         }
       }
       if (l > 0) {
         // dZ_{l-1}[rows,in] = (dZ_l[rows,out] (K-major) x W_l[in,out] (K-major B: k = out contiguous)) .* act'(A_{l-1})
         Layer& pl = layers[l - 1];
-        const GemmPlan gp = plan_gemm(rows, ly.in, ly.out, num_sms, false);
+        const GemmPlan gp = plan_gemm(rows, ly.in, ly.out, gemm_sms, false);
         CUtensorMap ta, tb;
         SB_TRY(make_tmap_bf16(&ta, dZ[l], rows, ly.out, ly.ld_out, 128));
         SB_TRY(make_tmap_bf16(&tb, ly.Wn, ly.in, ly.out, ly.ld_out, plan_box_rows_b(gp)));
@@ -382,12 +397,10 @@ int Net::enqueue_backward(int rows, float* grad) {
         SB_TRY((launch_gemm_tc<EPI_DA, false, false>(gp, ta, tb, p, stream, use_pdl)));
         mark("gemm_da");
       }
-      if (fork && on_layer_grads) {
-        if (l > 0) {
-          SB_CUDA(cudaEventRecord(ev_da[l], stream));
-          SB_CUDA(cudaStreamWaitEvent(comm, ev_da[l], 0));
-        }
-        SB_TRY(on_layer_grads(l, comm, 1));
+      if (fork && on_layer_grads && l > 0) {
+        SB_CUDA(cudaEventRecord(ev_da[l], stream));
+        SB_CUDA(cudaStreamWaitEvent(comm, ev_da[l], 0));
+        SB_TRY(on_layer_grads(l, comm, 1, 0, static_cast<long long>(ly.in) * ly.out));
       }
     } else {
       {

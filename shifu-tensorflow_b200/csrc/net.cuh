@@ -33,7 +33,10 @@ struct Net {
   // the output layer that follows it in the flat layout - has been enqueued; work is expected on `comm`
   // phase 0: dW_l enqueued (gradient segment complete) -> exchange; phase 1: dA_l enqueued too (W_l no longer read
   // by this step) -> the optimizer may overwrite W_l and its bf16 shadow
-  std::function<int(int /*layer*/, cudaStream_t /*comm*/, int /*phase*/)> on_layer_grads;
+  // [e0, e1) = element range of W_l covered (chunked dW); e1 == in*out marks the chunk that completes the layer
+  std::function<int(int /*layer*/, cudaStream_t /*comm*/, int /*phase*/, long long /*e0*/, long long /*e1*/)> on_layer_grads;
+  int gemm_sms = 0;                          // SMs the persistent GEMMs may occupy (num_sms minus those left to NCCL)
+  long long dw_chunk_bytes = 0;              // > 0: split a layer's dW GEMM so each gradient chunk is about this big
   std::vector<cudaEvent_t> ev_da;            // ev_da[l]: dA_l complete on `stream`
   std::vector<int> work_begin, work_end;     // optimizer work-table range of layer l (0..L)
   bool concurrent_bwd = true;
