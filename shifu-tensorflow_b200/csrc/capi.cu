@@ -76,7 +76,12 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind) {
   // flat segment [W_l, b_l] (+ the output layer for l = L-1) is all-reduced and its optimizer update applied on the
   // comm stream while the remaining dA / dW GEMMs still run - the role SyncReplicasOptimizer's accumulator + apply
   // play in the reference (res/ssgd_monitor.py:136-142), without the parameter server.
-  const bool pipelined = kind == G_STEP && n.concurrent_bwd && !n.profiling && n.side != nullptr && n.precision == SB_PREC_BF16;
+  // Measured on 2x B200 (profiles/scaling_r01.md): with NCCL as the exchange, ONE all-reduce of the whole flat gradient
+  // after the backward pass beats per-layer / per-chunk calls (each NCCL launch costs ~20-50 us and its CTAs evict
+  // persistent GEMM CTAs), so the pipelined variant is opt-in (SB_PIPELINE_AR=1).
+  static const bool want_pipeline = getenv("SB_PIPELINE_AR") != nullptr;
+  const bool pipelined = want_pipeline && kind == G_STEP && n.concurrent_bwd && !n.profiling && n.side != nullptr &&
+                         n.precision == SB_PREC_BF16;
   if (pipelined) {
     n.on_layer_grads = [t](int l, cudaStream_t cs, int phase, long long e0, long long e1) -> int {
       Net& nn = t->net;
@@ -240,17 +245,20 @@ int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, 
   if (world > 1) {
     // The GEMMs are persistent (one CTA per SM, ~200 KB smem each): an NCCL CTA that lands on an SM evicts a GEMM CTA
     // into a second wave.  Keep NCCL to a few CTAs and leave those SMs out of the GEMM grids.
-    int nccl_ctas = 8;
-    if (const char* e = getenv("SB_NCCL_CTAS")) nccl_ctas = atoi(e);
-    if (nccl_ctas < 1) nccl_ctas = 1;
-    if (nccl_ctas > 32) nccl_ctas = 32;
-    char buf[16];
-    snprintf(buf, sizeof(buf), "%d", nccl_ctas);
-    setenv("NCCL_MAX_CTAS", buf, 0);
-    n.gemm_sms = n.num_sms - nccl_ctas;
-    n.gemm_sms -= n.gemm_sms & 1;  // CTA pairs
-    n.dw_chunk_bytes = 2500000;
-    if (const char* e = getenv("SB_DW_CHUNK_BYTES")) n.dw_chunk_bytes = atoll(e);
+    // (only when the exchange is pipelined behind the backward pass, SB_PIPELINE_AR=1)
+    if (getenv("SB_PIPELINE_AR")) {
+      int nccl_ctas = 8;
+      if (const char* e = getenv("SB_NCCL_CTAS")) nccl_ctas = atoi(e);
+      if (nccl_ctas < 1) nccl_ctas = 1;
+      if (nccl_ctas > 32) nccl_ctas = 32;
+      char buf[16];
+      snprintf(buf, sizeof(buf), "%d", nccl_ctas);
+      setenv("NCCL_MAX_CTAS", buf, 0);
+      n.gemm_sms = n.num_sms - nccl_ctas;
+      n.gemm_sms -= n.gemm_sms & 1;  // CTA pairs
+      n.dw_chunk_bytes = 2500000;
+      if (const char* e = getenv("SB_DW_CHUNK_BYTES")) n.dw_chunk_bytes = atoll(e);
+    }
     NcclApi* api = nccl_api();
     if (!api) { n.destroy(); return set_error(SB_ERR_NCCL, "libnccl.so.2 could not be loaded"); }
     NcclUniqueId id;
