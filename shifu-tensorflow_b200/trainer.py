@@ -1,0 +1,310 @@
+"""Host-side mirror of the reference worker script `ssgd_monitor.py` (shifu-tensorflow-on-yarn/src/main/resources/),
+the plug-in the stock YARN executor launches through `shifu.application.python-script-path`
+(TensorflowTaskExecutor.java:273-275, 300-317).  Same seam, same names, same contract:
+
+  env in    JOB_NAME, TASK_ID, WORKER_CNT, CLUSTER_SPEC, TRAINING_DATA_PATH, TOTAL_TRAINING_DATA_NUMBER,
+            SELECTED_COLUMN_NUMS, WEIGHT_COLUMN_NUM, TARGET_COLUMN_NUM, TMP_MODEL_PATH, FINAL_MODEL_PATH,
+            SOCKET_SERVER_PORT                                   (ssgd_monitor.py:36-50)
+  files in  ./ModelConfig.json  (train.params.NumHiddenLayers / NumHiddenNodes / ActivationFunc / LearningRate,
+            train.numTrainEpochs, train.validSetRate; ssgd_monitor.py:92-95,133,178-183)
+  out       one line per epoch on 127.0.0.1:$SOCKET_SERVER_PORT
+            "worker_index:{},time:{},current_epoch:{},training_loss:{},valid_loss:{}\n"   (ssgd_monitor.py:288-293,
+            parsed by SocketServer.java:71-89); SavedModel + GenericModelConfig.json at FINAL_MODEL_PATH (chief);
+            exit code 0
+
+What changed underneath: the TF graph / Session / parameter servers are gone.  All arithmetic is the CUDA library
+behind the C-ABI (`_capi.Trainer`); workers are data-parallel ranks that exchange gradients over NCCL, `JOB_NAME=ps`
+processes simply idle (the stock AM insists on >= 1 PS).  The reference's `time.sleep(40)` grace
+periods and the 5 s sleep per epoch are not reproduced.
+
+Optional ModelConfig train.params the reference does not have (defaults = reference behaviour):
+  Optimizer  "adadelta" (default) | "adam" | "sgd" | "momentum"
+  Loss       "squared" (default: MSE on the sigmoid output, ssgd_monitor.py:129) | "log" (sigmoid cross-entropy)
+  Precision  "bf16" (default) | "fp32"
+  MiniBatchs mini-batch rows (default BATCH_SIZE = 100, ssgd_monitor.py:33)
+  Schedule   "epoch" (default: one update per epoch = mean of R mini-batch gradients, ssgd_monitor.py:136-141)
+             | "batch" (one update per mini-batch)
+"""
+from __future__ import annotations
+
+import gzip
+import io
+import json
+import logging
+import os
+import random
+import shutil
+import socket
+import struct
+import sys
+import time
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi as capi
+
+HIDDEN_NODES_COUNT = 20
+VALID_TRAINING_DATA_RATIO = 0.1
+BUILD_MODEL_BY_CONF_ENABLE = True
+REPLICAS_TO_AGGREGATE_RATIO = 1
+DELIMITER = '|'
+BATCH_SIZE = 100
+
+_OPT = {"adadelta": capi.OPT_ADADELTA, "adam": capi.OPT_ADAM, "sgd": capi.OPT_SGD, "momentum": capi.OPT_MOMENTUM}
+_LOSS = {"squared": capi.LOSS_MSE, "log": capi.LOSS_SIGMOID_CE}
+
+
+def get_activation_fun(name: Optional[str]) -> int:
+    """name -> activation id; None / unknown -> leaky_relu (ssgd_monitor.py:74-88)."""
+    if name is None:
+        return capi.ACT_LEAKYRELU
+    name = name.lower()
+    if 'sigmoid' == name:
+        return capi.ACT_SIGMOID
+    elif 'tanh' == name:
+        return capi.ACT_TANH
+    elif 'relu' == name:
+        return capi.ACT_RELU
+    elif 'leakyrelu' == name:
+        return capi.ACT_LEAKYRELU
+    else:
+        return capi.ACT_LEAKYRELU
+
+
+def generate_from_modelconf(model_conf: dict):
+    """-> (hidden widths, activation ids) (ssgd_monitor.py:91-107)."""
+    train_params = model_conf['train']['params']
+    num_hidden_layer = int(train_params['NumHiddenLayers'])
+    num_hidden_nodes = [int(s) for s in train_params['NumHiddenNodes']]
+    activation_func = [get_activation_fun(s) for s in train_params['ActivationFunc']]
+    return num_hidden_nodes[:num_hidden_layer], activation_func[:num_hidden_layer]
+
+
+def model(feature_count: int, model_conf: Optional[dict], max_batch: int) -> capi.NetDesc:
+    """The network + loss + optimizer of `model()` (ssgd_monitor.py:110-144) as a C-ABI net descriptor."""
+    if BUILD_MODEL_BY_CONF_ENABLE and model_conf is not None:
+        hidden, acts = generate_from_modelconf(model_conf)
+        params = model_conf['train']['params']
+        learning_rate = float(params['LearningRate'])
+    else:
+        hidden, acts, params = [HIDDEN_NODES_COUNT], [capi.ACT_TANH], {}
+        learning_rate = 0.003
+    opt = _OPT[str(params.get('Optimizer', 'adadelta')).lower()]
+    loss = _LOSS[str(params.get('Loss', 'squared')).lower()]
+    prec = capi.PREC_FP32 if str(params.get('Precision', 'bf16')).lower() == 'fp32' else capi.PREC_BF16
+    return capi.make_desc(feature_count, hidden, acts, loss=loss, optimizer=opt, learning_rate=learning_rate,
+                          max_batch=max_batch, precision=prec)
+
+
+def load_data(data_file: str, feature_column_nums: Optional[List[int]], target_column_num: int,
+              sample_weight_column_num: int, valid_ratio: float, rng=random) -> Dict[str, object]:
+    """Same semantics as the reference loader (ssgd_monitor.py:348-454): comma-separated list of gzip files, '|'
+    delimited lines, selected columns -> float (an unparsable cell is logged and skipped, :409-411), weight < 0 -> 1.0,
+    no weight column -> 1.0, Bernoulli(valid_ratio) split by `random.random() >= ratio -> train` (:396)."""
+    out = {k: [] for k in ("train_data", "train_target", "valid_data", "valid_target",
+                           "train_data_sample_weight", "valid_data_sample_weight")}
+    line_count = 0
+    for current_file in data_file.split(","):
+        logging.info("Now loading " + current_file)
+        with open(current_file, 'rb') as f:
+            gf = gzip.GzipFile(fileobj=io.BytesIO(f.read()))
+            for raw in gf:
+                line = raw.decode('utf-8')
+                if len(line) == 0:
+                    break
+                line_count += 1
+                columns = line.split(DELIMITER)
+                if feature_column_nums is None:
+                    feature_column_nums = [c for c in range(len(columns)) if c != target_column_num and
+                                           not (sample_weight_column_num >= 0 and c == sample_weight_column_num)]
+                pre = "train" if rng.random() >= valid_ratio else "valid"
+                out[pre + "_target"].append([float(columns[target_column_num])])
+                row = []
+                for c in feature_column_nums:
+                    try:
+                        row.append(float(columns[c].strip('\n')))
+                    except Exception:
+                        logging.info("Could not convert " + str(columns[c].strip('\n')) + " to float")
+                        logging.info("feature_column_num: " + str(c))
+                out[pre + "_data"].append(row)
+                if 0 <= sample_weight_column_num < len(columns):
+                    weight = float(columns[sample_weight_column_num].strip('\n'))
+                    if weight < 0.0:
+                        logging.info("Warning: weight is below 0. example:" + line)
+                        weight = 1.0
+                    out[pre + "_data_sample_weight"].append([weight])
+                else:
+                    out[pre + "_data_sample_weight"].append([1.0])
+    logging.info("Total data count: " + str(line_count) + ".")
+    out["feature_count"] = len(feature_column_nums) if feature_column_nums is not None else 0
+    return out
+
+
+def simple_save(trainer: capi.Trainer, export_dir: str) -> None:
+    """SavedModel (tag serve, signature serving_default shifu_input_0 -> shifu_output_0) + GenericModelConfig.json
+    (ssgd_monitor.py:457-490); an existing export_dir is replaced like tf.gfile.DeleteRecursively does."""
+    if os.path.exists(export_dir):
+        shutil.rmtree(export_dir)
+    trainer.export_savedmodel(export_dir)
+
+
+def _exchange_nccl_id(cluster_spec: dict, task_index: int, n_workers: int) -> Optional[bytes]:
+    """Rendezvous that replaces tf.train.Server / ClusterSpec (ssgd_monitor.py:152-166): worker 0 creates the NCCL
+    unique id and serves its 128 bytes on its own CLUSTER_SPEC address (the port the executor reserved for TF,
+    TensorflowTaskExecutor.java:93-111); the other workers fetch it from there."""
+    if n_workers <= 1:
+        return None
+    host, port = cluster_spec['worker'][0].rsplit(':', 1)
+    port = int(port)
+    if task_index == 0:
+        uid = capi.nccl_unique_id()
+        srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        srv.bind(('', port))
+        srv.listen(n_workers)
+        for _ in range(n_workers - 1):
+            conn, _addr = srv.accept()
+            conn.sendall(uid)
+            conn.close()
+        srv.close()
+        return uid
+    deadline = time.time() + 1200      # the AM gives stragglers 20 min (Constants.java:92-94)
+    while True:
+        try:
+            c = socket.create_connection((host, port), timeout=10)
+            break
+        except OSError:
+            if time.time() > deadline:
+                raise
+            time.sleep(0.5)
+    buf = b""
+    while len(buf) < capi.SB_NCCL_ID_BYTES:
+        chunk = c.recv(capi.SB_NCCL_ID_BYTES - len(buf))
+        if not chunk:
+            raise RuntimeError("NCCL id exchange: connection closed")
+        buf += chunk
+    c.close()
+    return buf
+
+
+def main(_=None, env=None, rng=random) -> int:
+    env = os.environ if env is None else env
+    logging.basicConfig(level=logging.INFO, format='%(asctime)s %(name)-12s %(levelname)-8s %(message)s',
+                        datefmt='%y-%m-%d %H:%M:%S')
+    # read from env (ssgd_monitor.py:36-50) - a missing key raises KeyError exactly like the reference
+    cluster_spec = json.loads(env["CLUSTER_SPEC"])
+    n_workers = int(env["WORKER_CNT"])
+    job_name = env["JOB_NAME"]
+    task_index = int(env["TASK_ID"])
+    socket_server_port = int(env["SOCKET_SERVER_PORT"])
+    total_training_data_number = int(env["TOTAL_TRAINING_DATA_NUMBER"])
+    feature_column_nums = [int(s) for s in str(env["SELECTED_COLUMN_NUMS"]).split(' ')]
+    feature_count = len(feature_column_nums)
+    sample_weight_column_num = int(env["WEIGHT_COLUMN_NUM"])
+    target_column_num = int(env["TARGET_COLUMN_NUM"])
+    tmp_model_path = env["TMP_MODEL_PATH"]
+    final_model_path = env["FINAL_MODEL_PATH"]
+    logging.info("job_name:%s, task_index:%d" % (job_name, task_index))
+
+    if job_name == 'ps':
+        # server.join() (ssgd_monitor.py:157-161): there is no parameter server any more; idle until YARN reaps us
+        while True:
+            time.sleep(3600)
+
+    socket_client = None
+    try:
+        socket_client = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        socket_client.connect(("127.0.0.1", socket_server_port))
+    except OSError:
+        if env.get("SB_REQUIRE_SOCKET", "1") != "0":
+            raise
+        socket_client = None
+    is_chief = (task_index == 0)
+    training_data_path = env["TRAINING_DATA_PATH"]
+
+    with open('./ModelConfig.json') as f:
+        model_conf = json.load(f)
+    epochs = int(model_conf['train']['numTrainEpochs'])
+    valid_ratio = model_conf['train']['validSetRate']
+    params = model_conf['train']['params']
+    batch_size = int(params.get('MiniBatchs', BATCH_SIZE))
+    per_batch_update = str(params.get('Schedule', 'epoch')).lower() == 'batch'
+
+    context = load_data(training_data_path, feature_column_nums, target_column_num, sample_weight_column_num,
+                        valid_ratio, rng=rng)
+    train_x = np.asarray(context["train_data"], dtype=np.float32)
+    if train_x.ndim != 2 or train_x.shape[1] != feature_count:
+        raise ValueError("training rows do not all have %d parsable features" % feature_count)
+    train_y = np.asarray(context["train_target"], dtype=np.float32).reshape(-1)
+    train_w = np.asarray(context["train_data_sample_weight"], dtype=np.float32).reshape(-1)
+    valid_x = np.asarray(context["valid_data"], dtype=np.float32).reshape(-1, feature_count)
+    valid_y = np.asarray(context["valid_target"], dtype=np.float32).reshape(-1)
+    valid_w = np.asarray(context["valid_data_sample_weight"], dtype=np.float32).reshape(-1)
+    logging.info("Testing set size: %d" % len(valid_x))
+    logging.info("Training set size: %d" % len(train_x))
+
+    # split data into batch (ssgd_monitor.py:189-192): int(N / BATCH_SIZE) near-equal batches
+    total_batch = max(1, int(len(train_x) / batch_size))
+    bounds = [b[0] for b in np.array_split(np.arange(len(train_x)), total_batch)] + [len(train_x)]
+    max_rows = max(bounds[i + 1] - bounds[i] for i in range(total_batch))
+
+    desc = model(feature_count, model_conf, max_rows)
+    device = int(env.get("SB_DEVICE", env.get("LOCAL_RANK", "0")))
+    nccl_id = _exchange_nccl_id(cluster_spec, task_index, n_workers)
+    trainer = capi.Trainer(desc, device=device, nccl_id=nccl_id, rank=task_index, world=n_workers)
+    ckpt = os.path.join(tmp_model_path, "model.ckpt")
+    if os.path.exists(ckpt):                      # MonitoredTrainingSession restores the latest checkpoint (:251-257)
+        trainer.load_checkpoint(ckpt)
+    else:
+        trainer.init_xavier(int(env.get("SB_SEED", "0")) or random.SystemRandom().randrange(1, 2 ** 31))
+    trainer.load_dataset(train_x, train_y, train_w)
+
+    # replicas_to_aggregate (ssgd_monitor.py:139): pushes per global update; spread over the workers
+    R = max(1, int(total_training_data_number * (1 - valid_ratio) / batch_size * REPLICAS_TO_AGGREGATE_RATIO))
+    pushes_per_update = max(1, R // max(1, n_workers))
+
+    logging.info('Starting training on worker %d' % task_index)
+    pending = 0
+    while trainer.global_step < epochs:           # StopAtStepHook(num_steps=EPOCH) (ssgd_monitor.py:235)
+        start = time.time()
+        l = 0.0
+        for i in range(total_batch):
+            off, rows = int(bounds[i]), int(bounds[i + 1] - bounds[i])
+            if per_batch_update:
+                l = trainer.step_resident(off, rows)
+            else:
+                l = trainer.accumulate_resident(off, rows)
+                pending += 1
+                if pending >= pushes_per_update:
+                    trainer.apply_accumulated()
+                    pending = 0
+            if trainer.global_step >= epochs:
+                break
+        training_time = time.time() - start
+        valid_loss = trainer.eval_loss(valid_x, valid_y, valid_w) if len(valid_x) else 0.0
+        gs = trainer.global_step
+        logging.info('Step: ' + str(gs) + ' worker: ' + str(task_index) + " training loss:" + str(l) +
+                     " valid loss:" + str(valid_loss))
+        message = "worker_index:{},time:{},current_epoch:{},training_loss:{},valid_loss:{}\n".format(
+            str(task_index), str(training_time), str(gs), str(l), str(valid_loss))
+        if socket_client is not None:
+            socket_client.send(message.encode('utf8'))
+        if is_chief:
+            os.makedirs(tmp_model_path, exist_ok=True)
+            trainer.save_checkpoint(ckpt)
+
+    logging.info('Done' + str(task_index))
+    if is_chief:
+        logging.info("Exporting saved_model to: {}".format(final_model_path))
+        simple_save(trainer, final_model_path)
+        logging.info("Exported saved_model")
+    trainer.close()
+    if socket_client is not None:
+        socket_client.close()
+    logging.info('Session from worker %d closed cleanly' % task_index)
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -1,0 +1,197 @@
+"""Host-side mirrors of the reference's two plug-in surfaces: the worker script (trainer.py <- ssgd_monitor.py) and the
+scorer (scorer.py <- TensorflowModel.java).  CPU tests cover the contract (names, env vars, errors, loader semantics,
+socket line, rendezvous); the gpu tests run the whole worker end to end."""
+import gzip
+import json
+import os
+import socket
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import shifu_oracle as so
+
+
+def _write_gz(path, X, y, w=None):
+    with gzip.open(path, "wb") as f:
+        for i in range(len(X)):
+            cols = [str(int(y[i]))] + [repr(float(v)) for v in X[i]]
+            if w is not None:
+                cols.append(repr(float(w[i])))
+            f.write(("|".join(cols) + "\n").encode())
+
+
+class _Seq:
+    def __init__(self, seed):
+        self.r = np.random.RandomState(seed)
+
+    def random(self):
+        return float(self.r.rand())
+
+
+def test_get_activation_fun_and_modelconf(sb):
+    from shifu_tensorflow_b200 import trainer as tr
+    assert [tr.get_activation_fun(n) for n in ("sigmoid", "TANH", "ReLU", "leakyrelu", "nope", None)] == [0, 1, 2, 3, 3, 3]
+    conf = {"train": {"params": {"NumHiddenLayers": 2, "NumHiddenNodes": [10, 5, 99], "ActivationFunc": ["tanh", "relu", "x"],
+                                  "LearningRate": 0.1}, "numTrainEpochs": 3, "validSetRate": 0.2}}
+    assert tr.generate_from_modelconf(conf) == ([10, 5], [1, 2])
+    d = tr.model(7, conf, 100)
+    assert (d.n_features, d.n_hidden, d.hidden[0], d.hidden[1], d.optimizer, d.loss) == (7, 2, 10, 5, sb.OPT_ADADELTA, sb.LOSS_MSE)
+    assert abs(d.learning_rate - 0.1) < 1e-7 and d.max_batch == 100
+
+
+def test_load_data_equals_oracle_loader(sb, tmp_path):
+    from shifu_tensorflow_b200 import trainer as tr
+    X, y, w = so.synth_batch(57, 6, 3, weights="mixed")
+    w = w.ravel(); w[5] = -2.0                      # negative weight -> 1.0
+    p = str(tmp_path / "part-0.gz")
+    _write_gz(p, X, y.ravel(), w)
+    a = tr.load_data(p, [1, 2, 3, 4, 5, 6], 0, 7, 0.25, rng=_Seq(1))
+    b = so.load_data([p], [1, 2, 3, 4, 5, 6], 0, 7, 0.25, rng=_Seq(1))
+    for k in a:
+        assert a[k] == b[k], k
+    assert len(a["train_data"]) + len(a["valid_data"]) == 57 and [1.0] in a["train_data_sample_weight"] + a["valid_data_sample_weight"]
+
+
+def test_missing_env_var_is_a_keyerror_like_the_reference(sb):
+    from shifu_tensorflow_b200 import trainer as tr
+    with pytest.raises(KeyError):
+        tr.main(env={"CLUSTER_SPEC": "{}"})
+
+
+def test_nccl_id_rendezvous_over_cluster_spec_address(sb, monkeypatch):
+    """worker 0 serves the 128-byte id on its CLUSTER_SPEC address, the others fetch it (replaces tf.train.Server)"""
+    from shifu_tensorflow_b200 import trainer as tr
+    fake = bytes(range(128))
+    monkeypatch.setattr(tr.capi, "nccl_unique_id", lambda: fake)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    spec = {"ps": ["127.0.0.1:1"], "worker": ["127.0.0.1:%d" % port, "127.0.0.1:2", "127.0.0.1:3"]}
+    got = {}
+    ths = [threading.Thread(target=lambda r=r: got.__setitem__(r, tr._exchange_nccl_id(spec, r, 3))) for r in range(3)]
+    [t.start() for t in ths]; [t.join(30) for t in ths]
+    assert got == {0: fake, 1: fake, 2: fake}
+    assert tr._exchange_nccl_id(spec, 0, 1) is None
+
+
+def test_scorer_init_errors_match_tensorflowmodel(sb):
+    from shifu_tensorflow_b200.scorer import TensorflowModel, IllegalStateException, IllegalArgumentException
+    m = TensorflowModel()
+    with pytest.raises(IllegalStateException, match="TF model not initialized."):
+        m.compute([0.0])
+    with pytest.raises(RuntimeError, match="Config is null"):
+        m.init(None)
+    with pytest.raises(RuntimeError, match="Properties is null"):
+        m.init({"inputnames": ["a"], "properties": {}})
+    base = {"modelpath": "/x", "outputnames": "o", "tags": ["serve"]}
+    for drop, msg in (("modelpath", "Model path is null"), ("outputnames", "Output names is null"), ("tags", "Tags is null")):
+        props = dict(base); props.pop(drop)
+        with pytest.raises(RuntimeError, match=msg):
+            TensorflowModel().init({"inputnames": ["a"], "properties": props})
+    with pytest.raises(RuntimeError, match="Input names is null"):
+        TensorflowModel().init({"inputnames": [], "properties": base})
+    with pytest.raises(IllegalArgumentException):
+        TensorflowModel().init({"inputnames": ["a"], "properties": dict(base, outputnames=["o1", "o2"])})
+
+
+def _run_worker(sb, tmp_path, n_rows, epochs, params_extra, seed=5):
+    from shifu_tensorflow_b200 import trainer as tr
+    F = 12
+    X, y, w = so.synth_batch(n_rows, F, 2, weights="ones")
+    data = str(tmp_path / "part-00000.gz")
+    _write_gz(data, X, y.ravel())
+    conf = {"train": {"params": dict({"NumHiddenLayers": 2, "NumHiddenNodes": [8, 4], "ActivationFunc": ["tanh", "relu"],
+                                      "LearningRate": 0.5, "Precision": "fp32"}, **params_extra),
+                      "numTrainEpochs": epochs, "validSetRate": 0.2}}
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    json.dump(conf, open("ModelConfig.json", "w"))
+    srv = socket.socket(); srv.bind(("127.0.0.1", 0)); srv.listen(1)
+    lines = []
+
+    def serve():
+        c, _ = srv.accept()
+        buf = b""
+        while True:
+            d = c.recv(4096)
+            if not d:
+                break
+            buf += d
+        lines.extend(buf.decode().splitlines())
+
+    th = threading.Thread(target=serve); th.start()
+    env = {"CLUSTER_SPEC": json.dumps({"ps": ["127.0.0.1:1"], "worker": ["127.0.0.1:2"]}), "WORKER_CNT": "1", "JOB_NAME": "worker",
+           "TASK_ID": "0", "SOCKET_SERVER_PORT": str(srv.getsockname()[1]), "TOTAL_TRAINING_DATA_NUMBER": str(n_rows),
+           "SELECTED_COLUMN_NUMS": " ".join(str(i) for i in range(1, F + 1)), "WEIGHT_COLUMN_NUM": "-1", "TARGET_COLUMN_NUM": "0",
+           "TMP_MODEL_PATH": str(tmp_path / "tmp_model"), "FINAL_MODEL_PATH": str(tmp_path / "final_model"),
+           "TRAINING_DATA_PATH": data, "SB_SEED": "11"}
+    try:
+        rc = tr.main(env=env, rng=_Seq(seed))
+    finally:
+        os.chdir(cwd)
+    th.join(10); srv.close()
+    return rc, lines, env, (X, y, w, F, conf)
+
+
+@pytest.mark.gpu
+def test_worker_end_to_end_reference_schedule(sb, tmp_path):
+    """the whole plug-in: env contract -> load_data -> epoch-sync Adadelta training -> socket lines -> SavedModel"""
+    rc, lines, env, (X, y, w, F, conf) = _run_worker(sb, tmp_path, 1000, 3, {})
+    assert rc == 0 and len(lines) >= 1
+    import re
+    pat = re.compile(r"^worker_index:(\d+),time:([0-9.e+-]+),current_epoch:(\d+),training_loss:([0-9.e+-]+),valid_loss:([0-9.e+-]+)$")
+    parsed = [pat.match(l) for l in lines]
+    assert all(parsed), lines                       # exactly what SocketServer.java:71-89 splits on ',' and ':'
+    assert int(parsed[-1].group(3)) == 3            # StopAtStepHook(num_steps=EPOCH)
+    final = env["FINAL_MODEL_PATH"]
+    assert sorted(os.listdir(final)) == ["GenericModelConfig.json", "saved_model.pb", "variables"]
+    assert os.path.exists(os.path.join(env["TMP_MODEL_PATH"], "model.ckpt"))
+    # the exported model scores through the scorer mirror exactly like the oracle does on the exported weights
+    from shifu_tensorflow_b200.scorer import TensorflowModel
+    cfg = json.load(open(os.path.join(final, "GenericModelConfig.json")))
+    cfg["properties"]["modelpath"] = final
+    m = TensorflowModel(); m.init(cfg); m.init(cfg)          # second init is a no-op
+    Fn, hidden, acts, out_act, flat = sb.capi.savedmodel_read(final, "shifu_input_0", "shifu_output_0")
+    net = so.NetDesc(Fn, hidden, acts)
+    want = so.score_rows(net, so.unflatten_params(net, flat), X[:50].astype(np.float64))
+    got = m.computeBatch(X[:50].astype(np.float64))
+    assert np.abs(got - want).max() <= 1e-5
+    assert abs(m.compute(X[3].astype(np.float64)) - want[3]) <= 1e-5
+    m.releaseResource()
+
+
+@pytest.mark.gpu
+def test_worker_matches_oracle_epoch_sync_trajectory(sb, tmp_path):
+    """same data, same split (seeded), same init -> the loss the worker reports per epoch equals the oracle's
+    epoch-sync trajectory (mean of the R mini-batch gradients, one Adadelta update per epoch) within 1e-4"""
+    from shifu_tensorflow_b200 import trainer as tr
+    rc, lines, env, (X, y, w, F, conf) = _run_worker(sb, tmp_path, 1000, 3, {})
+    ctx = tr.load_data(env["TRAINING_DATA_PATH"], list(range(1, F + 1)), 0, -1, 0.2, rng=_Seq(5))
+    tx = np.asarray(ctx["train_data"], np.float32); ty = np.asarray(ctx["train_target"], np.float32)
+    tw = np.asarray(ctx["train_data_sample_weight"], np.float32)
+    vx = np.asarray(ctx["valid_data"], np.float32); vy = np.asarray(ctx["valid_target"], np.float32)
+    vw = np.asarray(ctx["valid_data_sample_weight"], np.float32)
+    net = so.NetDesc(F, [8, 4], [so.ACT_TANH, so.ACT_RELU])
+    # the worker initialised with sb_trainer_init_xavier(seed 11): read the same start back from a fresh trainer
+    with sb.Trainer(tr.model(F, conf, 128)) as t0:
+        t0.init_xavier(11)
+        theta = t0.get_params()
+    opt = so.Optimizer(so.OptConfig(kind=so.OPT_ADADELTA, lr=0.5), theta.size)
+    batches = so.split_batches(len(tx), 100)
+    R = so.replicas_to_aggregate(1000, 0.2, 100)
+    valid_losses, pend, gsum = [], 0, np.zeros_like(theta)
+    steps = 0
+    while steps < 3:
+        for idx in batches:
+            P = so.unflatten_params(net, theta)
+            L, g, _ = so.loss_and_grads(net, P, tx[idx], ty[idx], tw[idx])
+            gsum += so.flatten_params(g); pend += 1
+            if pend >= R:
+                theta = opt.apply(theta, gsum / np.float32(pend)); gsum[:] = 0; pend = 0; steps += 1
+                if steps >= 3:
+                    break
+        A, z, yh = so.forward(net, so.unflatten_params(net, theta), vx)
+        valid_losses.append(float(so.loss_value(z, yh, vy, vw, so.LOSS_MSE)[0]))
+    got = [float(l.split("valid_loss:")[1]) for l in lines]
+    assert len(got) == len(valid_losses)
+    assert np.abs(np.array(got) - np.array(valid_losses)).max() <= 1e-4
