@@ -214,6 +214,12 @@ def main():
     desc = sb.make_desc(F, hidden, [sb.ACT_RELU] * len(hidden), loss=sb.LOSS_MSE, optimizer=OPT_ID[cfg["optimizer"]],
                         learning_rate=cfg["lr"], max_batch=B, precision=prec)
     t = sb.Trainer(desc, device=local_rank, nccl_id=nccl_id, rank=rank, world=world)
+    exchange = "none"
+    if world > 1:
+        exchange = "nccl"
+        if os.environ.get("SB_EXCHANGE", "p2p") == "p2p":
+            dist_util.enable_peer_exchange(dist, t, world, device="cuda")
+            exchange = "p2p (two-shot all-reduce kernel over CUDA-IPC peer memory)"
     t.init_xavier(SEED)  # same seed on every rank -> identical replicas
     X, y, w = synth_dataset(cfg, rank)
     t.load_dataset(X, y, w)
@@ -312,7 +318,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16" if prec == sb.PREC_BF16 else "f32", "data": "synthetic",
             "config": config_block(args.config, cfg, world),
             "clocks": clk, "e2e": e2e, "gpu_launches": t.kernels_per_step(B) * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "last_loss": last_loss,
+            "roofline": roofline, "cpu_baseline": cpu, "last_loss": last_loss, "gradient_exchange": exchange,
         }
         print(json.dumps(out), flush=True)
     t.close()

@@ -94,6 +94,13 @@ int sb_nccl_unique_id(void* out128);
 int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, int rank, int world,
                       sb_trainer_t** out);
 int sb_trainer_destroy(sb_trainer_t* t);
+/* Optional faster gradient exchange for ranks on one NVLink/NVSwitch node: a two-shot all-reduce kernel over CUDA-IPC
+ * peer memory instead of NCCL.  Every rank exports its exchange buffer (64-byte cudaIpcMemHandle_t), the host
+ * all-gathers the handles in rank order and hands the table to every rank.  Must be called on all ranks before the
+ * next step; without it the exchange is ncclAllReduce. */
+#define SB_IPC_HANDLE_BYTES 64
+int sb_trainer_ipc_handle(sb_trainer_t* t, void* out64);
+int sb_trainer_set_peer_handles(sb_trainer_t* t, const void* handles /* world x 64 bytes */, int32_t n_handles);
 int64_t sb_trainer_param_count(const sb_trainer_t* t);
 /* variable init / restore (tf.initialize_all_variables + Saver.restore, ssgd_monitor.py:238,327) */
 int sb_trainer_set_params(sb_trainer_t* t, const float* flat, int64_t n);

@@ -73,6 +73,8 @@ PROTOTYPES = {
     "sb_nccl_unique_id": (C.c_int, [_vp]),
     "sb_trainer_create": (C.c_int, [_P(NetDesc), C.c_int, _vp, C.c_int, C.c_int, _P(_vp)]),
     "sb_trainer_destroy": (C.c_int, [_vp]),
+    "sb_trainer_ipc_handle": (C.c_int, [_vp, _vp]),
+    "sb_trainer_set_peer_handles": (C.c_int, [_vp, _vp, C.c_int32]),
     "sb_trainer_param_count": (C.c_int64, [_vp]),
     "sb_trainer_set_params": (C.c_int, [_vp, _f32p, C.c_int64]),
     "sb_trainer_get_params": (C.c_int, [_vp, _f32p, C.c_int64]),
@@ -178,6 +180,17 @@ class Trainer:
 
     def __exit__(self, *exc):
         self.close()
+
+    # ---- peer-memory gradient exchange (CUDA IPC) ----
+    def ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        check(lib().sb_trainer_ipc_handle(self._h, C.cast(buf, _vp)))
+        return buf.raw
+
+    def set_peer_handles(self, handles: Sequence[bytes]):
+        blob = b"".join(handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        check(lib().sb_trainer_set_peer_handles(self._h, C.cast(buf, _vp), len(handles)))
 
     # ---- parameters ----
     def set_params(self, flat):

@@ -8,6 +8,7 @@
 #include "net.cuh"
 #include "gemm_tc_launch.cuh"
 #include "savedmodel.h"
+#include "allreduce_p2p.cuh"
 
 using namespace sb;
 
@@ -33,6 +34,14 @@ struct sb_trainer {
   long long ds_rows = 0;
   std::map<std::pair<int, int>, cudaGraphExec_t> graphs;  // (rows, kind) -> captured step
   std::map<int, int> kernels_per_step;
+  // peer-memory gradient exchange (CUDA IPC): xch = [gradient (padded) | P2PFlags] in ONE exported allocation
+  void* xch = nullptr;
+  long long xch_n4 = 0;            // float4 count of the padded gradient (multiple of world)
+  P2PFlags* flags = nullptr;
+  P2PPeers* d_peers = nullptr;     // device table of every rank's gradient / flags pointers
+  std::vector<void*> peer_bases;   // opened IPC mappings (to close)
+  bool p2p_ready = false;
+  unsigned int epoch = 0;
 };
 
 static float lr_for_step(const sb_trainer* t, long long step /*1-based*/) {
@@ -46,9 +55,14 @@ static float lr_for_step(const sb_trainer* t, long long step /*1-based*/) {
 static int enqueue_allreduce(sb_trainer* t, float* buf, long long off = 0, long long count = -1, cudaStream_t st = nullptr) {
   if (t->world <= 1) return SB_OK;
   NcclApi* api = nccl_api();
-  SB_CHECK(api && t->comm, SB_ERR_NCCL, "NCCL communicator missing");
+  SB_CHECK(t->p2p_ready || (api && t->comm), SB_ERR_NCCL, "no gradient exchange configured (NCCL communicator missing)");
   if (count < 0) count = t->net.n_params;
   if (!st) st = t->net.stream;
+  if (t->p2p_ready && buf == t->grad && off == 0 && count == t->net.n_params) {
+    allreduce_p2p_kernel<<<t->net.num_sms, 512, 0, st>>>(t->d_peers, t->net.desc, t->rank, t->world, t->xch_n4);
+    SB_CUDA(cudaGetLastError());
+    return SB_OK;
+  }
   int r = api->AllReduce(buf + off, buf + off, static_cast<size_t>(count), NCCL_FLOAT32, NCCL_SUM, t->comm, st);
   SB_CHECK(r == 0, SB_ERR_NCCL, "ncclAllReduce failed: %s", api->GetErrorString(r));
   return SB_OK;
@@ -152,7 +166,8 @@ static int run_step(sb_trainer* t, const float* X, const float* y, const float* 
     ++t->global_step;
     lr_t = lr_for_step(t, t->global_step);
   }
-  set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, X, y, w ? w : n.ones, lr_t, gscale);
+  if (kind == G_STEP) ++t->epoch;
+  set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, X, y, w ? w : n.ones, lr_t, gscale, t->epoch);
   SB_CUDA(cudaGetLastError());
   if (no_graph) SB_TRY(enqueue_step_body(t, rows, kind));
   else SB_CUDA(cudaGraphLaunch(ge, n.stream));
@@ -235,7 +250,17 @@ int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, 
   int s = t->net.init(desc, device, true);
   if (s != SB_OK) { t->net.destroy(); return s; }
   Net& n = t->net;
-  if ((s = n.dalloc(&t->grad, n.n_params)) || (s = n.dalloc(&t->s1, n.n_params)) || (s = n.dalloc(&t->s2, n.n_params)) ||
+  {
+    // gradient + exchange flags in one allocation so that a single IPC handle exports both
+    const long long unit = 4ll * world;
+    t->xch_n4 = ((n.n_params + unit - 1) / unit) * world;   // float4 count, multiple of world
+    const size_t bytes = static_cast<size_t>(t->xch_n4) * 16 + sizeof(P2PFlags);
+    if (cudaMalloc(&t->xch, bytes) != cudaSuccess) { n.destroy(); return set_error(SB_ERR_CUDA, "cudaMalloc(exchange) failed"); }
+    cudaMemset(t->xch, 0, bytes);
+    t->grad = static_cast<float*>(t->xch);
+    t->flags = reinterpret_cast<P2PFlags*>(static_cast<char*>(t->xch) + static_cast<size_t>(t->xch_n4) * 16);
+  }
+  if ((s = n.dalloc(&t->s1, n.n_params)) || (s = n.dalloc(&t->s2, n.n_params)) ||
       (s = n.dalloc(&t->acc, n.n_params))) { n.destroy(); return s; }
   if (cudaHostAlloc(reinterpret_cast<void**>(&t->h_scal), sizeof(float) * SCAL_COUNT, cudaHostAllocDefault) != cudaSuccess) {
     n.destroy();
@@ -271,6 +296,44 @@ int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, 
   return SB_OK;
 }
 
+int sb_trainer_ipc_handle(sb_trainer_t* t, void* out64) {
+  SB_CHECK(t && out64, SB_ERR_INVALID, "null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == SB_IPC_HANDLE_BYTES, "IPC handle size");
+  SB_CUDA(cudaSetDevice(t->net.device));
+  cudaIpcMemHandle_t h;
+  SB_CUDA(cudaIpcGetMemHandle(&h, t->xch));
+  memcpy(out64, &h, sizeof(h));
+  return SB_OK;
+}
+
+int sb_trainer_set_peer_handles(sb_trainer_t* t, const void* handles, int32_t n_handles) {
+  SB_CHECK(t && handles, SB_ERR_INVALID, "null argument");
+  SB_CHECK(n_handles == t->world && t->world <= SB_MAX_RANKS, SB_ERR_INVALID, "expected %d handles (<= %d), got %d", t->world,
+           SB_MAX_RANKS, n_handles);
+  SB_CUDA(cudaSetDevice(t->net.device));
+  SB_CUDA(cudaStreamSynchronize(t->net.stream));
+  P2PPeers hp;
+  memset(&hp, 0, sizeof(hp));
+  const size_t flag_off = static_cast<size_t>(t->xch_n4) * 16;
+  for (int q = 0; q < t->world; ++q) {
+    void* base = t->xch;
+    if (q != t->rank) {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, static_cast<const char*>(handles) + static_cast<size_t>(q) * sizeof(h), sizeof(h));
+      SB_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+      t->peer_bases.push_back(base);
+    }
+    hp.grad[q] = static_cast<float*>(base);
+    hp.flags[q] = reinterpret_cast<P2PFlags*>(static_cast<char*>(base) + flag_off);
+  }
+  if (!t->d_peers) SB_CUDA(cudaMalloc(&t->d_peers, sizeof(P2PPeers)));
+  SB_CUDA(cudaMemcpy(t->d_peers, &hp, sizeof(hp), cudaMemcpyHostToDevice));
+  for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);   // captured steps still carry the NCCL exchange
+  t->graphs.clear();
+  t->p2p_ready = true;
+  return SB_OK;
+}
+
 int sb_trainer_destroy(sb_trainer_t* t) {
   if (!t) return SB_OK;
   cudaSetDevice(t->net.device);
@@ -281,6 +344,9 @@ int sb_trainer_destroy(sb_trainer_t* t) {
   if (t->dsY) cudaFree(t->dsY);
   if (t->dsW) cudaFree(t->dsW);
   if (t->h_scal) cudaFreeHost(t->h_scal);
+  for (void* p : t->peer_bases) cudaIpcCloseMemHandle(p);
+  if (t->d_peers) cudaFree(t->d_peers);
+  if (t->xch) cudaFree(t->xch);
   t->net.destroy();
   delete t;
   return SB_OK;
@@ -353,12 +419,13 @@ int sb_trainer_apply_accumulated(sb_trainer_t* t) {
   SB_CUDA(cudaSetDevice(n.device));
   ++t->global_step;
   const float gscale = 1.f / (static_cast<float>(t->world) * static_cast<float>(t->n_acc));
-  set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, nullptr, nullptr, nullptr, lr_for_step(t, t->global_step), gscale);
+  ++t->epoch;
+  set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, nullptr, nullptr, nullptr, lr_for_step(t, t->global_step), gscale, t->epoch);
   SB_CUDA(cudaGetLastError());
-  SB_TRY(enqueue_allreduce(t, t->acc));
-  SB_TRY(enqueue_optimizer(t, t->acc));
-  // keep the applied mean gradient readable through sb_trainer_get_grads, then clear the accumulator
+  // exchange + apply through the (IPC-exported) gradient buffer; it then holds the applied mean for sb_trainer_get_grads
   SB_CUDA(cudaMemcpyAsync(t->grad, t->acc, sizeof(float) * n.n_params, cudaMemcpyDeviceToDevice, n.stream));
+  SB_TRY(enqueue_allreduce(t, t->grad));
+  SB_TRY(enqueue_optimizer(t, t->grad));
   const long long np = n.n_params;
   scale_kernel<<<static_cast<unsigned>((np + 255) / 256), 256, 0, n.stream>>>(t->grad, n.desc, np);
   SB_CUDA(cudaGetLastError());
@@ -441,8 +508,9 @@ int sb_trainer_profile_step(sb_trainer_t* t, int64_t row_offset, int32_t rows, c
   SB_CUDA(cudaSetDevice(n.device));
   ++t->global_step;
   const float gscale = 1.f / static_cast<float>(t->world);
+  ++t->epoch;
   set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, t->dsX + row_offset * n.F, t->dsY + row_offset, t->dsW + row_offset,
-                                           lr_for_step(t, t->global_step), gscale);
+                                           lr_for_step(t, t->global_step), gscale, t->epoch);
   n.profiling = true;
   n.prof_events.clear(); n.prof_names.clear();
   n.launches = 0;

@@ -15,10 +15,12 @@ struct BatchDesc {
   const float* w;  // [rows]
   float lr_t;      // Adam: lr * sqrt(1-b2^t)/(1-b1^t); others: lr
   float gscale;    // 1/world (and 1/n_accumulated for the epoch-sync schedule)
+  unsigned int epoch;  // exchange round (flag value of the peer-memory all-reduce)
 };
 
-static __global__ void set_batch_kernel(BatchDesc* d, const float* X, const float* y, const float* w, float lr_t, float gscale) {
-  d->X = X; d->y = y; d->w = w; d->lr_t = lr_t; d->gscale = gscale;
+static __global__ void set_batch_kernel(BatchDesc* d, const float* X, const float* y, const float* w, float lr_t, float gscale,
+                                        unsigned int epoch = 0) {
+  d->X = X; d->y = y; d->w = w; d->lr_t = lr_t; d->gscale = gscale; d->epoch = epoch;
 }
 
 // step scalars (device): [0] = sum_i w_i * per-row loss, [1] = n_nz (count of non-zero weights)

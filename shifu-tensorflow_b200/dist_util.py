@@ -39,3 +39,21 @@ def shard_rows(n_rows: int, rank: int, world: int) -> np.ndarray:
 def shard_files(files: List[str], rank: int, world: int) -> List[str]:
     """round-robin file split across workers, like TrainingDataSet.java:65-82"""
     return [f for i, f in enumerate(files) if i % world == rank]
+
+
+def all_gather_bytes(dist, payload: bytes, world: int, device="cpu") -> List[bytes]:
+    """every rank contributes len(payload) bytes; returns the list in rank order (IPC handle exchange)"""
+    import torch
+    mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(device)
+    outs = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(outs, mine)
+    return [bytes(o.cpu().numpy().tobytes()) for o in outs]
+
+
+def enable_peer_exchange(dist, trainer, world: int, device="cpu") -> bool:
+    """switch a trainer from NCCL to the peer-memory all-reduce kernel (all ranks must call this)"""
+    if world <= 1:
+        return False
+    trainer.set_peer_handles(all_gather_bytes(dist, trainer.ipc_handle(), world, device))
+    dist.barrier()
+    return True

@@ -16,7 +16,7 @@ def _free_port():
     return p
 
 
-def _rank_main(rank, world, port, out_dir, precision):
+def _rank_main(rank, world, port, out_dir, precision, exchange="nccl"):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import torch.distributed as dist
@@ -29,6 +29,8 @@ def _rank_main(rank, world, port, out_dir, precision):
     params = so.xavier_init(net, 4)
     desc = sb.make_desc(96, [64, 32], net.acts, optimizer=so.OPT_MOMENTUM, learning_rate=0.1, max_batch=128, precision=precision)
     t = sb.Trainer(desc, device=rank, nccl_id=uid, rank=rank, world=world)
+    if exchange == "p2p":
+        du.enable_peer_exchange(dist, t, world)
     t.set_params(so.flatten_params(params))
     losses = []
     for s in range(3):
@@ -41,13 +43,14 @@ def _rank_main(rank, world, port, out_dir, precision):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
 @pytest.mark.parametrize("precision", [0, 1])
-def test_two_gpu_data_parallel_matches_oracle(sb, tmp_path, precision):
+def test_two_gpu_data_parallel_matches_oracle(sb, tmp_path, precision, exchange):
     if sb.capi.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
     world, port = 2, _free_port()
-    mp.spawn(_rank_main, args=(world, port, str(tmp_path), precision), nprocs=world, join=True)
+    mp.spawn(_rank_main, args=(world, port, str(tmp_path), precision, exchange), nprocs=world, join=True)
     r = [np.load(str(tmp_path / ("r%d.npz" % i))) for i in range(world)]
     np.testing.assert_array_equal(r[0]["theta"], r[1]["theta"])      # replicas stay bit-identical
     np.testing.assert_array_equal(r[0]["grads"], r[1]["grads"])
