@@ -78,16 +78,29 @@ allreduce_p2p_kernel(const P2PPeers* __restrict__ peers, const BatchDesc* __rest
   // ---- phase B ----
   const long long slice = n4 / world;
   const long long base = slice * rank;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < slice; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long e = (base + i) * 4;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int q = 0; q < world; ++q) {
-      const float4 v = ld_peer_f4(peers->grad[q] + e);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  constexpr int U = 4;  // independent float4 per rank in flight per thread (NVLink latency ~2-3 us: keep the pipe full)
+  for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < slice; i0 += stride * U) {
+    float4 acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < world; ++q) {       // fixed rank order -> every rank computes bit-identical sums
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = i0 + u * stride;
+        v[u] = (i < slice) ? ld_peer_f4(peers->grad[q] + (base + i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
     }
-#pragma unroll 4
-    for (int q = 0; q < world; ++q) *reinterpret_cast<float4*>(peers->grad[q] + e) = acc;
+    for (int q = 0; q < world; ++q) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = i0 + u * stride;
+        if (i < slice) *reinterpret_cast<float4*>(peers->grad[q] + (base + i) * 4) = acc[u];
+      }
+    }
   }
   // ---- phase C ----
   __threadfence_system();
