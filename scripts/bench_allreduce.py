@@ -10,11 +10,11 @@ from shifu_tensorflow_b200 import dist_util
 rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-uid = dist_util.broadcast_bytes(dist, sb.capi.nccl_unique_id, 128, rank, device="cuda")
 res = {}
 for name, (F, hidden) in {"cfg1": (1000, [512, 256, 128]), "cfg2": (2000, [1024, 512, 256])}.items():
     for exch in ("nccl", "p2p"):
         B = 128
+        uid = dist_util.broadcast_bytes(dist, sb.capi.nccl_unique_id, 128, rank, device="cuda")  # one id per communicator
         desc = sb.make_desc(F, hidden, [2, 2, 2], optimizer=sb.OPT_SGD, learning_rate=0.0, max_batch=B, precision=sb.PREC_BF16)
         t = sb.Trainer(desc, device=local, nccl_id=uid, rank=rank, world=world)
         if exch == "p2p":
