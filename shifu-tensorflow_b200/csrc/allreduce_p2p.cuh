@@ -130,12 +130,13 @@ allreduce_p2p_kernel(const P2PPeers* __restrict__ peers, const BatchDesc* __rest
 // the chunks it touches, so the HBM-bound optimizer of chunk c overlaps the NVLink-bound exchange of chunk c+1.
 // ------------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void wait_chunk(const P2PFlags* mine, int c, int world, unsigned int epoch) {
-  // called by one warp: lane q polls rank q's flag of chunk c
-  const int lane = threadIdx.x & 31;
-  if (lane < world) {
-    unsigned long long t0 = 0;
-    unsigned int spins = 0;
-    while (static_cast<int>(ld_acquire_sys(&mine->cdone[c][lane]) - epoch) < 0) {
+  // called by ONE thread per block: polls the ranks' flags of chunk c with back-off, so that ~100 waiting blocks do not
+  // hammer the cache line the peers have to write through NVLink
+  unsigned long long t0 = 0;
+  unsigned int spins = 0;
+  for (int q = 0; q < world; ++q) {
+    while (static_cast<int>(ld_acquire_sys(&mine->cdone[c][q]) - epoch) < 0) {
+      __nanosleep(400);
       if ((++spins & 0xFFFu) == 0) {
         const unsigned long long now = globaltimer_ns();
         if (t0 == 0) t0 = now;
@@ -143,7 +144,6 @@ __device__ __forceinline__ void wait_chunk(const P2PFlags* mine, int c, int worl
       }
     }
   }
-  __syncwarp();
 }
 
 static __global__ void __launch_bounds__(512)
@@ -205,7 +205,7 @@ exchange_opt_kernel(const P2PPeers* __restrict__ peers, const BatchDesc* __restr
     const OptWork wk = work[w];
     const int c_hi = static_cast<int>(((wk.off + wk.count - 1) / 4) / chunk4);
     if (c_hi > ready_upto) {
-      if (threadIdx.x < 32)
+      if (threadIdx.x == 0)
         for (int c = ready_upto + 1; c <= c_hi && c < SB_XCH_CHUNKS; ++c) wait_chunk(mine, c, world, epoch);
       __syncthreads();
       ready_upto = c_hi;
