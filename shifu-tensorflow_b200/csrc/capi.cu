@@ -120,8 +120,10 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind) {
   SB_TRY(bs);
   if (kind == G_STEP) {
     if (pipelined) return SB_OK;
-    static const bool no_fuse = getenv("SB_NO_FUSED_EXCHANGE") != nullptr;
-    if (t->world > 1 && t->p2p_ready && !n.profiling && !no_fuse) {
+    // opt-in: measured slower than exchange kernel + optimizer kernel (profiles/scaling_r01.md) - the per-chunk
+    // system-scope fences serialise the NVLink latency eight times
+    static const bool fuse = getenv("SB_FUSED_EXCHANGE") != nullptr;
+    if (t->world > 1 && t->p2p_ready && !n.profiling && fuse) {
       // K6 + K7 in one kernel: chunked two-shot exchange over peer memory with the optimizer of finished chunks
       // running on the remaining SMs
       int n_xch = n.num_sms * 2 / 5;
