@@ -72,38 +72,44 @@ __device__ __forceinline__ void wait_flags(const unsigned int* slots, int world,
   __syncthreads();
 }
 
-// n4 = number of float4 in the (padded) vector, a multiple of world.
+// n4 = number of float4 in the (padded) vector, a multiple of world.  W = compile-time upper bound of `world`
+// (2 / 4 / 8 / 16): ALL W x U remote loads of a thread are issued before the first add, so one NVLink round trip
+// (~2-3 us) is paid per pass instead of one per rank.
+template <int W>
 static __global__ void __launch_bounds__(512)
 allreduce_p2p_kernel(const P2PPeers* __restrict__ peers, const BatchDesc* __restrict__ desc, int rank, int world, long long n4) {
+  constexpr int U = (W <= 2) ? 8 : (W <= 4 ? 4 : (W <= 8 ? 2 : 1));   // W * U = 16 float4 (256 B) in flight per thread
   const unsigned int epoch = desc->epoch;
   P2PFlags* mine = peers->flags[rank];
   // ---- phase A ----
   if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(&peers->flags[threadIdx.x]->arrive[rank], epoch);
   wait_flags(mine->arrive, world, epoch);
   // ---- phase B ----
+  float* gp[W];
+#pragma unroll
+  for (int q = 0; q < W; ++q) gp[q] = peers->grad[q < world ? q : rank];
   const long long slice = n4 / world;
   const long long base = slice * rank;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  constexpr int U = 4;  // independent float4 per rank in flight per thread (NVLink latency ~2-3 us: keep the pipe full)
   for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < slice; i0 += stride * U) {
-    float4 acc[U];
+    float4 v[W][U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int q = 0; q < world; ++q) {       // fixed rank order -> every rank computes bit-identical sums
-      float4 v[U];
+    for (int q = 0; q < W; ++q)
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long i = i0 + u * stride;
-        v[u] = (i < slice) ? ld_peer_f4(peers->grad[q] + (base + i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[q][u] = (q < world && i < slice) ? ld_peer_f4(gp[q] + (base + i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
-    }
-    for (int q = 0; q < world; ++q) {
+    for (int u = 0; u < U; ++u) {
+      float4 acc = v[0][u];                 // fixed rank order 0..world-1 -> every rank computes bit-identical sums
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long i = i0 + u * stride;
-        if (i < slice) *reinterpret_cast<float4*>(peers->grad[q] + (base + i) * 4) = acc[u];
+      for (int q = 1; q < W; ++q) { acc.x += v[q][u].x; acc.y += v[q][u].y; acc.z += v[q][u].z; acc.w += v[q][u].w; }
+      const long long i = i0 + u * stride;
+      if (i < slice) {
+#pragma unroll
+        for (int q = 0; q < W; ++q)
+          if (q < world) *reinterpret_cast<float4*>(gp[q] + (base + i) * 4) = acc;
       }
     }
   }
@@ -120,7 +126,6 @@ allreduce_p2p_kernel(const P2PPeers* __restrict__ peers, const BatchDesc* __rest
     wait_flags(mine->done, world, epoch);
   }
 }
-
 
 // ------------------------------------------------------------------------------------------------------------------
 // Fused gradient exchange + optimizer (K6 + K7 in one persistent kernel).  The flat vector is cut into SB_XCH_CHUNKS

@@ -59,7 +59,11 @@ static int enqueue_allreduce(sb_trainer* t, float* buf, long long off = 0, long 
   if (count < 0) count = t->net.n_params;
   if (!st) st = t->net.stream;
   if (t->p2p_ready && buf == t->grad && off == 0 && count == t->net.n_params) {
-    allreduce_p2p_kernel<<<t->net.num_sms, 512, 0, st>>>(t->d_peers, t->net.desc, t->rank, t->world, t->xch_n4);
+    const int g = t->net.num_sms;
+    if (t->world <= 2) allreduce_p2p_kernel<2><<<g, 512, 0, st>>>(t->d_peers, t->net.desc, t->rank, t->world, t->xch_n4);
+    else if (t->world <= 4) allreduce_p2p_kernel<4><<<g, 512, 0, st>>>(t->d_peers, t->net.desc, t->rank, t->world, t->xch_n4);
+    else if (t->world <= 8) allreduce_p2p_kernel<8><<<g, 512, 0, st>>>(t->d_peers, t->net.desc, t->rank, t->world, t->xch_n4);
+    else allreduce_p2p_kernel<16><<<g, 512, 0, st>>>(t->d_peers, t->net.desc, t->rank, t->world, t->xch_n4);
     SB_CUDA(cudaGetLastError());
     return SB_OK;
   }
@@ -84,8 +88,9 @@ static int enqueue_optimizer(sb_trainer* t, const float* g, int w0 = 0, int w1 =
 static int enqueue_step_body(sb_trainer* t, int rows, int kind) {
   Net& n = t->net;
   SB_TRY(n.enqueue_load(rows, t->grad, n.n_params));   // also clears the gradient buffer and the step scalars
-  SB_TRY(n.enqueue_hidden_forward(rows));
-  SB_TRY(n.enqueue_out(rows, true, true, nullptr, t->grad));
+  bool fused_out = false;
+  SB_TRY(n.enqueue_hidden_forward(rows, t->grad, &fused_out));
+  if (!fused_out) SB_TRY(n.enqueue_out(rows, true, true, nullptr, t->grad));
   // Gradient exchange pipelined behind the backward pass: as soon as layer l's dW GEMM is enqueued (side stream), its
   // flat segment [W_l, b_l] (+ the output layer for l = L-1) is all-reduced and its optimizer update applied on the
   // comm stream while the remaining dA / dW GEMMs still run - the role SyncReplicasOptimizer's accumulator + apply
@@ -535,8 +540,9 @@ int sb_trainer_profile_step(sb_trainer_t* t, int64_t row_offset, int32_t rows, c
   {
     n.mark("start"); --n.launches;
     s = n.enqueue_load(rows, t->grad, n.n_params);
-    if (s == SB_OK) s = n.enqueue_hidden_forward(rows);
-    if (s == SB_OK) s = n.enqueue_out(rows, true, true, nullptr, t->grad);
+    bool fused_out = false;
+    if (s == SB_OK) s = n.enqueue_hidden_forward(rows, t->grad, &fused_out);
+    if (s == SB_OK && !fused_out) s = n.enqueue_out(rows, true, true, nullptr, t->grad);
     if (s == SB_OK) s = n.enqueue_backward(rows, t->grad);
     if (s == SB_OK) s = enqueue_allreduce(t, t->grad);
     if (s == SB_OK && t->world > 1) { n.mark("allreduce"); --n.launches; }

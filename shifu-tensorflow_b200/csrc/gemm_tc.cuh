@@ -14,6 +14,11 @@
 //   EPI_DW  : dW_l = A_{l-1}^T dZ_l  A = A_{l-1} [rows,in] MN-major, B = dZ_l [rows,out] MN-major; split-K over the
 //                                    batch, fp32 red.add into the flat gradient
 //   EPI_F32 : plain fp32 store (kernel-level parity test hook)
+//   EPI_FWD_OUT : last hidden layer of a TRAINING step, output layer fused into the epilogue (K2 + K3 + K4 + output
+//                 backward in one kernel; needs N = h_L <= BN so a CTA holds whole rows of A_L in TMEM):
+//                 pass 1  a = act(acc + bias), z = a . w_o + b_o, y_hat = sigmoid(z), loss term, d z_hat
+//                 pass 2  (accumulator re-read from TMEM) dZ_L = dz * w_o * act'(a) -> bf16, db_L / dw_o column sums,
+//                         db_o, loss sum.  A_L itself never goes to HBM.
 //
 // Two tile configurations (template CG):
 //   CG = 1 : one CTA owns a 128 x BN tile (tcgen05.mma.cta_group::1, M = 128)         - small / narrow problems
@@ -32,10 +37,11 @@
 #include <cuda.h>
 #include "common.cuh"
 #include "ptx.cuh"
+#include "kernels.cuh"
 
 namespace sb {
 
-enum { EPI_FWD = 0, EPI_DA = 1, EPI_DW = 2, EPI_F32 = 3 };
+enum { EPI_FWD = 0, EPI_DA = 1, EPI_DW = 2, EPI_F32 = 3, EPI_FWD_OUT = 4 };
 
 struct GemmTcParams {
   int M, N, K;
@@ -54,6 +60,13 @@ struct GemmTcParams {
   float* accum;  // [M, ld_acc] fp32
   int ld_acc;
   int acc_vec4;  // 1 if 16-byte aligned rows -> red.global.add.v4.f32
+  // EPI_FWD_OUT (output layer + loss + its backward, res/ssgd_monitor.py:121,129)
+  const float* wo;          // [N] output-layer weights (fp32)
+  const float* bo;          // [1]
+  const BatchDesc* desc;    // y, w of the current batch
+  float* scal;              // SCAL_LOSS_SUM / SCAL_NNZ
+  int loss;                 // sb_loss
+  float *g_wo, *g_bo, *g_bL;  // gradient slots: dw_o [N], db_o [1], db_L [N]
   unsigned long long* trace;  // debug: CTA 0 writes %globaltimer stamps of its pipeline milestones (nullable)
 };
 
@@ -71,7 +84,7 @@ struct GemmTcCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*epilogue scratch*/;
   static constexpr int EPI_WARPS = 8;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
@@ -252,6 +265,109 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (w == w_first && warp == 2 && lane == 0) stamp(6);  // first accumulator complete
       const int row = tm * TILE_M + static_cast<int>(rank) * BM + quarter * 32 + lane;  // output row of this thread
       const bool row_ok = row < p.M;
+      if constexpr (EPI == EPI_FWD_OUT) {
+        // ---------- fused output layer (tiles_n == 1: this CTA's TMEM holds complete rows of A_L) ----------
+        const uint32_t zs = bar_base + 8u * (2 * STAGES + 4) + 16u + static_cast<uint32_t>(it & 1) * 1024u;  // zpart[2][128]
+        const int rl = quarter * 32 + lane;
+        auto load_act = [&](int c, float (&v)[32]) {   // a = act(acc + bias) for chunk c; 0 beyond N
+          const int col0 = c * 32;
+          uint32_t raw[32];
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, raw);
+          tmem_ld_wait();
+          float b[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(raw[j]); b[j] = (col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f; }
+          switch (p.act) {
+            case SB_ACT_RELU: epi_fwd_chunk<SB_ACT_RELU>(v, b); break;
+            case SB_ACT_SIGMOID: epi_fwd_chunk<SB_ACT_SIGMOID>(v, b); break;
+            case SB_ACT_TANH: epi_fwd_chunk<SB_ACT_TANH>(v, b); break;
+            case SB_ACT_LEAKYRELU: epi_fwd_chunk<SB_ACT_LEAKYRELU>(v, b); break;
+            default: epi_fwd_chunk<SB_ACT_NONE>(v, b); break;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j >= p.N) v[j] = 0.f;
+        };
+        // pass 1: partial dot product of this thread's row with w_o over this warp's chunks
+        float zp = 0.f;
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += 2) {
+          if (c * 32 >= p.N) break;
+          float v[32];
+          load_act(c, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) zp = fmaf(v[j], (c * 32 + j < p.N) ? __ldg(p.wo + c * 32 + j) : 0.f, zp);
+        }
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(zs + static_cast<uint32_t>(half * 128 + rl) * 4u), "f"(zp) : "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
+        float z0, z1;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z0) : "r"(zs + static_cast<uint32_t>(rl) * 4u) : "memory");
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z1) : "r"(zs + static_cast<uint32_t>(128 + rl) * 4u) : "memory");
+        const float z = z0 + z1 + __ldg(p.bo);
+        float dz = 0.f, lossv = 0.f;
+        if (row_ok) {
+          const float nnz = p.scal[SCAL_NNZ];
+          const float inv_nnz = nnz > 0.f ? 1.f / nnz : 0.f;
+          const float yh = sigmoidf_stable(z);
+          const float y = __ldg(p.desc->y + row), wgt = __ldg(p.desc->w + row);
+          if (p.loss == SB_LOSS_MSE) {
+            const float d = yh - y;
+            lossv = wgt * d * d;
+            dz = 2.f * wgt * d * yh * (1.f - yh) * inv_nnz;
+          } else {
+            lossv = wgt * (fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z))));
+            dz = wgt * (yh - y) * inv_nnz;
+          }
+        }
+        if (half == 0) {
+          const float ls = warp_sum(lossv), ds = warp_sum(dz);
+          if (lane == 0) { atomicAdd(p.scal + SCAL_LOSS_SUM, ls); atomicAdd(p.g_bo, ds); }
+        }
+        // pass 2: rank-1 backward of the output layer through act'
+#pragma unroll 1
+        for (int c = half; c < BN / 32; c += 2) {
+          const int col0 = c * 32;
+          if (col0 >= p.N) break;
+          float v[32], g[32];
+          load_act(c, v);
+          switch (p.act) {
+#define SB_G(ACT) _Pragma("unroll") for (int j = 0; j < 32; ++j) \
+              g[j] = dz * ((col0 + j < p.N) ? __ldg(p.wo + col0 + j) : 0.f) * act_grad_from_out(v[j], ACT);
+            case SB_ACT_RELU: SB_G(SB_ACT_RELU) break;
+            case SB_ACT_SIGMOID: SB_G(SB_ACT_SIGMOID) break;
+            case SB_ACT_TANH: SB_G(SB_ACT_TANH) break;
+            case SB_ACT_LEAKYRELU: SB_G(SB_ACT_LEAKYRELU) break;
+            default: SB_G(SB_ACT_NONE) break;
+#undef SB_G
+          }
+          if (row_ok) {
+            __nv_bfloat16* op = p.out + static_cast<size_t>(row) * p.ld_out + col0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (col0 + q * 8 < p.ld_out) {
+                uint4 o;
+                o.x = pack_bf16x2(g[q * 8 + 0], g[q * 8 + 1]);
+                o.y = pack_bf16x2(g[q * 8 + 2], g[q * 8 + 3]);
+                o.z = pack_bf16x2(g[q * 8 + 4], g[q * 8 + 5]);
+                o.w = pack_bf16x2(g[q * 8 + 6], g[q * 8 + 7]);
+                *reinterpret_cast<uint4*>(op + q * 8) = o;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= dz;          // dz * a  -> dw_o contributions (0 for rows >= M)
+          const float sb_ = warp_colsum_32x32(g, lane);
+          const float sw_ = warp_colsum_32x32(v, lane);
+          if (col0 + lane < p.N) { red_add_f32(p.g_bL + col0 + lane, sb_); red_add_f32(p.g_wo + col0 + lane, sw_); }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
+          else mbar_arrive(tempty_bar(acc));
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         const int col0 = tn * BN + c * 32;

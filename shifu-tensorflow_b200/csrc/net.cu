@@ -133,6 +133,7 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
   training = training_;
   if (const char* e = getenv("SB_NO_PDL")) use_pdl = !(e[0] == '1');
   if (const char* e = getenv("SB_NO_FORK")) concurrent_bwd = !(e[0] == '1');
+  if (const char* e = getenv("SB_NO_FUSE_OUT")) fuse_out_layer = !(e[0] == '1');
   gemm_sms = num_sms;
   SB_CUDA(cudaSetDevice(device));
   SB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -229,6 +230,7 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
   // opt in to > 48 KB dynamic shared memory once, outside of any stream capture
   if (bf) {
     SB_TRY((set_gemm_tc_attrs<EPI_FWD, false, true>()));
+    SB_TRY((set_gemm_tc_attrs<EPI_FWD_OUT, false, true>()));
     SB_TRY((set_gemm_tc_attrs<EPI_DA, false, false>()));
     SB_TRY((set_gemm_tc_attrs<EPI_DW, true, true>()));
   }
@@ -281,7 +283,8 @@ int Net::enqueue_load(int rows, float* zero_buf, long long zero_n) {
   return SB_OK;
 }
 
-int Net::enqueue_hidden_forward(int rows) {
+int Net::enqueue_hidden_forward(int rows, float* grad, bool* fused_out) {
+  if (fused_out) *fused_out = false;
   for (int l = 0; l < L; ++l) {
     Layer& ly = layers[l];
     if (precision == SB_PREC_BF16) {
@@ -295,6 +298,26 @@ int Net::enqueue_hidden_forward(int rows) {
       p.M = rows; p.N = ly.out; p.K = ly.in;
       p.bias = theta + ly.b_off; p.act = ly.act;
       p.out = A[l]; p.ld_out = ly.ld_out;
+      if (l == L - 1 && grad != nullptr && fuse_out_layer && training && ly.out <= 256) {
+        // K2 + K3 + K4 + output backward in one kernel: one n-tile must cover the whole layer width
+        GemmPlan fp = pl;
+        fp.split_k = 1; fp.kb_per_split = (ly.in + 63) / 64;
+        if (ly.out <= 64) { fp.cg = 1; fp.bn = 64; }
+        else if (ly.out <= 128) { fp.cg = 1; fp.bn = 128; }
+        else { fp.cg = 2; fp.bn = 256; }
+        const int slots = gemm_sms / fp.cg;
+        const int tiles = (rows + 128 * fp.cg - 1) / (128 * fp.cg);
+        fp.grid = (tiles < slots ? tiles : slots) * fp.cg;
+        Layer& ol = layers[L];
+        p.out = dZ[l];
+        p.wo = theta + ol.w_off; p.bo = theta + ol.b_off;
+        p.desc = desc; p.scal = scal; p.loss = loss;
+        p.g_wo = grad + ol.w_off; p.g_bo = grad + ol.b_off; p.g_bL = grad + ly.b_off;
+        SB_TRY((launch_gemm_tc<EPI_FWD_OUT, false, true>(fp, ta, tb, p, stream, use_pdl)));
+        if (fused_out) *fused_out = true;
+        mark("gemm_fwd_out");
+        continue;
+      }
       SB_TRY((launch_gemm_tc<EPI_FWD, false, true>(pl, ta, tb, p, stream, use_pdl)));
     } else {
       GemmF32Params p = {};
