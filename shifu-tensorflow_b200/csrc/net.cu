@@ -298,13 +298,13 @@ int Net::enqueue_hidden_forward(int rows, float* grad, bool* fused_out) {
       p.M = rows; p.N = ly.out; p.K = ly.in;
       p.bias = theta + ly.b_off; p.act = ly.act;
       p.out = A[l]; p.ld_out = ly.ld_out;
-      if (l == L - 1 && grad != nullptr && fuse_out_layer && training && ly.out <= 256) {
+      if (l == L - 1 && grad != nullptr && fuse_out_layer && training && ly.out <= 128) {
         // K2 + K3 + K4 + output backward in one kernel: one n-tile must cover the whole layer width
         GemmPlan fp = pl;
         fp.split_k = 1; fp.kb_per_split = (ly.in + 63) / 64;
+        // (the 256-wide pair tile works too, but at h_L = 256 it measured slower than GEMM + out_layer kernel)
         if (ly.out <= 64) { fp.cg = 1; fp.bn = 64; }
-        else if (ly.out <= 128) { fp.cg = 1; fp.bn = 128; }
-        else { fp.cg = 2; fp.bn = 256; }
+        else { fp.cg = 1; fp.bn = 128; }
         const int slots = gemm_sms / fp.cg;
         const int tiles = (rows + 128 * fp.cg - 1) / (128 * fp.cg);
         fp.grid = (tiles < slots ? tiles : slots) * fp.cg;

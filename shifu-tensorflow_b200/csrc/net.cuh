@@ -103,7 +103,7 @@ struct Net {
   // forward through the hidden layers (A_0 = current batch -> A_L)
   int enqueue_load(int rows, float* zero_buf = nullptr, long long zero_n = 0);
   // grad != nullptr (training step): the last hidden layer's GEMM also runs the output layer, the loss and the output
-  // backward in its epilogue when h_L <= 256; *fused_out tells the caller whether enqueue_out is still needed
+  // backward in its epilogue when h_L <= 128; *fused_out tells the caller whether enqueue_out is still needed
   int enqueue_hidden_forward(int rows, float* grad = nullptr, bool* fused_out = nullptr);
   bool fuse_out_layer = true;
   int enqueue_out(int rows, bool do_loss, bool do_bwd, float* yhat_dst, float* grad);

@@ -21,7 +21,7 @@ def test_model_score_matches_oracle(sb, precision, tol):
     want = so.score_rows(net, params, X.astype(np.float64))
     assert np.abs(got - want).max() <= tol
     if precision == 1:   # bf16 mode: tight against the bf16-emulating oracle
-        yb = so.loss_and_grads_bf16(net, params, X, np.zeros((len(X), 1), np.float32), np.ones((len(X), 1), np.float32))[2]
+        yb = so.loss_and_grads_bf16(net, params, X, np.zeros((len(X), 1), np.float32), np.ones((len(X), 1), np.float32), fused_out=False)[2]
         assert np.abs(got - yb.ravel()).max() <= 1e-3   # one bf16 ulp flip of an activation moves a score by ~2e-4
     # compute(MLData): one row of doubles (TensorflowModel.java:53-94)
     r = m.score_row_f64(X[7].astype(np.float64))
