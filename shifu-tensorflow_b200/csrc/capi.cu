@@ -30,9 +30,11 @@ struct sb_trainer {
   long long global_step = 0;
   float* h_scal = nullptr;  // pinned [SCAL_COUNT]
   // HBM-resident training set
-  float *dsX = nullptr, *dsY = nullptr, *dsW = nullptr;
+  float *dsX = nullptr, *dsY = nullptr, *dsW = nullptr;   // dsX only in fp32 mode
+  __nv_bfloat16* dsXb = nullptr;                           // bf16 mode: the set in GEMM-operand form [ds_rows, ldF]
+  int* dsP = nullptr;                                      // prefix counts of non-zero weights [ds_rows + 1]
   long long ds_rows = 0;
-  std::map<std::pair<int, int>, cudaGraphExec_t> graphs;  // (rows, kind) -> captured step
+  std::map<std::pair<int, int>, cudaGraphExec_t> graphs;  // (rows, kind * 2 + from_resident) -> captured step
   std::map<int, int> kernels_per_step;
   // peer-memory gradient exchange (CUDA IPC): xch = [gradient (padded) | P2PFlags] in ONE exported allocation
   void* xch = nullptr;
@@ -85,9 +87,16 @@ static int enqueue_optimizer(sb_trainer* t, const float* g, int w0 = 0, int w1 =
 }
 
 // the body of one step as a sequence of stream operations (captured into a CUDA graph)
-static int enqueue_step_body(sb_trainer* t, int rows, int kind) {
+static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = false) {
   Net& n = t->net;
-  SB_TRY(n.enqueue_load(rows, t->grad, n.n_params));   // also clears the gradient buffer and the step scalars
+  struct Scope { Net& n; ~Scope() { n.from_resident = false; } } scope{n};
+  n.from_resident = resident;
+  if (resident) {
+    // no load kernel: the batch is read by TMA from the bf16 resident set; set_batch_kernel already published n_nz
+    SB_CUDA(cudaMemsetAsync(t->grad, 0, sizeof(float) * n.n_params, n.stream));
+  } else {
+    SB_TRY(n.enqueue_load(rows, t->grad, n.n_params));   // also clears the gradient buffer and the step scalars
+  }
   bool fused_out = false;
   SB_TRY(n.enqueue_hidden_forward(rows, t->grad, &fused_out));
   if (!fused_out) SB_TRY(n.enqueue_out(rows, true, true, nullptr, t->grad));
@@ -153,15 +162,15 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind) {
   return SB_OK;
 }
 
-static int get_graph(sb_trainer* t, int rows, int kind, cudaGraphExec_t* out) {
-  auto key = std::make_pair(rows, kind);
+static int get_graph(sb_trainer* t, int rows, int kind, bool resident, cudaGraphExec_t* out) {
+  auto key = std::make_pair(rows, kind * 2 + (resident ? 1 : 0));
   auto it = t->graphs.find(key);
   if (it != t->graphs.end()) { *out = it->second; return SB_OK; }
   Net& n = t->net;
   n.launches = 0;
   cudaGraph_t g = nullptr;
   SB_CUDA(cudaStreamBeginCapture(n.stream, cudaStreamCaptureModeThreadLocal));
-  int s = enqueue_step_body(t, rows, kind);
+  int s = enqueue_step_body(t, rows, kind, resident);
   cudaError_t e = cudaStreamEndCapture(n.stream, &g);
   if (s != SB_OK) { if (g) cudaGraphDestroy(g); return s; }
   SB_CHECK(e == cudaSuccess, SB_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
@@ -169,28 +178,32 @@ static int get_graph(sb_trainer* t, int rows, int kind, cudaGraphExec_t* out) {
   SB_CUDA(cudaGraphInstantiate(&ge, g, 0));
   cudaGraphDestroy(g);
   t->graphs[key] = ge;
-  if (kind == G_STEP) t->kernels_per_step[rows] = n.launches + 1;  // + set_batch_kernel
+  if (kind == G_STEP && (resident || !t->dsXb)) t->kernels_per_step[rows] = n.launches + 1;  // + set_batch_kernel
   *out = ge;
   return SB_OK;
 }
 
 // X, y, w are DEVICE pointers here
-static int run_step(sb_trainer* t, const float* X, const float* y, const float* w, int rows, int kind) {
+static int run_step(sb_trainer* t, const float* X, const float* y, const float* w, int rows, int kind, long long resident_row0 = -1) {
   Net& n = t->net;
   SB_CHECK(rows > 0 && rows <= n.max_batch, SB_ERR_INVALID, "rows=%d outside (0, max_batch=%d]", rows, n.max_batch);
   SB_CUDA(cudaSetDevice(n.device));
   static const bool no_graph = getenv("SB_NO_GRAPH") != nullptr;
+  const bool resident = resident_row0 >= 0 && t->dsXb != nullptr;
   cudaGraphExec_t ge = nullptr;
-  if (!no_graph) SB_TRY(get_graph(t, rows, kind, &ge));
+  if (!no_graph) SB_TRY(get_graph(t, rows, kind, resident, &ge));
   float lr_t = t->lr, gscale = 1.f / static_cast<float>(t->world);
   if (kind == G_STEP) {
     ++t->global_step;
     lr_t = lr_for_step(t, t->global_step);
   }
   if (kind == G_STEP) ++t->epoch;
-  set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, X, y, w ? w : n.ones, lr_t, gscale, t->epoch);
+  if (resident)
+    set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, nullptr, y, w, lr_t, gscale, t->epoch, static_cast<int>(resident_row0), t->dsP, rows, n.scal);
+  else
+    set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, X, y, w ? w : n.ones, lr_t, gscale, t->epoch);
   SB_CUDA(cudaGetLastError());
-  if (no_graph) SB_TRY(enqueue_step_body(t, rows, kind));
+  if (no_graph) SB_TRY(enqueue_step_body(t, rows, kind, resident));
   else SB_CUDA(cudaGraphLaunch(ge, n.stream));
   SB_CUDA(cudaMemcpyAsync(t->h_scal, n.scal, sizeof(float) * SCAL_COUNT, cudaMemcpyDeviceToHost, n.stream));
   if (kind == G_ACC) ++t->n_acc;
@@ -362,6 +375,8 @@ int sb_trainer_destroy(sb_trainer_t* t) {
   for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);
   if (t->comm) { NcclApi* api = nccl_api(); if (api) api->CommDestroy(t->comm); }
   if (t->dsX) cudaFree(t->dsX);
+  if (t->dsXb) cudaFree(t->dsXb);
+  if (t->dsP) cudaFree(t->dsP);
   if (t->dsY) cudaFree(t->dsY);
   if (t->dsW) cudaFree(t->dsW);
   if (t->h_scal) cudaFreeHost(t->h_scal);
@@ -459,21 +474,55 @@ int sb_trainer_apply_accumulated(sb_trainer_t* t) {
 
 int sb_trainer_load_dataset(sb_trainer_t* t, const float* X, const float* y, const float* w, int64_t n_rows) {
   SB_CHECK(t && X && y, SB_ERR_INVALID, "null argument");
-  SB_CHECK(n_rows > 0, SB_ERR_INVALID, "n_rows must be > 0");
+  SB_CHECK(n_rows > 0 && n_rows < (1ll << 31), SB_ERR_INVALID, "n_rows must be in (0, 2^31)");
   Net& n = t->net;
   SB_CUDA(cudaSetDevice(n.device));
   SB_CUDA(cudaStreamSynchronize(n.stream));
-  if (t->dsX) { cudaFree(t->dsX); cudaFree(t->dsY); cudaFree(t->dsW); t->dsX = t->dsY = t->dsW = nullptr; }
-  SB_CUDA(cudaMalloc(&t->dsX, sizeof(float) * n_rows * n.F));
+  for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);   // captured steps carry tensor maps of the old set
+  t->graphs.clear();
+  if (t->dsX) cudaFree(t->dsX);
+  if (t->dsXb) cudaFree(t->dsXb);
+  if (t->dsY) cudaFree(t->dsY);
+  if (t->dsW) cudaFree(t->dsW);
+  if (t->dsP) cudaFree(t->dsP);
+  t->dsX = t->dsY = t->dsW = nullptr; t->dsXb = nullptr; t->dsP = nullptr; t->ds_rows = 0;
   SB_CUDA(cudaMalloc(&t->dsY, sizeof(float) * n_rows));
   SB_CUDA(cudaMalloc(&t->dsW, sizeof(float) * n_rows));
-  SB_CUDA(cudaMemcpyAsync(t->dsX, X, sizeof(float) * n_rows * n.F, cudaMemcpyHostToDevice, n.stream));
   SB_CUDA(cudaMemcpyAsync(t->dsY, y, sizeof(float) * n_rows, cudaMemcpyHostToDevice, n.stream));
   if (w) {
     SB_CUDA(cudaMemcpyAsync(t->dsW, w, sizeof(float) * n_rows, cudaMemcpyHostToDevice, n.stream));
   } else {
     fill_kernel<<<static_cast<unsigned>((n_rows + 255) / 256), 256, 0, n.stream>>>(t->dsW, 1.f, n_rows);
     SB_CUDA(cudaGetLastError());
+  }
+  if (n.precision == SB_PREC_BF16) {
+    // keep the set in HBM in the form the layer-0 GEMMs consume (bf16, row pitch ldF): converted once here, read by
+    // TMA every step.  Converted through a bounded fp32 window so a 100+ GB set never needs a second full copy.
+    SB_CUDA(cudaMalloc(&t->dsXb, sizeof(__nv_bfloat16) * static_cast<size_t>(n_rows) * n.ldF));
+    SB_CUDA(cudaMemsetAsync(t->dsXb, 0, sizeof(__nv_bfloat16) * static_cast<size_t>(n_rows) * n.ldF, n.stream));
+    const int64_t win = 32768;
+    float* tmp = nullptr;
+    SB_CUDA(cudaMalloc(&tmp, sizeof(float) * static_cast<size_t>(win < n_rows ? win : n_rows) * n.F));
+    for (int64_t r0 = 0; r0 < n_rows; r0 += win) {
+      const int64_t c = n_rows - r0 < win ? n_rows - r0 : win;
+      SB_CUDA(cudaMemcpyAsync(tmp, X + r0 * n.F, sizeof(float) * c * n.F, cudaMemcpyHostToDevice, n.stream));
+      cast_bf16_kernel<<<static_cast<unsigned>((c * n.F + 255) / 256), 256, 0, n.stream>>>(tmp, static_cast<int>(c), n.F,
+                                                                                           t->dsXb + r0 * n.ldF, n.ldF);
+      SB_CUDA(cudaGetLastError());
+      SB_CUDA(cudaStreamSynchronize(n.stream));   // X may be pageable: the window is reused
+    }
+    cudaFree(tmp);
+    std::vector<int> prefix(static_cast<size_t>(n_rows) + 1);
+    prefix[0] = 0;
+    for (int64_t i = 0; i < n_rows; ++i) prefix[i + 1] = prefix[i] + ((w == nullptr || w[i] != 0.f) ? 1 : 0);
+    SB_CUDA(cudaMalloc(&t->dsP, sizeof(int) * (n_rows + 1)));
+    SB_CUDA(cudaMemcpyAsync(t->dsP, prefix.data(), sizeof(int) * (n_rows + 1), cudaMemcpyHostToDevice, n.stream));
+    SB_CUDA(cudaStreamSynchronize(n.stream));
+    n.resident_Xb = t->dsXb;
+    n.resident_rows = n_rows;
+  } else {
+    SB_CUDA(cudaMalloc(&t->dsX, sizeof(float) * n_rows * n.F));
+    SB_CUDA(cudaMemcpyAsync(t->dsX, X, sizeof(float) * n_rows * n.F, cudaMemcpyHostToDevice, n.stream));
   }
   SB_CUDA(cudaStreamSynchronize(n.stream));
   t->ds_rows = n_rows;
@@ -482,11 +531,12 @@ int sb_trainer_load_dataset(sb_trainer_t* t, const float* X, const float* y, con
 
 static int resident_step(sb_trainer_t* t, int64_t row_offset, int32_t rows, int kind) {
   SB_CHECK(t, SB_ERR_INVALID, "null trainer");
-  SB_CHECK(t->dsX, SB_ERR_STATE, "no resident dataset loaded");
+  SB_CHECK(t->ds_rows > 0, SB_ERR_STATE, "no resident dataset loaded");
   SB_CHECK(row_offset >= 0 && rows > 0 && row_offset + rows <= t->ds_rows, SB_ERR_INVALID,
            "rows [%lld, %lld) outside the resident set of %lld rows", (long long)row_offset, (long long)(row_offset + rows),
            (long long)t->ds_rows);
-  return run_step(t, t->dsX + row_offset * t->net.F, t->dsY + row_offset, t->dsW + row_offset, rows, kind);
+  return run_step(t, t->dsX ? t->dsX + row_offset * t->net.F : nullptr, t->dsY + row_offset, t->dsW + row_offset, rows, kind,
+                  row_offset);
 }
 
 int sb_trainer_step_resident(sb_trainer_t* t, int64_t row_offset, int32_t rows, float* loss_out) {
@@ -514,7 +564,7 @@ void* sb_trainer_stream(sb_trainer_t* t) { return t ? reinterpret_cast<void*>(t-
 int sb_trainer_kernels_per_step(sb_trainer_t* t, int32_t rows) {
   SB_CHECK(t, SB_ERR_INVALID, "null trainer");
   cudaGraphExec_t ge;
-  SB_TRY(get_graph(t, rows, G_STEP, &ge));
+  SB_TRY(get_graph(t, rows, G_STEP, t->dsXb != nullptr, &ge));
   return t->kernels_per_step[rows];
 }
 
@@ -523,23 +573,30 @@ int sb_trainer_kernels_per_step(sb_trainer_t* t, int32_t rows) {
 int sb_trainer_profile_step(sb_trainer_t* t, int64_t row_offset, int32_t rows, char* names, int32_t names_cap, float* ms,
                             int32_t cap, int32_t* n_out) {
   SB_CHECK(t && ms && n_out, SB_ERR_INVALID, "null argument");
-  SB_CHECK(t->dsX, SB_ERR_STATE, "no resident dataset loaded");
+  SB_CHECK(t->ds_rows > 0, SB_ERR_STATE, "no resident dataset loaded");
   SB_CHECK(row_offset >= 0 && rows > 0 && rows <= t->net.max_batch && row_offset + rows <= t->ds_rows, SB_ERR_INVALID, "bad row range");
   Net& n = t->net;
   SB_CUDA(cudaSetDevice(n.device));
   ++t->global_step;
   const float gscale = 1.f / static_cast<float>(t->world);
   ++t->epoch;
-  set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, t->dsX + row_offset * n.F, t->dsY + row_offset, t->dsW + row_offset,
-                                           lr_for_step(t, t->global_step), gscale, t->epoch);
+  const bool resident = t->dsXb != nullptr;
+  if (resident)
+    set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, nullptr, t->dsY + row_offset, t->dsW + row_offset, lr_for_step(t, t->global_step),
+                                             gscale, t->epoch, static_cast<int>(row_offset), t->dsP, rows, n.scal);
+  else
+    set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, t->dsX + row_offset * n.F, t->dsY + row_offset, t->dsW + row_offset,
+                                             lr_for_step(t, t->global_step), gscale, t->epoch);
   n.profiling = true;
   n.prof_events.clear(); n.prof_names.clear();
   n.launches = 0;
   // the two memsets of the step body run before the start marker so they are not charged to load_batch
   int s = SB_OK;
   {
+    n.from_resident = resident;
+    if (resident) s = (cudaMemsetAsync(t->grad, 0, sizeof(float) * n.n_params, n.stream) == cudaSuccess) ? SB_OK : SB_ERR_CUDA;
     n.mark("start"); --n.launches;
-    s = n.enqueue_load(rows, t->grad, n.n_params);
+    if (!resident) s = n.enqueue_load(rows, t->grad, n.n_params);
     bool fused_out = false;
     if (s == SB_OK) s = n.enqueue_hidden_forward(rows, t->grad, &fused_out);
     if (s == SB_OK && !fused_out) s = n.enqueue_out(rows, true, true, nullptr, t->grad);
@@ -549,6 +606,7 @@ int sb_trainer_profile_step(sb_trainer_t* t, int64_t row_offset, int32_t rows, c
     if (s == SB_OK) s = enqueue_optimizer(t, t->grad);
   }
   n.profiling = false;
+  n.from_resident = false;
   cudaError_t e = cudaStreamSynchronize(n.stream);
   int cnt = 0;
   std::string joined;

@@ -67,6 +67,7 @@ struct GemmTcParams {
   float* scal;              // SCAL_LOSS_SUM / SCAL_NNZ
   int loss;                 // sb_loss
   float *g_wo, *g_bo, *g_bL;  // gradient slots: dw_o [N], db_o [1], db_L [N]
+  const BatchDesc* a_rows;  // non-null: operand A lives in the HBM-resident set; add a_rows->row0 to its row coordinate
   unsigned long long* trace;  // debug: CTA 0 writes %globaltimer stamps of its pipeline milestones (nullable)
 };
 
@@ -173,6 +174,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      const int a_row0 = (p.a_rows != nullptr) ? p.a_rows->row0 : 0;  // batch position inside the resident set
       for (int w = w_first; w < n_work; w += w_step) {
         const int tile = w % n_tiles, ks = w / n_tiles;
         const int tm = tile / tiles_n, tn = tile % tiles_n;
@@ -191,9 +193,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if constexpr (A_MN) {
 #pragma unroll
             for (int i = 0; i < BM / 64; ++i)  // 64(MN) x 64(K) boxes, 8 KB each, side by side along MN
-              load(smem_a(stage) + i * 8192, &tmA, m0 + i * 64, kb * BK);
+              load(smem_a(stage) + i * 8192, &tmA, m0 + i * 64, kb * BK + a_row0);   // rows of the set = K here
           } else {
-            load(smem_a(stage), &tmA, kb * BK, m0);
+            load(smem_a(stage), &tmA, kb * BK, m0 + a_row0);
           }
           if constexpr (B_MN) {
 #pragma unroll

@@ -16,11 +16,20 @@ struct BatchDesc {
   float lr_t;      // Adam: lr * sqrt(1-b2^t)/(1-b1^t); others: lr
   float gscale;    // 1/world (and 1/n_accumulated for the epoch-sync schedule)
   unsigned int epoch;  // exchange round (flag value of the peer-memory all-reduce)
+  int row0;            // first row of the batch inside the bf16 HBM-resident set (TMA row-coordinate offset)
 };
 
+// nz_prefix != nullptr (bf16 resident set): the batch is consumed by TMA straight from the resident set, there is no
+// load kernel, so this kernel also publishes n_nz = #{w != 0 in the batch} from the prefix counts built at load time
+// and clears the loss accumulator.
 static __global__ void set_batch_kernel(BatchDesc* d, const float* X, const float* y, const float* w, float lr_t, float gscale,
-                                        unsigned int epoch = 0) {
-  d->X = X; d->y = y; d->w = w; d->lr_t = lr_t; d->gscale = gscale; d->epoch = epoch;
+                                        unsigned int epoch = 0, int row0 = 0, const int* nz_prefix = nullptr, int rows = 0,
+                                        float* scal = nullptr) {
+  d->X = X; d->y = y; d->w = w; d->lr_t = lr_t; d->gscale = gscale; d->epoch = epoch; d->row0 = row0;
+  if (nz_prefix != nullptr) {
+    scal[1] = static_cast<float>(nz_prefix[row0 + rows] - nz_prefix[row0]);  // SCAL_NNZ
+    scal[0] = 0.f;                                                           // SCAL_LOSS_SUM
+  }
 }
 
 // step scalars (device): [0] = sum_i w_i * per-row loss, [1] = n_nz (count of non-zero weights)

@@ -291,13 +291,15 @@ int Net::enqueue_hidden_forward(int rows, float* grad, bool* fused_out) {
       // Z = A_{l-1}[rows,in] (K-major) x W_l[in,out] (MN-major B operand: n contiguous)
       const GemmPlan pl = plan_gemm(rows, ly.out, ly.in, gemm_sms, false);
       CUtensorMap ta, tb;
-      const __nv_bfloat16* src = (l == 0) ? Xb : A[l - 1];
-      SB_TRY(make_tmap_bf16(&ta, src, rows, ly.in, ly.ld_in, 128));
+      const bool res0 = (l == 0) && from_resident;
+      const __nv_bfloat16* src = (l == 0) ? (res0 ? resident_Xb : Xb) : A[l - 1];
+      SB_TRY(make_tmap_bf16(&ta, src, res0 ? static_cast<int>(resident_rows) : rows, ly.in, ly.ld_in, 128));
       SB_TRY(make_tmap_bf16(&tb, ly.Wn, ly.in, ly.out, ly.ld_out, 64));
       GemmTcParams p = {};
       p.M = rows; p.N = ly.out; p.K = ly.in;
       p.bias = theta + ly.b_off; p.act = ly.act;
       p.out = A[l]; p.ld_out = ly.ld_out;
+      p.a_rows = res0 ? desc : nullptr;
       if (l == L - 1 && grad != nullptr && fuse_out_layer && training && ly.out <= 128) {
         // K2 + K3 + K4 + output backward in one kernel: one n-tile must cover the whole layer width
         GemmPlan fp = pl;
@@ -382,15 +384,19 @@ int Net::enqueue_backward(int rows, float* grad) {
           SB_CUDA(cudaEventRecord(ev_dz[l], stream));
           SB_CUDA(cudaStreamWaitEvent(side, ev_dz[l], 0));
         }
-        const __nv_bfloat16* ap = (l == 0) ? Xb : A[l - 1];
+        const bool res0 = (l == 0) && from_resident;
+        const __nv_bfloat16* ap = (l == 0) ? (res0 ? resident_Xb : Xb) : A[l - 1];
         for (int r0 = 0; r0 < ly.in; r0 += chunk_rows) {
           const int r1 = (r0 + chunk_rows < ly.in) ? r0 + chunk_rows : ly.in;
           const GemmPlan pl = plan_gemm(r1 - r0, ly.out, rows, gemm_sms, true);
           CUtensorMap ta, tb;
-          SB_TRY(make_tmap_bf16(&ta, ap + r0, rows, r1 - r0, ly.ld_in, 64));
+          // resident set: rows past the batch end are real rows of other batches; the B operand (dZ_l, extent = rows) is
+          // zero-filled there, so they contribute nothing
+          SB_TRY(make_tmap_bf16(&ta, ap + r0, res0 ? static_cast<int>(resident_rows) : rows, r1 - r0, ly.ld_in, 64));
           SB_TRY(make_tmap_bf16(&tb, dZ[l], rows, ly.out, ly.ld_out, 64));
           GemmTcParams p = {};
           p.M = r1 - r0; p.N = ly.out; p.K = rows;
+          p.a_rows = res0 ? desc : nullptr;
           p.accum = grad + ly.w_off + static_cast<long long>(r0) * ly.out; p.ld_acc = ly.out;
           p.acc_vec4 = (ly.out % 4 == 0 && ly.w_off % 4 == 0) ? 1 : 0;
           SB_TRY((launch_gemm_tc<EPI_DW, true, true>(pl, ta, tb, p, fork ? side : stream, use_pdl && !fork)));

@@ -106,6 +106,11 @@ struct Net {
   // backward in its epilogue when h_L <= 128; *fused_out tells the caller whether enqueue_out is still needed
   int enqueue_hidden_forward(int rows, float* grad = nullptr, bool* fused_out = nullptr);
   bool fuse_out_layer = true;
+  // bf16 HBM-resident training set (trainer): when `from_resident` is set while enqueueing, layer 0's GEMMs read their A
+  // operand from it by TMA at row offset desc->row0 and no load_batch kernel runs
+  const __nv_bfloat16* resident_Xb = nullptr;
+  long long resident_rows = 0;
+  bool from_resident = false;
   int enqueue_out(int rows, bool do_loss, bool do_bwd, float* yhat_dst, float* grad);
   int enqueue_backward(int rows, float* grad);
 };

@@ -167,3 +167,28 @@ def test_epoch_sync_schedule_matches_syncreplicas_oracle(sb):
             t.apply_accumulated()
             assert np.abs(t.get_grads() - gsum / len(batches)).max() <= 1e-5
             assert np.abs(t.get_params() - theta).max() <= 1e-4
+
+
+@pytest.mark.gpu
+def test_bf16_resident_set_is_read_in_place(sb):
+    """bf16 mode keeps the resident set as bf16 in HBM and the layer-0 GEMMs TMA-load the batch from it at a row offset
+    (no load kernel).  Same rows fed from the host must give the same step; offsets / sizes deliberately ragged, the
+    last batch ends exactly at the end of the set, weights include zeros (n_nz comes from the prefix counts)."""
+    net, params, cfg, desc = make_pair(sb, 72, [40, 24], [so.ACT_RELU, so.ACT_TANH], optimizer=so.OPT_ADAM, max_batch=130,
+                                       precision=sb.PREC_BF16)
+    X, y, w = so.synth_batch(130 * 3 + 37, 72, 5, weights="mixed")
+    flat = so.flatten_params(params)
+    with sb.Trainer(desc) as a, sb.Trainer(desc) as b:
+        a.set_params(flat); b.set_params(flat)
+        b.load_dataset(X, y, w)
+        for off, n in [(0, 130), (130, 130), (263, 101), (390, 37), (3, 130)]:
+            la = a.step(X[off:off + n], y[off:off + n], w[off:off + n])
+            lb = b.step_resident(off, n)
+            assert abs(la - lb) <= 1e-6, (off, n, la, lb)
+            assert np.abs(a.get_grads() - b.get_grads()).max() <= 1e-6 * max(1.0, np.abs(a.get_grads()).max())
+        assert np.abs(a.get_params() - b.get_params()).max() <= 1e-6
+        # epoch-sync schedule over the resident set
+        la = a.accumulate(X[:130], y[:130], w[:130]); lb = b.accumulate_resident(0, 130)
+        assert abs(la - lb) <= 1e-6
+        a.apply_accumulated(); b.apply_accumulated()
+        assert np.abs(a.get_params() - b.get_params()).max() <= 1e-6
