@@ -265,14 +265,19 @@ optimizer_kernel(const OptWork* __restrict__ work, const BatchDesc* __restrict__
   pdl_launch_dependents();
   const OptWork wk = work[blockIdx.x];
   const float lr_t = desc->lr_t, gs = desc->gscale;
+  // HBM-bound: only touch the state streams the optimizer actually has (SGD: none, Momentum: s1, Adam/Adadelta: s1+s2)
+  const bool use_s1 = h.kind != SB_OPT_SGD;
+  const bool use_s2 = h.kind == SB_OPT_ADAM || h.kind == SB_OPT_ADADELTA;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int e = threadIdx.x + 256 * i;
     if (e < wk.count) {
       const long long idx = wk.off + e;
-      float a = s1[idx], b = s2[idx];
+      float a = use_s1 ? s1[idx] : 0.f, b = use_s2 ? s2[idx] : 0.f;
       const float t = opt_update(h, lr_t, theta[idx], grad[idx] * gs, a, b);
-      theta[idx] = t; s1[idx] = a; s2[idx] = b;
+      theta[idx] = t;
+      if (use_s1) s1[idx] = a;
+      if (use_s2) s2[idx] = b;
       if (wk.Wn != nullptr) {
         const long long m = idx - wk.mat_off;
         const long long r = m / wk.out_dim;
