@@ -175,6 +175,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default: min(steps, 50))")
+    ap.add_argument("--also", default="cfg2", help="second config measured on the resident leg only and reported under 'also' ('' = none)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -190,12 +191,10 @@ def main():
     import shifu_tensorflow_b200 as sb
 
     torch.cuda.set_device(local_rank)
-    nccl_id = None
+    from shifu_tensorflow_b200 import dist_util
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        from shifu_tensorflow_b200 import dist_util
-        nccl_id = dist_util.broadcast_bytes(dist, sb.capi.nccl_unique_id, sb.capi.SB_NCCL_ID_BYTES, rank, device="cuda")
 
     def barrier():
         if world > 1:
@@ -209,58 +208,7 @@ def main():
         dist.all_reduce(tns, op=dist.ReduceOp.MAX)
         return float(tns.item())
 
-    B, F, hidden = cfg["batch"], cfg["F"], cfg["hidden"]
     prec = sb.PREC_BF16 if args.precision == "bf16" else sb.PREC_FP32
-    desc = sb.make_desc(F, hidden, [sb.ACT_RELU] * len(hidden), loss=sb.LOSS_MSE, optimizer=OPT_ID[cfg["optimizer"]],
-                        learning_rate=cfg["lr"], max_batch=B, precision=prec)
-    t = sb.Trainer(desc, device=local_rank, nccl_id=nccl_id, rank=rank, world=world)
-    exchange = "none"
-    if world > 1:
-        exchange = "nccl"
-        if os.environ.get("SB_EXCHANGE", "p2p") == "p2p":
-            dist_util.enable_peer_exchange(dist, t, world, device="cuda")
-            exchange = "p2p (two-shot all-reduce kernel over CUDA-IPC peer memory)"
-    t.init_xavier(SEED)  # same seed on every rank -> identical replicas
-    X, y, w = synth_dataset(cfg, rank)
-    t.load_dataset(X, y, w)
-    nb = cfg["n_batches"]
-    stream = torch.cuda.ExternalStream(t.stream, device=torch.device("cuda", local_rank))
-
-    # ---------------- device-resident leg (value) ----------------
-    for i in range(args.warmup):
-        t.step_resident_async((i % nb) * B, B)
-    t.sync()
-    barrier()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
-        time.sleep(0.25)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    wall0 = time.perf_counter()
-    ev0.record(stream)
-    for i in range(args.steps):
-        t.step_resident_async(((args.warmup + i) % nb) * B, B)
-    ev1.record(stream)
-    t.sync()
-    barrier()
-    wall1 = time.perf_counter()
-    ms = max_over_ranks(ev0.elapsed_time(ev1))
-    clk = clocks.stop(wall0, wall1) if rank == 0 else None
-    last_loss = t.last_loss()
-    value = world * B * args.steps / (ms / 1e3)
-
-    # ---------------- per-kernel times for the roofline (live CUDA events, un-graphed steps) ----------------
-    prof = {}
-    n_prof = 5
-    for i in range(n_prof + 1):
-        rec = t.profile_step((i % nb) * B, B)
-        if i == 0:
-            continue  # first un-graphed step pays lazy module loading
-        for name, v in rec:
-            prof[name] = prof.get(name, 0.0) + v / n_prof
-    f_train, f_gemm, _ = flops_per_row(F, hidden)
-    gemm_ms = sum(v for k, v in prof.items() if k.startswith("gemm_"))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -268,60 +216,140 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
     peak_src = "measured burst (MEASURED_PEAKS.json bf16_tflops)" if peaks else "fallback 1.59 PF (B200_PROFILING.md)"
-    ach_tf = (B * f_gemm / (gemm_ms / 1e3)) / 1e12 if gemm_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                "traffic": None, "kernel": "gemm_tc_kernel (all hidden-layer fwd/dA/dW GEMMs of one step)",
-                "flops_per_launch_set": B * f_gemm, "kernel_ms_per_step": gemm_ms, "peak_source": peak_src,
-                "step_fraction_of_peak": (value / world * f_train / 1e12) / peak_tf,
-                "kernels_ms": {k: round(v, 5) for k, v in prof.items()}}
+    # DRAM bytes of the GEMM launches of one step, from the committed `ncu --set full` capture (dram__bytes_read+write
+    # summed over the 8 gemm_tc launches); algorithmic bytes (bf16 operands once + fp32 gradient) beside it
+    NCU_TRAFFIC = {"cfg1": 50.4e6, "cfg2": 200.8e6}
 
-    # ---------------- end-to-end leg: host (pinned) buffers through sb_trainer_step ----------------
-    e2e_steps = args.e2e_steps or min(args.steps, 50)
-    n_pin = 4
-    pin = []
-    for i in range(n_pin):
-        px = torch.empty((B, F), dtype=torch.float32).pin_memory()
-        py = torch.empty(B, dtype=torch.float32).pin_memory()
-        pw = torch.empty(B, dtype=torch.float32).pin_memory()
-        px.numpy()[:] = X[i * B:(i + 1) * B]; py.numpy()[:] = y[i * B:(i + 1) * B]; pw.numpy()[:] = w[i * B:(i + 1) * B]
-        pin.append((px.numpy(), py.numpy(), pw.numpy()))
-    for i in range(3):
-        t.step(*pin[i % n_pin])
-    barrier()
-    e0 = time.perf_counter()
-    for i in range(e2e_steps):
-        loss_h = t.step(*pin[i % n_pin])  # synchronous: H2D batch, step, D2H loss
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - e0)
-    e2e = {"value": world * B * e2e_steps / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": B * (F + 2) * 4,
-           "d2h_bytes_per_step": 16, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-           "timer": "host wall clock around synchronous sb_trainer_step calls (pinned host buffers), max over ranks"}
+    def measure(name, full):
+        c = CONFIGS[name]
+        B, F, hidden = c["batch"], c["F"], c["hidden"]
+        nb = c["n_batches"] if full else min(c["n_batches"], 16)
+        uid = None
+        if world > 1:
+            uid = dist_util.broadcast_bytes(dist, sb.capi.nccl_unique_id, sb.capi.SB_NCCL_ID_BYTES, rank, device="cuda")
+        desc = sb.make_desc(F, hidden, [sb.ACT_RELU] * len(hidden), loss=sb.LOSS_MSE, optimizer=OPT_ID[c["optimizer"]],
+                            learning_rate=c["lr"], max_batch=B, precision=prec)
+        t = sb.Trainer(desc, device=local_rank, nccl_id=uid, rank=rank, world=world)
+        exchange = "none"
+        if world > 1:
+            exchange = "nccl"
+            if os.environ.get("SB_EXCHANGE", "p2p") == "p2p":
+                dist_util.enable_peer_exchange(dist, t, world, device="cuda")
+                exchange = "p2p (two-shot all-reduce kernel over CUDA-IPC peer memory)"
+        t.init_xavier(SEED)  # same seed on every rank -> identical replicas
+        X, y, w = synth_dataset(c, rank, nb)
+        t.load_dataset(X, y, w)
+        stream = torch.cuda.ExternalStream(t.stream, device=torch.device("cuda", local_rank))
 
-    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle import shifu_oracle as so
-        from oracle.torch_cpu_worker import time_train
-        net = so.NetDesc(F, hidden, [so.ACT_RELU] * len(hidden))
-        nbc = min(4, nb)
-        batches = [(X[i * B:(i + 1) * B], y[i * B:(i + 1) * B], w[i * B:(i + 1) * B]) for i in range(nbc)]
-        r = time_train(net, so.xavier_init(net, 1), so.OptConfig(kind=OPT_ID[cfg["optimizer"]], lr=cfg["lr"]), batches,
-                       min_seconds=10.0, max_steps=400, threads=host_threads())
-        cpu = {"value": r["rows_per_sec"], "unit": "rows/s", "cores": r["cores"], "kind": "port",
-               "sample": "%d steps (%.1f s) of %s on torch-CPU fp32 = reference-equivalent worker loop (TF-1.x absent)" %
-                         (r["steps"], r["seconds"], args.config)}
+        # ---------------- device-resident leg (value) ----------------
+        for i in range(args.warmup):
+            t.step_resident_async((i % nb) * B, B)
+        t.sync()
+        barrier()
+        clocks = ClockSampler(local_rank)
+        if rank == 0 and full:
+            clocks.start()
+            time.sleep(0.25)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        wall0 = time.perf_counter()
+        ev0.record(stream)
+        for i in range(args.steps):
+            t.step_resident_async(((args.warmup + i) % nb) * B, B)
+        ev1.record(stream)
+        t.sync()
+        barrier()
+        wall1 = time.perf_counter()
+        ms = max_over_ranks(ev0.elapsed_time(ev1))
+        clk = clocks.stop(wall0, wall1) if (rank == 0 and full) else None
+        last_loss = t.last_loss()
+        value = world * B * args.steps / (ms / 1e3)
+
+        # ---------------- per-kernel times for the roofline (live CUDA events, un-graphed steps) ----------------
+        prof = {}
+        n_prof = 5
+        for i in range(n_prof + 1):
+            rec = t.profile_step((i % nb) * B, B)
+            if i == 0:
+                continue  # first un-graphed step pays lazy module loading
+            for kname, v in rec:
+                prof[kname] = prof.get(kname, 0.0) + v / n_prof
+        f_train, f_gemm, _ = flops_per_row(F, hidden)
+        gemm_ms = sum(v for k, v in prof.items() if k.startswith("gemm_"))
+        ach_tf = (B * f_gemm / (gemm_ms / 1e3)) / 1e12 if gemm_ms > 0 else 0.0
+        dims = [F] + list(hidden)
+        alg_bytes = sum(2 * (B * dims[i] + dims[i] * dims[i + 1] + B * dims[i + 1]) * 3 for i in range(len(hidden)))
+        roofline = {"bound": "tensor", "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                    "traffic": NCU_TRAFFIC.get(name), "traffic_source": "profiles/ncu_r01_%s_gemm_full.txt" % name,
+                    "algorithmic_operand_bytes": alg_bytes,
+                    "kernel": "gemm_tc_kernel (all hidden-layer fwd/dA/dW GEMMs of one step; tcgen05 + TMA)",
+                    "flops_per_launch_set": B * f_gemm, "kernel_ms_per_step": gemm_ms, "peak_source": peak_src,
+                    "step_fraction_of_peak": (value / world * f_train / 1e12) / peak_tf,
+                    "kernels_ms": {k: round(v, 5) for k, v in prof.items()}}
+        res = {"value": value, "ms_per_step": ms / args.steps, "roofline": roofline, "last_loss": last_loss, "clocks": clk,
+               "gradient_exchange": exchange, "gpu_launches": t.kernels_per_step(B) * args.steps,
+               "config": config_block(name, dict(c, n_batches=nb), world)}
+        if not full:
+            t.close()
+            return res
+
+        # ---------------- end-to-end leg: host (pinned) buffers through sb_trainer_step ----------------
+        e2e_steps = args.e2e_steps or min(args.steps, 50)
+        n_pin = 4
+        pin = []
+        for i in range(n_pin):
+            px = torch.empty((B, F), dtype=torch.float32).pin_memory()
+            py = torch.empty(B, dtype=torch.float32).pin_memory()
+            pw = torch.empty(B, dtype=torch.float32).pin_memory()
+            px.numpy()[:] = X[i * B:(i + 1) * B]; py.numpy()[:] = y[i * B:(i + 1) * B]; pw.numpy()[:] = w[i * B:(i + 1) * B]
+            pin.append((px.numpy(), py.numpy(), pw.numpy()))
+        for i in range(3):
+            t.step(*pin[i % n_pin])
+        barrier()
+        e0 = time.perf_counter()
+        for i in range(e2e_steps):
+            t.step(*pin[i % n_pin])  # synchronous: H2D batch, load/cast kernel, step, D2H loss
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - e0)
+        res["e2e"] = {"value": world * B * e2e_steps / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": B * (F + 2) * 4,
+                      "d2h_bytes_per_step": 16, "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+                      "timer": "host wall clock around synchronous sb_trainer_step calls (pinned host buffers), max over ranks"}
+
+        # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
+        res["cpu_baseline"] = None
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            from oracle import shifu_oracle as so
+            from oracle.torch_cpu_worker import time_train
+            net = so.NetDesc(F, hidden, [so.ACT_RELU] * len(hidden))
+            nbc = min(4, nb)
+            batches = [(X[i * B:(i + 1) * B], y[i * B:(i + 1) * B], w[i * B:(i + 1) * B]) for i in range(nbc)]
+            r = time_train(net, so.xavier_init(net, 1), so.OptConfig(kind=OPT_ID[c["optimizer"]], lr=c["lr"]), batches,
+                           min_seconds=10.0, max_steps=400, threads=host_threads())
+            res["cpu_baseline"] = {"value": r["rows_per_sec"], "unit": "rows/s", "cores": r["cores"], "kind": "port",
+                                   "sample": "%d steps (%.1f s) of %s on torch-CPU fp32 = reference-equivalent worker loop "
+                                             "(TF-1.x absent)" % (r["steps"], r["seconds"], name)}
+        t.close()
+        return res
+
+    main_res = measure(args.config, True)
+    # the data-parallel target of BASELINE.json is stated on cfg2 (2000 cols x 8192 rows/GPU): report it in the same line
+    second = None
+    if args.also and args.also != args.config:
+        second = measure(args.also, False)
 
     if rank == 0:
         out = {
-            "metric": "rows/sec tabular-DNN train", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if prec == sb.PREC_BF16 else "f32", "data": "synthetic",
-            "config": config_block(args.config, cfg, world),
-            "clocks": clk, "e2e": e2e, "gpu_launches": t.kernels_per_step(B) * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "last_loss": last_loss, "gradient_exchange": exchange,
+            "metric": "rows/sec tabular-DNN train", "value": main_res["value"], "unit": "rows/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == sb.PREC_BF16 else "f32", "data": "synthetic",
+            "config": main_res["config"], "clocks": main_res["clocks"], "e2e": main_res["e2e"],
+            "gpu_launches": main_res["gpu_launches"], "roofline": main_res["roofline"], "cpu_baseline": main_res["cpu_baseline"],
+            "last_loss": main_res["last_loss"], "gradient_exchange": main_res["gradient_exchange"],
         }
+        if second is not None:
+            out["also"] = {k: second[k] for k in ("value", "ms_per_step", "config", "roofline", "last_loss", "gpu_launches")}
+            out["also"]["unit"] = "rows/s"
         print(json.dumps(out), flush=True)
-    t.close()
     if world > 1:
         dist.destroy_process_group()
 
