@@ -736,10 +736,11 @@ struct sb_model {
   std::mutex mu;
 };
 
-static const int MODEL_CHUNK_ROWS = 16384;
+static const int MODEL_CHUNK_ROWS = 16384;        // fp32 parity mode
+static const int MODEL_CHUNK_ROWS_BF16 = 65536;   // bf16: bigger GEMMs per launch (workspace ~0.8 GB at 2000 cols)
 
 static int model_from_desc(sb_net_desc d, const float* flat, int64_t n, int device, sb_model_t** out) {
-  d.max_batch = MODEL_CHUNK_ROWS;
+  d.max_batch = d.precision == SB_PREC_BF16 ? MODEL_CHUNK_ROWS_BF16 : MODEL_CHUNK_ROWS;
   std::unique_ptr<sb_model> m(new sb_model());
   m->desc = d;
   int s = m->net.init(&d, device, false);
