@@ -215,109 +215,6 @@ out_layer_kernel(const OutLayerParams p) {
   }
 }
 
-// bf16 fast path of the output layer (h_L <= 1024, the common case): one warp per row, every lane owns 8-column
-// groups (16-byte loads / stores), the activations stay in registers between the dot product and the rank-1 backward,
-// column sums are kept per lane across the warp's rows and reduced through shared memory once per block.
-static __global__ void __launch_bounds__(256)
-out_layer_bf16_kernel(const OutLayerParams p) {
-  pdl_wait();
-  pdl_launch_dependents();
-  constexpr int MAXG = 4;                      // 8-column groups per lane: H <= 4 * 32 * 8 = 1024
-  extern __shared__ float col_acc[];           // [2][Hp]: db_L and dw_o partial sums of this block
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int Hp = (p.H + 7) & ~7;
-  for (int i = tid; i < 2 * Hp; i += 256) col_acc[i] = 0.f;
-  __syncthreads();
-  const __nv_bfloat16* __restrict__ A = reinterpret_cast<const __nv_bfloat16*>(p.A);
-  __nv_bfloat16* __restrict__ dZ = reinterpret_cast<__nv_bfloat16*>(p.dZ);
-  const float bo = __ldg(p.bo);
-  const float nnz = p.do_loss ? p.scal[SCAL_NNZ] : 1.f;
-  const float inv_nnz = nnz > 0.f ? 1.f / nnz : 0.f;
-  const int rows_per_block = 32;
-  const int r0 = blockIdx.x * rows_per_block;
-  float wo[MAXG][8];
-#pragma unroll
-  for (int g = 0; g < MAXG; ++g) {
-    const int c = (g * 32 + lane) * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) wo[g][j] = (c + j < p.H) ? __ldg(p.wo + c + j) : 0.f;
-  }
-  float s_db[MAXG][8], s_dw[MAXG][8];
-#pragma unroll
-  for (int g = 0; g < MAXG; ++g)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s_db[g][j] = 0.f; s_dw[g][j] = 0.f; }
-  float loss_part = 0.f, dbo_part = 0.f;
-  for (int rl = warp; rl < rows_per_block; rl += 8) {
-    const int r = r0 + rl;
-    if (r >= p.rows) break;
-    float a[MAXG][8];
-    float z = 0.f;
-#pragma unroll
-    for (int g = 0; g < MAXG; ++g) {
-      const int c = (g * 32 + lane) * 8;
-      uint4 raw = make_uint4(0, 0, 0, 0);
-      if (c < p.ldA && c < Hp) raw = __ldg(reinterpret_cast<const uint4*>(A + static_cast<size_t>(r) * p.ldA + c));
-      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        a[g][j] = (c + j < p.H) ? __bfloat162float(h[j]) : 0.f;
-        z = fmaf(a[g][j], wo[g][j], z);
-      }
-    }
-    z = warp_sum(z) + bo;
-    const float yh = sigmoidf_stable(z);
-    float dz = 0.f;
-    if (lane == 0 && p.yhat) p.yhat[r] = yh;
-    if (p.do_loss) {
-      const float y = __ldg(p.desc->y + r), w = __ldg(p.desc->w + r);
-      if (p.loss == SB_LOSS_MSE) {
-        const float d = yh - y;
-        if (lane == 0) loss_part += w * d * d;
-        dz = 2.f * w * d * yh * (1.f - yh) * inv_nnz;
-      } else {
-        if (lane == 0) loss_part += w * (fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z))));
-        dz = w * (yh - y) * inv_nnz;
-      }
-    }
-    if (!p.do_bwd) continue;
-    if (lane == 0) dbo_part += dz;
-#pragma unroll
-    for (int g = 0; g < MAXG; ++g) {
-      const int c = (g * 32 + lane) * 8;
-      if (c >= Hp) continue;
-      float gv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        gv[j] = (c + j < p.H) ? dz * wo[g][j] * act_grad_from_out(a[g][j], p.act) : 0.f;
-        s_db[g][j] += gv[j];
-        s_dw[g][j] = fmaf(dz, a[g][j], s_dw[g][j]);
-      }
-      if (c < p.ld_dZ) {
-        uint4 o;
-        o.x = pack_bf16x2(gv[0], gv[1]); o.y = pack_bf16x2(gv[2], gv[3]);
-        o.z = pack_bf16x2(gv[4], gv[5]); o.w = pack_bf16x2(gv[6], gv[7]);
-        *reinterpret_cast<uint4*>(dZ + static_cast<size_t>(r) * p.ld_dZ + c) = o;
-      }
-    }
-  }
-  if (p.do_loss && lane == 0 && loss_part != 0.f) atomicAdd(p.scal + SCAL_LOSS_SUM, loss_part);
-  if (!p.do_bwd) return;
-  if (lane == 0 && dbo_part != 0.f) atomicAdd(p.g_bo, dbo_part);
-#pragma unroll
-  for (int g = 0; g < MAXG; ++g) {
-    const int c = (g * 32 + lane) * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (c + j < p.H) { atomicAdd(&col_acc[c + j], s_db[g][j]); atomicAdd(&col_acc[Hp + c + j], s_dw[g][j]); }
-  }
-  __syncthreads();
-  for (int j = tid; j < p.H; j += 256) {
-    atomicAdd(p.g_bL + j, col_acc[j]);
-    atomicAdd(p.g_wo + j, col_acc[Hp + j]);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // K7 fused multi-tensor optimizer over the flat parameter vector (TF 1.x kernel forms: ApplyAdadelta
 // res/ssgd_monitor.py:138, ApplyAdam res/ssgd.py:57, ApplyGradientDescent res/ssgd_monitor_bk.py:81,

@@ -351,12 +351,7 @@ int Net::enqueue_out(int rows, bool do_loss, bool do_bwd, float* yhat_dst, float
   if (precision == SB_PREC_BF16) {
     p.A = A[L - 1]; p.ldA = hl.ld_out;
     if (do_bwd) { p.dZ = dZ[L - 1]; p.ld_dZ = hl.ld_out; }
-    if (hl.out <= 1024) {
-      const size_t smem = 2 * static_cast<size_t>((hl.out + 7) & ~7) * sizeof(float);
-      SB_TRY(launch(out_layer_bf16_kernel, dim3(grid), dim3(256), smem, stream, use_pdl, p));
-    } else {
-      SB_TRY(launch(out_layer_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, use_pdl, p));
-    }
+    SB_TRY(launch(out_layer_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, use_pdl, p));
   } else {
     p.A = Af[L - 1]; p.ldA = hl.out;
     if (do_bwd) { p.dZ = dZf[L - 1]; p.ld_dZ = hl.out; }
