@@ -117,6 +117,12 @@ int sb_trainer_get_grads(sb_trainer_t* t, float* flat, int64_t n);
 int sb_trainer_step(sb_trainer_t* t, const float* X, const float* y, const float* w, int32_t rows,
                     float* loss_out);
 
+/* Same step, pipelined: returns as soon as the work is queued.  The H2D copy of this batch goes through a second
+ * staging slot on a copy stream and overlaps the previous step's compute; the loss of the most recent step is read
+ * with sb_trainer_last_loss (which waits).  X / y / w must be pinned (sb_host_alloc or equivalent) for the copy to be
+ * truly asynchronous and must stay untouched until two further steps have been queued or sb_trainer_sync returned. */
+int sb_trainer_step_async(sb_trainer_t* t, const float* X, const float* y, const float* w, int32_t rows);
+
 /* Reference epoch-sync schedule (SyncReplicasOptimizer, ssgd_monitor.py:136-141): accumulate the
  * gradient of one mini-batch without updating; then apply the MEAN of the n accumulated
  * mini-batch gradients (averaged over ranks as well) as ONE optimizer update. */
@@ -183,6 +189,26 @@ int sb_model_score_row_f64(sb_model_t* m, const double* row, int32_t n, double* 
 int sb_model_score_device(sb_model_t* m, const float* dX, int64_t rows, float* dOut);
 int sb_model_sync(sb_model_t* m);
 void* sb_model_stream(sb_model_t* m);
+
+/* ---- text ingest: the per-cell float() loop of load_data (ssgd_monitor.py:387-419) on the GPU ----
+ * text: the gunzipped, delim-separated lines (must end with '\n'), HOST memory.  col_map[c] gives the role of text
+ * column c: >= 0 feature index (into X [rows, n_feat] row-major), SB_COL_TARGET, SB_COL_WEIGHT, SB_COL_SKIP; columns
+ * >= n_map are skipped.  y <- float(target cell); w <- weight cell with "negative -> 1.0", 1.0 when the line has no
+ * weight column.  Every value is float32(float64(text)) exactly as numpy feeds the reference's fp32 placeholders.
+ * Cells the exact fast path declines (> 15-19 significant digits, |exp| > 22, nan/inf, malformed) are NOT written:
+ * they are listed in flags[0..min(n_flags, flag_cap)) for the caller to resolve with its own float(); slot -100 marks
+ * a line whose number of feature cells / target cell is wrong. */
+#define SB_COL_SKIP (-1)
+#define SB_COL_TARGET (-2)
+#define SB_COL_WEIGHT (-3)
+typedef struct { int64_t row; int32_t slot; int32_t len; int64_t offset; } sb_cell_flag;
+int sb_text_parse(const char* text, int64_t n_bytes, char delim, const int32_t* col_map, int32_t n_map, int32_t n_feat,
+                  float* X, float* y, float* w, int64_t max_rows, int64_t* n_rows_out, sb_cell_flag* flags,
+                  int64_t flag_cap, int64_t* n_flags_out, int device);
+/* test hook: the same parsing state machine run on the host (CPU unit tests of the number parser; not a product path) */
+int sb_debug_text_parse_host(const char* text, int64_t n_bytes, char delim, const int32_t* col_map, int32_t n_map,
+                             int32_t n_feat, float* X, float* y, float* w, int64_t max_rows, int64_t* n_rows_out,
+                             sb_cell_flag* flags, int64_t flag_cap, int64_t* n_flags_out);
 
 /* ---- file-format helpers used by the host mirrors and tests ---- */
 /* write a SavedModel for an arbitrary MLP (host only, no GPU needed) */

@@ -53,6 +53,13 @@ def make_desc(n_features: int, hidden: Sequence[int], acts: Sequence[int], loss:
     return d
 
 
+class CellFlag(C.Structure):
+    _fields_ = [("row", C.c_int64), ("slot", C.c_int32), ("len", C.c_int32), ("offset", C.c_int64)]
+
+
+COL_SKIP, COL_TARGET, COL_WEIGHT = -1, -2, -3
+
+
 class ShifuB200Error(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__("[%d] %s" % (code, msg))
@@ -81,6 +88,7 @@ PROTOTYPES = {
     "sb_trainer_init_xavier": (C.c_int, [_vp, C.c_uint64]),
     "sb_trainer_get_grads": (C.c_int, [_vp, _f32p, C.c_int64]),
     "sb_trainer_step": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_int32, _f32p]),
+    "sb_trainer_step_async": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_int32]),
     "sb_trainer_accumulate": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_int32, _f32p]),
     "sb_trainer_apply_accumulated": (C.c_int, [_vp]),
     "sb_trainer_load_dataset": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_int64]),
@@ -108,6 +116,10 @@ PROTOTYPES = {
     "sb_model_score_device": (C.c_int, [_vp, _vp, C.c_int64, _vp]),
     "sb_model_sync": (C.c_int, [_vp]),
     "sb_model_stream": (C.c_void_p, [_vp]),
+    "sb_text_parse": (C.c_int, [_cp, C.c_int64, C.c_char, _P(C.c_int32), C.c_int32, C.c_int32, _f32p, _f32p, _f32p, C.c_int64,
+                                _P(C.c_int64), _P(CellFlag), C.c_int64, _P(C.c_int64), C.c_int]),
+    "sb_debug_text_parse_host": (C.c_int, [_cp, C.c_int64, C.c_char, _P(C.c_int32), C.c_int32, C.c_int32, _f32p, _f32p, _f32p,
+                                           C.c_int64, _P(C.c_int64), _P(CellFlag), C.c_int64, _P(C.c_int64)]),
     "sb_savedmodel_write": (C.c_int, [_cp, _P(NetDesc), _f32p, C.c_int64]),
     "sb_savedmodel_read": (C.c_int, [_cp, _cp, _cp, _cp, _P(NetDesc), _P(C.c_int32), _f32p, C.c_int64, _P(C.c_int64)]),
     "sb_debug_gemm_bf16": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
@@ -227,6 +239,11 @@ class Trainer:
         loss = C.c_float()
         check(lib().sb_trainer_step(self._h, _ptr(X), _ptr(y), _ptr(w), rows, C.byref(loss)))
         return float(loss.value)
+
+    def step_async(self, X, y, w=None) -> None:
+        """queue one step on HOST buffers without waiting (X/y/w should be pinned and not reused for two more steps)"""
+        X, y, w, rows = self._xyw(X, y, w)
+        check(lib().sb_trainer_step_async(self._h, _ptr(X), _ptr(y), _ptr(w), rows))
 
     def accumulate(self, X, y, w=None) -> float:
         X, y, w, rows = self._xyw(X, y, w)
@@ -415,3 +432,30 @@ def debug_gemm_bench(M: int, N: int, K: int, split_k: int = 1, a_mn: bool = Fals
     check(lib().sb_debug_gemm_bench(_ptr(A), _ptr(B), _ptr(D), M, N, K, split_k, int(a_mn), int(b_mn), cg, bn, device,
                                     iters, C.byref(ms)))
     return float(ms.value)
+
+
+def text_parse(text: bytes, col_map: Sequence[int], n_feat: int, delim: str = "|", device: int = 0, host_debug: bool = False,
+               flag_cap: int = 65536):
+    """GPU ingest of delimiter-separated numeric text -> (X [rows, n_feat] f32, y [rows] f32, w [rows] f32, flags).
+    flags = [(row, slot, offset, length)] for cells the exact fast path declined; the caller resolves them with float().
+    host_debug=True runs the identical state machine on the host (unit tests only)."""
+    if not text.endswith(b"\n"):
+        text = text + b"\n"
+    max_rows = text.count(b"\n")
+    cm = (C.c_int32 * len(col_map))(*[int(c) for c in col_map])
+    X = np.zeros((max_rows, n_feat), np.float32)
+    y = np.zeros(max_rows, np.float32)
+    w = np.ones(max_rows, np.float32)
+    flags = (CellFlag * flag_cap)()
+    n_rows, n_flags = C.c_int64(0), C.c_int64(0)
+    args = [text, len(text), delim.encode()[:1], cm, len(col_map), n_feat, _ptr(X), _ptr(y), _ptr(w), max_rows, C.byref(n_rows),
+            flags, flag_cap, C.byref(n_flags)]
+    if host_debug:
+        check(lib().sb_debug_text_parse_host(*args))
+    else:
+        check(lib().sb_text_parse(*args, device))
+    if n_flags.value > flag_cap:
+        raise ShifuB200Error(SB_ERR_FORMAT, "%d cells need the slow path, more than flag_cap=%d" % (n_flags.value, flag_cap))
+    fl = [(int(flags[i].row), int(flags[i].slot), int(flags[i].offset), int(flags[i].len)) for i in range(n_flags.value)]
+    n = n_rows.value
+    return X[:n], y[:n], w[:n], fl, text

@@ -44,6 +44,12 @@ struct sb_trainer {
   std::vector<void*> peer_bases;   // opened IPC mappings (to close)
   bool p2p_ready = false;
   unsigned int epoch = 0;
+  // pipelined host-buffer steps (sb_trainer_step_async): second staging slot + copy stream, so the H2D of batch i+1
+  // overlaps the compute of batch i
+  cudaStream_t copy_stream = nullptr;
+  float *st2X = nullptr, *st2Y = nullptr, *st2W = nullptr;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  unsigned long long async_steps = 0;
 };
 
 static float lr_for_step(const sb_trainer* t, long long step /*1-based*/) {
@@ -380,6 +386,11 @@ int sb_trainer_destroy(sb_trainer_t* t) {
   if (t->dsY) cudaFree(t->dsY);
   if (t->dsW) cudaFree(t->dsW);
   if (t->h_scal) cudaFreeHost(t->h_scal);
+  if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (t->ev_copied[i]) cudaEventDestroy(t->ev_copied[i]);
+    if (t->ev_consumed[i]) cudaEventDestroy(t->ev_consumed[i]);
+  }
   for (void* p : t->peer_bases) cudaIpcCloseMemHandle(p);
   if (t->d_peers) cudaFree(t->d_peers);
   if (t->xch) cudaFree(t->xch);
@@ -439,6 +450,39 @@ int sb_trainer_step(sb_trainer_t* t, const float* X, const float* y, const float
   SB_TRY(stage_host_batch(t, X, y, w, rows));
   SB_TRY(run_step(t, t->net.stX, t->net.stY, w ? t->net.stW : nullptr, rows, G_STEP));
   return finish_loss(t, loss_out);
+}
+
+int sb_trainer_step_async(sb_trainer_t* t, const float* X, const float* y, const float* w, int32_t rows) {
+  SB_CHECK(t && X && y, SB_ERR_INVALID, "null argument");
+  Net& n = t->net;
+  SB_CHECK(rows > 0 && rows <= n.max_batch, SB_ERR_INVALID, "rows=%d outside (0, max_batch=%d]", rows, n.max_batch);
+  SB_CUDA(cudaSetDevice(n.device));
+  if (!t->copy_stream) {
+    SB_CUDA(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+    SB_TRY(n.dalloc(&t->st2X, static_cast<size_t>(n.max_batch) * n.F));
+    SB_TRY(n.dalloc(&t->st2Y, n.max_batch));
+    SB_TRY(n.dalloc(&t->st2W, n.max_batch));
+    for (int i = 0; i < 2; ++i) {
+      SB_CUDA(cudaEventCreateWithFlags(&t->ev_copied[i], cudaEventDisableTiming));
+      SB_CUDA(cudaEventCreateWithFlags(&t->ev_consumed[i], cudaEventDisableTiming));
+    }
+    SB_CUDA(cudaStreamSynchronize(n.stream));   // the zero-fill of the new staging buffers ran on the main stream
+  }
+  const int slot = static_cast<int>(t->async_steps & 1);
+  float* sx = slot ? t->st2X : n.stX;
+  float* sy = slot ? t->st2Y : n.stY;
+  float* sw = slot ? t->st2W : n.stW;
+  // the slot is free once the step that consumed it two calls ago has finished
+  if (t->async_steps >= 2) SB_CUDA(cudaStreamWaitEvent(t->copy_stream, t->ev_consumed[slot], 0));
+  SB_CUDA(cudaMemcpyAsync(sx, X, sizeof(float) * rows * static_cast<size_t>(n.F), cudaMemcpyHostToDevice, t->copy_stream));
+  SB_CUDA(cudaMemcpyAsync(sy, y, sizeof(float) * rows, cudaMemcpyHostToDevice, t->copy_stream));
+  if (w) SB_CUDA(cudaMemcpyAsync(sw, w, sizeof(float) * rows, cudaMemcpyHostToDevice, t->copy_stream));
+  SB_CUDA(cudaEventRecord(t->ev_copied[slot], t->copy_stream));
+  SB_CUDA(cudaStreamWaitEvent(n.stream, t->ev_copied[slot], 0));
+  SB_TRY(run_step(t, sx, sy, w ? sw : nullptr, rows, G_STEP));
+  SB_CUDA(cudaEventRecord(t->ev_consumed[slot], n.stream));
+  ++t->async_steps;
+  return SB_OK;
 }
 
 int sb_trainer_accumulate(sb_trainer_t* t, const float* X, const float* y, const float* w, int32_t rows, float* loss_out) {

@@ -141,6 +141,49 @@ def load_data(data_file: str, feature_column_nums: Optional[List[int]], target_c
     return out
 
 
+def load_data_gpu(data_file: str, feature_column_nums: Optional[List[int]], target_column_num: int,
+                  sample_weight_column_num: int, valid_ratio: float, rng=random, device: int = 0) -> Dict[str, object]:
+    """load_data with the per-cell float() loop moved to the GPU (sb_text_parse): the host only gunzips and draws the
+    train/valid coin per line (same `rng.random() >= ratio -> train` stream, ssgd_monitor.py:396); cells the exact
+    fast path declines come back as a list and are resolved with float() here, exactly like the reference would.
+    Returns numpy arrays under the same keys as load_data."""
+    chunks = []
+    for current_file in data_file.split(","):
+        with open(current_file, 'rb') as f:
+            data = gzip.GzipFile(fileobj=io.BytesIO(f.read())).read()
+        if data and not data.endswith(b"\n"):
+            data += b"\n"
+        chunks.append(data)
+    text = b"".join(chunks)
+    first = text[:text.index(b"\n")].decode('utf-8').split(DELIMITER)
+    if feature_column_nums is None:
+        feature_column_nums = [c for c in range(len(first)) if c != target_column_num and
+                               not (sample_weight_column_num >= 0 and c == sample_weight_column_num)]
+    n_map = max([target_column_num, sample_weight_column_num] + list(feature_column_nums)) + 1
+    col_map = [capi.COL_SKIP] * n_map
+    for j, c in enumerate(feature_column_nums):
+        col_map[c] = j
+    col_map[target_column_num] = capi.COL_TARGET
+    if sample_weight_column_num >= 0:
+        col_map[sample_weight_column_num] = capi.COL_WEIGHT
+    X, y, w, flags, text = capi.text_parse(text, col_map, len(feature_column_nums), DELIMITER, device=device)
+    for row, slot, off, ln in flags:
+        if slot == -100:
+            raise ValueError("line %d does not have the selected columns" % row)
+        cell = text[off:off + ln].decode('utf-8')
+        v = float(cell.strip('\n'))        # ValueError here = the cell the reference would log and skip
+        if slot >= 0:
+            X[row, slot] = v
+        elif slot == capi.COL_TARGET:
+            y[row] = v
+        else:
+            w[row] = 1.0 if v < 0.0 else v
+    coins = np.fromiter((rng.random() >= valid_ratio for _ in range(len(y))), dtype=bool, count=len(y))
+    return {"train_data": X[coins], "train_target": y[coins].reshape(-1, 1), "train_data_sample_weight": w[coins].reshape(-1, 1),
+            "valid_data": X[~coins], "valid_target": y[~coins].reshape(-1, 1), "valid_data_sample_weight": w[~coins].reshape(-1, 1),
+            "feature_count": len(feature_column_nums)}
+
+
 def simple_save(trainer: capi.Trainer, export_dir: str) -> None:
     """SavedModel (tag serve, signature serving_default shifu_input_0 -> shifu_output_0) + GenericModelConfig.json
     (ssgd_monitor.py:457-490); an existing export_dir is replaced like tf.gfile.DeleteRecursively does."""
@@ -231,8 +274,13 @@ def main(_=None, env=None, rng=random) -> int:
     batch_size = int(params.get('MiniBatchs', BATCH_SIZE))
     per_batch_update = str(params.get('Schedule', 'epoch')).lower() == 'batch'
 
-    context = load_data(training_data_path, feature_column_nums, target_column_num, sample_weight_column_num,
-                        valid_ratio, rng=rng)
+    device = int(env.get("SB_DEVICE", env.get("LOCAL_RANK", "0")))
+    if env.get("SB_HOST_LOADER", "0") == "1":
+        context = load_data(training_data_path, feature_column_nums, target_column_num, sample_weight_column_num,
+                            valid_ratio, rng=rng)
+    else:
+        context = load_data_gpu(training_data_path, feature_column_nums, target_column_num, sample_weight_column_num,
+                                valid_ratio, rng=rng, device=device)
     train_x = np.asarray(context["train_data"], dtype=np.float32)
     if train_x.ndim != 2 or train_x.shape[1] != feature_count:
         raise ValueError("training rows do not all have %d parsable features" % feature_count)
@@ -250,7 +298,6 @@ def main(_=None, env=None, rng=random) -> int:
     max_rows = max(bounds[i + 1] - bounds[i] for i in range(total_batch))
 
     desc = model(feature_count, model_conf, max_rows)
-    device = int(env.get("SB_DEVICE", env.get("LOCAL_RANK", "0")))
     nccl_id = _exchange_nccl_id(cluster_spec, task_index, n_workers)
     trainer = capi.Trainer(desc, device=device, nccl_id=nccl_id, rank=task_index, world=n_workers)
     ckpt = os.path.join(tmp_model_path, "model.ckpt")

@@ -192,3 +192,20 @@ def test_bf16_resident_set_is_read_in_place(sb):
         assert abs(la - lb) <= 1e-6
         a.apply_accumulated(); b.apply_accumulated()
         assert np.abs(a.get_params() - b.get_params()).max() <= 1e-6
+
+
+@pytest.mark.gpu
+def test_step_async_pipeline_equals_synchronous_steps(sb):
+    """sb_trainer_step_async (double-buffered H2D on a copy stream) must produce exactly the synchronous trajectory"""
+    net, params, cfg, desc = make_pair(sb, 64, [48, 24], [so.ACT_RELU, so.ACT_TANH], optimizer=so.OPT_ADAM, max_batch=96,
+                                       precision=sb.PREC_FP32)
+    batches = [so.synth_batch(96 if s % 3 else 80, 64, 50 + s, weights="mixed") for s in range(7)]
+    flat = so.flatten_params(params)
+    with sb.Trainer(desc) as a, sb.Trainer(desc) as b:
+        a.set_params(flat); b.set_params(flat)
+        for X, y, w in batches:
+            la = a.step(X, y, w)
+            b.step_async(X, y, w)
+        assert abs(b.last_loss() - la) <= 1e-7
+        np.testing.assert_array_equal(a.get_params(), b.get_params())
+        assert b.global_step == 7
