@@ -17,6 +17,7 @@ run trainer_fp32 300 tests/test_trainer_parity.py -k "fp32 or resident or epoch"
 run trainer_bf16 300 tests/test_trainer_parity.py -k bf16
 run scorer 300 tests/test_scorer_parity.py
 run host_mirrors 300 tests/test_host_mirrors.py
+run text_ingest 300 tests/test_text_ingest.py
 run multi_gpu 300 tests/test_multi_gpu.py
 echo "=== smoke" | tee -a gpurun_out/suite.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "exit=$? $(tail -1 gpurun_out/smoke.log)" | tee -a gpurun_out/suite.log
