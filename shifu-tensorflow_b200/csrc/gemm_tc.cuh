@@ -271,14 +271,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ---------- fused output layer (tiles_n == 1: this CTA's TMEM holds complete rows of A_L) ----------
         const uint32_t zs = bar_base + 8u * (2 * STAGES + 4) + 16u + static_cast<uint32_t>(it & 1) * 1024u;  // zpart[2][128]
         const int rl = quarter * 32 + lane;
+        // 32 consecutive fp32 of a parameter vector: 8 x 16-byte loads when the chunk is complete and aligned
+        auto load_vec32 = [&](const float* base, int col0, float (&o)[32]) {
+          if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(base + col0) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(base + col0) + q);
+              o[4 * q] = t.x; o[4 * q + 1] = t.y; o[4 * q + 2] = t.z; o[4 * q + 3] = t.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = (col0 + j < p.N) ? __ldg(base + col0 + j) : 0.f;
+          }
+        };
         auto load_act = [&](int c, float (&v)[32]) {   // a = act(acc + bias) for chunk c; 0 beyond N
           const int col0 = c * 32;
           uint32_t raw[32];
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, raw);
           tmem_ld_wait();
           float b[32];
+          load_vec32(p.bias, col0, b);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(raw[j]); b[j] = (col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f; }
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
           switch (p.act) {
             case SB_ACT_RELU: epi_fwd_chunk<SB_ACT_RELU>(v, b); break;
             case SB_ACT_SIGMOID: epi_fwd_chunk<SB_ACT_SIGMOID>(v, b); break;
@@ -286,19 +300,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             case SB_ACT_LEAKYRELU: epi_fwd_chunk<SB_ACT_LEAKYRELU>(v, b); break;
             default: epi_fwd_chunk<SB_ACT_NONE>(v, b); break;
           }
+          if (col0 + 32 > p.N) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j >= p.N) v[j] = 0.f;
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j >= p.N) v[j] = 0.f;
+          }
         };
         // pass 1: partial dot product of this thread's row with w_o over this warp's chunks
         float zp = 0.f;
 #pragma unroll 1
         for (int c = half; c < BN / 32; c += 2) {
           if (c * 32 >= p.N) break;
-          float v[32];
+          float v[32], wv[32];
           load_act(c, v);
+          load_vec32(p.wo, c * 32, wv);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) zp = fmaf(v[j], (c * 32 + j < p.N) ? __ldg(p.wo + c * 32 + j) : 0.f, zp);
+          for (int j = 0; j < 32; ++j) zp = fmaf(v[j], wv[j], zp);
         }
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(zs + static_cast<uint32_t>(half * 128 + rl) * 4u), "f"(zp) : "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
@@ -332,9 +349,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (col0 >= p.N) break;
           float v[32], g[32];
           load_act(c, v);
+          load_vec32(p.wo, col0, g);   // g starts as w_o (0 beyond N)
           switch (p.act) {
-#define SB_G(ACT) _Pragma("unroll") for (int j = 0; j < 32; ++j) \
-              g[j] = dz * ((col0 + j < p.N) ? __ldg(p.wo + col0 + j) : 0.f) * act_grad_from_out(v[j], ACT);
+#define SB_G(ACT) _Pragma("unroll") for (int j = 0; j < 32; ++j) g[j] = dz * g[j] * act_grad_from_out(v[j], ACT);
             case SB_ACT_RELU: SB_G(SB_ACT_RELU) break;
             case SB_ACT_SIGMOID: SB_G(SB_ACT_SIGMOID) break;
             case SB_ACT_TANH: SB_G(SB_ACT_TANH) break;
