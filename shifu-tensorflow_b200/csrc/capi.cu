@@ -289,6 +289,11 @@ int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, 
   t->hyper.beta1 = desc->beta1; t->hyper.beta2 = desc->beta2; t->hyper.momentum = desc->momentum;
   int s = t->net.init(desc, device, true);
   if (s != SB_OK) { t->net.destroy(); return s; }
+  if (!getenv("SB_NO_CARVEOUT")) {   // see Net::init: no L1 / shared-memory re-partition between the kernels of a step
+    cudaFuncSetAttribute(set_batch_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(optimizer_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(axpy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
   Net& n = t->net;
   {
     // gradient + exchange flags in one allocation so that a single IPC handle exports both

@@ -233,6 +233,13 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
     SB_TRY((set_gemm_tc_attrs<EPI_FWD_OUT, false, true>()));
     SB_TRY((set_gemm_tc_attrs<EPI_DA, false, false>()));
     SB_TRY((set_gemm_tc_attrs<EPI_DW, true, true>()));
+    // keep the SMs in the GEMMs' shared-memory carve-out for every kernel of the step, so that no launch in the chain
+    // has to re-partition L1 / shared memory (experiment: SB_NO_CARVEOUT=1 restores the defaults)
+    if (!getenv("SB_NO_CARVEOUT")) {
+      const int co = cudaSharedmemCarveoutMaxShared;
+      cudaFuncSetAttribute(load_batch_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+      cudaFuncSetAttribute(out_layer_kernel<__nv_bfloat16>, cudaFuncAttributePreferredSharedMemoryCarveout, co);
+    }
   }
   return SB_OK;
 }
