@@ -22,16 +22,11 @@ namespace sb {
 
 #define SB_MAX_RANKS 16
 
-#define SB_XCH_CHUNKS 8
-
 struct P2PFlags {                      // lives right behind the gradient in the IPC-exported allocation
   unsigned int arrive[SB_MAX_RANKS];   // arrive[q] written by rank q
   unsigned int done[SB_MAX_RANKS];     // done[q]   written by rank q
   unsigned int blocks_done;            // local: grid-wide completion counter of phase B
   unsigned int pad[31];
-  // fused exchange+optimizer kernel: per-chunk completion
-  unsigned int cdone[SB_XCH_CHUNKS][SB_MAX_RANKS];   // cdone[c][q]: rank q has written its slice of chunk c everywhere
-  unsigned int cblocks[SB_XCH_CHUNKS];               // local: exchange blocks that finished chunk c
 };
 
 struct P2PPeers {                      // device-resident table, same order on every rank
@@ -124,109 +119,6 @@ allreduce_p2p_kernel(const P2PPeers* __restrict__ peers, const BatchDesc* __rest
     __threadfence_system();
     if (threadIdx.x < world) st_release_sys(&peers->flags[threadIdx.x]->done[rank], epoch);
     wait_flags(mine->done, world, epoch);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// Fused gradient exchange + optimizer (K6 + K7 in one persistent kernel).  The flat vector is cut into SB_XCH_CHUNKS
-// chunks.  Blocks [0, n_xch) run the two-shot exchange chunk by chunk (each rank reduces its slice of the chunk from all
-// peers over NVLink and stores the sum into every rank's buffer, then publishes cdone[c][rank]); blocks [n_xch, grid)
-// are optimizer workers: work item w (a run of <= 1024 parameters) is updated as soon as every rank has published
-// the chunks it touches, so the HBM-bound optimizer of chunk c overlaps the NVLink-bound exchange of chunk c+1.
-// ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void wait_chunk(const P2PFlags* mine, int c, int world, unsigned int epoch) {
-  // called by ONE thread per block: polls the ranks' flags of chunk c with back-off, so that ~100 waiting blocks do not
-  // hammer the cache line the peers have to write through NVLink
-  unsigned long long t0 = 0;
-  unsigned int spins = 0;
-  for (int q = 0; q < world; ++q) {
-    while (static_cast<int>(ld_acquire_sys(&mine->cdone[c][q]) - epoch) < 0) {
-      __nanosleep(400);
-      if ((++spins & 0xFFFu) == 0) {
-        const unsigned long long now = globaltimer_ns();
-        if (t0 == 0) t0 = now;
-        else if (now - t0 > 20000000000ull) __trap();
-      }
-    }
-  }
-}
-
-static __global__ void __launch_bounds__(512)
-exchange_opt_kernel(const P2PPeers* __restrict__ peers, const BatchDesc* __restrict__ desc, int rank, int world, long long n4,
-                    int n_xch, const OptWork* __restrict__ work, int n_work, OptHyper h, float* __restrict__ theta,
-                    float* __restrict__ s1, float* __restrict__ s2) {
-  const unsigned int epoch = desc->epoch;
-  P2PFlags* mine = peers->flags[rank];
-  const long long chunk4 = n4 / SB_XCH_CHUNKS;          // float4 per chunk (n4 is a multiple of CHUNKS * world)
-  if (static_cast<int>(blockIdx.x) < n_xch) {
-    // ================= exchange role =================
-    if (blockIdx.x == 0 && threadIdx.x < world) st_release_sys(&peers->flags[threadIdx.x]->arrive[rank], epoch);
-    wait_flags(mine->arrive, world, epoch);
-    const long long slice = chunk4 / world;
-    const long long stride = static_cast<long long>(n_xch) * blockDim.x;
-    constexpr int U = 4;
-    for (int c = 0; c < SB_XCH_CHUNKS; ++c) {
-      const long long base = c * chunk4 + slice * rank;
-      for (long long i0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i0 < slice; i0 += stride * U) {
-        float4 acc[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int q = 0; q < world; ++q) {
-          float4 v[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u * stride;
-            v[u] = (i < slice) ? ld_peer_f4(peers->grad[q] + (base + i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
-        }
-        for (int q = 0; q < world; ++q) {
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u * stride;
-            if (i < slice) *reinterpret_cast<float4*>(peers->grad[q] + (base + i) * 4) = acc[u];
-          }
-        }
-      }
-      __threadfence_system();
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        if (atomicAdd(&mine->cblocks[c], 1u) == static_cast<unsigned int>(n_xch) - 1) {
-          mine->cblocks[c] = 0;
-          __threadfence_system();
-          for (int q = 0; q < world; ++q) st_release_sys(&peers->flags[q]->cdone[c][rank], epoch);
-        }
-      }
-    }
-    return;
-  }
-  // ================= optimizer role =================
-  const float lr_t = desc->lr_t, gs = desc->gscale;
-  const float* __restrict__ grad = peers->grad[rank];
-  const int n_opt = gridDim.x - n_xch;
-  int ready_upto = -1;  // chunks [0, ready_upto] are known complete (monotone: work items are visited in order)
-  for (int w = blockIdx.x - n_xch; w < n_work; w += n_opt) {
-    const OptWork wk = work[w];
-    const int c_hi = static_cast<int>(((wk.off + wk.count - 1) / 4) / chunk4);
-    if (c_hi > ready_upto) {
-      if (threadIdx.x == 0)
-        for (int c = ready_upto + 1; c <= c_hi && c < SB_XCH_CHUNKS; ++c) wait_chunk(mine, c, world, epoch);
-      __syncthreads();
-      ready_upto = c_hi;
-    }
-    for (int e = threadIdx.x; e < wk.count; e += blockDim.x) {
-      const long long idx = wk.off + e;
-      float a = s1[idx], b = s2[idx];
-      const float g = __ldcv(grad + idx);   // written by peers over NVLink during this kernel: bypass L1
-      const float t = opt_update(h, lr_t, theta[idx], g * gs, a, b);
-      theta[idx] = t; s1[idx] = a; s2[idx] = b;
-      if (wk.Wn != nullptr) {
-        const long long m = idx - wk.mat_off;
-        const long long r = m / wk.out_dim;
-        wk.Wn[r * wk.ld_out + (m - r * wk.out_dim)] = __float2bfloat16_rn(t);
-      }
-    }
   }
 }
 

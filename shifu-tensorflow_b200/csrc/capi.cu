@@ -140,22 +140,6 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   SB_TRY(bs);
   if (kind == G_STEP) {
     if (pipelined) return SB_OK;
-    // opt-in: measured slower than exchange kernel + optimizer kernel (profiles/scaling_r01.md) - the per-chunk
-    // system-scope fences serialise the NVLink latency eight times
-    static const bool fuse = getenv("SB_FUSED_EXCHANGE") != nullptr;
-    if (t->world > 1 && t->p2p_ready && !n.profiling && fuse) {
-      // K6 + K7 in one kernel: chunked two-shot exchange over peer memory with the optimizer of finished chunks
-      // running on the remaining SMs
-      int n_xch = n.num_sms * 2 / 5;
-      if (const char* e = getenv("SB_XCH_BLOCKS")) n_xch = atoi(e);
-      if (n_xch < 1) n_xch = 1;
-      if (n_xch > n.num_sms - 8) n_xch = n.num_sms - 8;
-      exchange_opt_kernel<<<n.num_sms, 512, 0, n.stream>>>(t->d_peers, n.desc, t->rank, t->world, t->xch_n4, n_xch, n.work, n.n_work,
-                                                           t->hyper, n.theta, t->s1, t->s2);
-      SB_CUDA(cudaGetLastError());
-      n.mark("exchange_opt");
-      return SB_OK;
-    }
     SB_TRY(enqueue_allreduce(t, t->grad));
     if (t->world > 1 && n.profiling) { n.mark("allreduce"); --n.launches; }
     SB_TRY(enqueue_optimizer(t, t->grad));
@@ -297,8 +281,8 @@ int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, 
   Net& n = t->net;
   {
     // gradient + exchange flags in one allocation so that a single IPC handle exports both
-    const long long unit = 4ll * world * SB_XCH_CHUNKS;
-    t->xch_n4 = ((n.n_params + unit - 1) / unit) * world * SB_XCH_CHUNKS;   // float4 count, multiple of chunks * world
+    const long long unit = 4ll * world;
+    t->xch_n4 = ((n.n_params + unit - 1) / unit) * world;   // float4 count, a multiple of world (equal slices)
     const size_t bytes = static_cast<size_t>(t->xch_n4) * 16 + sizeof(P2PFlags);
     if (cudaMalloc(&t->xch, bytes) != cudaSuccess) { n.destroy(); return set_error(SB_ERR_CUDA, "cudaMalloc(exchange) failed"); }
     cudaMemset(t->xch, 0, bytes);
