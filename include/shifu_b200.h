@@ -234,6 +234,11 @@ int sb_debug_gemm_bf16_cfg(const float* A, const float* B, float* D, int32_t M, 
 
 /* micro-benchmark of one tile configuration: average device milliseconds per launch over `iters` back-to-back launches
  * (CUDA events on the launching stream, operands L2-warm) */
+/* Timeline of the last step (trainer created with SB_STEP_TRACE=1 in the environment): for each GEMM launch of the
+ * step, 16 %globaltimer stamps (ns) of its CTA 0: [0] entry, [1] setup done, [2] dependencies resolved, [3] first TMA
+ * issued, [4] first stage landed, [5] MMAs of the first tile issued, [6] first accumulator complete, [7] first
+ * epilogue done, [8] exit.  names = comma-separated kernel roles.  Measurement aid; no reference counterpart. */
+int sb_debug_step_trace(sb_trainer_t* t, uint64_t* stamps, int32_t cap_kernels, char* names, int32_t names_cap, int32_t* n_kernels);
 int sb_debug_gemm_bench(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k,
                         int32_t a_mn, int32_t b_mn, int32_t cfg_cg, int32_t cfg_bn, int device, int32_t iters,
                         float* ms_out);

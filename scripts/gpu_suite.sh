@@ -13,9 +13,10 @@ run() { # name, timeout, args...
 run gemm_identity 180 tests/test_gemm_tc.py -k identity
 run gemm_shapes 300 tests/test_gemm_tc.py -k matches
 run gemm_tiles 300 tests/test_gemm_tc.py -k every_tile
-run trainer_fp32 300 tests/test_trainer_parity.py -k "fp32 or resident or epoch"
+run trainer_fp32 300 tests/test_trainer_parity.py -k "fp32 or resident or epoch or async"
 run trainer_bf16 300 tests/test_trainer_parity.py -k bf16
 run scorer 300 tests/test_scorer_parity.py
+run full_size 600 tests/test_full_size_properties.py
 run host_mirrors 300 tests/test_host_mirrors.py
 run text_ingest 300 tests/test_text_ingest.py
 run multi_gpu 300 tests/test_multi_gpu.py

@@ -124,6 +124,7 @@ PROTOTYPES = {
     "sb_savedmodel_read": (C.c_int, [_cp, _cp, _cp, _cp, _P(NetDesc), _P(C.c_int32), _f32p, C.c_int64, _P(C.c_int64)]),
     "sb_debug_gemm_bf16": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
     "sb_debug_gemm_bf16_ex": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
+    "sb_debug_step_trace": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_int32)]),
     "sb_debug_gemm_bench": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                       C.c_int32, C.c_int32, C.c_int, C.c_int32, _f32p]),
     "sb_debug_gemm_bf16_cfg": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -311,6 +312,14 @@ class Trainer:
         check(lib().sb_trainer_predict(self._h, _ptr(X), X.shape[0], _ptr(out)))
         return out
 
+    def debug_step_trace(self):
+        """-> (names, stamps[k,16] uint64 ns) of the last step's GEMM launches (needs SB_STEP_TRACE=1 at creation)"""
+        buf = np.zeros((32, 16), np.uint64)
+        names = C.create_string_buffer(1024)
+        k = C.c_int32()
+        check(lib().sb_debug_step_trace(self._h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), 32, names, 1024, C.byref(k)))
+        return names.value.decode().split(","), buf[:k.value].copy()
+
     @property
     def global_step(self) -> int:
         return int(lib().sb_trainer_global_step(self._h))
@@ -354,6 +363,12 @@ class Model:
             self._h = None
 
     __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
     def score(self, X) -> np.ndarray:
         X = _f32(X)

@@ -28,7 +28,8 @@ struct sb_trainer {
   int n_acc = 0;
   float grad_out_scale = 1.f;  // what sb_trainer_get_grads multiplies the raw buffer by
   long long global_step = 0;
-  float* h_scal = nullptr;  // pinned [SCAL_COUNT]
+  float* h_scal = nullptr;  // pinned + mapped [SCAL_COUNT]: written by the tail kernel of every step
+  float* d_hscal = nullptr; // device-side alias of h_scal
   // HBM-resident training set
   float *dsX = nullptr, *dsY = nullptr, *dsW = nullptr;   // dsX only in fp32 mode
   __nv_bfloat16* dsXb = nullptr;                           // bf16 mode: the set in GEMM-operand form [ds_rows, ldF]
@@ -50,6 +51,14 @@ struct sb_trainer {
   float *st2X = nullptr, *st2Y = nullptr, *st2W = nullptr;
   cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   unsigned long long async_steps = 0;
+  // resident steps: the batch descriptor of step i+1 is written on `prep` while step i still runs (two descriptor /
+  // scalar pairs, one captured graph per pair), so set_batch_kernel leaves the critical path (-2.9 us per cfg1 step)
+  BatchDesc* descs[2] = {nullptr, nullptr};
+  float* scals[2] = {nullptr, nullptr};
+  cudaStream_t prep = nullptr;
+  cudaEvent_t ev_prep[2] = {nullptr, nullptr}, ev_pos[2] = {nullptr, nullptr};
+  unsigned long long prep_steps = 0;
+  bool have_pos = false;   // ev_pos[] of the previous step is valid (no other user of the descriptors in between)
 };
 
 static float lr_for_step(const sb_trainer* t, long long step /*1-based*/) {
@@ -80,26 +89,45 @@ static int enqueue_allreduce(sb_trainer* t, float* buf, long long off = 0, long 
   return SB_OK;
 }
 
-static int enqueue_optimizer(sb_trainer* t, const float* g, int w0 = 0, int w1 = -1, cudaStream_t st = nullptr) {
+static int enqueue_optimizer(sb_trainer* t, const float* g, int w0 = 0, int w1 = -1, cudaStream_t st = nullptr,
+                             bool publish_scalars = false, bool pdl = false) {
   Net& n = t->net;
   if (w1 < 0) w1 = n.n_work;
   if (!st) st = n.stream;
   if (w1 <= w0) return SB_OK;
-  // plain dependency, no PDL attribute (runs after a stream join / on the comm stream)
-  optimizer_kernel<<<w1 - w0, 256, 0, st>>>(n.work + w0, n.desc, t->hyper, n.theta, g, t->s1, t->s2);
-  SB_CUDA(cudaGetLastError());
+  // pdl = false: plain dependency (runs after a stream join / on the comm stream)
+  SB_TRY(n.launch(optimizer_kernel, dim3(static_cast<unsigned>(w1 - w0)), dim3(256), 0, st, pdl, n.work + w0, n.desc, t->hyper,
+                  n.theta, g, t->s1, t->s2, n.scal, publish_scalars ? t->d_hscal : static_cast<float*>(nullptr)));
   n.mark("optimizer");
   return SB_OK;
+}
+
+// SB_PIPELINE_AR=1 (opt-in): per-layer exchange + update on the comm stream; then no single tail kernel exists and the
+// step scalars are read back with a copy instead
+static bool step_is_pipelined(const sb_trainer* t, int kind) {
+  static const bool want_pipeline = getenv("SB_PIPELINE_AR") != nullptr;
+  const Net& n = t->net;
+  return want_pipeline && kind == G_STEP && n.concurrent_bwd && !n.profiling && n.side != nullptr &&
+         n.precision == SB_PREC_BF16;
 }
 
 // the body of one step as a sequence of stream operations (captured into a CUDA graph)
 static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = false) {
   Net& n = t->net;
-  struct Scope { Net& n; ~Scope() { n.from_resident = false; } } scope{n};
+  struct Scope { Net& n; ~Scope() { n.from_resident = false; n.zero_buf = nullptr; n.dw0_on_main = n.defer_join = false; } } scope{n};
   n.from_resident = resident;
+  n.trace_k = 0;
   if (resident) {
-    // no load kernel: the batch is read by TMA from the bf16 resident set; set_batch_kernel already published n_nz
-    SB_CUDA(cudaMemsetAsync(t->grad, 0, sizeof(float) * n.n_params, n.stream));
+    // no load kernel: the batch is read by TMA from the bf16 resident set; set_batch_kernel already published n_nz.
+    // The gradient buffer is first written by the last forward layer's epilogue, so with more than one hidden layer the
+    // layer-0 forward GEMM clears it (its epilogue warps idle until their first accumulator completes); a memset node
+    // at the head of the chain cost ~3 us per step.
+    if (n.L > 1) {
+      n.zero_buf = reinterpret_cast<float4*>(t->grad);   // cudaMalloc'ed, padded to xch_n4 float4
+      n.zero_n4 = t->xch_n4;
+    } else {
+      SB_CUDA(cudaMemsetAsync(t->grad, 0, sizeof(float) * n.n_params, n.stream));
+    }
   } else {
     SB_TRY(n.enqueue_load(rows, t->grad, n.n_params));   // also clears the gradient buffer and the step scalars
   }
@@ -113,9 +141,7 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   // Measured on 2x B200 (profiles/scaling_r01.md): with NCCL as the exchange, ONE all-reduce of the whole flat gradient
   // after the backward pass beats per-layer / per-chunk calls (each NCCL launch costs ~20-50 us and its CTAs evict
   // persistent GEMM CTAs), so the pipelined variant is opt-in (SB_PIPELINE_AR=1).
-  static const bool want_pipeline = getenv("SB_PIPELINE_AR") != nullptr;
-  const bool pipelined = want_pipeline && kind == G_STEP && n.concurrent_bwd && !n.profiling && n.side != nullptr &&
-                         n.precision == SB_PREC_BF16;
+  const bool pipelined = step_is_pipelined(t, kind);
   if (pipelined) {
     n.on_layer_grads = [t](int l, cudaStream_t cs, int phase, long long e0, long long e1) -> int {
       Net& nn = t->net;
@@ -135,25 +161,41 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   } else {
     n.on_layer_grads = nullptr;
   }
+  // Single GPU, one update per mini-batch: no exchange, so nothing needs ALL gradients at once.  dW_0 runs on the main
+  // stream behind the last dA GEMM and is followed (PDL) by the optimizer of layer 0 alone; the side stream updates the
+  // other layers right after their dW GEMMs; the two streams only join at the end of the graph.
+  static const bool old_sched = getenv("SB_OLD_SCHED") != nullptr;
+  const bool split_tail = !old_sched && kind == G_STEP && t->world == 1 && !pipelined && n.concurrent_bwd && !n.profiling &&
+                          n.side != nullptr && n.precision == SB_PREC_BF16 && n.L > 1;
+  n.dw0_on_main = n.defer_join = split_tail;
   int bs = n.enqueue_backward(rows, t->grad);
   n.on_layer_grads = nullptr;
   SB_TRY(bs);
+  if (split_tail) {
+    SB_TRY(enqueue_optimizer(t, t->grad, n.work_begin[0], n.work_end[0], n.stream, true, n.use_pdl));
+    // the other layers' shadows are read by the dA GEMMs on the main stream: update them only after the last one
+    SB_CUDA(cudaStreamWaitEvent(n.side, n.ev_da_done, 0));
+    SB_TRY(enqueue_optimizer(t, t->grad, n.work_end[0], n.n_work, n.side));
+    SB_CUDA(cudaEventRecord(n.ev_join, n.side));
+    SB_CUDA(cudaStreamWaitEvent(n.stream, n.ev_join, 0));
+    return SB_OK;
+  }
   if (kind == G_STEP) {
     if (pipelined) return SB_OK;
     SB_TRY(enqueue_allreduce(t, t->grad));
     if (t->world > 1 && n.profiling) { n.mark("allreduce"); --n.launches; }
-    SB_TRY(enqueue_optimizer(t, t->grad));
+    SB_TRY(enqueue_optimizer(t, t->grad, 0, -1, nullptr, true));
   } else {
     const long long np = n.n_params;
-    axpy_kernel<<<static_cast<unsigned>((np + 255) / 256), 256, 0, n.stream>>>(t->acc, t->grad, np);
+    axpy_kernel<<<static_cast<unsigned>((np + 255) / 256), 256, 0, n.stream>>>(t->acc, t->grad, np, n.scal, t->d_hscal);
     SB_CUDA(cudaGetLastError());
     n.mark("accumulate");
   }
   return SB_OK;
 }
 
-static int get_graph(sb_trainer* t, int rows, int kind, bool resident, cudaGraphExec_t* out) {
-  auto key = std::make_pair(rows, kind * 2 + (resident ? 1 : 0));
+static int get_graph(sb_trainer* t, int rows, int kind, bool resident, int pair, cudaGraphExec_t* out) {
+  auto key = std::make_pair(rows, kind * 4 + (resident ? 2 : 0) + pair);
   auto it = t->graphs.find(key);
   if (it != t->graphs.end()) { *out = it->second; return SB_OK; }
   Net& n = t->net;
@@ -180,22 +222,46 @@ static int run_step(sb_trainer* t, const float* X, const float* y, const float* 
   SB_CUDA(cudaSetDevice(n.device));
   static const bool no_graph = getenv("SB_NO_GRAPH") != nullptr;
   const bool resident = resident_row0 >= 0 && t->dsXb != nullptr;
+  // descriptor / scalar pair of this step: resident graph steps alternate, everything else uses pair 0
+  static const bool want_prep = !(getenv("SB_PREP") && getenv("SB_PREP")[0] == '0');
+  const bool prep = want_prep && resident && !no_graph && t->prep != nullptr;
+  const int pair = prep ? static_cast<int>(t->prep_steps & 1) : 0;
+  n.desc = t->descs[pair];
+  n.scal = t->scals[pair];
   cudaGraphExec_t ge = nullptr;
-  if (!no_graph) SB_TRY(get_graph(t, rows, kind, resident, &ge));
+  if (!no_graph) SB_TRY(get_graph(t, rows, kind, resident, pair, &ge));
   float lr_t = t->lr, gscale = 1.f / static_cast<float>(t->world);
   if (kind == G_STEP) {
     ++t->global_step;
     lr_t = lr_for_step(t, t->global_step);
   }
   if (kind == G_STEP) ++t->epoch;
-  if (resident)
-    set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, nullptr, y, w, lr_t, gscale, t->epoch, static_cast<int>(resident_row0), t->dsP, rows, n.scal);
-  else
-    set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, X, y, w ? w : n.ones, lr_t, gscale, t->epoch);
+  if (prep) {
+    // pair `pair` was last read by the step two back and by whatever followed it on the main stream before the previous
+    // step's graph: ev_pos[pair ^ 1] (recorded right before that graph) covers both.  First step of a run: join the
+    // main stream's current position.
+    if (!t->have_pos) SB_CUDA(cudaEventRecord(t->ev_pos[pair ^ 1], n.stream));
+    SB_CUDA(cudaStreamWaitEvent(t->prep, t->ev_pos[pair ^ 1], 0));
+    set_batch_kernel<<<1, 1, 0, t->prep>>>(n.desc, nullptr, y, w, lr_t, gscale, t->epoch, static_cast<int>(resident_row0), t->dsP, rows, n.scal);
+    SB_CUDA(cudaGetLastError());
+    SB_CUDA(cudaEventRecord(t->ev_prep[pair], t->prep));
+    SB_CUDA(cudaEventRecord(t->ev_pos[pair], n.stream));
+    SB_CUDA(cudaStreamWaitEvent(n.stream, t->ev_prep[pair], 0));
+    t->have_pos = true;
+    ++t->prep_steps;
+  } else {
+    t->have_pos = false;
+    if (resident)
+      set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, nullptr, y, w, lr_t, gscale, t->epoch, static_cast<int>(resident_row0), t->dsP, rows, n.scal);
+    else
+      set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, X, y, w ? w : n.ones, lr_t, gscale, t->epoch);
+  }
   SB_CUDA(cudaGetLastError());
   if (no_graph) SB_TRY(enqueue_step_body(t, rows, kind, resident));
   else SB_CUDA(cudaGraphLaunch(ge, n.stream));
-  SB_CUDA(cudaMemcpyAsync(t->h_scal, n.scal, sizeof(float) * SCAL_COUNT, cudaMemcpyDeviceToHost, n.stream));
+  // the step's tail kernel (optimizer / accumulate) wrote (loss sum, n_nz) into h_scal; visible after a stream sync
+  if (step_is_pipelined(t, kind))
+    SB_CUDA(cudaMemcpyAsync(t->h_scal, n.scal, sizeof(float) * SCAL_COUNT, cudaMemcpyDeviceToHost, n.stream));
   if (kind == G_ACC) ++t->n_acc;
   t->grad_out_scale = (kind == G_STEP) ? gscale : 1.f;
   return SB_OK;
@@ -291,11 +357,26 @@ int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, 
   }
   if ((s = n.dalloc(&t->s1, n.n_params)) || (s = n.dalloc(&t->s2, n.n_params)) ||
       (s = n.dalloc(&t->acc, n.n_params))) { n.destroy(); return s; }
-  if (cudaHostAlloc(reinterpret_cast<void**>(&t->h_scal), sizeof(float) * SCAL_COUNT, cudaHostAllocDefault) != cudaSuccess) {
+  if (cudaHostAlloc(reinterpret_cast<void**>(&t->h_scal), sizeof(float) * SCAL_COUNT, cudaHostAllocMapped) != cudaSuccess) {
     n.destroy();
     return set_error(SB_ERR_CUDA, "cudaHostAlloc failed");
   }
   memset(t->h_scal, 0, sizeof(float) * SCAL_COUNT);
+  t->descs[0] = n.desc;
+  t->scals[0] = n.scal;
+  if ((s = n.dalloc(&t->descs[1], 1)) || (s = n.dalloc(&t->scals[1], SCAL_COUNT))) { n.destroy(); return s; }
+  if (cudaStreamCreateWithFlags(&t->prep, cudaStreamNonBlocking) != cudaSuccess) { n.destroy(); return set_error(SB_ERR_CUDA, "cudaStreamCreate failed"); }
+  for (int i = 0; i < 2; ++i) {
+    if (cudaEventCreateWithFlags(&t->ev_prep[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&t->ev_pos[i], cudaEventDisableTiming) != cudaSuccess) {
+      n.destroy();
+      return set_error(SB_ERR_CUDA, "cudaEventCreate failed");
+    }
+  }
+  if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&t->d_hscal), t->h_scal, 0) != cudaSuccess) {
+    t->net.destroy();
+    return set_error(SB_ERR_CUDA, "cudaHostGetDevicePointer failed");
+  }
   if (world > 1) {
     // The GEMMs are persistent (one CTA per SM, ~200 KB smem each): an NCCL CTA that lands on an SM evicts a GEMM CTA
     // into a second wave.  Keep NCCL to a few CTAs and leave those SMs out of the GEMM grids.
@@ -376,7 +457,10 @@ int sb_trainer_destroy(sb_trainer_t* t) {
   if (t->dsW) cudaFree(t->dsW);
   if (t->h_scal) cudaFreeHost(t->h_scal);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
+  if (t->prep) { cudaStreamSynchronize(t->prep); cudaStreamDestroy(t->prep); }
   for (int i = 0; i < 2; ++i) {
+    if (t->ev_prep[i]) cudaEventDestroy(t->ev_prep[i]);
+    if (t->ev_pos[i]) cudaEventDestroy(t->ev_pos[i]);
     if (t->ev_copied[i]) cudaEventDestroy(t->ev_copied[i]);
     if (t->ev_consumed[i]) cudaEventDestroy(t->ev_consumed[i]);
   }
@@ -597,7 +681,12 @@ void* sb_trainer_stream(sb_trainer_t* t) { return t ? reinterpret_cast<void*>(t-
 int sb_trainer_kernels_per_step(sb_trainer_t* t, int32_t rows) {
   SB_CHECK(t, SB_ERR_INVALID, "null trainer");
   cudaGraphExec_t ge;
-  SB_TRY(get_graph(t, rows, G_STEP, t->dsXb != nullptr, &ge));
+  Net& n = t->net;
+  BatchDesc* d0 = n.desc; float* s0 = n.scal;
+  n.desc = t->descs[0]; n.scal = t->scals[0];      // the graph bakes the pair's pointers
+  const int s = get_graph(t, rows, G_STEP, t->dsXb != nullptr, 0, &ge);
+  n.desc = d0; n.scal = s0;
+  SB_TRY(s);
   return t->kernels_per_step[rows];
 }
 
@@ -883,6 +972,23 @@ void* sb_model_stream(sb_model_t* m) { return m ? reinterpret_cast<void*>(m->net
 // ================================================================================================
 static int debug_gemm_impl(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k,
                            int32_t a_mn, int32_t b_mn, int32_t cfg_cg, int32_t cfg_bn, int device, int iters, float* ms_out);
+
+int sb_debug_step_trace(sb_trainer_t* t, uint64_t* stamps, int32_t cap_kernels, char* names, int32_t names_cap, int32_t* n_kernels) {
+  SB_CHECK(t && stamps && n_kernels, SB_ERR_INVALID, "null argument");
+  Net& n = t->net;
+  SB_CHECK(n.step_trace != nullptr, SB_ERR_STATE, "create the trainer with SB_STEP_TRACE=1 in the environment");
+  SB_CUDA(cudaSetDevice(n.device));
+  SB_CUDA(cudaStreamSynchronize(n.stream));
+  const int k = n.trace_k < cap_kernels ? n.trace_k : cap_kernels;
+  SB_CUDA(cudaMemcpy(stamps, n.step_trace, sizeof(uint64_t) * 16 * k, cudaMemcpyDeviceToHost));
+  *n_kernels = k;
+  if (names && names_cap > 0) {
+    std::string all;
+    for (int i = 0; i < k; ++i) { if (i) all += ','; all += n.trace_names[i]; }
+    snprintf(names, names_cap, "%s", all.c_str());
+  }
+  return SB_OK;
+}
 
 int sb_debug_gemm_bf16_cfg(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k,
                            int32_t a_mn, int32_t b_mn, int32_t cfg_cg, int32_t cfg_bn, int device) {

@@ -68,6 +68,10 @@ struct GemmTcParams {
   int loss;                 // sb_loss
   float *g_wo, *g_bo, *g_bL;  // gradient slots: dw_o [N], db_o [1], db_L [N]
   const BatchDesc* a_rows;  // non-null: operand A lives in the HBM-resident set; add a_rows->row0 to its row coordinate
+  // optional: the epilogue warps clear this buffer (16-byte units) while they wait for their first accumulator.  Used by
+  // the layer-0 forward GEMM of a resident step to clear the step's gradient buffer (no memset node on the chain).
+  float4* zero_buf;
+  long long zero_n4;
   unsigned long long* trace;  // debug: CTA 0 writes %globaltimer stamps of its pipeline milestones (nullable)
 };
 
@@ -85,7 +89,8 @@ struct GemmTcCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*epilogue scratch*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*epilogue scratch*/ +
+                                    2048 /*EPI_FWD_OUT: bias + w_o of the tile*/;
   static constexpr int EPI_WARPS = 8;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
@@ -256,33 +261,71 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================= epilogue warps (2..9), every CTA: its own 128 rows x BN columns =================
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;    // which of the two warps sharing the quarter
+    const int et = static_cast<int>(threadIdx.x) - 64;   // 0..255 inside the epilogue group
+    if (p.zero_buf != nullptr) {
+      // idle time before the first accumulator completes: clear the step's gradient buffer (read by nobody before the
+      // next kernel boundary)
+      const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (long long i = blockIdx.x * 256ll + et; i < p.zero_n4; i += gridDim.x * 256ll) p.zero_buf[i] = z4;
+    }
+    // EPI_FWD_OUT: bias and w_o of the (single) n-tile staged in shared memory once, before the accumulator wait, so the
+    // two epilogue passes read them with broadcast ld.shared instead of dependent global loads
+    const uint32_t sm_vec = bar_base + 8u * (2 * STAGES + 4) + 16u + 2048u;   // [bias BN floats][w_o BN floats]
+    if constexpr (EPI == EPI_FWD_OUT) {
+#pragma unroll
+      for (int j = et; j < 2 * BN; j += 256) {
+        const int col = (j < BN) ? j : j - BN;
+        const float* src = (j < BN) ? p.bias : p.wo;
+        const float v = (col < p.N) ? __ldg(src + col) : 0.f;
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(sm_vec + static_cast<uint32_t>(j) * 4u), "f"(v) : "memory");
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     int it = 0;
     for (int w = w_first; w < n_work; w += w_step, ++it) {
       const int tile = w % n_tiles;
       const int tm = tile / tiles_n, tn = tile % tiles_n;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
+      const int row = tm * TILE_M + static_cast<int>(rank) * BM + quarter * 32 + lane;  // output row of this thread
+      const bool row_ok = row < p.M;
+      // operands of the epilogue that do not depend on the accumulator are fetched BEFORE waiting for it (the epilogue
+      // warps idle during the main loop): per-row label / weight / n_nz / b_o of the fused output layer, and the first
+      // chunk of A_{l-1} of the dA epilogue (the next chunk's is fetched while the current one is processed)
+      float pre_y = 0.f, pre_w = 0.f, pre_nnz = 0.f, pre_bo = 0.f;
+      uint4 aux_nxt[4];
+      auto load_aux = [&](int c, uint4 (&a)[4]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q] = make_uint4(0, 0, 0, 0);
+        const int c0 = tn * BN + c * 32;
+        if (row_ok && c < BN / 32 && c0 < p.N) {
+          const uint4* ap = reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(row) * p.ld_aux + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (c0 + q * 8 < p.ld_aux) a[q] = __ldg(ap + q);
+        }
+      };
+      if constexpr (EPI == EPI_FWD_OUT) {
+        if (row_ok) { pre_y = __ldg(p.desc->y + row); pre_w = __ldg(p.desc->w + row); }
+        pre_nnz = p.scal[SCAL_NNZ];
+        pre_bo = __ldg(p.bo);
+      }
+      if constexpr (EPI == EPI_DA) load_aux(half, aux_nxt);
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       if (w == w_first && warp == 2 && lane == 0) stamp(6);  // first accumulator complete
-      const int row = tm * TILE_M + static_cast<int>(rank) * BM + quarter * 32 + lane;  // output row of this thread
-      const bool row_ok = row < p.M;
       if constexpr (EPI == EPI_FWD_OUT) {
         // ---------- fused output layer (tiles_n == 1: this CTA's TMEM holds complete rows of A_L) ----------
         const uint32_t zs = bar_base + 8u * (2 * STAGES + 4) + 16u + static_cast<uint32_t>(it & 1) * 1024u;  // zpart[2][128]
         const int rl = quarter * 32 + lane;
-        // 32 consecutive fp32 of a parameter vector: 8 x 16-byte loads when the chunk is complete and aligned
-        auto load_vec32 = [&](const float* base, int col0, float (&o)[32]) {
-          if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(base + col0) & 15) == 0)) {
+        // 32 consecutive fp32 of the staged bias (which = 0) / w_o (which = 1): 8 broadcast 16-byte ld.shared
+        auto load_vec32 = [&](int which, int col0, float (&o)[32]) {
+          const uint32_t a = sm_vec + static_cast<uint32_t>(which * BN + col0) * 4u;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(base + col0) + q);
-              o[4 * q] = t.x; o[4 * q + 1] = t.y; o[4 * q + 2] = t.z; o[4 * q + 3] = t.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = (col0 + j < p.N) ? __ldg(base + col0 + j) : 0.f;
-          }
+          for (int q = 0; q < 8; ++q)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(o[4 * q]), "=f"(o[4 * q + 1]), "=f"(o[4 * q + 2]), "=f"(o[4 * q + 3])
+                         : "r"(a + 16u * q));
         };
         auto load_act = [&](int c, float (&v)[32]) {   // a = act(acc + bias) for chunk c; 0 beyond N
           const int col0 = c * 32;
@@ -290,7 +333,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, raw);
           tmem_ld_wait();
           float b[32];
-          load_vec32(p.bias, col0, b);
+          load_vec32(0, col0, b);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
           switch (p.act) {
@@ -313,7 +356,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (c * 32 >= p.N) break;
           float v[32], wv[32];
           load_act(c, v);
-          load_vec32(p.wo, c * 32, wv);
+          load_vec32(1, c * 32, wv);
 #pragma unroll
           for (int j = 0; j < 32; ++j) zp = fmaf(v[j], wv[j], zp);
         }
@@ -322,13 +365,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float z0, z1;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z0) : "r"(zs + static_cast<uint32_t>(rl) * 4u) : "memory");
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z1) : "r"(zs + static_cast<uint32_t>(128 + rl) * 4u) : "memory");
-        const float z = z0 + z1 + __ldg(p.bo);
+        const float z = z0 + z1 + pre_bo;
         float dz = 0.f, lossv = 0.f;
         if (row_ok) {
-          const float nnz = p.scal[SCAL_NNZ];
+          const float nnz = pre_nnz;
           const float inv_nnz = nnz > 0.f ? 1.f / nnz : 0.f;
           const float yh = sigmoidf_stable(z);
-          const float y = __ldg(p.desc->y + row), wgt = __ldg(p.desc->w + row);
+          const float y = pre_y, wgt = pre_w;
           if (p.loss == SB_LOSS_MSE) {
             const float d = yh - y;
             lossv = wgt * d * d;
@@ -349,7 +392,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (col0 >= p.N) break;
           float v[32], g[32];
           load_act(c, v);
-          load_vec32(p.wo, col0, g);   // g starts as w_o (0 beyond N)
+          load_vec32(1, col0, g);      // g starts as w_o (0 beyond N)
           switch (p.act) {
 #define SB_G(ACT) _Pragma("unroll") for (int j = 0; j < 32; ++j) g[j] = dz * g[j] * act_grad_from_out(v[j], ACT);
             case SB_ACT_RELU: SB_G(SB_ACT_RELU) break;
@@ -419,16 +462,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             default: epi_fwd_chunk<SB_ACT_NONE>(v, b); break;
           }
         } else if constexpr (EPI == EPI_DA) {
-          // multiply by act'(A_{l-1}[row, col]) read as bf16 (64 B per thread per chunk)
+          // multiply by act'(A_{l-1}[row, col]) read as bf16 (64 B per thread per chunk, fetched one chunk ahead)
           uint4 a4[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) a4[q] = make_uint4(0, 0, 0, 0);
-          if (row_ok) {
-            const uint4* ap = reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(row) * p.ld_aux + col0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (col0 + q * 8 < p.ld_aux) a4[q] = __ldg(ap + q);
-          }
+          for (int q = 0; q < 4; ++q) a4[q] = aux_nxt[q];
+          load_aux(c + 2, aux_nxt);
           const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(a4);
           switch (p.act) {
             case SB_ACT_RELU: epi_da_chunk<SB_ACT_RELU>(v, ah); break;

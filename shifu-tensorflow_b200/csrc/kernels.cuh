@@ -215,6 +215,118 @@ out_layer_kernel(const OutLayerParams p) {
   }
 }
 
+// bf16 variant of the kernel above for H <= 256 * NCH: ONE pass over A_L.  A warp owns whole rows (rows w, w+8, ... of
+// the block's slice); lane i owns columns [256 c + 8 i, +8) of every 256-column chunk c of every row, moved with 16-byte
+// loads / stores.  Because the lane <-> column mapping is the same for every row, the row's dot product is one xor-shuffle
+// reduction and the dw_o / db_L column sums stay in registers over all rows of the warp; a block reduces them through
+// shared memory and issues ONE atomic per column (the 32-rows-per-block kernel above read A_L twice with 2-byte
+// accesses and took 20 us at cfg2 sizes, scripts/step_timeline.py).
+template <int NCH>
+__global__ void __launch_bounds__(256)
+out_layer_rows_kernel(const OutLayerParams p, int rows_per_block) {
+  pdl_wait();
+  pdl_launch_dependents();
+  __shared__ float red[2][8][256];
+  __shared__ float red_s[2][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const __nv_bfloat16* __restrict__ A = reinterpret_cast<const __nv_bfloat16*>(p.A);
+  __nv_bfloat16* __restrict__ dZ = reinterpret_cast<__nv_bfloat16*>(p.dZ);
+  const float bo = __ldg(p.bo);
+  const float nnz = p.do_loss ? p.scal[SCAL_NNZ] : 1.f;
+  const float inv_nnz = nnz > 0.f ? 1.f / nnz : 0.f;
+  float wo[NCH][8], s_dw[NCH][8], s_db[NCH][8];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = c * 256 + lane * 8 + k;
+      wo[c][k] = (j < p.H) ? __ldg(p.wo + j) : 0.f;
+      s_dw[c][k] = 0.f; s_db[c][k] = 0.f;
+    }
+  float loss_part = 0.f, dz_sum = 0.f;
+  const int r_begin = blockIdx.x * rows_per_block;
+  const int r_end = min(p.rows, r_begin + rows_per_block);
+  for (int r = r_begin + warp; r < r_end; r += 8) {
+    float a[NCH][8];
+    float z = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col0 = c * 256 + lane * 8;
+      uint4 raw = make_uint4(0, 0, 0, 0);
+      if (col0 < p.ldA && col0 < p.H) raw = *reinterpret_cast<const uint4*>(A + static_cast<size_t>(r) * p.ldA + col0);
+      const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        a[c][k] = (col0 + k < p.H) ? __bfloat162float(h[k]) : 0.f;   // pad columns of A_L hold act(0), not 0
+        z = fmaf(a[c][k], wo[c][k], z);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    z += bo;
+    const float yh = sigmoidf_stable(z);
+    if (p.yhat && lane == 0) p.yhat[r] = yh;
+    float dz = 0.f;
+    if (p.do_loss) {
+      const float y = __ldg(p.desc->y + r), w = __ldg(p.desc->w + r);
+      if (p.loss == SB_LOSS_MSE) {
+        const float d = yh - y;
+        loss_part += w * d * d;
+        dz = 2.f * w * d * yh * (1.f - yh) * inv_nnz;
+      } else {
+        loss_part += w * (fmaxf(z, 0.f) - z * y + log1pf(expf(-fabsf(z))));
+        dz = w * (yh - y) * inv_nnz;
+      }
+    }
+    if (p.do_bwd) {
+      dz_sum += dz;
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int col0 = c * 256 + lane * 8;
+        float g[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          g[k] = dz * wo[c][k] * act_grad_from_out(a[c][k], p.act);   // wo = 0 beyond H -> g = 0 in pad columns
+          s_db[c][k] += g[k];
+          s_dw[c][k] = fmaf(dz, a[c][k], s_dw[c][k]);
+        }
+        if (col0 < p.ld_dZ && col0 < p.H) {
+          uint4 o;
+          o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]);
+          o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
+          *reinterpret_cast<uint4*>(dZ + static_cast<size_t>(r) * p.ld_dZ + col0) = o;
+        }
+      }
+    }
+  }
+  // block reduction: scalars first, then one 256-column chunk at a time
+  if (lane == 0) { red_s[0][warp] = loss_part; red_s[1][warp] = dz_sum; }
+  __syncthreads();
+  if (tid == 0) {
+    float l = 0.f, d = 0.f;
+    for (int i = 0; i < 8; ++i) { l += red_s[0][i]; d += red_s[1][i]; }
+    if (p.do_loss) atomicAdd(p.scal + SCAL_LOSS_SUM, l);
+    if (p.do_bwd) atomicAdd(p.g_bo, d);
+  }
+  if (!p.do_bwd) return;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if (c * 256 >= p.H) break;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { red[0][warp][lane * 8 + k] = s_dw[c][k]; red[1][warp][lane * 8 + k] = s_db[c][k]; }
+    __syncthreads();
+    const int j = c * 256 + tid;
+    if (j < p.H) {
+      float dw = 0.f, db = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { dw += red[0][i][tid]; db += red[1][i][tid]; }
+      atomicAdd(p.g_wo + j, dw);
+      atomicAdd(p.g_bL + j, db);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K7 fused multi-tensor optimizer over the flat parameter vector (TF 1.x kernel forms: ApplyAdadelta
 // res/ssgd_monitor.py:138, ApplyAdam res/ssgd.py:57, ApplyGradientDescent res/ssgd_monitor_bk.py:81,
@@ -260,9 +372,16 @@ struct OptWork {
 
 static __global__ void __launch_bounds__(256)
 optimizer_kernel(const OptWork* __restrict__ work, const BatchDesc* __restrict__ desc, OptHyper h,
-                 float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ s1, float* __restrict__ s2) {
+                 float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ s1, float* __restrict__ s2,
+                 const float* __restrict__ scal = nullptr, float* __restrict__ host_scal = nullptr) {
   pdl_wait();
   pdl_launch_dependents();
+  // last kernel of a step: publish the step scalars (loss sum, n_nz) straight into mapped pinned host memory - a posted
+  // PCIe write off the critical path instead of a D2H copy node between two steps (measured: -8.7 us per cfg1 step)
+  if (host_scal != nullptr && blockIdx.x == 0 && threadIdx.x < SCAL_COUNT) {
+    host_scal[threadIdx.x] = scal[threadIdx.x];
+    __threadfence_system();
+  }
   const OptWork wk = work[blockIdx.x];
   const float lr_t = desc->lr_t, gs = desc->gscale;
   // HBM-bound: only touch the state streams the optimizer actually has (SGD: none, Momentum: s1, Adam/Adadelta: s1+s2)
@@ -332,9 +451,21 @@ shadow_refresh_kernel(const OptWork* __restrict__ work, const float* __restrict_
 }
 
 // acc += g  (epoch-sync schedule: ConditionalAccumulator.apply_grad, res/ssgd_monitor.py:136-141)
-static __global__ void axpy_kernel(float* __restrict__ acc, const float* __restrict__ g, long long n) {
+static __global__ void axpy_kernel(float* __restrict__ acc, const float* __restrict__ g, long long n,
+                                   const float* __restrict__ scal = nullptr, float* __restrict__ host_scal = nullptr) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i < n) acc[i] += g[i];
+  if (host_scal != nullptr && i < SCAL_COUNT) {   // tail kernel of an accumulate step: publish (loss sum, n_nz) to the host
+    host_scal[i] = scal[i];
+    __threadfence_system();
+  }
+}
+// p[0..n) = 0, 16 bytes per thread where aligned (clears the step's gradient buffer on the side stream)
+static __global__ void __launch_bounds__(256) zero_f32_kernel(float* __restrict__ p, long long n) {
+  const long long n4 = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) ? (n >> 2) : 0;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < n4; i += gridDim.x * 256ll)
+    reinterpret_cast<float4*>(p)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long i = n4 * 4 + blockIdx.x * 256ll + threadIdx.x; i < n; i += gridDim.x * 256ll) p[i] = 0.f;
 }
 static __global__ void scale_kernel(float* __restrict__ g, const BatchDesc* __restrict__ desc, long long n) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;

@@ -134,14 +134,19 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
   if (const char* e = getenv("SB_NO_PDL")) use_pdl = !(e[0] == '1');
   if (const char* e = getenv("SB_NO_FORK")) concurrent_bwd = !(e[0] == '1');
   if (const char* e = getenv("SB_NO_FUSE_OUT")) fuse_out_layer = !(e[0] == '1');
+  const bool want_trace = getenv("SB_STEP_TRACE") != nullptr;
   gemm_sms = num_sms;
   SB_CUDA(cudaSetDevice(device));
-  SB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  // the main chain is the critical path: its CTAs are scheduled ahead of the side stream's (dW GEMMs, second optimizer)
+  int prio_least = 0, prio_greatest = 0;
+  SB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  SB_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_greatest));
   if (training_) {
-    SB_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    SB_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_least));
     ev_dz.resize(d->n_hidden);
     for (auto& e : ev_dz) SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     SB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    SB_CUDA(cudaEventCreateWithFlags(&ev_da_done, cudaEventDisableTiming));
     SB_CUDA(cudaStreamCreateWithFlags(&comm, cudaStreamNonBlocking));
     ev_dw.resize(d->n_hidden);
     for (auto& e : ev_dw) SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -174,6 +179,7 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
   SB_TRY(dalloc(&theta, n_params));
   SB_TRY(dalloc(&scal, SCAL_COUNT));
   SB_TRY(dalloc(&desc, 1));
+  if (want_trace) SB_TRY(dalloc(&step_trace, 32 * 16));
   SB_TRY(dalloc(&yhat, max_batch));
   SB_TRY(dalloc(&ones, max_batch));
   SB_TRY(dalloc(&stX, static_cast<size_t>(max_batch) * F));
@@ -252,6 +258,8 @@ void Net::destroy() {
   ev_dz.clear();
   if (ev_join) cudaEventDestroy(ev_join);
   ev_join = nullptr;
+  if (ev_da_done) cudaEventDestroy(ev_da_done);
+  ev_da_done = nullptr;
   for (cudaEvent_t e : ev_dw) cudaEventDestroy(e);
   ev_dw.clear();
   for (cudaEvent_t e : ev_da) cudaEventDestroy(e);
@@ -322,11 +330,17 @@ int Net::enqueue_hidden_forward(int rows, float* grad, bool* fused_out) {
         p.wo = theta + ol.w_off; p.bo = theta + ol.b_off;
         p.desc = desc; p.scal = scal; p.loss = loss;
         p.g_wo = grad + ol.w_off; p.g_bo = grad + ol.b_off; p.g_bL = grad + ly.b_off;
+        p.trace = next_trace("fwd_out");
         SB_TRY((launch_gemm_tc<EPI_FWD_OUT, false, true>(fp, ta, tb, p, stream, use_pdl)));
         if (fused_out) *fused_out = true;
         mark("gemm_fwd_out");
         continue;
       }
+      if (l == 0 && zero_buf != nullptr) {
+        p.zero_buf = zero_buf; p.zero_n4 = zero_n4;
+        zero_buf = nullptr;
+      }
+      p.trace = next_trace("fwd");
       SB_TRY((launch_gemm_tc<EPI_FWD, false, true>(pl, ta, tb, p, stream, use_pdl)));
     } else {
       GemmF32Params p = {};
@@ -355,10 +369,22 @@ int Net::enqueue_out(int rows, bool do_loss, bool do_bwd, float* yhat_dst, float
     p.g_wo = grad + ol.w_off; p.g_bo = grad + ol.b_off; p.g_bL = grad + hl.b_off;
   }
   const int grid = (rows + 31) / 32;
+  static const bool old_out = getenv("SB_OLD_OUT") != nullptr;
   if (precision == SB_PREC_BF16) {
     p.A = A[L - 1]; p.ldA = hl.ld_out;
     if (do_bwd) { p.dZ = dZ[L - 1]; p.ld_dZ = hl.ld_out; }
-    SB_TRY(launch(out_layer_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, use_pdl, p));
+    if (hl.out <= 1024 && !old_out) {
+      // one-pass kernel: rows per block sized for ~2 blocks per SM, at least one row per warp
+      int rpb = (rows + 2 * num_sms - 1) / (2 * num_sms);
+      rpb = ((rpb + 7) / 8) * 8;
+      if (rpb < 8) rpb = 8;
+      const dim3 g((rows + rpb - 1) / rpb);
+      if (hl.out <= 256) SB_TRY(launch(out_layer_rows_kernel<1>, g, dim3(256), 0, stream, use_pdl, p, rpb));
+      else if (hl.out <= 512) SB_TRY(launch(out_layer_rows_kernel<2>, g, dim3(256), 0, stream, use_pdl, p, rpb));
+      else SB_TRY(launch(out_layer_rows_kernel<4>, g, dim3(256), 0, stream, use_pdl, p, rpb));
+    } else {
+      SB_TRY(launch(out_layer_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, use_pdl, p));
+    }
   } else {
     p.A = Af[L - 1]; p.ldA = hl.out;
     if (do_bwd) { p.dZ = dZf[L - 1]; p.ld_dZ = hl.out; }
@@ -387,7 +413,10 @@ int Net::enqueue_backward(int rows, float* grad) {
           if (n_chunks > 8) n_chunks = 8;
         }
         int chunk_rows = round_up((ly.in + n_chunks - 1) / n_chunks, 128);
-        if (fork) {
+        // dW_0 has nothing to overlap with (no dA_0): PDL-chained on the main stream right behind the last dA GEMM it
+        // starts ~6 us earlier than as a cross-stream launch (measured, scripts/step_timeline.py)
+        const bool on_main = !fork || (l == 0 && dw0_on_main && L > 1);
+        if (!on_main) {
           SB_CUDA(cudaEventRecord(ev_dz[l], stream));
           SB_CUDA(cudaStreamWaitEvent(side, ev_dz[l], 0));
         }
@@ -406,7 +435,8 @@ int Net::enqueue_backward(int rows, float* grad) {
           p.a_rows = res0 ? desc : nullptr;
           p.accum = grad + ly.w_off + static_cast<long long>(r0) * ly.out; p.ld_acc = ly.out;
           p.acc_vec4 = (ly.out % 4 == 0 && ly.w_off % 4 == 0) ? 1 : 0;
-          SB_TRY((launch_gemm_tc<EPI_DW, true, true>(pl, ta, tb, p, fork ? side : stream, use_pdl && !fork)));
+          p.trace = next_trace("dW");
+          SB_TRY((launch_gemm_tc<EPI_DW, true, true>(pl, ta, tb, p, on_main ? stream : side, use_pdl && on_main)));
           mark("gemm_dw");
           if (fork && on_layer_grads) {
             const long long e0 = static_cast<long long>(r0) * ly.out, e1 = static_cast<long long>(r1) * ly.out;
@@ -430,8 +460,10 @@ int Net::enqueue_backward(int rows, float* grad) {
         p.aux = A[l - 1]; p.ld_aux = pl.ld_out;
         p.out = dZ[l - 1]; p.ld_out = pl.ld_out;
         p.colsum = grad + pl.b_off;
+        p.trace = next_trace("dA");
         SB_TRY((launch_gemm_tc<EPI_DA, false, false>(gp, ta, tb, p, stream, use_pdl)));
         mark("gemm_da");
+        if (l == 1 && fork && defer_join) SB_CUDA(cudaEventRecord(ev_da_done, stream));
       }
       if (fork && on_layer_grads && l > 0) {
         SB_CUDA(cudaEventRecord(ev_da[l], stream));
@@ -467,7 +499,7 @@ int Net::enqueue_backward(int rows, float* grad) {
       }
     }
   }
-  if (fork) {
+  if (fork && !defer_join) {
     SB_CUDA(cudaEventRecord(ev_join, side));
     SB_CUDA(cudaStreamWaitEvent(stream, ev_join, 0));
     if (on_layer_grads) {

@@ -27,6 +27,14 @@ struct Net {
   std::vector<cudaEvent_t> ev_dz;            // ev_dz[l]: dZ_l is complete on `stream`
   cudaEvent_t ev_join = nullptr;
   cudaStream_t comm = nullptr;               // per-layer gradient all-reduce + optimizer, pipelined behind the dW GEMMs
+  // resident steps: the layer-0 forward GEMM's epilogue warps clear this buffer (the step's gradient) while they wait for
+  // their first accumulator; consumed (and reset) by enqueue_hidden_forward
+  float4* zero_buf = nullptr;
+  long long zero_n4 = 0;
+  // single-GPU step tail: dW_0 stays on the main stream (PDL-chained after the last dA) and the caller enqueues the
+  // optimizer per stream instead of joining first
+  bool dw0_on_main = false, defer_join = false;
+  cudaEvent_t ev_da_done = nullptr;          // the last dA GEMM (last reader of the bf16 weight shadows) is complete
   std::vector<cudaEvent_t> ev_dw;            // ev_dw[l]: dW_l (and db_l) complete on `side`
   cudaEvent_t ev_comm = nullptr;
   // called (while enqueueing the backward pass) once the gradient segment of hidden layer l - and, for l = L-1, of
@@ -61,6 +69,16 @@ struct Net {
   OptWork* work = nullptr;
   int n_work = 0;
   int launches = 0;  // kernels enqueued since last reset (for gpu_launches accounting)
+  // SB_STEP_TRACE=1: every GEMM of a step stamps %globaltimer milestones of its CTA 0 into 16 slots (debug timeline)
+  unsigned long long* step_trace = nullptr;
+  int trace_k = 0;
+  std::vector<std::string> trace_names;
+  unsigned long long* next_trace(const char* name) {
+    if (!step_trace || trace_k >= 32) return nullptr;
+    if (static_cast<int>(trace_names.size()) <= trace_k) trace_names.resize(trace_k + 1);
+    trace_names[trace_k] = name;
+    return step_trace + 16 * (trace_k++);
+  }
   // optional per-launch CUDA-event timing (sb_trainer_profile_step): one event after every launch
   bool profiling = false;
   std::vector<cudaEvent_t> prof_events;

@@ -105,3 +105,34 @@ def test_checkpoint_roundtrip_resumes_identically(sb, tmp_path):
         assert b.global_step == 2
         b.step(*batches[2]); b.step(*batches[3])
         np.testing.assert_array_equal(b.get_params(), want)
+
+
+@pytest.mark.gpu
+def test_model_score_is_reentrant_across_threads(sb):
+    """Computable.compute may be called from several scorer threads at once (TensorflowModel has no locking,
+    TensorflowModel.java:53-94; Session.run is thread-safe) -> sb_model_score / score_row_f64 on ONE handle from 8
+    threads must give exactly the single-threaded answers."""
+    import threading
+    net, params, cfg, desc = make_pair(sb, 120, [64, 32], [so.ACT_RELU, so.ACT_TANH], max_batch=256, precision=sb.PREC_FP32)
+    flat = so.flatten_params(params)
+    rng = np.random.RandomState(9)
+    Xs = [rng.standard_normal((rows, 120)).astype(np.float32) for rows in (1, 7, 256, 300, 1000, 33, 512, 2)]
+    with sb.Model.create(desc, flat) as m:
+        want = [m.score(X) for X in Xs]
+        want_row = m.score_row_f64(Xs[3][5].astype(np.float64))
+        got, errs = [None] * len(Xs), []
+
+        def work(i):
+            try:
+                for _ in range(20):
+                    got[i] = m.score(Xs[i])
+                    if i == 3:
+                        assert m.score_row_f64(Xs[3][5].astype(np.float64)) == want_row
+            except Exception as e:      # noqa: BLE001 - surfaced below
+                errs.append(e)
+
+        th = [threading.Thread(target=work, args=(i,)) for i in range(len(Xs))]
+        [t.start() for t in th]; [t.join() for t in th]
+        assert not errs, errs
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a, b)
