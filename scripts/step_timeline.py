@@ -24,9 +24,10 @@ with sb.Trainer(desc) as t:
         t0 = st[order[0], 0]
         print("--- %s step timeline (us since first GEMM entry), repetition %d" % (name, rep))
         print("%-8s %8s %8s %8s %8s %8s %8s | %s" % ("kernel", "entry", "deps_ok", "tma0", "acc0", "epi0", "exit", "entry - latest earlier exit"))
+        def rel(v):
+            return (v - t0) / 1e3 if v > 0 else float("nan")
         for k in order:
             s = st[k]
-            earlier = [st[j, 8] for j in order if st[j, 8] <= s[0] + 0 and j != k]
+            earlier = [st[j, 8] for j in order if 0 < st[j, 8] <= s[0] and j != k]
             gap = (s[0] - max(earlier)) / 1e3 if earlier else float("nan")
-            print("%-8s %8.2f %8.2f %8.2f %8.2f %8.2f %8.2f | %6.2f" % (names[k], (s[0] - t0) / 1e3, (s[2] - t0) / 1e3, (s[3] - t0) / 1e3,
-                                                                  (s[6] - t0) / 1e3, (s[7] - t0) / 1e3, (s[8] - t0) / 1e3, gap))
+            print("%-8s %8.2f %8.2f %8.2f %8.2f %8.2f %8.2f | %6.2f" % (names[k], rel(s[0]), rel(s[2]), rel(s[3]), rel(s[6]), rel(s[7]), rel(s[8]), gap))

@@ -97,7 +97,8 @@ static int enqueue_optimizer(sb_trainer* t, const float* g, int w0 = 0, int w1 =
   if (w1 <= w0) return SB_OK;
   // pdl = false: plain dependency (runs after a stream join / on the comm stream)
   SB_TRY(n.launch(optimizer_kernel, dim3(static_cast<unsigned>(w1 - w0)), dim3(256), 0, st, pdl, n.work + w0, n.desc, t->hyper,
-                  n.theta, g, t->s1, t->s2, n.scal, publish_scalars ? t->d_hscal : static_cast<float*>(nullptr)));
+                  n.theta, g, t->s1, t->s2, n.scal, publish_scalars ? t->d_hscal : static_cast<float*>(nullptr),
+                  n.next_trace(st == n.stream ? "opt" : "opt_side")));
   n.mark("optimizer");
   return SB_OK;
 }

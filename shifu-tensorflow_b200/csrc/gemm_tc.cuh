@@ -90,7 +90,7 @@ struct GemmTcCfg {
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*epilogue scratch*/ +
-                                    2048 /*EPI_FWD_OUT: bias + w_o of the tile*/;
+                                    2048 /*bias (+ w_o) of the tile*/ + 8 * 2048 /*per-warp transpose tile*/;
   static constexpr int EPI_WARPS = 8;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
@@ -271,6 +271,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // EPI_FWD_OUT: bias and w_o of the (single) n-tile staged in shared memory once, before the accumulator wait, so the
     // two epilogue passes read them with broadcast ld.shared instead of dependent global loads
     const uint32_t sm_vec = bar_base + 8u * (2 * STAGES + 4) + 16u + 2048u;   // [bias BN floats][w_o BN floats]
+    // Coalescing: tcgen05.ld hands thread t the 32 columns of ROW t, so a direct 16-byte access per thread touches 32
+    // different rows (32 L1 wavefronts per instruction).  Every global access of the epilogue therefore goes through a
+    // warp-private 32 x 64 B tile in shared memory (16-byte pieces XOR-swizzled by row pair -> conflict-free on both
+    // sides): on the global side lane l handles piece (l & 3) of rows 8 i + (l >> 2), i = 0..3, i.e. four lanes cover
+    // 64 contiguous bytes of a row and one instruction touches 8 rows instead of 32.
+    const uint32_t sm_stage = sm_vec + 2048u + static_cast<uint32_t>(warp - 2) * 2048u;
+    const int lrow = lane >> 2, lpc = lane & 3;
+    auto stg = [&](int r, int pc) { return sm_stage + static_cast<uint32_t>(r) * 64u + static_cast<uint32_t>((pc ^ ((r >> 1) & 3)) << 4); };
+    auto sts4 = [](uint32_t a, const uint4& v) {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    };
+    auto lds4 = [](uint32_t a) {
+      uint4 v;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+      return v;
+    };
+    auto row_to_lanes = [&](const uint4 (&mine)[4], uint4 (&out)[4]) {   // thread-owns-row -> lane-coalesced
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sts4(stg(lane, q), mine[q]);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) out[i] = lds4(stg(8 * i + lrow, lpc));
+      __syncwarp();
+    };
+    auto lanes_to_row = [&](const uint4 (&in)[4], uint4 (&mine)[4]) {    // lane-coalesced -> thread-owns-row
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sts4(stg(8 * i + lrow, lpc), in[i]);
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) mine[q] = lds4(stg(lane, q));
+      __syncwarp();
+    };
     if constexpr (EPI == EPI_FWD_OUT) {
 #pragma unroll
       for (int j = et; j < 2 * BN; j += 256) {
@@ -294,15 +326,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // chunk of A_{l-1} of the dA epilogue (the next chunk's is fetched while the current one is processed)
       float pre_y = 0.f, pre_w = 0.f, pre_nnz = 0.f, pre_bo = 0.f;
       uint4 aux_nxt[4];
-      auto load_aux = [&](int c, uint4 (&a)[4]) {
+      const int row_base = tm * TILE_M + static_cast<int>(rank) * BM + quarter * 32;   // first row of this warp's 32
+      // store a 32 x 64 B tile held one-row-per-thread (4 pieces each) to a row-major bf16 matrix, coalesced
+      auto store_rows_bf16 = [&](const uint4 (&mine)[4], __nv_bfloat16* base, int ld, int col0_, bool all_cols) {
+        uint4 oc[4];
+        row_to_lanes(mine, oc);
+        const int gc = col0_ + 8 * lpc;
+        if (all_cols || gc < ld) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) a[q] = make_uint4(0, 0, 0, 0);
-        const int c0 = tn * BN + c * 32;
-        if (row_ok && c < BN / 32 && c0 < p.N) {
-          const uint4* ap = reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(row) * p.ld_aux + c0);
+          for (int i = 0; i < 4; ++i) {
+            const int gr = row_base + 8 * i + lrow;
+            if (gr < p.M) *reinterpret_cast<uint4*>(base + static_cast<size_t>(gr) * ld + gc) = oc[i];
+          }
+        }
+      };
+      auto load_aux = [&](int c, uint4 (&a)[4]) {   // lane-coalesced fetch of chunk c of A_{l-1}; zeros outside
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (c0 + q * 8 < p.ld_aux) a[q] = __ldg(ap + q);
+        for (int i = 0; i < 4; ++i) a[i] = make_uint4(0, 0, 0, 0);
+        const int gc = tn * BN + c * 32 + 8 * lpc;
+        if (c < BN / 32 && tn * BN + c * 32 < p.N && gc < p.ld_aux) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int gr = row_base + 8 * i + lrow;
+            if (gr < p.M) a[i] = __ldg(reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(gr) * p.ld_aux + gc));
+          }
         }
       };
       if constexpr (EPI == EPI_FWD_OUT) {
@@ -311,6 +358,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         pre_bo = __ldg(p.bo);
       }
       if constexpr (EPI == EPI_DA) load_aux(half, aux_nxt);
+      const uint32_t sm_bias = sm_vec + static_cast<uint32_t>(it & 1) * (BN * 4u);   // EPI_FWD: this tile's bias, double-buffered
+      if constexpr (EPI == EPI_FWD) {
+        // (a warp reaches this barrier only after finishing the previous tile, so buffer it & 1 is no longer read)
+#pragma unroll
+        for (int j = et; j < BN; j += 256) {
+          const int col = tn * BN + j;
+          const float bv = (col < p.N) ? __ldg(p.bias + col) : 0.f;
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sm_bias + static_cast<uint32_t>(j) * 4u), "f"(bv) : "memory");
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       if (w == w_first && warp == 2 && lane == 0) stamp(6);  // first accumulator complete
@@ -402,19 +460,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             default: SB_G(SB_ACT_NONE) break;
 #undef SB_G
           }
-          if (row_ok) {
-            __nv_bfloat16* op = p.out + static_cast<size_t>(row) * p.ld_out + col0;
+          {
+            uint4 o[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              if (col0 + q * 8 < p.ld_out) {
-                uint4 o;
-                o.x = pack_bf16x2(g[q * 8 + 0], g[q * 8 + 1]);
-                o.y = pack_bf16x2(g[q * 8 + 2], g[q * 8 + 3]);
-                o.z = pack_bf16x2(g[q * 8 + 4], g[q * 8 + 5]);
-                o.w = pack_bf16x2(g[q * 8 + 6], g[q * 8 + 7]);
-                *reinterpret_cast<uint4*>(op + q * 8) = o;
-              }
+              o[q].x = pack_bf16x2(g[q * 8 + 0], g[q * 8 + 1]);
+              o[q].y = pack_bf16x2(g[q * 8 + 2], g[q * 8 + 3]);
+              o[q].z = pack_bf16x2(g[q * 8 + 4], g[q * 8 + 5]);
+              o[q].w = pack_bf16x2(g[q * 8 + 6], g[q * 8 + 7]);
             }
+            store_rows_bf16(o, p.out, p.ld_out, col0, false);
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= dz;          // dz * a  -> dw_o contributions (0 for rows >= M)
@@ -443,17 +498,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool full = col0 + 32 <= p.N;  // warp-uniform fast path
 
         if constexpr (EPI == EPI_FWD) {
-          float b[32];
-          if (full && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 15) == 0)) {
+          float b[32];   // staged before the accumulator wait (0 beyond N)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q);
-              b[4 * q] = t.x; b[4 * q + 1] = t.y; b[4 * q + 2] = t.z; b[4 * q + 3] = t.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) b[j] = (col0 + j < p.N) ? __ldg(p.bias + col0 + j) : 0.f;
-          }
+          for (int q = 0; q < 8; ++q)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(b[4 * q]), "=f"(b[4 * q + 1]), "=f"(b[4 * q + 2]), "=f"(b[4 * q + 3])
+                         : "r"(sm_bias + static_cast<uint32_t>(c * 32 + 4 * q) * 4u));
           switch (p.act) {
             case SB_ACT_RELU: epi_fwd_chunk<SB_ACT_RELU>(v, b); break;
             case SB_ACT_SIGMOID: epi_fwd_chunk<SB_ACT_SIGMOID>(v, b); break;
@@ -464,8 +514,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else if constexpr (EPI == EPI_DA) {
           // multiply by act'(A_{l-1}[row, col]) read as bf16 (64 B per thread per chunk, fetched one chunk ahead)
           uint4 a4[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) a4[q] = aux_nxt[q];
+          lanes_to_row(aux_nxt, a4);
           load_aux(c + 2, aux_nxt);
           const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(a4);
           switch (p.act) {
@@ -483,20 +532,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
 
         if constexpr (EPI == EPI_FWD || EPI == EPI_DA) {
-          if (row_ok) {
-            // row-major bf16: 4 x 16 B per thread (ld_out is a multiple of 8, pad columns belong to the buffer)
-            __nv_bfloat16* op = p.out + static_cast<size_t>(row) * p.ld_out + col0;
+          {
+            // row-major bf16 (ld_out is a multiple of 8, pad columns belong to the buffer)
+            uint4 o[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              if (full || col0 + q * 8 < p.ld_out) {
-                uint4 o;
-                o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-                o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-                o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-                o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-                *reinterpret_cast<uint4*>(op + q * 8) = o;
-              }
+              o[q].x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+              o[q].y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+              o[q].z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+              o[q].w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
             }
+            store_rows_bf16(o, p.out, p.ld_out, col0, full);
           }
           if constexpr (EPI == EPI_DA) {
             if (p.colsum != nullptr) {
@@ -506,16 +552,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         } else if constexpr (EPI == EPI_DW) {
-          if (row_ok) {
-            float* gp = p.accum + static_cast<size_t>(row) * p.ld_acc + col0;
-            if (p.acc_vec4 && full) {
+          if (p.acc_vec4 && full) {
+            // fp32 rows are 128 B per 32-column chunk: two 64-byte halves through the transpose tile, then
+            // red.global.add.v4.f32 with four lanes per 64 contiguous bytes
 #pragma unroll
-              for (int q = 0; q < 8; ++q) red_add_v4_f32(gp + q * 4, v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-            } else {
+            for (int h = 0; h < 2; ++h) {
+              uint4 mine[4], oc[4];
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) red_add_f32(gp + j, v[j]);
+              for (int q = 0; q < 4; ++q)
+                mine[q] = make_uint4(__float_as_uint(v[16 * h + 4 * q]), __float_as_uint(v[16 * h + 4 * q + 1]),
+                                     __float_as_uint(v[16 * h + 4 * q + 2]), __float_as_uint(v[16 * h + 4 * q + 3]));
+              row_to_lanes(mine, oc);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int gr = row_base + 8 * i + lrow;
+                if (gr < p.M)
+                  red_add_v4_f32(p.accum + static_cast<size_t>(gr) * p.ld_acc + col0 + 16 * h + 4 * lpc, __uint_as_float(oc[i].x),
+                                 __uint_as_float(oc[i].y), __uint_as_float(oc[i].z), __uint_as_float(oc[i].w));
+              }
             }
+          } else if (row_ok) {
+            float* gp = p.accum + static_cast<size_t>(row) * p.ld_acc + col0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) red_add_f32(gp + j, v[j]);
           }
         } else {  // EPI_F32
           if (row_ok) {

@@ -373,9 +373,12 @@ struct OptWork {
 static __global__ void __launch_bounds__(256)
 optimizer_kernel(const OptWork* __restrict__ work, const BatchDesc* __restrict__ desc, OptHyper h,
                  float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ s1, float* __restrict__ s2,
-                 const float* __restrict__ scal = nullptr, float* __restrict__ host_scal = nullptr) {
+                 const float* __restrict__ scal = nullptr, float* __restrict__ host_scal = nullptr,
+                 unsigned long long* __restrict__ trace = nullptr) {
+  if (trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) trace[0] = globaltimer_ns();   // debug timeline: entry
   pdl_wait();
   pdl_launch_dependents();
+  if (trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) trace[2] = globaltimer_ns();   // dependencies resolved
   // last kernel of a step: publish the step scalars (loss sum, n_nz) straight into mapped pinned host memory - a posted
   // PCIe write off the critical path instead of a D2H copy node between two steps (measured: -8.7 us per cfg1 step)
   if (host_scal != nullptr && blockIdx.x == 0 && threadIdx.x < SCAL_COUNT) {
@@ -431,6 +434,7 @@ optimizer_kernel(const OptWork* __restrict__ work, const BatchDesc* __restrict__
       }
     }
   }
+  if (trace != nullptr && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) trace[8] = globaltimer_ns();   // last block done
 }
 
 // Refresh the bf16 shadows from the fp32 master without touching state (after set_params / restore).

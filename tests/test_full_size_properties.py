@@ -10,8 +10,8 @@ for the reference's loss (MSE on sigmoid, SUM_BY_NONZERO_WEIGHTS, ssgd_monitor.p
   * the mean of the gradients of R equal shards is the gradient of the whole batch (the data-parallel identity the
     all-reduce relies on), and accumulate-R-then-apply equals one step on the whole batch
   * scores do not depend on how the rows are chunked, and the trainer's predict equals the exported scorer
-Float tolerance: the only difference between the two sides of each identity is fp32 summation order (red.add order,
-split-K plan), stated per test relative to max|g|."""
+Float tolerance: the only difference between the two sides of each identity is fp32 summation order (atomic-add
+order, split-K plan): 5e-6 relative on the loss (a sum of thousands of fp32 terms), per test relative to max|g| on gradients."""
 import numpy as np
 import pytest
 
@@ -50,12 +50,12 @@ def test_full_size_weight_linearity_and_zero_weight_rows(sb, name):
         L2, g2 = _grad(t, X, y, 2.0 * w)
         gmax = np.abs(g1).max()
         assert gmax > 0 and np.isfinite(g1).all()
-        assert abs(L2 - 2 * L1) <= 1e-6 * abs(L1) + 1e-9
+        assert abs(L2 - 2 * L1) <= 5e-6 * abs(L1) + 1e-9
         assert np.abs(g2 - 2 * g1).max() <= 1e-5 * gmax          # power-of-two scaling commutes with bf16 rounding
         # rows with w == 0 removed from the batch: same loss, same gradient (divisor = number of non-zero weights)
         keep = (w[:, 0] != 0)
         L3, g3 = _grad(t, np.ascontiguousarray(X[keep]), y[keep], w[keep])
-        assert abs(L3 - L1) <= 1e-6 * abs(L1) + 1e-9
+        assert abs(L3 - L1) <= 5e-6 * abs(L1) + 1e-9
         assert np.abs(g3 - g1).max() <= 2e-5 * gmax
         # all-zero weights: loss 0, gradient 0 (the _safe_div of SUM_BY_NONZERO_WEIGHTS)
         L0, g0 = _grad(t, X, y, np.zeros_like(w))
@@ -71,7 +71,7 @@ def test_full_size_row_permutation_invariance(sb, name):
         L1, g1 = _grad(t, X, y, w)
         p = np.random.RandomState(0).permutation(c["rows"])
         L2, g2 = _grad(t, np.ascontiguousarray(X[p]), y[p], w[p])
-        assert abs(L2 - L1) <= 1e-6 * abs(L1)
+        assert abs(L2 - L1) <= 5e-6 * abs(L1)
         assert np.abs(g2 - g1).max() <= 2e-5 * np.abs(g1).max()
 
 
@@ -93,7 +93,7 @@ def test_full_size_shard_mean_is_whole_batch_gradient(sb, name, precision):
             s = slice(r * n, (r + 1) * n)
             Lr, gr = _grad(t, np.ascontiguousarray(X[s]), y[s], w[s])
             Ls.append(Lr); gs += gr
-        assert abs(np.mean(Ls) - L) <= 2e-6 * abs(L)
+        assert abs(np.mean(Ls) - L) <= 5e-6 * abs(L)
         assert np.abs(gs / R - g).max() <= 2e-5 * np.abs(g).max()
 
 
@@ -134,7 +134,7 @@ def test_full_size_gradient_is_deterministic_enough_and_finite(sb, name):
         X, y, w = so.synth_batch(c["rows"], c["F"], 15, weights="mixed")
         L1, g1 = _grad(t, X, y, w)
         L2, g2 = _grad(t, X, y, w)
-        assert abs(L1 - L2) <= 1e-6 * abs(L1)
+        assert abs(L1 - L2) <= 5e-6 * abs(L1)
         assert np.abs(g1 - g2).max() <= 1e-6 * np.abs(g1).max()
 
 
