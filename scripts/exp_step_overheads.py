@@ -28,8 +28,7 @@ with sb.Trainer(desc) as t:
 def main():
     out = {}
     for cfg in ("cfg1", "cfg2"):
-        for name, env in [("base", {}), ("no_desc_prefetch", {"SB_PREP": "0"}), ("old_tail_schedule", {"SB_OLD_SCHED": "1"}),
-                          ("old_out_layer", {"SB_OLD_OUT": "1"}), ("no_pdl", {"SB_NO_PDL": "1"}), ("no_graph", {"SB_NO_GRAPH": "1"})]:
+        for name, env in [("base", {}), ("no_dw_budget", {"SB_NO_DW_BUDGET": "1"}), ("old_tail_schedule", {"SB_OLD_SCHED": "1"}), ("no_desc_prefetch", {"SB_PREP": "0"})]:
             e = dict(os.environ); e.update(env)
             r = subprocess.run([sys.executable, "-c", CHILD, cfg], env=e, capture_output=True, text=True, timeout=300)
             out["%s/%s" % (cfg, name)] = r.stdout.strip().splitlines()[-1] if r.returncode == 0 and r.stdout.strip() else "ERR " + r.stderr[-300:]

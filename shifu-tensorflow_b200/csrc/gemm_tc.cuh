@@ -107,10 +107,16 @@ __device__ __forceinline__ void epi_da_chunk(float (&v)[32], const __nv_bfloat16
   for (int j = 0; j < 32; ++j) v[j] *= act_grad_from_out(__bfloat162float(ah[j]), ACT);
 }
 
-template <int BN, int EPI, bool A_MN, bool B_MN, int CG>
+// ACT_T: activation fixed at compile time (EPI_FWD_OUT: its two-pass epilogue with every activation variant inlined was
+// 7.4 k instructions and spent 38 % of its warp samples waiting for instruction fetch, profiles/ncu_r01_*), or
+// SB_ACT_AT_RUNTIME = read p.act.
+constexpr int SB_ACT_AT_RUNTIME = -100;
+
+template <int BN, int EPI, bool A_MN, bool B_MN, int CG, int ACT_T = SB_ACT_AT_RUNTIME>
 __global__ void __launch_bounds__(GemmTcCfg<BN, CG>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
   using Cfg = GemmTcCfg<BN, CG>;
+  const int act_sel = (ACT_T == SB_ACT_AT_RUNTIME) ? p.act : ACT_T;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES, TILE_M = Cfg::TILE_M, BN_CTA = Cfg::BN_CTA;
 
   extern __shared__ uint8_t smem_raw[];
@@ -394,7 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           load_vec32(0, col0, b);
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          switch (p.act) {
+          switch (act_sel) {
             case SB_ACT_RELU: epi_fwd_chunk<SB_ACT_RELU>(v, b); break;
             case SB_ACT_SIGMOID: epi_fwd_chunk<SB_ACT_SIGMOID>(v, b); break;
             case SB_ACT_TANH: epi_fwd_chunk<SB_ACT_TANH>(v, b); break;
@@ -451,7 +457,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float v[32], g[32];
           load_act(c, v);
           load_vec32(1, col0, g);      // g starts as w_o (0 beyond N)
-          switch (p.act) {
+          switch (act_sel) {
 #define SB_G(ACT) _Pragma("unroll") for (int j = 0; j < 32; ++j) g[j] = dz * g[j] * act_grad_from_out(v[j], ACT);
             case SB_ACT_RELU: SB_G(SB_ACT_RELU) break;
             case SB_ACT_SIGMOID: SB_G(SB_ACT_SIGMOID) break;
@@ -504,7 +510,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                          : "=f"(b[4 * q]), "=f"(b[4 * q + 1]), "=f"(b[4 * q + 2]), "=f"(b[4 * q + 3])
                          : "r"(sm_bias + static_cast<uint32_t>(c * 32 + 4 * q) * 4u));
-          switch (p.act) {
+          switch (act_sel) {
             case SB_ACT_RELU: epi_fwd_chunk<SB_ACT_RELU>(v, b); break;
             case SB_ACT_SIGMOID: epi_fwd_chunk<SB_ACT_SIGMOID>(v, b); break;
             case SB_ACT_TANH: epi_fwd_chunk<SB_ACT_TANH>(v, b); break;
@@ -517,7 +523,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           lanes_to_row(aux_nxt, a4);
           load_aux(c + 2, aux_nxt);
           const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(a4);
-          switch (p.act) {
+          switch (act_sel) {
             case SB_ACT_RELU: epi_da_chunk<SB_ACT_RELU>(v, ah); break;
             case SB_ACT_SIGMOID: epi_da_chunk<SB_ACT_SIGMOID>(v, ah); break;
             case SB_ACT_TANH: epi_da_chunk<SB_ACT_TANH>(v, ah); break;

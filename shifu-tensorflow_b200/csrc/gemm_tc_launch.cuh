@@ -4,7 +4,7 @@
 
 namespace sb {
 
-template <int BN, int EPI, bool A_MN, bool B_MN, int CG>
+template <int BN, int EPI, bool A_MN, bool B_MN, int CG, int ACT_T = SB_ACT_AT_RUNTIME>
 static int launch_gemm_tc_one(const GemmPlan& pl, const CUtensorMap& a, const CUtensorMap& b, const GemmTcParams& p, cudaStream_t st,
                               bool pdl) {
   using Cfg = GemmTcCfg<BN, CG>;
@@ -27,30 +27,61 @@ static int launch_gemm_tc_one(const GemmPlan& pl, const CUtensorMap& a, const CU
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  SB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, A_MN, B_MN, CG>, a, b, p));
+  SB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, A_MN, B_MN, CG, ACT_T>, a, b, p));
   return SB_OK;
+}
+
+// EPI_FWD_OUT: one instantiation per (tile width 64 | 128, activation), single CTAs only
+template <int BN, bool A_MN, bool B_MN>
+static int launch_fwd_out_act(const GemmPlan& pl, const CUtensorMap& a, const CUtensorMap& b, const GemmTcParams& p, cudaStream_t st,
+                              bool pdl) {
+  switch (p.act) {
+    case SB_ACT_SIGMOID: return launch_gemm_tc_one<BN, EPI_FWD_OUT, A_MN, B_MN, 1, SB_ACT_SIGMOID>(pl, a, b, p, st, pdl);
+    case SB_ACT_TANH: return launch_gemm_tc_one<BN, EPI_FWD_OUT, A_MN, B_MN, 1, SB_ACT_TANH>(pl, a, b, p, st, pdl);
+    case SB_ACT_RELU: return launch_gemm_tc_one<BN, EPI_FWD_OUT, A_MN, B_MN, 1, SB_ACT_RELU>(pl, a, b, p, st, pdl);
+    case SB_ACT_LEAKYRELU: return launch_gemm_tc_one<BN, EPI_FWD_OUT, A_MN, B_MN, 1, SB_ACT_LEAKYRELU>(pl, a, b, p, st, pdl);
+    default: return launch_gemm_tc_one<BN, EPI_FWD_OUT, A_MN, B_MN, 1, SB_ACT_NONE>(pl, a, b, p, st, pdl);
+  }
 }
 
 template <int EPI, bool A_MN, bool B_MN>
 int launch_gemm_tc(const GemmPlan& pl, const CUtensorMap& a, const CUtensorMap& b, GemmTcParams p, cudaStream_t st, bool pdl = false) {
   p.split_k = pl.split_k;
   p.kb_per_split = pl.kb_per_split;
+  if constexpr (EPI == EPI_FWD_OUT) {
+    if (pl.cg == 1 && pl.bn == 64) return launch_fwd_out_act<64, A_MN, B_MN>(pl, a, b, p, st, pdl);
+    if (pl.cg == 1 && pl.bn == 128) return launch_fwd_out_act<128, A_MN, B_MN>(pl, a, b, p, st, pdl);
+    return set_error(SB_ERR_INVALID, "fused output layer: no instantiation for cg=%d bn=%d", pl.cg, pl.bn);
+  } else {
   if (pl.cg == 1 && pl.bn == 64) return launch_gemm_tc_one<64, EPI, A_MN, B_MN, 1>(pl, a, b, p, st, pdl);
   if (pl.cg == 1 && pl.bn == 128) return launch_gemm_tc_one<128, EPI, A_MN, B_MN, 1>(pl, a, b, p, st, pdl);
   if (pl.cg == 2 && pl.bn == 128) return launch_gemm_tc_one<128, EPI, A_MN, B_MN, 2>(pl, a, b, p, st, pdl);
   if (pl.cg == 2 && pl.bn == 256) return launch_gemm_tc_one<256, EPI, A_MN, B_MN, 2>(pl, a, b, p, st, pdl);
   return set_error(SB_ERR_INVALID, "no gemm_tc instantiation for cg=%d bn=%d", pl.cg, pl.bn);
+  }
 }
 
 // opt in to > 48 KB dynamic shared memory (once per process per instantiation, outside of stream capture)
 template <int EPI, bool A_MN, bool B_MN>
 int set_gemm_tc_attrs() {
+  if constexpr (EPI == EPI_FWD_OUT) {
+#define SB_ATTR_ACT(BN, ACT)                                                                                          \
+  SB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI_FWD_OUT, A_MN, B_MN, 1, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                               GemmTcCfg<BN, 1>::SMEM_BYTES))
+#define SB_ATTR_ALL(BN) SB_ATTR_ACT(BN, SB_ACT_NONE); SB_ATTR_ACT(BN, SB_ACT_SIGMOID); SB_ATTR_ACT(BN, SB_ACT_TANH); \
+                        SB_ATTR_ACT(BN, SB_ACT_RELU); SB_ATTR_ACT(BN, SB_ACT_LEAKYRELU)
+    SB_ATTR_ALL(64); SB_ATTR_ALL(128);
+#undef SB_ATTR_ALL
+#undef SB_ATTR_ACT
+    return SB_OK;
+  } else {
 #define SB_ATTR(BN, CG)                                                                                            \
   SB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, A_MN, B_MN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                GemmTcCfg<BN, CG>::SMEM_BYTES))
   SB_ATTR(64, 1); SB_ATTR(128, 1); SB_ATTR(128, 2); SB_ATTR(256, 2);
 #undef SB_ATTR
   return SB_OK;
+  }
 }
 
 // box rows of the tensor map of a K-major B operand / tile geometry helpers

@@ -399,6 +399,29 @@ int Net::enqueue_backward(int rows, float* grad) {
   // dW_l and dA_l both consume dZ_l and are independent of each other: the dW GEMMs go to the side stream and
   // overlap the dA chain (they are each well under one wave at cfg1 sizes).  Not while profiling (clean times).
   const bool fork = concurrent_bwd && !profiling && side != nullptr && precision == SB_PREC_BF16;
+  // dW_1 (side stream) and dW_0 (main stream) run at the same time, one CTA per SM each.  If their natural grids do not
+  // fit the machine together, dW_1's second wave only starts when dW_0's CTAs exit (measured: the side optimizer then
+  // finishes 4 us after the main one, scripts/step_timeline.py).  Compare, in k-blocks per CTA, "natural grids, dW_1
+  // finishing after dW_0" against "dW_1 on a third of the SMs, dW_0 on the rest" and take the shorter.
+  int dw_sms[2] = {gemm_sms, gemm_sms};
+  static const bool no_budget = getenv("SB_NO_DW_BUDGET") != nullptr;
+  if (fork && dw0_on_main && L > 1 && !on_layer_grads && !no_budget) {
+    const GemmPlan n0 = plan_gemm(layers[0].in, layers[0].out, rows, gemm_sms, true);
+    const GemmPlan n1 = plan_gemm(layers[1].in, layers[1].out, rows, gemm_sms, true);
+    if (n0.grid + n1.grid > gemm_sms) {
+      const GemmPlan b1 = plan_gemm(layers[1].in, layers[1].out, rows, gemm_sms / 3, true);
+      const GemmPlan b0 = plan_gemm(layers[0].in, layers[0].out, rows, gemm_sms - b1.grid, true);
+      auto waves = [&](const GemmPlan& pl, int M, int N, int sms) {   // k-blocks one CTA works through
+        const int tiles = ((M + 128 * pl.cg - 1) / (128 * pl.cg)) * ((N + pl.bn - 1) / pl.bn) * pl.split_k;
+        const int slots = sms / pl.cg;
+        return ((tiles + slots - 1) / slots) * pl.kb_per_split;
+      };
+      const int t_nat = waves(n0, layers[0].in, layers[0].out, gemm_sms) + waves(n1, layers[1].in, layers[1].out, gemm_sms);
+      const int t0 = waves(b0, layers[0].in, layers[0].out, gemm_sms - b1.grid);
+      const int t1 = waves(b1, layers[1].in, layers[1].out, gemm_sms / 3);
+      if ((t0 > t1 ? t0 : t1) < t_nat) { dw_sms[1] = gemm_sms / 3; dw_sms[0] = gemm_sms - b1.grid; }
+    }
+  }
   for (int l = L - 1; l >= 0; --l) {
     Layer& ly = layers[l];
     if (precision == SB_PREC_BF16) {
@@ -424,7 +447,7 @@ int Net::enqueue_backward(int rows, float* grad) {
         const __nv_bfloat16* ap = (l == 0) ? (res0 ? resident_Xb : Xb) : A[l - 1];
         for (int r0 = 0; r0 < ly.in; r0 += chunk_rows) {
           const int r1 = (r0 + chunk_rows < ly.in) ? r0 + chunk_rows : ly.in;
-          const GemmPlan pl = plan_gemm(r1 - r0, ly.out, rows, gemm_sms, true);
+          const GemmPlan pl = plan_gemm(r1 - r0, ly.out, rows, l < 2 ? dw_sms[l] : gemm_sms, true);
           CUtensorMap ta, tb;
           // resident set: rows past the batch end are real rows of other batches; the B operand (dZ_l, extent = rows) is
           // zero-filled there, so they contribute nothing
