@@ -218,7 +218,7 @@ def main():
     peak_src = "measured burst (MEASURED_PEAKS.json bf16_tflops)" if peaks else "fallback 1.59 PF (B200_PROFILING.md)"
     # DRAM bytes of the GEMM launches of one step, from the committed `ncu --set full` capture (dram__bytes_read+write
     # summed over the 8 gemm_tc launches); algorithmic bytes (bf16 operands once + fp32 gradient) beside it
-    NCU_TRAFFIC = {"cfg1": 50.4e6, "cfg2": 200.8e6}
+    NCU_TRAFFIC = {"cfg1": 50.7e6, "cfg2": 206.5e6}
 
     def measure(name, full):
         c = CONFIGS[name]

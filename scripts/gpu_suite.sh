@@ -23,5 +23,5 @@ run multi_gpu 300 tests/test_multi_gpu.py
 echo "=== smoke" | tee -a gpurun_out/suite.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "exit=$? $(tail -1 gpurun_out/smoke.log)" | tee -a gpurun_out/suite.log
 echo "=== bench" | tee -a gpurun_out/suite.log
-timeout 600 python bench.py --steps 100 --warmup 10 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "exit=$?" | tee -a gpurun_out/suite.log
+timeout 600 python bench.py --steps 200 --warmup 20 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "exit=$?" | tee -a gpurun_out/suite.log
 tail -c 3000 gpurun_out/bench.log

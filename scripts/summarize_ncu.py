@@ -12,7 +12,10 @@ seq = [(r[ki], float(r[vi].replace(",", "")) / 1000.0, r[gi]) for r in data if l
 idx = [i for i, s in enumerate(seq) if "set_batch" in s[0]]
 # steady-state graph-replayed steps: between consecutive set_batch launches that are followed by a full step
 steps = [seq[a:b] for a, b in zip(idx[:-1], idx[1:]) if b - a >= 8]
-steps = steps[len(steps) // 2:len(steps) // 2 + 3] or steps[-1:]
+# graph-replayed resident steps split the optimizer over two streams (two launches); the un-graphed profile_step and
+# the host-buffer steps (load_batch) are skipped
+graph_steps = [s for s in steps if sum("optimizer" in k[0] for k in s) == 2 and not any("load_batch" in k[0] for k in s)]
+steps = graph_steps[len(graph_steps) // 2:] or steps[len(steps) // 2:len(steps) // 2 + 3] or steps[-1:]
 out.append("# ncu --metrics gpu__time_duration.sum --clock-control none, `bench.py --steps 6 --warmup 3` (%s), 1x B200" % tag)
 out.append("# per-launch device time of ONE steady-state training step (serialised, cold cache: compare SHARES)")
 st = steps[0]

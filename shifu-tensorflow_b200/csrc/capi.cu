@@ -168,7 +168,11 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   static const bool old_sched = getenv("SB_OLD_SCHED") != nullptr;
   const bool split_tail = !old_sched && kind == G_STEP && t->world == 1 && !pipelined && n.concurrent_bwd && !n.profiling &&
                           n.side != nullptr && n.precision == SB_PREC_BF16 && n.L > 1;
-  n.dw0_on_main = n.defer_join = split_tail;
+  // (dW_0 on the main stream also when an exchange or the accumulate kernel follows: it is then joined with the side
+  // stream as before)
+  n.dw0_on_main = !old_sched && !pipelined && n.concurrent_bwd && !n.profiling && n.side != nullptr &&
+                  n.precision == SB_PREC_BF16 && n.L > 1;
+  n.defer_join = split_tail;
   int bs = n.enqueue_backward(rows, t->grad);
   n.on_layer_grads = nullptr;
   SB_TRY(bs);

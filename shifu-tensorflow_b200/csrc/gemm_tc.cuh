@@ -155,6 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     fence_barrier_init();
   }
+  __syncwarp();
   if constexpr (CG == 2) cluster_sync_all();  // both CTAs alive before the pair-wide TMEM allocation
   if (warp == 2) {
     if constexpr (CG == 2) tmem_alloc_cg2<Cfg::TMEM_COLS>(tmem_slot);
@@ -223,6 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    __syncwarp();   // the whole warp reaches the final block barrier together (bar.sync counts warps, not lanes)
   } else if (warp == 1) {
     // ================= MMA issuer (leader CTA only when CG = 2) =================
     if (lane == 0 && leader) {
@@ -263,6 +265,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (w == w_first) stamp(5);  // all MMAs of the first tile issued
       }
     }
+    __syncwarp();
   } else {
     // ================= epilogue warps (2..9), every CTA: its own 128 rows x BN columns =================
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
