@@ -74,6 +74,7 @@ template <int W>
 static __global__ void __launch_bounds__(512)
 allreduce_p2p_kernel(const P2PPeers* __restrict__ peers, const BatchDesc* __restrict__ desc, int rank, int world, long long n4) {
   constexpr int U = (W <= 2) ? 8 : (W <= 4 ? 4 : (W <= 8 ? 2 : 1));   // W * U = 16 float4 (256 B) in flight per thread
+  pdl_launch_dependents();   // the optimizer behind it may be scheduled now; it waits (griddepcontrol.wait) for this grid
   const unsigned int epoch = desc->epoch;
   P2PFlags* mine = peers->flags[rank];
   // ---- phase A ----

@@ -189,7 +189,8 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
     if (pipelined) return SB_OK;
     SB_TRY(enqueue_allreduce(t, t->grad));
     if (t->world > 1 && n.profiling) { n.mark("allreduce"); --n.launches; }
-    SB_TRY(enqueue_optimizer(t, t->grad, 0, -1, nullptr, true));
+    // directly behind the peer-memory exchange kernel the optimizer is a programmatic dependent (no launch gap)
+    SB_TRY(enqueue_optimizer(t, t->grad, 0, -1, nullptr, true, n.use_pdl && t->world > 1 && t->p2p_ready && !n.profiling));
   } else {
     const long long np = n.n_params;
     axpy_kernel<<<static_cast<unsigned>((np + 255) / 256), 256, 0, n.stream>>>(t->acc, t->grad, np, n.scal, t->d_hscal);
