@@ -242,8 +242,14 @@ def main():
         stream = torch.cuda.ExternalStream(t.stream, device=torch.device("cuda", local_rank))
 
         # ---------------- device-resident leg (value) ----------------
-        for i in range(args.warmup):
-            t.step_resident_async((i % nb) * B, B)
+        # the per-epoch batch loop as ONE call (sb_trainer_run_resident: four steps per captured graph) on a single GPU;
+        # one call per step (sb_trainer_step_resident_async) with a gradient exchange (SB_BENCH_PER_STEP=1 forces it)
+        per_step_calls = (world > 1 and os.environ.get("SB_BENCH_RUN_API") != "1") or os.environ.get("SB_BENCH_PER_STEP") == "1"
+        if per_step_calls:
+            for i in range(args.warmup):
+                t.step_resident_async((i % nb) * B, B)
+        else:
+            t.run_resident([(i % nb) * B for i in range(args.warmup)], B)
         t.sync()
         barrier()
         clocks = ClockSampler(local_rank)
@@ -254,8 +260,11 @@ def main():
         barrier()
         wall0 = time.perf_counter()
         ev0.record(stream)
-        for i in range(args.steps):
-            t.step_resident_async(((args.warmup + i) % nb) * B, B)
+        if per_step_calls:
+            for i in range(args.steps):
+                t.step_resident_async(((args.warmup + i) % nb) * B, B)
+        else:
+            t.run_resident([((args.warmup + i) % nb) * B for i in range(args.steps)], B)
         ev1.record(stream)
         t.sync()
         barrier()
@@ -288,6 +297,8 @@ def main():
                     "kernels_ms": {k: round(v, 5) for k, v in prof.items()}}
         res = {"value": value, "ms_per_step": ms / args.steps, "roofline": roofline, "last_loss": last_loss, "clocks": clk,
                "gradient_exchange": exchange, "gpu_launches": t.kernels_per_step(B) * args.steps,
+               "step_api": "sb_trainer_step_resident_async per step" if per_step_calls else
+                           "sb_trainer_run_resident (one call for all steps, four steps per captured graph)",
                "config": config_block(name, dict(c, n_batches=nb), world)}
         if not full:
             t.close()

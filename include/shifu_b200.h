@@ -137,6 +137,11 @@ int sb_trainer_load_dataset(sb_trainer_t* t, const float* X, const float* y, con
 int sb_trainer_step_resident(sb_trainer_t* t, int64_t row_offset, int32_t rows, float* loss_out);
 /* same, but does not wait for the GPU: the loss of step i is readable after sb_trainer_sync */
 int sb_trainer_step_resident_async(sb_trainer_t* t, int64_t row_offset, int32_t rows);
+/* The inner loop of an epoch in one call (`for i in range(total_batch): sess.run(train_step)`, ssgd_monitor.py:268-276):
+ * n_steps consecutive update steps over rows [row_offsets[i], row_offsets[i]+rows) of the resident set, identical to
+ * n_steps calls of sb_trainer_step_resident_async.  Does not wait for the GPU; steps are replayed four per captured
+ * graph, so the turn-around between two graphs is paid once per four steps. */
+int sb_trainer_run_resident(sb_trainer_t* t, const int64_t* row_offsets, int32_t n_steps, int32_t rows);
 int sb_trainer_accumulate_resident(sb_trainer_t* t, int64_t row_offset, int32_t rows, float* loss_out);
 int sb_trainer_last_loss(sb_trainer_t* t, float* loss_out);
 int sb_trainer_sync(sb_trainer_t* t);

@@ -94,6 +94,7 @@ PROTOTYPES = {
     "sb_trainer_load_dataset": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_int64]),
     "sb_trainer_step_resident": (C.c_int, [_vp, C.c_int64, C.c_int32, _f32p]),
     "sb_trainer_step_resident_async": (C.c_int, [_vp, C.c_int64, C.c_int32]),
+    "sb_trainer_run_resident": (C.c_int, [_vp, C.POINTER(C.c_int64), C.c_int32, C.c_int32]),
     "sb_trainer_accumulate_resident": (C.c_int, [_vp, C.c_int64, C.c_int32, _f32p]),
     "sb_trainer_last_loss": (C.c_int, [_vp, _f32p]),
     "sb_trainer_sync": (C.c_int, [_vp]),
@@ -267,6 +268,11 @@ class Trainer:
 
     def step_resident_async(self, row_offset: int, rows: int):
         check(lib().sb_trainer_step_resident_async(self._h, row_offset, rows))
+
+    def run_resident(self, row_offsets, rows: int):
+        """n update steps over the resident set in one call (asynchronous; the reference's per-epoch batch loop)"""
+        offs = np.ascontiguousarray(row_offsets, dtype=np.int64).reshape(-1)
+        check(lib().sb_trainer_run_resident(self._h, offs.ctypes.data_as(C.POINTER(C.c_int64)), offs.size, rows))
 
     def accumulate_resident(self, row_offset: int, rows: int) -> float:
         loss = C.c_float()

@@ -59,6 +59,15 @@ struct sb_trainer {
   cudaEvent_t ev_prep[2] = {nullptr, nullptr}, ev_pos[2] = {nullptr, nullptr};
   unsigned long long prep_steps = 0;
   bool have_pos = false;   // ev_pos[] of the previous step is valid (no other user of the descriptors in between)
+  // sb_trainer_run_resident: RUN_S steps per captured graph (kernel -> kernel edges instead of a graph turn-around
+  // between steps), two alternating descriptor sets so that the descriptors of chunk i+1 are written while chunk i runs
+  enum { RUN_S = 4 };
+  BatchDesc* run_descs[2][RUN_S] = {};
+  float* run_scals[2][RUN_S] = {};
+  cudaEvent_t ev_run_prep[2] = {nullptr, nullptr}, ev_run_done[2] = {nullptr, nullptr};
+  bool run_used[2] = {false, false};
+  unsigned long long run_chunks = 0;
+  std::map<int, cudaGraphExec_t> run_graphs;   // rows * 2 + set
 };
 
 static float lr_for_step(const sb_trainer* t, long long step /*1-based*/) {
@@ -444,7 +453,12 @@ int sb_trainer_set_peer_handles(sb_trainer_t* t, const void* handles, int32_t n_
   }
   if (!t->d_peers) SB_CUDA(cudaMalloc(&t->d_peers, sizeof(P2PPeers)));
   SB_CUDA(cudaMemcpy(t->d_peers, &hp, sizeof(hp), cudaMemcpyHostToDevice));
-  for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);   // captured steps still carry the NCCL exchange
+  for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : t->run_graphs) cudaGraphExecDestroy(kv.second);
+  for (int i = 0; i < 2; ++i) {
+    if (t->ev_run_prep[i]) cudaEventDestroy(t->ev_run_prep[i]);
+    if (t->ev_run_done[i]) cudaEventDestroy(t->ev_run_done[i]);
+  }   // captured steps still carry the NCCL exchange
   t->graphs.clear();
   t->p2p_ready = true;
   return SB_OK;
@@ -660,6 +674,90 @@ static int resident_step(sb_trainer_t* t, int64_t row_offset, int32_t rows, int 
            (long long)t->ds_rows);
   return run_step(t, t->dsX ? t->dsX + row_offset * t->net.F : nullptr, t->dsY + row_offset, t->dsW + row_offset, rows, kind,
                   row_offset);
+}
+
+// RUN_S consecutive steps as ONE graph over descriptor set `set`
+static int get_run_graph(sb_trainer* t, int rows, int set, cudaGraphExec_t* out) {
+  const int key = rows * 2 + set;
+  auto it = t->run_graphs.find(key);
+  if (it != t->run_graphs.end()) { *out = it->second; return SB_OK; }
+  Net& n = t->net;
+  BatchDesc* d0 = n.desc; float* s0 = n.scal;
+  cudaGraph_t g = nullptr;
+  SB_CUDA(cudaStreamBeginCapture(n.stream, cudaStreamCaptureModeThreadLocal));
+  int s = SB_OK;
+  for (int k = 0; k < sb_trainer::RUN_S && s == SB_OK; ++k) {
+    n.desc = t->run_descs[set][k];
+    n.scal = t->run_scals[set][k];
+    s = enqueue_step_body(t, rows, G_STEP, true);
+  }
+  n.desc = d0; n.scal = s0;
+  cudaError_t e = cudaStreamEndCapture(n.stream, &g);
+  if (s != SB_OK) { if (g) cudaGraphDestroy(g); return s; }
+  SB_CHECK(e == cudaSuccess, SB_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+  cudaGraphExec_t ge = nullptr;
+  SB_CUDA(cudaGraphInstantiate(&ge, g, 0));
+  cudaGraphDestroy(g);
+  t->run_graphs[key] = ge;
+  *out = ge;
+  return SB_OK;
+}
+
+int sb_trainer_run_resident(sb_trainer_t* t, const int64_t* row_offsets, int32_t n_steps, int32_t rows) {
+  SB_CHECK(t && row_offsets, SB_ERR_INVALID, "null argument");
+  SB_CHECK(n_steps >= 0, SB_ERR_INVALID, "n_steps must be >= 0");
+  SB_CHECK(t->ds_rows > 0, SB_ERR_STATE, "no resident dataset loaded");
+  Net& n = t->net;
+  SB_CHECK(rows > 0 && rows <= n.max_batch, SB_ERR_INVALID, "rows=%d outside (0, max_batch=%d]", rows, n.max_batch);
+  for (int i = 0; i < n_steps; ++i)
+    SB_CHECK(row_offsets[i] >= 0 && row_offsets[i] + rows <= t->ds_rows, SB_ERR_INVALID,
+             "step %d: rows [%lld, %lld) outside the resident set of %lld rows", i, (long long)row_offsets[i],
+             (long long)(row_offsets[i] + rows), (long long)t->ds_rows);
+  constexpr int S = sb_trainer::RUN_S;
+  static const bool no_graph = getenv("SB_NO_GRAPH") != nullptr;
+  static const bool no_multi = getenv("SB_NO_MULTI_STEP") != nullptr;
+  int i = 0;
+  if (t->dsXb != nullptr && t->prep != nullptr && !no_graph && !no_multi) {
+    SB_CUDA(cudaSetDevice(n.device));
+    if (t->run_descs[0][0] == nullptr) {
+      for (int set = 0; set < 2; ++set) {
+        for (int k = 0; k < S; ++k) {
+          SB_TRY(n.dalloc(&t->run_descs[set][k], 1));
+          SB_TRY(n.dalloc(&t->run_scals[set][k], SCAL_COUNT));
+        }
+        SB_CUDA(cudaEventCreateWithFlags(&t->ev_run_prep[set], cudaEventDisableTiming));
+        SB_CUDA(cudaEventCreateWithFlags(&t->ev_run_done[set], cudaEventDisableTiming));
+      }
+      SB_CUDA(cudaStreamSynchronize(n.stream));   // the zero-fill of the new descriptors ran on the main stream
+    }
+    const float gscale = 1.f / static_cast<float>(t->world);
+    for (; i + S <= n_steps; i += S) {
+      const int set = static_cast<int>(t->run_chunks & 1);
+      cudaGraphExec_t ge = nullptr;
+      SB_TRY(get_run_graph(t, rows, set, &ge));
+      // this set was last read by the chunk two launches back
+      if (t->run_used[set]) SB_CUDA(cudaStreamWaitEvent(t->prep, t->ev_run_done[set], 0));
+      for (int k = 0; k < S; ++k) {
+        const long long off = row_offsets[i + k];
+        ++t->global_step;
+        ++t->epoch;
+        set_batch_kernel<<<1, 1, 0, t->prep>>>(t->run_descs[set][k], nullptr, t->dsY + off, t->dsW + off,
+                                               lr_for_step(t, t->global_step), gscale, t->epoch, static_cast<int>(off), t->dsP,
+                                               rows, t->run_scals[set][k]);
+      }
+      SB_CUDA(cudaGetLastError());
+      SB_CUDA(cudaEventRecord(t->ev_run_prep[set], t->prep));
+      SB_CUDA(cudaStreamWaitEvent(n.stream, t->ev_run_prep[set], 0));
+      SB_CUDA(cudaGraphLaunch(ge, n.stream));
+      SB_CUDA(cudaEventRecord(t->ev_run_done[set], n.stream));
+      t->run_used[set] = true;
+      ++t->run_chunks;
+      t->have_pos = false;          // the single-step descriptor prefetch re-joins the main stream
+      t->grad_out_scale = gscale;
+    }
+  }
+  for (; i < n_steps; ++i) SB_TRY(resident_step(t, row_offsets[i], rows, G_STEP));
+  return SB_OK;
 }
 
 int sb_trainer_step_resident(sb_trainer_t* t, int64_t row_offset, int32_t rows, float* loss_out) {

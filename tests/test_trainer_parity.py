@@ -211,3 +211,35 @@ def test_step_async_pipeline_equals_synchronous_steps(sb):
         assert abs(b.last_loss() - la) <= 1e-7
         np.testing.assert_allclose(a.get_params(), b.get_params(), rtol=0, atol=2e-6)
         assert b.global_step == 7
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_steps", [1, 4, 7, 9])
+def test_run_resident_equals_step_resident(sb, n_steps):
+    """sb_trainer_run_resident (four steps per captured graph, descriptors of the next chunk written ahead) must follow
+    the trajectory of n single sb_trainer_step_resident calls, and single steps must continue correctly after it.
+    Momentum keeps the comparison linear in the gradient (atomic-add order noise ~1e-7)."""
+    rows, nb, F = 64, 5, 72
+    net, params, cfg, desc = make_pair(sb, F, [48, 24], [so.ACT_RELU, so.ACT_TANH], optimizer=so.OPT_MOMENTUM, lr=0.05,
+                                       max_batch=rows, precision=sb.PREC_BF16)
+    X, y, w = so.synth_batch(rows * nb, F, 21, weights="mixed")
+    offs = [((i * 3) % nb) * rows for i in range(n_steps)]
+    flat = so.flatten_params(params)
+    with sb.Trainer(desc) as a, sb.Trainer(desc) as b:
+        for t in (a, b):
+            t.set_params(flat); t.load_dataset(X, y, w)
+        la = None
+        for o in offs:
+            la = a.step_resident(o, rows)
+        b.run_resident(offs, rows)
+        assert abs(b.last_loss() - la) <= 1e-6
+        assert b.global_step == n_steps == a.global_step
+        np.testing.assert_allclose(a.get_params(), b.get_params(), rtol=0, atol=2e-6)
+        assert np.abs(a.get_params() - flat).max() > 1e-4          # something was learned
+        # single steps after a run (the descriptor prefetch re-joins the main stream), then another run
+        assert abs(a.step_resident(rows, rows) - b.step_resident(rows, rows)) <= 1e-6
+        b.run_resident(offs[::-1] + offs, rows)
+        for o in offs[::-1] + offs:
+            la = a.step_resident(o, rows)
+        assert abs(b.last_loss() - la) <= 1e-6
+        np.testing.assert_allclose(a.get_params(), b.get_params(), rtol=0, atol=5e-6)
