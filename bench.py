@@ -242,9 +242,9 @@ def main():
         stream = torch.cuda.ExternalStream(t.stream, device=torch.device("cuda", local_rank))
 
         # ---------------- device-resident leg (value) ----------------
-        # the per-epoch batch loop as ONE call (sb_trainer_run_resident: four steps per captured graph) on a single GPU;
-        # one call per step (sb_trainer_step_resident_async) with a gradient exchange (SB_BENCH_PER_STEP=1 forces it)
-        per_step_calls = (world > 1 and os.environ.get("SB_BENCH_RUN_API") != "1") or os.environ.get("SB_BENCH_PER_STEP") == "1"
+        # the per-epoch batch loop as ONE call (sb_trainer_run_resident: four steps per captured graph);
+        # SB_BENCH_PER_STEP=1: one call per step (sb_trainer_step_resident_async) instead
+        per_step_calls = os.environ.get("SB_BENCH_PER_STEP") == "1"
         if per_step_calls:
             for i in range(args.warmup):
                 t.step_resident_async((i % nb) * B, B)
