@@ -231,6 +231,20 @@ def _exchange_nccl_id(cluster_spec: dict, task_index: int, n_workers: int) -> Op
     return buf
 
 
+def equal_size_runs(bounds):
+    """bounds = batch start offsets + [n_rows] (np.array_split: sizes differ by at most one row) ->
+    [(first batch index, number of consecutive batches, rows per batch)]"""
+    runs, i, nb = [], 0, len(bounds) - 1
+    while i < nb:
+        rows = int(bounds[i + 1] - bounds[i])
+        j = i
+        while j < nb and int(bounds[j + 1] - bounds[j]) == rows:
+            j += 1
+        runs.append((i, j - i, rows))
+        i = j
+    return runs
+
+
 def main(_=None, env=None, rng=random) -> int:
     env = os.environ if env is None else env
     logging.basicConfig(level=logging.INFO, format='%(asctime)s %(name)-12s %(levelname)-8s %(message)s',
@@ -316,18 +330,25 @@ def main(_=None, env=None, rng=random) -> int:
     while trainer.global_step < epochs:           # StopAtStepHook(num_steps=EPOCH) (ssgd_monitor.py:235)
         start = time.time()
         l = 0.0
-        for i in range(total_batch):
-            off, rows = int(bounds[i]), int(bounds[i + 1] - bounds[i])
-            if per_batch_update:
-                l = trainer.step_resident(off, rows)
-            else:
+        if per_batch_update:
+            # the whole `for i in range(total_batch): sess.run(train_step)` loop (ssgd_monitor.py:272-276) as one
+            # asynchronous call per run of equally sized batches (np.array_split sizes differ by at most one row)
+            for first, count, rows in equal_size_runs(bounds):
+                n = min(count, epochs - trainer.global_step)
+                if n <= 0:
+                    break
+                trainer.run_resident([int(b) for b in bounds[first:first + n]], rows)
+            l = trainer.last_loss()
+        else:
+            for i in range(total_batch):
+                off, rows = int(bounds[i]), int(bounds[i + 1] - bounds[i])
                 l = trainer.accumulate_resident(off, rows)
                 pending += 1
                 if pending >= pushes_per_update:
                     trainer.apply_accumulated()
                     pending = 0
-            if trainer.global_step >= epochs:
-                break
+                if trainer.global_step >= epochs:
+                    break
         training_time = time.time() - start
         valid_loss = trainer.eval_loss(valid_x, valid_y, valid_w) if len(valid_x) else 0.0
         gs = trainer.global_step

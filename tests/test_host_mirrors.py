@@ -195,3 +195,19 @@ def test_worker_matches_oracle_epoch_sync_trajectory(sb, tmp_path):
     got = [float(l.split("valid_loss:")[1]) for l in lines]
     assert len(got) == len(valid_losses)
     assert np.abs(np.array(got) - np.array(valid_losses)).max() <= 1e-4
+
+
+def test_equal_size_runs_cover_array_split_batches(sb):
+    """the per-batch schedule hands runs of equally sized mini-batches to sb_trainer_run_resident: np.array_split
+    (ssgd_monitor.py:189-192) yields sizes that differ by at most one row, i.e. at most two runs"""
+    from shifu_tensorflow_b200 import trainer as tr
+    for n_rows, total_batch in [(1000, 10), (1003, 10), (7, 7), (95, 4), (5, 1)]:
+        bounds = [b[0] for b in np.array_split(np.arange(n_rows), total_batch)] + [n_rows]
+        runs = tr.equal_size_runs(bounds)
+        assert len(runs) <= 2
+        covered = []
+        for first, count, rows in runs:
+            for k in range(count):
+                assert bounds[first + k + 1] - bounds[first + k] == rows
+                covered.append(first + k)
+        assert covered == list(range(total_batch))
