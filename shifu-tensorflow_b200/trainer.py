@@ -231,6 +231,15 @@ def _exchange_nccl_id(cluster_spec: dict, task_index: int, n_workers: int) -> Op
     return buf
 
 
+def row_shard(spec: str, *arrays):
+    """spec "g/G": rows g::G of every array, truncated to len // G rows (identical on all G ranks)"""
+    g, G = (int(v) for v in spec.split("/"))
+    if not (0 <= g < G):
+        raise ValueError("SB_ROW_SHARD must be g/G with 0 <= g < G, got %r" % spec)
+    n = len(arrays[0]) // G
+    return tuple(np.ascontiguousarray(a[g::G][:n]) for a in arrays)
+
+
 def equal_size_runs(bounds):
     """bounds = batch start offsets + [n_rows] (np.array_split: sizes differ by at most one row) ->
     [(first batch index, number of consecutive batches, rows per batch)]"""
@@ -303,6 +312,11 @@ def main(_=None, env=None, rng=random) -> int:
     valid_x = np.asarray(context["valid_data"], dtype=np.float32).reshape(-1, feature_count)
     valid_y = np.asarray(context["valid_target"], dtype=np.float32).reshape(-1)
     valid_w = np.asarray(context["valid_data_sample_weight"], dtype=np.float32).reshape(-1)
+    if env.get("SB_ROW_SHARD"):
+        # launcher.py: every local rank of a container reads the container's files and keeps rows g::G, cut to the
+        # same length on every rank so that all ranks run the same number of exchanges
+        train_x, train_y, train_w = row_shard(env["SB_ROW_SHARD"], train_x, train_y, train_w)
+        valid_x, valid_y, valid_w = row_shard(env["SB_ROW_SHARD"], valid_x, valid_y, valid_w)
     logging.info("Testing set size: %d" % len(valid_x))
     logging.info("Training set size: %d" % len(train_x))
 
