@@ -453,13 +453,10 @@ int sb_trainer_set_peer_handles(sb_trainer_t* t, const void* handles, int32_t n_
   }
   if (!t->d_peers) SB_CUDA(cudaMalloc(&t->d_peers, sizeof(P2PPeers)));
   SB_CUDA(cudaMemcpy(t->d_peers, &hp, sizeof(hp), cudaMemcpyHostToDevice));
-  for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);
-  for (auto& kv : t->run_graphs) cudaGraphExecDestroy(kv.second);
-  for (int i = 0; i < 2; ++i) {
-    if (t->ev_run_prep[i]) cudaEventDestroy(t->ev_run_prep[i]);
-    if (t->ev_run_done[i]) cudaEventDestroy(t->ev_run_done[i]);
-  }   // captured steps still carry the NCCL exchange
+  for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);   // captured steps still carry the NCCL exchange
   t->graphs.clear();
+  for (auto& kv : t->run_graphs) cudaGraphExecDestroy(kv.second);
+  t->run_graphs.clear();
   t->p2p_ready = true;
   return SB_OK;
 }
@@ -469,6 +466,11 @@ int sb_trainer_destroy(sb_trainer_t* t) {
   cudaSetDevice(t->net.device);
   if (t->net.stream) cudaStreamSynchronize(t->net.stream);
   for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : t->run_graphs) cudaGraphExecDestroy(kv.second);
+  for (int i = 0; i < 2; ++i) {
+    if (t->ev_run_prep[i]) cudaEventDestroy(t->ev_run_prep[i]);
+    if (t->ev_run_done[i]) cudaEventDestroy(t->ev_run_done[i]);
+  }
   if (t->comm) { NcclApi* api = nccl_api(); if (api) api->CommDestroy(t->comm); }
   if (t->dsX) cudaFree(t->dsX);
   if (t->dsXb) cudaFree(t->dsXb);
@@ -617,6 +619,8 @@ int sb_trainer_load_dataset(sb_trainer_t* t, const float* X, const float* y, con
   SB_CUDA(cudaStreamSynchronize(n.stream));
   for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);   // captured steps carry tensor maps of the old set
   t->graphs.clear();
+  for (auto& kv : t->run_graphs) cudaGraphExecDestroy(kv.second);
+  t->run_graphs.clear();
   if (t->dsX) cudaFree(t->dsX);
   if (t->dsXb) cudaFree(t->dsXb);
   if (t->dsY) cudaFree(t->dsY);
