@@ -5,6 +5,9 @@ dummydl_known_answers.json : forward outputs of the reference's SavedModel fixtu
     (shifu-tensorflow-eval/src/test/resources/dummydl, loaded by TensorflowModelTest.java:35-60) computed by the
     oracle reader + fp32 numpy forward.  NOT TF-verified (TF is not installable here); they agree with the values
     SURVEY.md section 8c lists, which were derived independently.
+dummydl_op_attrs.json : for every op type in the fixture's GraphDef (written by a real TF 1.x), the attribute keys its
+    nodes carry, plus the attribute keys of the SignatureDef / SaverDef plumbing - the structural reference our own
+    SavedModel writer is linted against (tests/test_formats.py).
 dummydl_head.npz : the first 3 and the last layer of that model + a 16-row input/output pair, small enough to
     commit, so the GPU box can check the scorer kernels against the fixture's real weights.
 """
@@ -37,6 +40,13 @@ def main():
     Y = tff.mlp_forward(sub, X)
     np.savez_compressed(os.path.join(HERE, "dummydl_head.npz"), X=X, Y=Y,
                         **{"W%d" % i: l[0] for i, l in enumerate(sub)}, **{"b%d" % i: l[1] for i, l in enumerate(sub)})
+    nodes, sigs = tff.read_graph_nodes(os.path.join(FIXTURE, "saved_model.pb"))
+    ops = {}
+    for _name, (op, _inputs, attrs) in nodes.items():
+        ops.setdefault(op, set()).update(attrs.keys())
+    json.dump({"source": "dummydl/saved_model.pb (TF-written GraphDef), via oracle/tf_formats.read_graph_nodes",
+               "op_attr_keys": {op: sorted(keys) for op, keys in sorted(ops.items())}, "signatures": sorted(sigs)},
+              open(os.path.join(HERE, "dummydl_op_attrs.json"), "w"), indent=1)
     print("wrote", os.listdir(HERE))
 
 

@@ -104,3 +104,27 @@ def test_reader_errors(sb, tmp_path):
     with pytest.raises(sb.ShifuB200Error) as e:
         sb.capi.savedmodel_read(d, "shifu_input_0", "shifu_output_0")
     assert e.value.code == sb.capi.SB_ERR_FORMAT
+
+
+def test_writer_nodes_carry_the_attributes_tf_writes(sb, tmp_path):
+    """Structural lint of our SavedModel writer against a GraphDef written by a real TF 1.x (the reference's dummydl
+    fixture, attribute keys committed as tests/golden/dummydl_op_attrs.json): every op type we emit that TF also emitted
+    there must carry exactly TF's attribute keys, minus the optional `_output_shapes` / `_class` hints (we may add
+    `_class` colocation on Assign / Identity like TF does).  An importer rejects nodes with missing non-default attrs."""
+    golden = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "dummydl_op_attrs.json")))["op_attr_keys"]
+    net = so.NetDesc(13, [8, 5, 3], [so.ACT_SIGMOID, so.ACT_RELU, so.ACT_TANH])
+    d = str(tmp_path / "export")
+    sb.capi.savedmodel_write(d, sb.make_desc(13, net.hidden, net.acts), so.flatten_params(so.xavier_init(net, 9)))
+    nodes, _ = tff.read_graph_nodes(os.path.join(d, "saved_model.pb"))
+    ours = {}
+    for _name, (op, _inputs, attrs) in nodes.items():
+        ours.setdefault(op, set()).update(attrs.keys())
+    optional = {"_output_shapes", "_class"}
+    checked = 0
+    for op, keys in ours.items():
+        if op not in golden:
+            assert op in ("Tanh", "LeakyRelu"), "op %s is not in the TF-written fixture" % op   # unary ops: attr T (+ alpha)
+            continue
+        assert keys - optional == set(golden[op]) - optional, (op, sorted(keys), golden[op])
+        checked += 1
+    assert checked >= 8 and {"Placeholder", "VariableV2", "MatMul", "Add", "Sigmoid", "RestoreV2", "Assign"} <= set(ours)
