@@ -6,10 +6,10 @@
            bench.py --gpus N --steps K --warmup W
 
 One "step" = one pass of the hot path over one mini-batch: load -> forward -> loss -> backward -> gradient mean
-over ranks (NCCL) -> optimizer update.  `value` times steps whose mini-batches are already resident in HBM
-(sb_trainer_step_resident_async, CUDA events on the trainer's stream, max over ranks); `e2e` times the same step
-through the public C-ABI call with HOST (pinned) buffers, H2D of the batch and D2H of the loss inside the timed
-region.  Weak scaling: every rank owns its own `batch` rows per step.  PyTorch is used for plumbing only
+over ranks (peer-memory all-reduce kernel, NCCL as fallback) -> optimizer update.  `value` times steps whose
+mini-batches are already resident in HBM (sb_trainer_run_resident = the per-epoch batch loop in one call, CUDA events on
+the trainer's stream, max over ranks); `e2e` times the same step through the public C-ABI call with HOST (pinned)
+buffers, H2D of every batch and the read-back of the loss scalars inside the timed region.  Weak scaling: every rank owns its own `batch` rows per step.  PyTorch is used for plumbing only
 (rendezvous, barrier, max-reduce, events); all compute is libshifu_b200.so.
 """
 from __future__ import annotations
