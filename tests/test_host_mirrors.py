@@ -94,7 +94,7 @@ def test_scorer_init_errors_match_tensorflowmodel(sb):
         TensorflowModel().init({"inputnames": ["a"], "properties": dict(base, outputnames=["o1", "o2"])})
 
 
-def _run_worker(sb, tmp_path, n_rows, epochs, params_extra, seed=5):
+def _run_worker(sb, tmp_path, n_rows, epochs, params_extra, seed=5, env_extra=None):
     from shifu_tensorflow_b200 import trainer as tr
     F = 12
     X, y, w = so.synth_batch(n_rows, F, 2, weights="ones")
@@ -125,6 +125,7 @@ def _run_worker(sb, tmp_path, n_rows, epochs, params_extra, seed=5):
            "SELECTED_COLUMN_NUMS": " ".join(str(i) for i in range(1, F + 1)), "WEIGHT_COLUMN_NUM": "-1", "TARGET_COLUMN_NUM": "0",
            "TMP_MODEL_PATH": str(tmp_path / "tmp_model"), "FINAL_MODEL_PATH": str(tmp_path / "final_model"),
            "TRAINING_DATA_PATH": data, "SB_SEED": "11"}
+    env.update(env_extra or {})
     try:
         rc = tr.main(env=env, rng=_Seq(seed))
     finally:
@@ -211,3 +212,96 @@ def test_equal_size_runs_cover_array_split_batches(sb):
                 assert bounds[first + k + 1] - bounds[first + k] == rows
                 covered.append(first + k)
         assert covered == list(range(total_batch))
+
+
+class _FakeTrainer:
+    """stands in for capi.Trainer so that the worker's control flow (schedules, stop condition, metrics lines,
+    checkpoint / export calls) runs without a GPU; every call is recorded"""
+    instances = []
+
+    def __init__(self, desc, device=0, nccl_id=None, rank=0, world=1):
+        self.desc, self.rank, self.world = desc, rank, world
+        self.calls, self._gs, self._acc, self.n_rows = [], 0, 0, 0
+        _FakeTrainer.instances.append(self)
+
+    global_step = property(lambda self: self._gs)
+
+    def init_xavier(self, seed): self.calls.append(("init_xavier", seed))
+    def load_checkpoint(self, path): self.calls.append(("load_checkpoint", path))
+    def load_dataset(self, X, y, w=None):
+        assert X.dtype == np.float32 and X.ndim == 2 and len(X) == len(y) == len(w)
+        self.n_rows = len(X); self.calls.append(("load_dataset", len(X)))
+    def _check(self, off, rows):
+        assert 0 <= off and rows > 0 and off + rows <= self.n_rows and rows <= self.desc.max_batch
+    def step_resident(self, off, rows):
+        self._check(off, rows); self._gs += 1; self.calls.append(("step", off, rows)); return 0.5
+    def run_resident(self, offs, rows):
+        for o in offs: self._check(o, rows)
+        self._gs += len(offs); self.calls.append(("run", list(offs), rows))
+    def last_loss(self): return 0.25
+    def accumulate_resident(self, off, rows):
+        self._check(off, rows); self._acc += 1; self.calls.append(("acc", off, rows)); return 0.3
+    def apply_accumulated(self):
+        assert self._acc > 0
+        self.calls.append(("apply", self._acc)); self._acc = 0; self._gs += 1
+    def eval_loss(self, X, y, w=None): self.calls.append(("eval", len(X))); return 0.125
+    def save_checkpoint(self, path): open(path, "w").write("ckpt"); self.calls.append(("save", path))
+    def export_savedmodel(self, d): os.makedirs(d); self.calls.append(("export", d))
+    def close(self): self.calls.append(("close",))
+
+
+@pytest.fixture
+def fake_trainer(sb, monkeypatch):
+    from shifu_tensorflow_b200 import trainer as tr
+    _FakeTrainer.instances = []
+    monkeypatch.setattr(tr.capi, "Trainer", _FakeTrainer)
+    return _FakeTrainer
+
+
+def test_worker_control_flow_per_batch_schedule(sb, tmp_path, fake_trainer):
+    """Schedule "batch": numTrainEpochs counts update steps (StopAtStepHook on global_step, ssgd_monitor.py:235); the
+    epoch's batch loop goes through run_resident in runs of equally sized batches and stops exactly at the step limit"""
+    rc, lines, env, _ = _run_worker(sb, tmp_path, 1000, 11, {"Schedule": "batch", "MiniBatchs": 100},
+                                    env_extra={"SB_HOST_LOADER": "1"})
+    assert rc == 0
+    t = fake_trainer.instances[0]
+    n_train = t.n_rows
+    total_batch = n_train // 100
+    runs = [c for c in t.calls if c[0] == "run"]
+    steps = [(o, c[2]) for c in runs for o in c[1]]
+    assert len(steps) == 11 == t.global_step                       # stopped at the limit, inside the second epoch
+    bounds = [b[0] for b in np.array_split(np.arange(n_train), total_batch)] + [n_train]
+    want = [(int(bounds[i]), int(bounds[i + 1] - bounds[i])) for i in range(total_batch)]
+    assert steps == (want + want)[:11]                             # batch order of np.array_split, epoch after epoch
+    assert not [c for c in t.calls if c[0] in ("acc", "apply", "step")]
+    assert len(lines) == 2 and lines[0].startswith("worker_index:0,time:") and ",current_epoch:%d," % total_batch in lines[0]
+    assert ",current_epoch:11,training_loss:0.25,valid_loss:0.125" in lines[1]
+    assert [c[0] for c in t.calls].count("save") == 2 and t.calls[-2][0] == "export" and t.calls[-1] == ("close",)
+    assert os.path.isdir(env["FINAL_MODEL_PATH"])
+
+
+def test_worker_control_flow_epoch_schedule_and_restart(sb, tmp_path, fake_trainer):
+    """reference schedule: R = N_train / batch mini-batch gradients per update, one update (= one global step) per
+    epoch; a checkpoint left in TMP_MODEL_PATH is restored instead of a fresh init (ssgd_monitor.py:251-257)"""
+    rc, lines, env, _ = _run_worker(sb, tmp_path, 1000, 3, {}, env_extra={"SB_HOST_LOADER": "1"})
+    assert rc == 0
+    t = fake_trainer.instances[0]
+    applies = [c for c in t.calls if c[0] == "apply"]
+    accs = [c for c in t.calls if c[0] == "acc"]
+    assert len(applies) == 3 == t.global_step and len(lines) == 3
+    assert len(accs) == sum(a[1] for a in applies)
+    assert ("init_xavier", 11) in t.calls and not [c for c in t.calls if c[0] == "load_checkpoint"]
+    assert [l.split(",")[2] for l in lines] == ["current_epoch:1", "current_epoch:2", "current_epoch:3"]
+    # second run over the same TMP_MODEL_PATH: restores
+    import shutil
+    shutil.rmtree(env["FINAL_MODEL_PATH"])
+    rc, _, _, _ = _run_worker(sb, tmp_path, 1000, 3, {}, env_extra={"SB_HOST_LOADER": "1"})
+    t2 = fake_trainer.instances[1]
+    assert rc == 0 and [c for c in t2.calls if c[0] == "load_checkpoint"] and not [c for c in t2.calls if c[0] == "init_xavier"]
+
+
+def test_worker_row_shard_from_the_launcher(sb, tmp_path, fake_trainer):
+    rc, _, _, _ = _run_worker(sb, tmp_path, 1000, 1, {}, env_extra={"SB_HOST_LOADER": "1"})
+    whole = fake_trainer.instances[0].n_rows
+    rc2, _, _, _ = _run_worker(sb, tmp_path, 1000, 1, {}, env_extra={"SB_HOST_LOADER": "1", "SB_ROW_SHARD": "1/4"})
+    assert rc == 0 and rc2 == 0 and fake_trainer.instances[1].n_rows == whole // 4
