@@ -249,7 +249,8 @@ def main():
             for i in range(args.warmup):
                 t.step_resident_async((i % nb) * B, B)
         else:
-            t.run_resident([(i % nb) * B for i in range(args.warmup)], B)
+            # at least two chunks of four steps, so that both captured multi-step graphs exist before the timed region
+            t.run_resident([(i % nb) * B for i in range(max(args.warmup, 8))], B)
         t.sync()
         barrier()
         clocks = ClockSampler(local_rank)
