@@ -251,6 +251,8 @@ def main():
         else:
             # at least two chunks of four steps, so that both captured multi-step graphs exist before the timed region
             t.run_resident([(i % nb) * B for i in range(max(args.warmup, 8))], B)
+            for i in range(2):      # and the two single-step graphs a step count that is not a multiple of four ends with
+                t.step_resident_async((i % nb) * B, B)
         t.sync()
         barrier()
         clocks = ClockSampler(local_rank)
