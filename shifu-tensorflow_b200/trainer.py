@@ -231,6 +231,84 @@ def _exchange_nccl_id(cluster_spec: dict, task_index: int, n_workers: int) -> Op
     return buf
 
 
+def _recv_exact(c: socket.socket, n: int) -> bytes:
+    buf = b""
+    while len(buf) < n:
+        chunk = c.recv(n - len(buf))
+        if not chunk:
+            raise RuntimeError("rendezvous: connection closed")
+        buf += chunk
+    return buf
+
+
+def allgather_bytes(cluster_spec: dict, task_index: int, n_workers: int, payload: bytes, timeout: float = 1200.0) -> List[bytes]:
+    """Every worker contributes one byte string, every worker gets all of them in rank order.  Worker 0 is the hub on
+    its CLUSTER_SPEC address - the port the NCCL-id rendezvous used.  The two cannot interleave: a worker only gets
+    here after its Trainer exists, and creating it (ncclCommInitRank) returns only once EVERY rank, worker 0 included,
+    has joined the communicator, i.e. after worker 0 has finished serving the id."""
+    if n_workers <= 1:
+        return [payload]
+    host, port = cluster_spec['worker'][0].rsplit(':', 1)
+    port = int(port)
+    if task_index == 0:
+        srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        srv.bind(('', port))
+        srv.listen(n_workers)
+        parts: Dict[int, bytes] = {0: payload}
+        conns = []
+        try:
+            while len(parts) < n_workers:
+                conn, _addr = srv.accept()
+                rank, size = struct.unpack("<ii", _recv_exact(conn, 8))
+                parts[rank] = _recv_exact(conn, size)
+                conns.append(conn)
+            blob = b"".join(struct.pack("<i", len(parts[r])) + parts[r] for r in range(n_workers))
+            for conn in conns:
+                conn.sendall(blob)
+        finally:
+            for conn in conns:
+                conn.close()
+            srv.close()
+        return [parts[r] for r in range(n_workers)]
+    deadline = time.time() + timeout
+    while True:
+        try:
+            c = socket.create_connection((host, port), timeout=10)
+            break
+        except OSError:
+            if time.time() > deadline:
+                raise
+            time.sleep(0.2)
+    with c:
+        c.settimeout(timeout)
+        c.sendall(struct.pack("<ii", task_index, len(payload)) + payload)
+        out = []
+        for _ in range(n_workers):
+            (size,) = struct.unpack("<i", _recv_exact(c, 4))
+            out.append(_recv_exact(c, size))
+    return out
+
+
+def enable_peer_exchange(trainer, cluster_spec: dict, task_index: int, n_workers: int) -> bool:
+    """When every rank runs on this host (launcher.py: one rank per GPU of the node), switch the gradient exchange from
+    NCCL to the peer-memory all-reduce kernel: all-gather (hostname, CUDA-IPC handle), map the peers
+    (sb_trainer_set_peer_handles), then a second round as a barrier.  Returns False (NCCL stays) across hosts."""
+    if n_workers <= 1 or n_workers > 16:
+        return False
+    me = socket.gethostname().encode("utf8")
+    got = allgather_bytes(cluster_spec, task_index, n_workers, struct.pack("<H", len(me)) + me + trainer.ipc_handle())
+    hosts, handles = [], []
+    for b in got:
+        (n,) = struct.unpack("<H", b[:2])
+        hosts.append(b[2:2 + n]); handles.append(b[2 + n:])
+    if len(set(hosts)) != 1:
+        return False
+    trainer.set_peer_handles(handles)
+    allgather_bytes(cluster_spec, task_index, n_workers, b"mapped")
+    return True
+
+
 def row_shard(spec: str, *arrays):
     """spec "g/G": rows g::G of every array, truncated to len // G rows (identical on all G ranks)"""
     g, G = (int(v) for v in spec.split("/"))
@@ -328,6 +406,9 @@ def main(_=None, env=None, rng=random) -> int:
     desc = model(feature_count, model_conf, max_rows)
     nccl_id = _exchange_nccl_id(cluster_spec, task_index, n_workers)
     trainer = capi.Trainer(desc, device=device, nccl_id=nccl_id, rank=task_index, world=n_workers)
+    if n_workers > 1 and env.get("SB_EXCHANGE", "p2p") != "nccl":
+        if enable_peer_exchange(trainer, cluster_spec, task_index, n_workers):
+            logging.info("gradient exchange: peer-memory all-reduce kernel (all %d ranks on this host)" % n_workers)
     ckpt = os.path.join(tmp_model_path, "model.ckpt")
     if os.path.exists(ckpt):                      # MonitoredTrainingSession restores the latest checkpoint (:251-257)
         trainer.load_checkpoint(ckpt)

@@ -305,3 +305,53 @@ def test_worker_row_shard_from_the_launcher(sb, tmp_path, fake_trainer):
     whole = fake_trainer.instances[0].n_rows
     rc2, _, _, _ = _run_worker(sb, tmp_path, 1000, 1, {}, env_extra={"SB_HOST_LOADER": "1", "SB_ROW_SHARD": "1/4"})
     assert rc == 0 and rc2 == 0 and fake_trainer.instances[1].n_rows == whole // 4
+
+
+def test_allgather_bytes_and_peer_exchange_decision(sb):
+    """TCP hub all-gather on worker 0's CLUSTER_SPEC address (rank order, ragged payloads), and the rule that the
+    peer-memory exchange is only switched on when every rank reports the same host"""
+    from shifu_tensorflow_b200 import trainer as tr
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    spec = {"ps": [], "worker": ["127.0.0.1:%d" % port] + ["10.0.0.%d:1" % i for i in range(1, 4)]}
+    n = 4
+    out, errs = [None] * n, []
+
+    def rank(r):
+        try:
+            out[r] = tr.allgather_bytes(spec, r, n, b"x" * r + bytes([r]))
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=rank, args=(r,)) for r in (3, 1, 0, 2)]
+    [t.start() for t in th]; [t.join(20) for t in th]
+    assert not errs, errs
+    want = [b"x" * r + bytes([r]) for r in range(n)]
+    assert all(o == want for o in out)
+
+    class T:                                     # records what the trainer is asked to do
+        def __init__(self, r): self.r, self.peers = r, None
+        def ipc_handle(self): return bytes([self.r]) * 64
+        def set_peer_handles(self, hs): self.peers = list(hs)
+
+    for same_host, expect in ((True, True), (False, False)):
+        ts, res = [T(r) for r in range(n)], [None] * n
+        names = iter(["nodeA"] * n if same_host else ["nodeA", "nodeA", "nodeB", "nodeA"])
+        lock = threading.Lock()
+        real = socket.gethostname
+
+        def fake_hostname():
+            with lock:
+                return next(names)
+
+        def run(r):
+            res[r] = tr.enable_peer_exchange(ts[r], spec, r, n)
+
+        tr.socket.gethostname = fake_hostname
+        try:
+            th = [threading.Thread(target=run, args=(r,)) for r in range(n)]
+            [t.start() for t in th]; [t.join(30) for t in th]
+        finally:
+            tr.socket.gethostname = real
+        assert res == [expect] * n
+        for t in ts:
+            assert (t.peers == [bytes([q]) * 64 for q in range(n)]) if expect else (t.peers is None)
