@@ -101,6 +101,13 @@ int sb_trainer_destroy(sb_trainer_t* t);
 #define SB_IPC_HANDLE_BYTES 64
 int sb_trainer_ipc_handle(sb_trainer_t* t, void* out64);
 int sb_trainer_set_peer_handles(sb_trainer_t* t, const void* handles /* world x 64 bytes */, int32_t n_handles);
+/* back to NCCL: unmap the peers (call on every rank when any rank failed to map, so that no rank runs the peer kernels) */
+int sb_trainer_clear_peer_handles(sb_trainer_t* t);
+/* The same peer table for trainers that live in ONE process (one host thread driving several GPUs, or several replicas
+ * on one GPU in the tests): instead of IPC handles, pass every rank's exchange allocation (sb_trainer_exchange_base) as a
+ * plain device pointer, in rank order; peer access between the devices is enabled here.  bases[own rank] is ignored. */
+void* sb_trainer_exchange_base(sb_trainer_t* t);
+int sb_trainer_set_peer_pointers(sb_trainer_t* t, void* const* bases, int32_t n);
 int64_t sb_trainer_param_count(const sb_trainer_t* t);
 /* variable init / restore (tf.initialize_all_variables + Saver.restore, ssgd_monitor.py:238,327) */
 int sb_trainer_set_params(sb_trainer_t* t, const float* flat, int64_t n);
@@ -129,6 +136,10 @@ int sb_trainer_step_async(sb_trainer_t* t, const float* X, const float* y, const
 int sb_trainer_accumulate(sb_trainer_t* t, const float* X, const float* y, const float* w, int32_t rows,
                           float* loss_out);
 int sb_trainer_apply_accumulated(sb_trainer_t* t);
+/* Same, with the divisor given explicitly: the update uses (sum over ranks of the locally accumulated gradients) /
+ * total_pushes.  This is ConditionalAccumulator.take_grad(R) when ranks accepted different numbers of pushes (stale pushes
+ * are dropped per worker, ssgd_monitor.py:136-141; the host-side token bookkeeping lives in trainer.py). */
+int sb_trainer_apply_accumulated_mean(sb_trainer_t* t, int64_t total_pushes);
 
 /* HBM-resident training set: load_data + np.array_split (ssgd_monitor.py:186-192) keep the whole
  * set in RAM and slice mini-batches from it; here the set lives in HBM and each step reads its
@@ -143,8 +154,21 @@ int sb_trainer_step_resident_async(sb_trainer_t* t, int64_t row_offset, int32_t 
  * graph, so the turn-around between two graphs is paid once per four steps. */
 int sb_trainer_run_resident(sb_trainer_t* t, const int64_t* row_offsets, int32_t n_steps, int32_t rows);
 int sb_trainer_accumulate_resident(sb_trainer_t* t, int64_t row_offset, int32_t rows, float* loss_out);
+/* forward + loss only over resident rows, no gradient, no update: what a sess.run whose push the accumulator drops as stale
+ * still reports (its loss), ssgd_monitor.py:276 */
+int sb_trainer_loss_resident(sb_trainer_t* t, int64_t row_offset, int32_t rows, float* loss_out);
 int sb_trainer_last_loss(sb_trainer_t* t, float* loss_out);
+/* the loss curve: mini-batch loss of update steps first_step .. first_step + n - 1 (1-based global_step values; the last
+ * 8192 steps are kept).  Every step's tail kernel posts its (loss sum, n_nz) into pinned host memory, so asynchronous
+ * calls (sb_trainer_run_resident / _step_async) lose no per-step loss (`loss` fetched by every sess.run, ssgd_monitor.py:276).
+ * Waits for the queued work. */
+int sb_trainer_loss_history(sb_trainer_t* t, int64_t first_step, int32_t n, float* out);
 int sb_trainer_sync(sb_trainer_t* t);
+/* Make every replica identical to rank `root`: parameters, optimizer state and the step counter (ncclBroadcast on the
+ * trainer's communicator).  The reference keeps ONE copy of the variables on the parameter servers, initialised or restored
+ * by the chief only (ssgd_monitor.py:203-206, 251-257); replicas get the same effect by calling this on all ranks after
+ * init / restore on the root.  No-op when world == 1. */
+int sb_trainer_broadcast_state(sb_trainer_t* t, int32_t root);
 /* cudaStream_t the trainer launches on (for CUDA-event timing by the caller) */
 void* sb_trainer_stream(sb_trainer_t* t);
 /* number of this library's kernels launched by one step at this batch size (bench.py's gpu_launches) */

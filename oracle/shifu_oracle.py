@@ -484,3 +484,29 @@ def loss_and_grads_bf16(net: NetDesc, params, X, y, w, loss=LOSS_MSE, fused_out=
             Wl = q(params[2 * l]).astype(f64)
             g_un = (dZ @ Wl.T) * act_grad_from_output(A[l].astype(np.float32), net.acts[l - 1]).astype(f64)
     return Lv, grads, yhat
+
+
+class Bf16Trainer:
+    """Multi-step companion of loss_and_grads_bf16: fp32 master weights + fp32 optimizer state, every step's loss and
+    gradient computed with the bf16 roundings of the CUDA performance mode (the bf16 weight shadows are re-rounded from
+    the fp32 master after every update, exactly like optimizer_kernel refreshes them).  Checker for loss CURVES of
+    SB_PREC_BF16 (tests/test_benchmarked_paths.py); same interface as CleanTrainer."""
+
+    def __init__(self, net: NetDesc, params, opt: OptConfig, loss=LOSS_MSE, fused_out=True):
+        self.net, self.loss, self.fused_out = net, loss, fused_out
+        self.theta = flatten_params(params).astype(np.float32)
+        self.opt = Optimizer(opt, self.theta.size, np.float32)
+        self.last_grads = None
+
+    def step(self, shards):
+        P = unflatten_params(self.net, self.theta)
+        gsum, losses = None, []
+        for (X, y, w) in shards:
+            L, g, _ = loss_and_grads_bf16(self.net, P, X, y, w, self.loss, fused_out=self.fused_out)
+            g = flatten_params(g)
+            gsum = g if gsum is None else gsum + g
+            losses.append(L)
+        g = gsum / np.float32(len(shards))
+        self.last_grads = g
+        self.theta = self.opt.apply(self.theta, g)
+        return losses

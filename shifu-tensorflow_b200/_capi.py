@@ -82,6 +82,9 @@ PROTOTYPES = {
     "sb_trainer_destroy": (C.c_int, [_vp]),
     "sb_trainer_ipc_handle": (C.c_int, [_vp, _vp]),
     "sb_trainer_set_peer_handles": (C.c_int, [_vp, _vp, C.c_int32]),
+    "sb_trainer_clear_peer_handles": (C.c_int, [_vp]),
+    "sb_trainer_exchange_base": (C.c_void_p, [_vp]),
+    "sb_trainer_set_peer_pointers": (C.c_int, [_vp, _P(_vp), C.c_int32]),
     "sb_trainer_param_count": (C.c_int64, [_vp]),
     "sb_trainer_set_params": (C.c_int, [_vp, _f32p, C.c_int64]),
     "sb_trainer_get_params": (C.c_int, [_vp, _f32p, C.c_int64]),
@@ -91,12 +94,16 @@ PROTOTYPES = {
     "sb_trainer_step_async": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_int32]),
     "sb_trainer_accumulate": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_int32, _f32p]),
     "sb_trainer_apply_accumulated": (C.c_int, [_vp]),
+    "sb_trainer_apply_accumulated_mean": (C.c_int, [_vp, C.c_int64]),
+    "sb_trainer_loss_resident": (C.c_int, [_vp, C.c_int64, C.c_int32, _f32p]),
+    "sb_trainer_broadcast_state": (C.c_int, [_vp, C.c_int32]),
     "sb_trainer_load_dataset": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_int64]),
     "sb_trainer_step_resident": (C.c_int, [_vp, C.c_int64, C.c_int32, _f32p]),
     "sb_trainer_step_resident_async": (C.c_int, [_vp, C.c_int64, C.c_int32]),
     "sb_trainer_run_resident": (C.c_int, [_vp, C.POINTER(C.c_int64), C.c_int32, C.c_int32]),
     "sb_trainer_accumulate_resident": (C.c_int, [_vp, C.c_int64, C.c_int32, _f32p]),
     "sb_trainer_last_loss": (C.c_int, [_vp, _f32p]),
+    "sb_trainer_loss_history": (C.c_int, [_vp, C.c_int64, C.c_int32, _f32p]),
     "sb_trainer_sync": (C.c_int, [_vp]),
     "sb_trainer_stream": (C.c_void_p, [_vp]),
     "sb_trainer_kernels_per_step": (C.c_int, [_vp, C.c_int32]),
@@ -206,6 +213,18 @@ class Trainer:
         buf = C.create_string_buffer(blob, len(blob))
         check(lib().sb_trainer_set_peer_handles(self._h, C.cast(buf, _vp), len(handles)))
 
+    def clear_peer_handles(self):
+        check(lib().sb_trainer_clear_peer_handles(self._h))
+
+    @property
+    def exchange_base(self) -> int:
+        return int(lib().sb_trainer_exchange_base(self._h) or 0)
+
+    def set_peer_pointers(self, bases: Sequence[int]):
+        """in-process peers: every rank's exchange_base in rank order"""
+        arr = (C.c_void_p * len(bases))(*[C.c_void_p(int(b)) for b in bases])
+        check(lib().sb_trainer_set_peer_pointers(self._h, arr, len(bases)))
+
     # ---- parameters ----
     def set_params(self, flat):
         flat = _f32(flat).reshape(-1)
@@ -253,8 +272,20 @@ class Trainer:
         check(lib().sb_trainer_accumulate(self._h, _ptr(X), _ptr(y), _ptr(w), rows, C.byref(loss)))
         return float(loss.value)
 
-    def apply_accumulated(self):
-        check(lib().sb_trainer_apply_accumulated(self._h))
+    def apply_accumulated(self, total_pushes: Optional[int] = None):
+        """one update from the accumulated gradients; total_pushes = divisor over ALL ranks (default world * n_acc)"""
+        if total_pushes is None:
+            check(lib().sb_trainer_apply_accumulated(self._h))
+        else:
+            check(lib().sb_trainer_apply_accumulated_mean(self._h, int(total_pushes)))
+
+    def loss_resident(self, row_offset: int, rows: int) -> float:
+        loss = C.c_float()
+        check(lib().sb_trainer_loss_resident(self._h, row_offset, rows, C.byref(loss)))
+        return float(loss.value)
+
+    def broadcast_state(self, root: int = 0):
+        check(lib().sb_trainer_broadcast_state(self._h, root))
 
     def load_dataset(self, X, y, w=None):
         X, y, w, rows = self._xyw(X, y, w)
@@ -283,6 +314,12 @@ class Trainer:
         loss = C.c_float()
         check(lib().sb_trainer_last_loss(self._h, C.byref(loss)))
         return float(loss.value)
+
+    def loss_history(self, first_step: int, n: int) -> np.ndarray:
+        """mini-batch losses of update steps first_step .. first_step+n-1 (1-based global_step); waits for the GPU"""
+        out = np.empty(n, np.float32)
+        check(lib().sb_trainer_loss_history(self._h, first_step, n, _ptr(out)))
+        return out
 
     def sync(self):
         check(lib().sb_trainer_sync(self._h))

@@ -30,6 +30,11 @@ struct sb_trainer {
   long long global_step = 0;
   float* h_scal = nullptr;  // pinned + mapped [SCAL_COUNT]: written by the tail kernel of every step
   float* d_hscal = nullptr; // device-side alias of h_scal
+  // loss curve: (loss sum, n_nz) of the last HIST update steps, ring indexed by global_step % HIST, pinned + mapped
+  enum { HIST = 8192 };
+  float2* h_hist = nullptr;
+  float2* d_hist = nullptr;
+  float2* hist_slot(long long step) { return d_hist ? d_hist + (step % HIST) : nullptr; }
   // HBM-resident training set
   float *dsX = nullptr, *dsY = nullptr, *dsW = nullptr;   // dsX only in fp32 mode
   __nv_bfloat16* dsXb = nullptr;                           // bf16 mode: the set in GEMM-operand form [ds_rows, ldF]
@@ -257,7 +262,8 @@ static int run_step(sb_trainer* t, const float* X, const float* y, const float* 
     // main stream's current position.
     if (!t->have_pos) SB_CUDA(cudaEventRecord(t->ev_pos[pair ^ 1], n.stream));
     SB_CUDA(cudaStreamWaitEvent(t->prep, t->ev_pos[pair ^ 1], 0));
-    set_batch_kernel<<<1, 1, 0, t->prep>>>(n.desc, nullptr, y, w, lr_t, gscale, t->epoch, static_cast<int>(resident_row0), t->dsP, rows, n.scal);
+    set_batch_kernel<<<1, 1, 0, t->prep>>>(n.desc, nullptr, y, w, lr_t, gscale, t->epoch, static_cast<int>(resident_row0), t->dsP, rows, n.scal,
+                                           kind == G_STEP ? t->hist_slot(t->global_step) : nullptr);
     SB_CUDA(cudaGetLastError());
     SB_CUDA(cudaEventRecord(t->ev_prep[pair], t->prep));
     SB_CUDA(cudaEventRecord(t->ev_pos[pair], n.stream));
@@ -267,9 +273,11 @@ static int run_step(sb_trainer* t, const float* X, const float* y, const float* 
   } else {
     t->have_pos = false;
     if (resident)
-      set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, nullptr, y, w, lr_t, gscale, t->epoch, static_cast<int>(resident_row0), t->dsP, rows, n.scal);
+      set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, nullptr, y, w, lr_t, gscale, t->epoch, static_cast<int>(resident_row0), t->dsP, rows, n.scal,
+                                               kind == G_STEP ? t->hist_slot(t->global_step) : nullptr);
     else
-      set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, X, y, w ? w : n.ones, lr_t, gscale, t->epoch);
+      set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, X, y, w ? w : n.ones, lr_t, gscale, t->epoch, 0, nullptr, 0, nullptr,
+                                               kind == G_STEP ? t->hist_slot(t->global_step) : nullptr);
   }
   SB_CUDA(cudaGetLastError());
   if (no_graph) SB_TRY(enqueue_step_body(t, rows, kind, resident));
@@ -282,8 +290,21 @@ static int run_step(sb_trainer* t, const float* X, const float* y, const float* 
   return SB_OK;
 }
 
+// an NCCL failure on another rank (peer died, transport error) is reported asynchronously: surface it at every point where
+// the host waits for the device instead of hanging in the next collective
+static int poll_nccl(sb_trainer* t) {
+  if (!t->comm) return SB_OK;
+  NcclApi* api = nccl_api();
+  if (!api || !api->CommGetAsyncError) return SB_OK;
+  int err = 0;
+  if (api->CommGetAsyncError(t->comm, &err) == 0 && err != 0)
+    return set_error(SB_ERR_NCCL, "NCCL asynchronous error on rank %d: %s", t->rank, api->GetErrorString(err));
+  return SB_OK;
+}
+
 static int finish_loss(sb_trainer* t, float* loss_out) {
   SB_CUDA(cudaStreamSynchronize(t->net.stream));
+  SB_TRY(poll_nccl(t));
   if (loss_out) {
     const float nnz = t->h_scal[SCAL_NNZ];
     *loss_out = nnz > 0.f ? t->h_scal[SCAL_LOSS_SUM] / nnz : 0.f;
@@ -377,6 +398,12 @@ int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, 
     return set_error(SB_ERR_CUDA, "cudaHostAlloc failed");
   }
   memset(t->h_scal, 0, sizeof(float) * SCAL_COUNT);
+  if (cudaHostAlloc(reinterpret_cast<void**>(&t->h_hist), sizeof(float2) * sb_trainer::HIST, cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer(reinterpret_cast<void**>(&t->d_hist), t->h_hist, 0) != cudaSuccess) {
+    n.destroy();
+    return set_error(SB_ERR_CUDA, "cudaHostAlloc(loss history) failed");
+  }
+  memset(t->h_hist, 0, sizeof(float2) * sb_trainer::HIST);
   t->descs[0] = n.desc;
   t->scals[0] = n.scal;
   if ((s = n.dalloc(&t->descs[1], 1)) || (s = n.dalloc(&t->scals[1], SCAL_COUNT))) { n.destroy(); return s; }
@@ -431,34 +458,95 @@ int sb_trainer_ipc_handle(sb_trainer_t* t, void* out64) {
   return SB_OK;
 }
 
+static void drop_step_graphs(sb_trainer* t) {
+  for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);   // captured steps carry the exchange they were captured with
+  t->graphs.clear();
+  for (auto& kv : t->run_graphs) cudaGraphExecDestroy(kv.second);
+  t->run_graphs.clear();
+}
+
+static void close_peer_mappings(sb_trainer* t) {
+  for (void* p : t->peer_bases) cudaIpcCloseMemHandle(p);
+  t->peer_bases.clear();
+}
+
+// peers' exchange allocations -> device table; bases[rank] is ignored (own allocation)
+static int install_peer_table(sb_trainer* t, void* const* bases) {
+  P2PPeers hp;
+  memset(&hp, 0, sizeof(hp));
+  const size_t flag_off = static_cast<size_t>(t->xch_n4) * 16;
+  for (int q = 0; q < t->world; ++q) {
+    void* base = (q == t->rank) ? t->xch : bases[q];
+    hp.grad[q] = static_cast<float*>(base);
+    hp.flags[q] = reinterpret_cast<P2PFlags*>(static_cast<char*>(base) + flag_off);
+  }
+  if (!t->d_peers) SB_CUDA(cudaMalloc(&t->d_peers, sizeof(P2PPeers)));
+  SB_CUDA(cudaMemcpy(t->d_peers, &hp, sizeof(hp), cudaMemcpyHostToDevice));
+  drop_step_graphs(t);
+  t->p2p_ready = true;
+  return SB_OK;
+}
+
 int sb_trainer_set_peer_handles(sb_trainer_t* t, const void* handles, int32_t n_handles) {
   SB_CHECK(t && handles, SB_ERR_INVALID, "null argument");
   SB_CHECK(n_handles == t->world && t->world <= SB_MAX_RANKS, SB_ERR_INVALID, "expected %d handles (<= %d), got %d", t->world,
            SB_MAX_RANKS, n_handles);
   SB_CUDA(cudaSetDevice(t->net.device));
   SB_CUDA(cudaStreamSynchronize(t->net.stream));
-  P2PPeers hp;
-  memset(&hp, 0, sizeof(hp));
-  const size_t flag_off = static_cast<size_t>(t->xch_n4) * 16;
+  close_peer_mappings(t);
+  t->p2p_ready = false;
+  void* bases[SB_MAX_RANKS] = {};
   for (int q = 0; q < t->world; ++q) {
-    void* base = t->xch;
-    if (q != t->rank) {
-      cudaIpcMemHandle_t h;
-      memcpy(&h, static_cast<const char*>(handles) + static_cast<size_t>(q) * sizeof(h), sizeof(h));
-      SB_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
-      t->peer_bases.push_back(base);
+    if (q == t->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(handles) + static_cast<size_t>(q) * sizeof(h), sizeof(h));
+    cudaError_t e = cudaIpcOpenMemHandle(&bases[q], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      close_peer_mappings(t);   // all or nothing: a half-mapped table must never be used
+      return set_error(SB_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d) failed: %s (no P2P path / separate IPC namespace?)", q,
+                       cudaGetErrorString(e));
     }
-    hp.grad[q] = static_cast<float*>(base);
-    hp.flags[q] = reinterpret_cast<P2PFlags*>(static_cast<char*>(base) + flag_off);
+    t->peer_bases.push_back(bases[q]);
   }
-  if (!t->d_peers) SB_CUDA(cudaMalloc(&t->d_peers, sizeof(P2PPeers)));
-  SB_CUDA(cudaMemcpy(t->d_peers, &hp, sizeof(hp), cudaMemcpyHostToDevice));
-  for (auto& kv : t->graphs) cudaGraphExecDestroy(kv.second);   // captured steps still carry the NCCL exchange
-  t->graphs.clear();
-  for (auto& kv : t->run_graphs) cudaGraphExecDestroy(kv.second);
-  t->run_graphs.clear();
-  t->p2p_ready = true;
+  return install_peer_table(t, bases);
+}
+
+int sb_trainer_clear_peer_handles(sb_trainer_t* t) {
+  SB_CHECK(t, SB_ERR_INVALID, "null trainer");
+  SB_CUDA(cudaSetDevice(t->net.device));
+  SB_CUDA(cudaStreamSynchronize(t->net.stream));
+  close_peer_mappings(t);
+  if (t->p2p_ready) drop_step_graphs(t);
+  t->p2p_ready = false;
   return SB_OK;
+}
+
+void* sb_trainer_exchange_base(sb_trainer_t* t) { return t ? t->xch : nullptr; }
+
+int sb_trainer_set_peer_pointers(sb_trainer_t* t, void* const* bases, int32_t n) {
+  SB_CHECK(t && bases, SB_ERR_INVALID, "null argument");
+  SB_CHECK(n == t->world && t->world <= SB_MAX_RANKS, SB_ERR_INVALID, "expected %d pointers (<= %d), got %d", t->world,
+           SB_MAX_RANKS, n);
+  SB_CUDA(cudaSetDevice(t->net.device));
+  SB_CUDA(cudaStreamSynchronize(t->net.stream));
+  for (int q = 0; q < t->world; ++q) {
+    if (q == t->rank) continue;
+    SB_CHECK(bases[q] != nullptr, SB_ERR_INVALID, "pointer of rank %d is null", q);
+    cudaPointerAttributes at;
+    SB_CUDA(cudaPointerGetAttributes(&at, bases[q]));
+    SB_CHECK(at.type == cudaMemoryTypeDevice, SB_ERR_INVALID, "pointer of rank %d is not device memory", q);
+    if (at.device != t->net.device) {
+      int can = 0;
+      SB_CUDA(cudaDeviceCanAccessPeer(&can, t->net.device, at.device));
+      SB_CHECK(can, SB_ERR_CUDA, "device %d cannot access device %d (no P2P path)", t->net.device, at.device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return set_error(SB_ERR_CUDA, "cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+    }
+  }
+  close_peer_mappings(t);
+  return install_peer_table(t, bases);
 }
 
 int sb_trainer_destroy(sb_trainer_t* t) {
@@ -478,6 +566,7 @@ int sb_trainer_destroy(sb_trainer_t* t) {
   if (t->dsY) cudaFree(t->dsY);
   if (t->dsW) cudaFree(t->dsW);
   if (t->h_scal) cudaFreeHost(t->h_scal);
+  if (t->h_hist) cudaFreeHost(t->h_hist);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   if (t->prep) { cudaStreamSynchronize(t->prep); cudaStreamDestroy(t->prep); }
   for (int i = 0; i < 2; ++i) {
@@ -587,13 +676,25 @@ int sb_trainer_accumulate(sb_trainer_t* t, const float* X, const float* y, const
   return finish_loss(t, loss_out);
 }
 
+static int apply_accumulated_impl(sb_trainer_t* t, int64_t total_pushes);
+
 int sb_trainer_apply_accumulated(sb_trainer_t* t) {
   SB_CHECK(t, SB_ERR_INVALID, "null trainer");
   SB_CHECK(t->n_acc > 0, SB_ERR_STATE, "no accumulated gradients");
+  return apply_accumulated_impl(t, static_cast<int64_t>(t->world) * t->n_acc);
+}
+
+int sb_trainer_apply_accumulated_mean(sb_trainer_t* t, int64_t total_pushes) {
+  SB_CHECK(t, SB_ERR_INVALID, "null trainer");
+  SB_CHECK(total_pushes > 0, SB_ERR_INVALID, "total_pushes must be > 0");
+  return apply_accumulated_impl(t, total_pushes);
+}
+
+static int apply_accumulated_impl(sb_trainer_t* t, int64_t total_pushes) {
   Net& n = t->net;
   SB_CUDA(cudaSetDevice(n.device));
   ++t->global_step;
-  const float gscale = 1.f / (static_cast<float>(t->world) * static_cast<float>(t->n_acc));
+  const float gscale = 1.f / static_cast<float>(total_pushes);
   ++t->epoch;
   set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, nullptr, nullptr, nullptr, lr_for_step(t, t->global_step), gscale, t->epoch);
   SB_CUDA(cudaGetLastError());
@@ -747,7 +848,7 @@ int sb_trainer_run_resident(sb_trainer_t* t, const int64_t* row_offsets, int32_t
         ++t->epoch;
         set_batch_kernel<<<1, 1, 0, t->prep>>>(t->run_descs[set][k], nullptr, t->dsY + off, t->dsW + off,
                                                lr_for_step(t, t->global_step), gscale, t->epoch, static_cast<int>(off), t->dsP,
-                                               rows, t->run_scals[set][k]);
+                                               rows, t->run_scals[set][k], t->hist_slot(t->global_step));
       }
       SB_CUDA(cudaGetLastError());
       SB_CUDA(cudaEventRecord(t->ev_run_prep[set], t->prep));
@@ -775,6 +876,77 @@ int sb_trainer_accumulate_resident(sb_trainer_t* t, int64_t row_offset, int32_t 
   SB_TRY(resident_step(t, row_offset, rows, G_ACC));
   return finish_loss(t, loss_out);
 }
+int sb_trainer_loss_resident(sb_trainer_t* t, int64_t row_offset, int32_t rows, float* loss_out) {
+  SB_CHECK(t && loss_out, SB_ERR_INVALID, "null argument");
+  SB_CHECK(t->ds_rows > 0, SB_ERR_STATE, "no resident dataset loaded");
+  Net& n = t->net;
+  SB_CHECK(row_offset >= 0 && rows > 0 && rows <= n.max_batch && row_offset + rows <= t->ds_rows, SB_ERR_INVALID,
+           "rows [%lld, %lld) outside the resident set of %lld rows", (long long)row_offset, (long long)(row_offset + rows),
+           (long long)t->ds_rows);
+  SB_CUDA(cudaSetDevice(n.device));
+  n.desc = t->descs[0];
+  n.scal = t->scals[0];
+  t->have_pos = false;
+  const bool resident = t->dsXb != nullptr;
+  if (resident)
+    set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, nullptr, t->dsY + row_offset, t->dsW + row_offset, 0.f, 1.f, t->epoch,
+                                             static_cast<int>(row_offset), t->dsP, rows, n.scal);
+  else
+    set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, t->dsX + row_offset * n.F, t->dsY + row_offset, t->dsW + row_offset, 0.f, 1.f,
+                                             t->epoch);
+  SB_CUDA(cudaGetLastError());
+  struct Scope { Net& n; ~Scope() { n.from_resident = false; } } scope{n};
+  n.from_resident = resident;
+  if (!resident) SB_TRY(n.enqueue_load(rows));
+  SB_TRY(n.enqueue_hidden_forward(rows));
+  SB_TRY(n.enqueue_out(rows, true, false, nullptr, nullptr));
+  float h[SCAL_COUNT];
+  SB_CUDA(cudaMemcpyAsync(h, n.scal, sizeof(h), cudaMemcpyDeviceToHost, n.stream));
+  SB_CUDA(cudaStreamSynchronize(n.stream));
+  *loss_out = h[SCAL_NNZ] > 0.f ? h[SCAL_LOSS_SUM] / h[SCAL_NNZ] : 0.f;
+  return SB_OK;
+}
+
+int sb_trainer_broadcast_state(sb_trainer_t* t, int32_t root) {
+  SB_CHECK(t, SB_ERR_INVALID, "null trainer");
+  if (t->world <= 1) return SB_OK;
+  SB_CHECK(root >= 0 && root < t->world, SB_ERR_INVALID, "root %d outside [0, %d)", root, t->world);
+  NcclApi* api = nccl_api();
+  SB_CHECK(api && t->comm, SB_ERR_NCCL, "no NCCL communicator");
+  Net& n = t->net;
+  SB_CUDA(cudaSetDevice(n.device));
+  long long* d_step = nullptr;
+  SB_CUDA(cudaMalloc(&d_step, sizeof(long long)));
+  SB_CUDA(cudaMemcpyAsync(d_step, &t->global_step, sizeof(long long), cudaMemcpyHostToDevice, n.stream));
+  int r = api->Broadcast(n.theta, n.theta, static_cast<size_t>(n.n_params), NCCL_FLOAT32, root, t->comm, n.stream);
+  if (r == 0) r = api->Broadcast(t->s1, t->s1, static_cast<size_t>(n.n_params), NCCL_FLOAT32, root, t->comm, n.stream);
+  if (r == 0) r = api->Broadcast(t->s2, t->s2, static_cast<size_t>(n.n_params), NCCL_FLOAT32, root, t->comm, n.stream);
+  if (r == 0) r = api->Broadcast(d_step, d_step, 1, NCCL_INT64, root, t->comm, n.stream);
+  if (r != 0) { cudaFree(d_step); return set_error(SB_ERR_NCCL, "ncclBroadcast failed: %s", api->GetErrorString(r)); }
+  long long step = 0;
+  SB_CUDA(cudaMemcpyAsync(&step, d_step, sizeof(long long), cudaMemcpyDeviceToHost, n.stream));
+  SB_TRY(n.refresh_shadows());
+  SB_CUDA(cudaStreamSynchronize(n.stream));
+  cudaFree(d_step);
+  t->global_step = step;
+  return poll_nccl(t);
+}
+
+int sb_trainer_loss_history(sb_trainer_t* t, int64_t first_step, int32_t n, float* out) {
+  SB_CHECK(t && out, SB_ERR_INVALID, "null argument");
+  SB_CHECK(n >= 0 && first_step >= 1 && first_step + n - 1 <= t->global_step, SB_ERR_INVALID,
+           "steps [%lld, %lld] outside [1, global_step=%lld]", (long long)first_step, (long long)(first_step + n - 1), (long long)t->global_step);
+  SB_CHECK(t->global_step - first_step < sb_trainer::HIST, SB_ERR_INVALID, "only the last %d steps are kept", (int)sb_trainer::HIST);
+  SB_CUDA(cudaSetDevice(t->net.device));
+  SB_CUDA(cudaStreamSynchronize(t->net.stream));
+  SB_TRY(poll_nccl(t));
+  for (int i = 0; i < n; ++i) {
+    const float2 v = t->h_hist[(first_step + i) % sb_trainer::HIST];
+    out[i] = v.y > 0.f ? v.x / v.y : 0.f;
+  }
+  return SB_OK;
+}
+
 int sb_trainer_last_loss(sb_trainer_t* t, float* loss_out) {
   SB_CHECK(t && loss_out, SB_ERR_INVALID, "null argument");
   return finish_loss(t, loss_out);
@@ -782,6 +954,7 @@ int sb_trainer_last_loss(sb_trainer_t* t, float* loss_out) {
 int sb_trainer_sync(sb_trainer_t* t) {
   SB_CHECK(t, SB_ERR_INVALID, "null trainer");
   SB_CUDA(cudaStreamSynchronize(t->net.stream));
+  SB_TRY(poll_nccl(t));
   return SB_OK;
 }
 void* sb_trainer_stream(sb_trainer_t* t) { return t ? reinterpret_cast<void*>(t->net.stream) : nullptr; }
@@ -936,6 +1109,9 @@ int sb_trainer_load_checkpoint(sb_trainer_t* t, const char* path) {
   ok = ok && fread(buf.data(), sizeof(float), buf.size(), f) == buf.size();
   fclose(f);
   SB_CHECK(ok, SB_ERR_FORMAT, "%s is not a checkpoint of this network", path);
+  SB_CHECK(hdr[4] == static_cast<uint64_t>(t->hyper.kind), SB_ERR_FORMAT,
+           "%s was written by optimizer %d, this trainer uses optimizer %d: the saved optimizer state does not apply", path,
+           static_cast<int>(hdr[4]), t->hyper.kind);
   SB_CUDA(cudaSetDevice(n.device));
   SB_CUDA(cudaMemcpyAsync(n.theta, buf.data(), sizeof(float) * n.n_params, cudaMemcpyHostToDevice, n.stream));
   SB_CUDA(cudaMemcpyAsync(t->s1, buf.data() + n.n_params, sizeof(float) * n.n_params, cudaMemcpyHostToDevice, n.stream));

@@ -615,6 +615,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tcgen05_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (threadIdx.x == 0) stamp(8);  // all roles finished
+  // in-graph kernel span: slot 2 (dependencies resolved, CTA 0) .. slot 10 (latest exit over ALL CTAs; %globaltimer only
+  // grows, so atomicMax needs no reset between steps)
+  if (p.trace != nullptr && threadIdx.x == 0) atomicMax(p.trace + 10, static_cast<unsigned long long>(globaltimer_ns()));
   if (warp == 2) {
     tcgen05_fence_after();
     if constexpr (CG == 2) tmem_dealloc_cg2<Cfg::TMEM_COLS>(tmem_base);

@@ -17,6 +17,7 @@ struct BatchDesc {
   float gscale;    // 1/world (and 1/n_accumulated for the epoch-sync schedule)
   unsigned int epoch;  // exchange round (flag value of the peer-memory all-reduce)
   int row0;            // first row of the batch inside the bf16 HBM-resident set (TMA row-coordinate offset)
+  float2* hist;        // nullable: slot of this step in the pinned-host loss history (loss sum, n_nz), written by the step's tail
 };
 
 // nz_prefix != nullptr (bf16 resident set): the batch is consumed by TMA straight from the resident set, there is no
@@ -24,8 +25,8 @@ struct BatchDesc {
 // and clears the loss accumulator.
 static __global__ void set_batch_kernel(BatchDesc* d, const float* X, const float* y, const float* w, float lr_t, float gscale,
                                         unsigned int epoch = 0, int row0 = 0, const int* nz_prefix = nullptr, int rows = 0,
-                                        float* scal = nullptr) {
-  d->X = X; d->y = y; d->w = w; d->lr_t = lr_t; d->gscale = gscale; d->epoch = epoch; d->row0 = row0;
+                                        float* scal = nullptr, float2* hist = nullptr) {
+  d->X = X; d->y = y; d->w = w; d->lr_t = lr_t; d->gscale = gscale; d->epoch = epoch; d->row0 = row0; d->hist = hist;
   if (nz_prefix != nullptr) {
     scal[1] = static_cast<float>(nz_prefix[row0 + rows] - nz_prefix[row0]);  // SCAL_NNZ
     scal[0] = 0.f;                                                           // SCAL_LOSS_SUM
@@ -119,7 +120,16 @@ struct OutLayerParams {
   float* yhat;               // nullable [rows]
   void* dZ; int ld_dZ;       // [rows, ld_dZ] bf16 or fp32
   float* g_wo; float* g_bo; float* g_bL;  // gradient slots (atomic accumulate)
+  unsigned long long* trace;              // debug timeline (nullable): [0] entry, [2] deps resolved (block 0), [10] last exit
 };
+
+// in-graph kernel span for the step timeline: begin = block 0's stamp after griddepcontrol.wait, end = atomicMax over blocks
+__device__ __forceinline__ void trace_begin(unsigned long long* trace, bool entry) {
+  if (trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) trace[entry ? 0 : 2] = globaltimer_ns();
+}
+__device__ __forceinline__ void trace_end(unsigned long long* trace) {
+  if (trace != nullptr && threadIdx.x == 0) atomicMax(trace + 10, static_cast<unsigned long long>(globaltimer_ns()));
+}
 
 template <typename T> __device__ __forceinline__ float ld_as_float(const T* p);
 template <> __device__ __forceinline__ float ld_as_float<float>(const float* p) { return __ldg(p); }
@@ -131,8 +141,10 @@ template <> __device__ __forceinline__ void st_from_float<__nv_bfloat16>(__nv_bf
 template <typename T>
 __global__ void __launch_bounds__(256)
 out_layer_kernel(const OutLayerParams p) {
+  trace_begin(p.trace, true);
   pdl_wait();
   pdl_launch_dependents();
+  trace_begin(p.trace, false);
   __shared__ float dz_row[32];
   __shared__ float blk_red[8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -181,7 +193,7 @@ out_layer_kernel(const OutLayerParams p) {
       atomicAdd(p.scal + SCAL_LOSS_SUM, s);
     }
   }
-  if (!p.do_bwd) return;
+  if (!p.do_bwd) { trace_end(p.trace); return; }
   __syncthreads();
 
   // ---- phase 2: rank-1 backward over column chunks of 128 ----
@@ -213,6 +225,7 @@ out_layer_kernel(const OutLayerParams p) {
       atomicAdd(p.g_bL + j, s_db);
     }
   }
+  trace_end(p.trace);
 }
 
 // bf16 variant of the kernel above for H <= 256 * NCH: ONE pass over A_L.  A warp owns whole rows (rows w, w+8, ... of
@@ -224,8 +237,10 @@ out_layer_kernel(const OutLayerParams p) {
 template <int NCH>
 __global__ void __launch_bounds__(256)
 out_layer_rows_kernel(const OutLayerParams p, int rows_per_block) {
+  trace_begin(p.trace, true);
   pdl_wait();
   pdl_launch_dependents();
+  trace_begin(p.trace, false);
   __shared__ float red[2][8][256];
   __shared__ float red_s[2][8];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -308,7 +323,7 @@ out_layer_rows_kernel(const OutLayerParams p, int rows_per_block) {
     if (p.do_loss) atomicAdd(p.scal + SCAL_LOSS_SUM, l);
     if (p.do_bwd) atomicAdd(p.g_bo, d);
   }
-  if (!p.do_bwd) return;
+  if (!p.do_bwd) { trace_end(p.trace); return; }
 #pragma unroll
   for (int c = 0; c < NCH; ++c) {
     if (c * 256 >= p.H) break;
@@ -325,6 +340,7 @@ out_layer_rows_kernel(const OutLayerParams p, int rows_per_block) {
       atomicAdd(p.g_bL + j, db);
     }
   }
+  trace_end(p.trace);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -383,6 +399,7 @@ optimizer_kernel(const OptWork* __restrict__ work, const BatchDesc* __restrict__
   // PCIe write off the critical path instead of a D2H copy node between two steps (measured: -8.7 us per cfg1 step)
   if (host_scal != nullptr && blockIdx.x == 0 && threadIdx.x < SCAL_COUNT) {
     host_scal[threadIdx.x] = scal[threadIdx.x];
+    if (threadIdx.x == 0 && desc->hist != nullptr) *desc->hist = make_float2(scal[SCAL_LOSS_SUM], scal[SCAL_NNZ]);   // loss curve
     __threadfence_system();
   }
   const OptWork wk = work[blockIdx.x];
@@ -415,6 +432,7 @@ optimizer_kernel(const OptWork* __restrict__ work, const BatchDesc* __restrict__
         *reinterpret_cast<uint2*>(wk.Wn + r * wk.ld_out + (m - r * wk.out_dim)) = o;
       }
     }
+    trace_end(trace);
     return;
   }
 #pragma unroll
@@ -434,7 +452,7 @@ optimizer_kernel(const OptWork* __restrict__ work, const BatchDesc* __restrict__
       }
     }
   }
-  if (trace != nullptr && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) trace[8] = globaltimer_ns();   // last block done
+  trace_end(trace);
 }
 
 // Refresh the bf16 shadows from the fp32 master without touching state (after set_params / restore).

@@ -16,12 +16,14 @@ struct NcclApi {
   int (*CommInitRank)(NcclComm*, int, NcclUniqueId, int);
   int (*CommDestroy)(NcclComm);
   int (*AllReduce)(const void*, void*, size_t, int /*dtype*/, int /*op*/, NcclComm, cudaStream_t);
+  int (*Broadcast)(const void*, void*, size_t, int /*dtype*/, int /*root*/, NcclComm, cudaStream_t);
+  int (*CommGetAsyncError)(NcclComm, int*);
   const char* (*GetErrorString)(int);
   int (*GetVersion)(int*);
   bool ok;
 };
 
-enum { NCCL_FLOAT32 = 7, NCCL_SUM = 0 };
+enum { NCCL_INT64 = 4, NCCL_FLOAT32 = 7, NCCL_SUM = 0 };
 
 inline NcclApi* nccl_api() {
   static NcclApi api = {};
@@ -35,9 +37,11 @@ inline NcclApi* nccl_api() {
   api.CommInitRank = reinterpret_cast<int (*)(NcclComm*, int, NcclUniqueId, int)>(dlsym(h, "ncclCommInitRank"));
   api.CommDestroy = reinterpret_cast<int (*)(NcclComm)>(dlsym(h, "ncclCommDestroy"));
   api.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t)>(dlsym(h, "ncclAllReduce"));
+  api.Broadcast = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t)>(dlsym(h, "ncclBroadcast"));
+  api.CommGetAsyncError = reinterpret_cast<int (*)(NcclComm, int*)>(dlsym(h, "ncclCommGetAsyncError"));
   api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
   api.GetVersion = reinterpret_cast<int (*)(int*)>(dlsym(h, "ncclGetVersion"));
-  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.GetErrorString;
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce && api.Broadcast && api.GetErrorString;
   return api.ok ? &api : nullptr;
 }
 

@@ -365,6 +365,7 @@ int Net::enqueue_out(int rows, bool do_loss, bool do_bwd, float* yhat_dst, float
   p.desc = desc; p.scal = scal; p.loss = loss; p.act = hl.act;
   p.do_bwd = do_bwd ? 1 : 0; p.do_loss = do_loss ? 1 : 0;
   p.yhat = yhat_dst;
+  p.trace = next_trace("out_layer");
   if (do_bwd) {
     p.g_wo = grad + ol.w_off; p.g_bo = grad + ol.b_off; p.g_bL = grad + hl.b_off;
   }

@@ -22,8 +22,17 @@ Optional ModelConfig train.params the reference does not have (defaults = refere
   Loss       "squared" (default: MSE on the sigmoid output, ssgd_monitor.py:129) | "log" (sigmoid cross-entropy)
   Precision  "bf16" (default) | "fp32"
   MiniBatchs mini-batch rows (default BATCH_SIZE = 100, ssgd_monitor.py:33)
-  Schedule   "epoch" (default: one update per epoch = mean of R mini-batch gradients, ssgd_monitor.py:136-141)
-             | "batch" (one update per mini-batch)
+  Schedule   "sync_replicas" (default; "epoch" is accepted as an alias): the reference's SyncReplicasOptimizer schedule
+             (ssgd_monitor.py:136-141,218,259-260) - every run pushes its mini-batch gradient, a push tagged with a stale
+             local step is dropped, after R = replicas_to_aggregate accepted pushes their MEAN is applied as ONE update
+             (class SyncReplicasSchedule below restates the token / accumulator bookkeeping on the host)
+             | "batch" (one update per mini-batch, the north-star wording)
+
+File paths (TRAINING_DATA_PATH, TMP_MODEL_PATH, FINAL_MODEL_PATH) may carry a scheme.  The stock AM hands out fully
+qualified HDFS URIs (TrainingDataSet.java:74) which the reference reads through tf.gfile; here `hdfs://`, `viewfs://`,
+`webhdfs://`, `s3a://` ... go through the `hdfs dfs` command line of the container (class _Fs), `file://` and plain
+paths are local, and the checkpoint / SavedModel are staged locally and uploaded.  A scheme path without a usable
+`hdfs` binary fails fast with a clear message instead of a FileNotFoundError deep inside the loader.
 """
 from __future__ import annotations
 
@@ -36,7 +45,9 @@ import random
 import shutil
 import socket
 import struct
+import subprocess
 import sys
+import tempfile
 import time
 from typing import Dict, List, Optional, Sequence
 
@@ -97,6 +108,62 @@ def model(feature_count: int, model_conf: Optional[dict], max_batch: int) -> cap
                           max_batch=max_batch, precision=prec)
 
 
+class _Fs:
+    """tf.gfile stand-in: local paths directly, scheme paths through `hdfs dfs` (present in every YARN container)."""
+    CLI = os.environ.get("SB_HDFS_CLI", "hdfs")
+
+    @staticmethod
+    def is_remote(path: str) -> bool:
+        return "://" in path and not path.startswith("file://")
+
+    @staticmethod
+    def local(path: str) -> str:
+        return path[len("file://"):] if path.startswith("file://") else path
+
+    @classmethod
+    def _run(cls, args: List[str], what: str, capture: bool = False):
+        try:
+            r = subprocess.run([cls.CLI, "dfs"] + args, stdout=subprocess.PIPE if capture else subprocess.DEVNULL,
+                               stderr=subprocess.PIPE)
+        except FileNotFoundError:
+            raise RuntimeError("%s needs the `%s` command on PATH (set SB_HDFS_CLI), or use a local / NFS path" % (what, cls.CLI))
+        if r.returncode != 0:
+            raise IOError("%s failed (%s dfs %s): %s" % (what, cls.CLI, " ".join(args), r.stderr.decode("utf8", "replace").strip()))
+        return r.stdout
+
+    @classmethod
+    def read_bytes(cls, path: str) -> bytes:
+        if cls.is_remote(path):
+            return cls._run(["-cat", path], "reading " + path, capture=True)
+        with open(cls.local(path), 'rb') as f:
+            return f.read()
+
+    @classmethod
+    def exists(cls, path: str) -> bool:
+        if not cls.is_remote(path):
+            return os.path.exists(cls.local(path))
+        try:
+            cls._run(["-test", "-e", path], "probing " + path)
+            return True
+        except IOError:
+            return False
+
+    @classmethod
+    def fetch(cls, path: str, local_dst: str) -> None:
+        cls._run(["-get", "-f", path, local_dst], "downloading " + path)
+
+    @classmethod
+    def upload(cls, local_src: str, path: str, replace_dir: bool = False) -> None:
+        if replace_dir:
+            try:
+                cls._run(["-rm", "-r", "-f", path], "replacing " + path)
+            except IOError:
+                pass
+        parent = path.rstrip("/").rsplit("/", 1)[0]
+        cls._run(["-mkdir", "-p", parent], "creating " + parent)
+        cls._run(["-put", "-f", local_src, path], "uploading " + path)
+
+
 def load_data(data_file: str, feature_column_nums: Optional[List[int]], target_column_num: int,
               sample_weight_column_num: int, valid_ratio: float, rng=random) -> Dict[str, object]:
     """Same semantics as the reference loader (ssgd_monitor.py:348-454): comma-separated list of gzip files, '|'
@@ -107,35 +174,34 @@ def load_data(data_file: str, feature_column_nums: Optional[List[int]], target_c
     line_count = 0
     for current_file in data_file.split(","):
         logging.info("Now loading " + current_file)
-        with open(current_file, 'rb') as f:
-            gf = gzip.GzipFile(fileobj=io.BytesIO(f.read()))
-            for raw in gf:
-                line = raw.decode('utf-8')
-                if len(line) == 0:
-                    break
-                line_count += 1
-                columns = line.split(DELIMITER)
-                if feature_column_nums is None:
-                    feature_column_nums = [c for c in range(len(columns)) if c != target_column_num and
-                                           not (sample_weight_column_num >= 0 and c == sample_weight_column_num)]
-                pre = "train" if rng.random() >= valid_ratio else "valid"
-                out[pre + "_target"].append([float(columns[target_column_num])])
-                row = []
-                for c in feature_column_nums:
-                    try:
-                        row.append(float(columns[c].strip('\n')))
-                    except Exception:
-                        logging.info("Could not convert " + str(columns[c].strip('\n')) + " to float")
-                        logging.info("feature_column_num: " + str(c))
-                out[pre + "_data"].append(row)
-                if 0 <= sample_weight_column_num < len(columns):
-                    weight = float(columns[sample_weight_column_num].strip('\n'))
-                    if weight < 0.0:
-                        logging.info("Warning: weight is below 0. example:" + line)
-                        weight = 1.0
-                    out[pre + "_data_sample_weight"].append([weight])
-                else:
-                    out[pre + "_data_sample_weight"].append([1.0])
+        gf = gzip.GzipFile(fileobj=io.BytesIO(_Fs.read_bytes(current_file)))
+        for raw in gf:
+            line = raw.decode('utf-8')
+            if len(line) == 0:
+                break
+            line_count += 1
+            columns = line.split(DELIMITER)
+            if feature_column_nums is None:
+                feature_column_nums = [c for c in range(len(columns)) if c != target_column_num and
+                                       not (sample_weight_column_num >= 0 and c == sample_weight_column_num)]
+            pre = "train" if rng.random() >= valid_ratio else "valid"
+            out[pre + "_target"].append([float(columns[target_column_num])])
+            row = []
+            for c in feature_column_nums:
+                try:
+                    row.append(float(columns[c].strip('\n')))
+                except Exception:
+                    logging.info("Could not convert " + str(columns[c].strip('\n')) + " to float")
+                    logging.info("feature_column_num: " + str(c))
+            out[pre + "_data"].append(row)
+            if 0 <= sample_weight_column_num < len(columns):
+                weight = float(columns[sample_weight_column_num].strip('\n'))
+                if weight < 0.0:
+                    logging.info("Warning: weight is below 0. example:" + line)
+                    weight = 1.0
+                out[pre + "_data_sample_weight"].append([weight])
+            else:
+                out[pre + "_data_sample_weight"].append([1.0])
     logging.info("Total data count: " + str(line_count) + ".")
     out["feature_count"] = len(feature_column_nums) if feature_column_nums is not None else 0
     return out
@@ -149,8 +215,7 @@ def load_data_gpu(data_file: str, feature_column_nums: Optional[List[int]], targ
     Returns numpy arrays under the same keys as load_data."""
     chunks = []
     for current_file in data_file.split(","):
-        with open(current_file, 'rb') as f:
-            data = gzip.GzipFile(fileobj=io.BytesIO(f.read())).read()
+        data = gzip.GzipFile(fileobj=io.BytesIO(_Fs.read_bytes(current_file))).read()
         if data and not data.endswith(b"\n"):
             data += b"\n"
         chunks.append(data)
@@ -187,48 +252,102 @@ def load_data_gpu(data_file: str, feature_column_nums: Optional[List[int]], targ
 def simple_save(trainer: capi.Trainer, export_dir: str) -> None:
     """SavedModel (tag serve, signature serving_default shifu_input_0 -> shifu_output_0) + GenericModelConfig.json
     (ssgd_monitor.py:457-490); an existing export_dir is replaced like tf.gfile.DeleteRecursively does."""
+    if _Fs.is_remote(export_dir):
+        stage = tempfile.mkdtemp(prefix="sb_export_")
+        try:
+            local = os.path.join(stage, "model")
+            trainer.export_savedmodel(local)
+            _Fs.upload(local, export_dir, replace_dir=True)
+        finally:
+            shutil.rmtree(stage, ignore_errors=True)
+        return
+    export_dir = _Fs.local(export_dir)
     if os.path.exists(export_dir):
         shutil.rmtree(export_dir)
     trainer.export_savedmodel(export_dir)
 
 
-def _exchange_nccl_id(cluster_spec: dict, task_index: int, n_workers: int) -> Optional[bytes]:
-    """Rendezvous that replaces tf.train.Server / ClusterSpec (ssgd_monitor.py:152-166): worker 0 creates the NCCL
-    unique id and serves its 128 bytes on its own CLUSTER_SPEC address (the port the executor reserved for TF,
-    TensorflowTaskExecutor.java:93-111); the other workers fetch it from there."""
-    if n_workers <= 1:
-        return None
-    host, port = cluster_spec['worker'][0].rsplit(':', 1)
-    port = int(port)
-    if task_index == 0:
-        uid = capi.nccl_unique_id()
-        srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
-        srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
-        srv.bind(('', port))
-        srv.listen(n_workers)
-        for _ in range(n_workers - 1):
-            conn, _addr = srv.accept()
-            conn.sendall(uid)
-            conn.close()
-        srv.close()
-        return uid
-    deadline = time.time() + 1200      # the AM gives stragglers 20 min (Constants.java:92-94)
-    while True:
-        try:
-            c = socket.create_connection((host, port), timeout=10)
-            break
-        except OSError:
-            if time.time() > deadline:
-                raise
-            time.sleep(0.5)
-    buf = b""
-    while len(buf) < capi.SB_NCCL_ID_BYTES:
-        chunk = c.recv(capi.SB_NCCL_ID_BYTES - len(buf))
-        if not chunk:
-            raise RuntimeError("NCCL id exchange: connection closed")
-        buf += chunk
-    c.close()
-    return buf
+class Rendezvous:
+    """The host-side channel that replaces tf.train.Server / ClusterSpec (ssgd_monitor.py:152-166): worker 0 listens ONCE
+    on its own CLUSTER_SPEC address (the port the executor reserved for TF, TensorflowTaskExecutor.java:93-111), every
+    other worker connects once, and the connections stay open for every later round (NCCL id, IPC handles, ok flags).
+    Rounds are tagged, every socket operation has a deadline, so a worker that died is an error here instead of a hang."""
+
+    def __init__(self, cluster_spec: dict, task_index: int, n_workers: int, timeout: float = 1200.0):
+        # 1200 s: the AM gives stragglers 20 min before it fails the job (Constants.java:92-94)
+        self.rank, self.n, self.timeout, self.round = task_index, n_workers, timeout, 0
+        self.conns: Dict[int, socket.socket] = {}
+        self.hub: Optional[socket.socket] = None
+        if n_workers <= 1:
+            return
+        host, port = cluster_spec['worker'][0].rsplit(':', 1)
+        port = int(port)
+        deadline = time.time() + timeout
+        if task_index == 0:
+            srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+            srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+            srv.bind(('', port))
+            srv.listen(n_workers)
+            try:
+                while len(self.conns) < n_workers - 1:
+                    srv.settimeout(max(0.1, deadline - time.time()))
+                    try:
+                        conn, _addr = srv.accept()
+                    except socket.timeout:
+                        missing = sorted(set(range(1, n_workers)) - set(self.conns))
+                        raise RuntimeError("rendezvous: workers %s did not connect within %.0f s" % (missing, timeout))
+                    conn.settimeout(timeout)
+                    (r,) = struct.unpack("<i", _recv_exact(conn, 4))
+                    self.conns[r] = conn
+            finally:
+                srv.close()
+        else:
+            while True:
+                try:
+                    c = socket.create_connection((host, port), timeout=10)
+                    break
+                except OSError:
+                    if time.time() > deadline:
+                        raise RuntimeError("rendezvous: worker 0 at %s:%d unreachable for %.0f s" % (host, port, timeout))
+                    time.sleep(0.2)
+            c.settimeout(timeout)
+            c.sendall(struct.pack("<i", task_index))
+            self.hub = c
+
+    def allgather(self, payload: bytes) -> List[bytes]:
+        """every worker contributes one byte string, every worker gets all of them in rank order"""
+        if self.n <= 1:
+            return [payload]
+        self.round += 1
+        if self.rank == 0:
+            parts: Dict[int, bytes] = {0: payload}
+            for r, conn in self.conns.items():
+                rnd, size = struct.unpack("<ii", _recv_exact(conn, 8))
+                if rnd != self.round:
+                    raise RuntimeError("rendezvous: worker %d is in round %d, worker 0 in round %d" % (r, rnd, self.round))
+                parts[r] = _recv_exact(conn, size)
+            blob = b"".join(struct.pack("<i", len(parts[r])) + parts[r] for r in range(self.n))
+            for conn in self.conns.values():
+                conn.sendall(blob)
+            return [parts[r] for r in range(self.n)]
+        self.hub.sendall(struct.pack("<ii", self.round, len(payload)) + payload)
+        out = []
+        for _ in range(self.n):
+            (size,) = struct.unpack("<i", _recv_exact(self.hub, 4))
+            out.append(_recv_exact(self.hub, size))
+        return out
+
+    def bcast(self, payload: Optional[bytes]) -> bytes:
+        """worker 0's payload on every worker"""
+        return self.allgather(payload if self.rank == 0 and payload is not None else b"")[0]
+
+    def close(self):
+        for c in list(self.conns.values()) + ([self.hub] if self.hub is not None else []):
+            try:
+                c.close()
+            except OSError:
+                pass
+        self.conns, self.hub = {}, None
 
 
 def _recv_exact(c: socket.socket, n: int) -> bytes:
@@ -241,72 +360,99 @@ def _recv_exact(c: socket.socket, n: int) -> bytes:
     return buf
 
 
-def allgather_bytes(cluster_spec: dict, task_index: int, n_workers: int, payload: bytes, timeout: float = 1200.0) -> List[bytes]:
-    """Every worker contributes one byte string, every worker gets all of them in rank order.  Worker 0 is the hub on
-    its CLUSTER_SPEC address - the port the NCCL-id rendezvous used.  The two cannot interleave: a worker only gets
-    here after its Trainer exists, and creating it (ncclCommInitRank) returns only once EVERY rank, worker 0 included,
-    has joined the communicator, i.e. after worker 0 has finished serving the id."""
-    if n_workers <= 1:
-        return [payload]
-    host, port = cluster_spec['worker'][0].rsplit(':', 1)
-    port = int(port)
-    if task_index == 0:
-        srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
-        srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
-        srv.bind(('', port))
-        srv.listen(n_workers)
-        parts: Dict[int, bytes] = {0: payload}
-        conns = []
-        try:
-            while len(parts) < n_workers:
-                conn, _addr = srv.accept()
-                rank, size = struct.unpack("<ii", _recv_exact(conn, 8))
-                parts[rank] = _recv_exact(conn, size)
-                conns.append(conn)
-            blob = b"".join(struct.pack("<i", len(parts[r])) + parts[r] for r in range(n_workers))
-            for conn in conns:
-                conn.sendall(blob)
-        finally:
-            for conn in conns:
-                conn.close()
-            srv.close()
-        return [parts[r] for r in range(n_workers)]
-    deadline = time.time() + timeout
-    while True:
-        try:
-            c = socket.create_connection((host, port), timeout=10)
-            break
-        except OSError:
-            if time.time() > deadline:
-                raise
-            time.sleep(0.2)
-    with c:
-        c.settimeout(timeout)
-        c.sendall(struct.pack("<ii", task_index, len(payload)) + payload)
-        out = []
-        for _ in range(n_workers):
-            (size,) = struct.unpack("<i", _recv_exact(c, 4))
-            out.append(_recv_exact(c, size))
-    return out
+def exchange_nccl_id(rdv: Rendezvous) -> Optional[bytes]:
+    """worker 0 creates the 128-byte NCCL unique id, every worker gets it"""
+    if rdv.n <= 1:
+        return None
+    return rdv.bcast(capi.nccl_unique_id() if rdv.rank == 0 else None)
 
 
-def enable_peer_exchange(trainer, cluster_spec: dict, task_index: int, n_workers: int) -> bool:
+def enable_peer_exchange(trainer, rdv: Rendezvous) -> bool:
     """When every rank runs on this host (launcher.py: one rank per GPU of the node), switch the gradient exchange from
-    NCCL to the peer-memory all-reduce kernel: all-gather (hostname, CUDA-IPC handle), map the peers
-    (sb_trainer_set_peer_handles), then a second round as a barrier.  Returns False (NCCL stays) across hosts."""
-    if n_workers <= 1 or n_workers > 16:
+    NCCL to the peer-memory kernels: all-gather (hostname, CUDA-IPC handle), map the peers (sb_trainer_set_peer_handles),
+    then all-gather an ok flag - the switch only happens if EVERY rank mapped every peer (cudaIpcOpenMemHandle fails
+    without P2P / NVLink, across IPC namespaces, or on distinct hosts that share a hostname); otherwise every rank
+    drops its mappings again and NCCL stays.  Returns whether the peer exchange is on."""
+    n = rdv.n
+    if n <= 1 or n > 16:
         return False
     me = socket.gethostname().encode("utf8")
-    got = allgather_bytes(cluster_spec, task_index, n_workers, struct.pack("<H", len(me)) + me + trainer.ipc_handle())
+    got = rdv.allgather(struct.pack("<H", len(me)) + me + trainer.ipc_handle())
     hosts, handles = [], []
     for b in got:
-        (n,) = struct.unpack("<H", b[:2])
-        hosts.append(b[2:2 + n]); handles.append(b[2 + n:])
+        (k,) = struct.unpack("<H", b[:2])
+        hosts.append(b[2:2 + k]); handles.append(b[2 + k:])
     if len(set(hosts)) != 1:
         return False
-    trainer.set_peer_handles(handles)
-    allgather_bytes(cluster_spec, task_index, n_workers, b"mapped")
-    return True
+    ok, why = True, ""
+    try:
+        trainer.set_peer_handles(handles)
+    except Exception as e:          # noqa: BLE001 - any failure here means "keep NCCL", never "crash the job"
+        ok, why = False, str(e)
+    flags = rdv.allgather(b"\x01" if ok else b"\x00" + why.encode("utf8", "replace")[:200])
+    if all(f[:1] == b"\x01" for f in flags):
+        return True
+    bad = ["worker %d: %s" % (r, f[1:].decode("utf8", "replace")) for r, f in enumerate(flags) if f[:1] != b"\x01"]
+    logging.warning("peer-memory exchange unavailable, staying on NCCL (%s)" % "; ".join(bad))
+    if ok and hasattr(trainer, "clear_peer_handles"):
+        trainer.clear_peer_handles()
+    return False
+
+
+class SyncReplicasSchedule:
+    """Host bookkeeping of tf.train.SyncReplicasOptimizer + ConditionalAccumulator as the reference drives them
+    (ssgd_monitor.py:136-142 builds it with replicas_to_aggregate = R, :218/:259-260 seed R tokens valued 0, every
+    sess.run(train_step) :276 pushes then dequeues).  TF-library semantics, restated (not in the reference tree): a push
+    carries the worker's local_step and is DROPPED when that is older than the accumulator's step; after R accepted
+    pushes their mean is applied once, global_step += 1 and R tokens valued global_step are enqueued; every run ends by
+    dequeuing one token, which becomes the worker's local_step.
+
+    All workers step in lock-step here (one synchronous exchange per round), so "arrival order" is rank order within a
+    round; with one worker this is exactly oracle/shifu_oracle.py:SyncReplicasTrainer.  Every rank runs the same
+    deterministic bookkeeping for ALL ranks, so no extra communication is needed to agree on who was accepted.
+
+    A worker whose dequeue finds the token queue empty BLOCKS inside its sess.run until the next update enqueues tokens
+    (served first come, first served); while blocked it issues no further runs.
+
+    round() -> (ran, accepted, apply, pushes)
+        ran[r]       rank r executes a run in this round (False: it is still blocked in its previous run's dequeue)
+        accepted[r]  rank r's gradient of this round counts (else the run only reports its loss)
+        apply        the accumulator filled in this round: apply the mean of `pushes` (= R) accepted gradients now"""
+
+    def __init__(self, R: int, n_workers: int = 1):
+        self.R, self.n = max(1, int(R)), max(1, int(n_workers))
+        self.global_step = 0
+        self.local_step = [0] * self.n
+        self.tokens: List[int] = [0] * self.R
+        self.acc_n = 0
+        self.waiting: List[int] = []          # ranks blocked in the token dequeue, in arrival order
+
+    def _serve(self):
+        while self.waiting and self.tokens:
+            self.local_step[self.waiting.pop(0)] = self.tokens.pop(0)
+
+    def round(self):
+        blocked = set(self.waiting)
+        ran = [r not in blocked for r in range(self.n)]
+        if not any(ran):
+            raise RuntimeError("every worker is blocked on the sync token queue: the reference would hang here "
+                               "(replicas_to_aggregate=%d, %d workers)" % (self.R, self.n))
+        accepted, apply_now, pushes = [False] * self.n, False, 0
+        for r in range(self.n):
+            if not ran[r]:
+                continue
+            if self.local_step[r] >= self.global_step:       # a push tagged with an older step is dropped
+                accepted[r] = True
+                self.acc_n += 1
+            if self.acc_n >= self.R:                          # take_grad(R): at most once per round, later pushes are stale
+                apply_now, pushes = True, self.acc_n
+                self.acc_n = 0
+                self.global_step += 1
+                self.tokens.extend([self.global_step] * self.R)
+                self._serve()
+            self.waiting.append(r)                            # dequeue one token (or block until there is one)
+            self._serve()
+        return ran, accepted, apply_now, pushes
 
 
 def row_shard(spec: str, *arrays):
@@ -373,7 +519,10 @@ def main(_=None, env=None, rng=random) -> int:
     valid_ratio = model_conf['train']['validSetRate']
     params = model_conf['train']['params']
     batch_size = int(params.get('MiniBatchs', BATCH_SIZE))
-    per_batch_update = str(params.get('Schedule', 'epoch')).lower() == 'batch'
+    schedule = str(params.get('Schedule', 'sync_replicas')).lower()
+    if schedule not in ('sync_replicas', 'epoch', 'batch'):
+        raise ValueError("train.params.Schedule must be sync_replicas (alias epoch) or batch, got %r" % schedule)
+    per_batch_update = schedule == 'batch'
 
     device = int(env.get("SB_DEVICE", env.get("LOCAL_RANK", "0")))
     if env.get("SB_HOST_LOADER", "0") == "1":
@@ -404,24 +553,39 @@ def main(_=None, env=None, rng=random) -> int:
     max_rows = max(bounds[i + 1] - bounds[i] for i in range(total_batch))
 
     desc = model(feature_count, model_conf, max_rows)
-    nccl_id = _exchange_nccl_id(cluster_spec, task_index, n_workers)
+    rdv = Rendezvous(cluster_spec, task_index, n_workers)
+    nccl_id = exchange_nccl_id(rdv)
     trainer = capi.Trainer(desc, device=device, nccl_id=nccl_id, rank=task_index, world=n_workers)
     if n_workers > 1 and env.get("SB_EXCHANGE", "p2p") != "nccl":
-        if enable_peer_exchange(trainer, cluster_spec, task_index, n_workers):
-            logging.info("gradient exchange: peer-memory all-reduce kernel (all %d ranks on this host)" % n_workers)
-    ckpt = os.path.join(tmp_model_path, "model.ckpt")
-    if os.path.exists(ckpt):                      # MonitoredTrainingSession restores the latest checkpoint (:251-257)
-        trainer.load_checkpoint(ckpt)
-    else:
-        trainer.init_xavier(int(env.get("SB_SEED", "0")) or random.SystemRandom().randrange(1, 2 ** 31))
+        if enable_peer_exchange(trainer, rdv):
+            logging.info("gradient exchange: peer-memory kernels (all %d ranks on this host)" % n_workers)
+    # The reference has ONE copy of the variables (on the parameter servers); the chief alone initialises or restores it
+    # (MonitoredTrainingSession(is_chief=...), ssgd_monitor.py:251-257).  Replicas: worker 0 initialises / restores, then
+    # parameters, optimizer state and global_step are broadcast, so every rank starts from the same state and runs the
+    # same number of exchanges even when only worker 0 can see the checkpoint.
+    remote_tmp = _Fs.is_remote(tmp_model_path)
+    ckpt_dir = tempfile.mkdtemp(prefix="sb_ckpt_") if remote_tmp else _Fs.local(tmp_model_path)
+    ckpt = os.path.join(ckpt_dir, "model.ckpt")
+    if is_chief or n_workers == 1:
+        if remote_tmp and _Fs.exists(tmp_model_path.rstrip("/") + "/model.ckpt"):
+            _Fs.fetch(tmp_model_path.rstrip("/") + "/model.ckpt", ckpt)
+        if os.path.exists(ckpt):                  # MonitoredTrainingSession restores the latest checkpoint (:251-257)
+            trainer.load_checkpoint(ckpt)
+        else:
+            trainer.init_xavier(int(env.get("SB_SEED", "0")) or random.SystemRandom().randrange(1, 2 ** 31))
+    if n_workers > 1:
+        trainer.broadcast_state(0)
+    rdv.close()
     trainer.load_dataset(train_x, train_y, train_w)
 
-    # replicas_to_aggregate (ssgd_monitor.py:139): pushes per global update; spread over the workers
+    # replicas_to_aggregate (ssgd_monitor.py:139): accepted pushes per global update, over all workers
     R = max(1, int(total_training_data_number * (1 - valid_ratio) / batch_size * REPLICAS_TO_AGGREGATE_RATIO))
-    pushes_per_update = max(1, R // max(1, n_workers))
+    sched = SyncReplicasSchedule(R, n_workers)
+    sched.global_step = trainer.global_step       # a restored run continues from the checkpoint's step (tokens restart at it)
+    sched.local_step = [sched.global_step] * n_workers
+    sched.tokens = [sched.global_step] * sched.R
 
     logging.info('Starting training on worker %d' % task_index)
-    pending = 0
     while trainer.global_step < epochs:           # StopAtStepHook(num_steps=EPOCH) (ssgd_monitor.py:235)
         start = time.time()
         l = 0.0
@@ -435,13 +599,18 @@ def main(_=None, env=None, rng=random) -> int:
                 trainer.run_resident([int(b) for b in bounds[first:first + n]], rows)
             l = trainer.last_loss()
         else:
-            for i in range(total_batch):
-                off, rows = int(bounds[i]), int(bounds[i + 1] - bounds[i])
-                l = trainer.accumulate_resident(off, rows)
-                pending += 1
-                if pending >= pushes_per_update:
-                    trainer.apply_accumulated()
-                    pending = 0
+            i = 0
+            while i < total_batch:
+                ran, accepted, apply_now, pushes = sched.round()
+                if ran[task_index]:
+                    off, rows = int(bounds[i]), int(bounds[i + 1] - bounds[i])
+                    if accepted[task_index]:
+                        l = trainer.accumulate_resident(off, rows)
+                    else:
+                        l = trainer.loss_resident(off, rows)     # stale push: the run still reports its loss (:276)
+                    i += 1
+                if apply_now:
+                    trainer.apply_accumulated(pushes)
                 if trainer.global_step >= epochs:
                     break
         training_time = time.time() - start
@@ -454,8 +623,10 @@ def main(_=None, env=None, rng=random) -> int:
         if socket_client is not None:
             socket_client.send(message.encode('utf8'))
         if is_chief:
-            os.makedirs(tmp_model_path, exist_ok=True)
+            os.makedirs(ckpt_dir, exist_ok=True)
             trainer.save_checkpoint(ckpt)
+            if remote_tmp:
+                _Fs.upload(ckpt, tmp_model_path.rstrip("/") + "/model.ckpt")
 
     logging.info('Done' + str(task_index))
     if is_chief:

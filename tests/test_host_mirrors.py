@@ -60,18 +60,52 @@ def test_missing_env_var_is_a_keyerror_like_the_reference(sb):
         tr.main(env={"CLUSTER_SPEC": "{}"})
 
 
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    return port
+
+
+def _in_threads(n, fn, order=None):
+    out, errs = [None] * n, []
+
+    def run(r):
+        try:
+            out[r] = fn(r)
+        except Exception as e:      # noqa: BLE001
+            errs.append((r, e))
+
+    th = [threading.Thread(target=run, args=(r,)) for r in (order or range(n))]
+    [t.start() for t in th]; [t.join(60) for t in th]
+    assert not errs, errs
+    return out
+
+
 def test_nccl_id_rendezvous_over_cluster_spec_address(sb, monkeypatch):
     """worker 0 serves the 128-byte id on its CLUSTER_SPEC address, the others fetch it (replaces tf.train.Server)"""
     from shifu_tensorflow_b200 import trainer as tr
     fake = bytes(range(128))
     monkeypatch.setattr(tr.capi, "nccl_unique_id", lambda: fake)
-    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    spec = {"ps": ["127.0.0.1:1"], "worker": ["127.0.0.1:%d" % port, "127.0.0.1:2", "127.0.0.1:3"]}
-    got = {}
-    ths = [threading.Thread(target=lambda r=r: got.__setitem__(r, tr._exchange_nccl_id(spec, r, 3))) for r in range(3)]
-    [t.start() for t in ths]; [t.join(30) for t in ths]
-    assert got == {0: fake, 1: fake, 2: fake}
-    assert tr._exchange_nccl_id(spec, 0, 1) is None
+    spec = {"ps": ["127.0.0.1:1"], "worker": ["127.0.0.1:%d" % _free_port(), "127.0.0.1:2", "127.0.0.1:3"]}
+
+    def rank(r):
+        rdv = tr.Rendezvous(spec, r, 3, timeout=30)
+        try:
+            return tr.exchange_nccl_id(rdv)
+        finally:
+            rdv.close()
+
+    assert _in_threads(3, rank) == [fake, fake, fake]
+    assert tr.exchange_nccl_id(tr.Rendezvous(spec, 0, 1)) is None
+
+
+def test_rendezvous_times_out_instead_of_hanging(sb):
+    """a worker that never shows up is an error on worker 0 within the deadline, not an accept() that blocks forever"""
+    from shifu_tensorflow_b200 import trainer as tr
+    spec = {"worker": ["127.0.0.1:%d" % _free_port(), "x:1"]}
+    with pytest.raises(RuntimeError, match="did not connect"):
+        tr.Rendezvous(spec, 0, 2, timeout=0.5)
+    with pytest.raises(RuntimeError, match="unreachable"):
+        tr.Rendezvous({"worker": ["127.0.0.1:%d" % _free_port(), "x:1"]}, 1, 2, timeout=0.5)
 
 
 def test_scorer_init_errors_match_tensorflowmodel(sb):
@@ -162,11 +196,13 @@ def test_worker_end_to_end_reference_schedule(sb, tmp_path):
 
 
 @pytest.mark.gpu
-def test_worker_matches_oracle_epoch_sync_trajectory(sb, tmp_path):
-    """same data, same split (seeded), same init -> the loss the worker reports per epoch equals the oracle's
-    epoch-sync trajectory (mean of the R mini-batch gradients, one Adadelta update per epoch) within 1e-4"""
+def test_worker_matches_oracle_sync_replicas_trajectory(sb, tmp_path):
+    """same data, same split (seeded), same init -> the losses the worker reports per epoch (training loss of the last
+    mini-batch, full validation loss, global step) equal oracle.SyncReplicasTrainer driven by the reference's loop
+    (ssgd_monitor.py:268-285: for i in range(total_batch): sess.run(train_step); then the validation run) within 1e-4"""
     from shifu_tensorflow_b200 import trainer as tr
-    rc, lines, env, (X, y, w, F, conf) = _run_worker(sb, tmp_path, 1000, 3, {})
+    rc, lines, env, (X, y, w, F, conf) = _run_worker(sb, tmp_path, 1000, 4, {"Precision": "fp32"})
+    assert rc == 0
     ctx = tr.load_data(env["TRAINING_DATA_PATH"], list(range(1, F + 1)), 0, -1, 0.2, rng=_Seq(5))
     tx = np.asarray(ctx["train_data"], np.float32); ty = np.asarray(ctx["train_target"], np.float32)
     tw = np.asarray(ctx["train_data_sample_weight"], np.float32)
@@ -177,25 +213,21 @@ def test_worker_matches_oracle_epoch_sync_trajectory(sb, tmp_path):
     with sb.Trainer(tr.model(F, conf, 128)) as t0:
         t0.init_xavier(11)
         theta = t0.get_params()
-    opt = so.Optimizer(so.OptConfig(kind=so.OPT_ADADELTA, lr=0.5), theta.size)
-    batches = so.split_batches(len(tx), 100)
     R = so.replicas_to_aggregate(1000, 0.2, 100)
-    valid_losses, pend, gsum = [], 0, np.zeros_like(theta)
-    steps = 0
-    while steps < 3:
+    ref = so.SyncReplicasTrainer(net, so.unflatten_params(net, theta), so.OptConfig(kind=so.OPT_ADADELTA, lr=0.5), R)
+    batches = so.split_batches(len(tx), 100)
+    want = []
+    while ref.global_step < 4:
         for idx in batches:
-            P = so.unflatten_params(net, theta)
-            L, g, _ = so.loss_and_grads(net, P, tx[idx], ty[idx], tw[idx])
-            gsum += so.flatten_params(g); pend += 1
-            if pend >= R:
-                theta = opt.apply(theta, gsum / np.float32(pend)); gsum[:] = 0; pend = 0; steps += 1
-                if steps >= 3:
-                    break
-        A, z, yh = so.forward(net, so.unflatten_params(net, theta), vx)
-        valid_losses.append(float(so.loss_value(z, yh, vy, vw, so.LOSS_MSE)[0]))
-    got = [float(l.split("valid_loss:")[1]) for l in lines]
-    assert len(got) == len(valid_losses)
-    assert np.abs(np.array(got) - np.array(valid_losses)).max() <= 1e-4
+            L, gs = ref.run(tx[idx], ty[idx], tw[idx])
+            if gs >= 4:
+                break
+        A, z, yh = so.forward(net, so.unflatten_params(net, ref.theta), vx)
+        want.append((gs, float(L), float(so.loss_value(z, yh, vy, vw, so.LOSS_MSE)[0])))
+    got = [(int(l.split("current_epoch:")[1].split(",")[0]), float(l.split("training_loss:")[1].split(",")[0]),
+            float(l.split("valid_loss:")[1])) for l in lines]
+    assert [g[0] for g in got] == [x[0] for x in want]
+    assert np.abs(np.array(got)[:, 1:] - np.array(want)[:, 1:]).max() <= 1e-4
 
 
 def test_equal_size_runs_cover_array_split_batches(sb):
@@ -241,8 +273,11 @@ class _FakeTrainer:
     def last_loss(self): return 0.25
     def accumulate_resident(self, off, rows):
         self._check(off, rows); self._acc += 1; self.calls.append(("acc", off, rows)); return 0.3
-    def apply_accumulated(self):
-        assert self._acc > 0
+    def loss_resident(self, off, rows):
+        self._check(off, rows); self.calls.append(("loss", off, rows)); return 0.3
+    def broadcast_state(self, root=0): self.calls.append(("bcast", root))
+    def apply_accumulated(self, total_pushes=None):
+        assert self._acc > 0 and (total_pushes is None or total_pushes == self._acc)
         self.calls.append(("apply", self._acc)); self._acc = 0; self._gs += 1
     def eval_loss(self, X, y, w=None): self.calls.append(("eval", len(X))); return 0.125
     def save_checkpoint(self, path): open(path, "w").write("ckpt"); self.calls.append(("save", path))
@@ -288,10 +323,15 @@ def test_worker_control_flow_epoch_schedule_and_restart(sb, tmp_path, fake_train
     t = fake_trainer.instances[0]
     applies = [c for c in t.calls if c[0] == "apply"]
     accs = [c for c in t.calls if c[0] == "acc"]
-    assert len(applies) == 3 == t.global_step and len(lines) == 3
-    assert len(accs) == sum(a[1] for a in applies)
+    R = so.replicas_to_aggregate(1000, 0.2, 100)
+    assert len(applies) == 3 == t.global_step
+    assert [a[1] for a in applies] == [R] * 3 and len(accs) == 3 * R       # every update is the mean of R accepted pushes
+    # the first push after the first update still carries local_step 0 and is dropped (it only reports its loss); the
+    # update points therefore drift against the for-loop's epoch boundaries exactly like in the reference
+    assert len([c for c in t.calls if c[0] == "loss"]) == 1
     assert ("init_xavier", 11) in t.calls and not [c for c in t.calls if c[0] == "load_checkpoint"]
-    assert [l.split(",")[2] for l in lines] == ["current_epoch:1", "current_epoch:2", "current_epoch:3"]
+    epochs_seen = [int(l.split(",")[2].split(":")[1]) for l in lines]
+    assert epochs_seen == sorted(epochs_seen) and epochs_seen[-1] == 3 and len(lines) >= 3
     # second run over the same TMP_MODEL_PATH: restores
     import shutil
     shutil.rmtree(env["FINAL_MODEL_PATH"])
@@ -307,35 +347,38 @@ def test_worker_row_shard_from_the_launcher(sb, tmp_path, fake_trainer):
     assert rc == 0 and rc2 == 0 and fake_trainer.instances[1].n_rows == whole // 4
 
 
-def test_allgather_bytes_and_peer_exchange_decision(sb):
-    """TCP hub all-gather on worker 0's CLUSTER_SPEC address (rank order, ragged payloads), and the rule that the
-    peer-memory exchange is only switched on when every rank reports the same host"""
+def test_rendezvous_allgather_rounds_and_peer_exchange_decision(sb):
+    """one persistent hub on worker 0's CLUSTER_SPEC address: several all-gather rounds over the same connections (rank
+    order, ragged payloads); the peer-memory exchange is switched on only when every rank reports the same host AND every
+    rank mapped its peers - one failing rank sends everybody back to NCCL"""
     from shifu_tensorflow_b200 import trainer as tr
-    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    spec = {"ps": [], "worker": ["127.0.0.1:%d" % port] + ["10.0.0.%d:1" % i for i in range(1, 4)]}
     n = 4
-    out, errs = [None] * n, []
+    spec = {"ps": [], "worker": ["127.0.0.1:%d" % _free_port()] + ["10.0.0.%d:1" % i for i in range(1, 4)]}
 
-    def rank(r):
+    def rounds(r):
+        rdv = tr.Rendezvous(spec, r, n, timeout=30)
         try:
-            out[r] = tr.allgather_bytes(spec, r, n, b"x" * r + bytes([r]))
-        except Exception as e:      # noqa: BLE001
-            errs.append(e)
+            return [rdv.allgather(b"x" * r + bytes([r, k])) for k in range(5)], rdv.bcast(b"root" if r == 0 else None)
+        finally:
+            rdv.close()
 
-    th = [threading.Thread(target=rank, args=(r,)) for r in (3, 1, 0, 2)]
-    [t.start() for t in th]; [t.join(20) for t in th]
-    assert not errs, errs
-    want = [b"x" * r + bytes([r]) for r in range(n)]
-    assert all(o == want for o in out)
+    for got, root in _in_threads(n, rounds, order=(3, 1, 0, 2)):
+        assert got == [[b"x" * r + bytes([r, k]) for r in range(n)] for k in range(5)] and root == b"root"
 
     class T:                                     # records what the trainer is asked to do
-        def __init__(self, r): self.r, self.peers = r, None
+        def __init__(self, r, fail): self.r, self.peers, self.fail, self.cleared = r, None, fail, False
         def ipc_handle(self): return bytes([self.r]) * 64
-        def set_peer_handles(self, hs): self.peers = list(hs)
+        def set_peer_handles(self, hs):
+            if self.fail:
+                raise RuntimeError("cudaIpcOpenMemHandle failed")
+            self.peers = list(hs)
+        def clear_peer_handles(self): self.cleared, self.peers = True, None
 
-    for same_host, expect in ((True, True), (False, False)):
-        ts, res = [T(r) for r in range(n)], [None] * n
-        names = iter(["nodeA"] * n if same_host else ["nodeA", "nodeA", "nodeB", "nodeA"])
+    for hosts, failing, expect in ((["nodeA"] * n, None, True), (["nodeA", "nodeA", "nodeB", "nodeA"], None, False),
+                                   (["nodeA"] * n, 2, False)):
+        spec = {"ps": [], "worker": ["127.0.0.1:%d" % _free_port()] + ["10.0.0.%d:1" % i for i in range(1, 4)]}
+        ts = [T(r, r == failing) for r in range(n)]
+        names = iter(hosts)
         lock = threading.Lock()
         real = socket.gethostname
 
@@ -344,14 +387,117 @@ def test_allgather_bytes_and_peer_exchange_decision(sb):
                 return next(names)
 
         def run(r):
-            res[r] = tr.enable_peer_exchange(ts[r], spec, r, n)
+            rdv = tr.Rendezvous(spec, r, n, timeout=30)
+            try:
+                return tr.enable_peer_exchange(ts[r], rdv)
+            finally:
+                rdv.close()
 
         tr.socket.gethostname = fake_hostname
         try:
-            th = [threading.Thread(target=run, args=(r,)) for r in range(n)]
-            [t.start() for t in th]; [t.join(30) for t in th]
+            res = _in_threads(n, run)
         finally:
             tr.socket.gethostname = real
         assert res == [expect] * n
         for t in ts:
-            assert (t.peers == [bytes([q]) * 64 for q in range(n)]) if expect else (t.peers is None)
+            if expect:
+                assert t.peers == [bytes([q]) * 64 for q in range(n)]
+            else:
+                assert t.peers is None and (failing is None or t.cleared or t.fail)
+
+
+def test_sync_replicas_schedule_is_the_oracle_state_machine(sb):
+    """trainer.SyncReplicasSchedule (host bookkeeping the worker runs) against oracle.SyncReplicasTrainer (the restatement
+    of SyncReplicasOptimizer, ssgd_monitor.py:136-142,218,259-260): same accepted / dropped pushes, same update points"""
+    from shifu_tensorflow_b200 import trainer as tr
+    net = so.NetDesc(6, [4], [so.ACT_TANH])
+    params = so.xavier_init(net, 3)
+    X, y, w = so.synth_batch(40, 6, 1)
+    for R in (1, 2, 3, 7):
+        ref = so.SyncReplicasTrainer(net, params, so.OptConfig(kind=so.OPT_SGD, lr=0.1), R)
+        sched = tr.SyncReplicasSchedule(R, 1)
+        for k in range(6 * R + 5):
+            acc_before, gs_before = ref.acc_n, ref.global_step
+            fresh = ref.local_step >= ref.global_step
+            ref.run(X, y, w)
+            ran, accepted, apply_now, pushes = sched.round()
+            assert ran == [True] and accepted == [fresh], (R, k)
+            assert apply_now == (ref.global_step == gs_before + 1), (R, k)
+            if apply_now:
+                assert pushes == R
+            assert sched.global_step == ref.global_step and sched.local_step[0] == ref.local_step
+    # several workers in lock-step, rank order = arrival order: R accepted pushes per update, at most one update per
+    # round, a push behind the update in the same round is stale
+    for R, n in ((4, 2), (5, 2), (3, 4), (1, 4), (8, 8)):
+        sched = tr.SyncReplicasSchedule(R, n)
+        acc, updates = 0, 0
+        for k in range(60):
+            ran, accepted, apply_now, pushes = sched.round()
+            assert any(ran) and all(ran[r] or not accepted[r] for r in range(n))
+            acc += sum(accepted)
+            if apply_now:
+                assert pushes == R == acc
+                acc, updates = 0, updates + 1
+            assert acc < R
+        assert updates >= 60 * min(n, R) // (R + n) and sched.global_step == updates
+
+
+_FAKE_HDFS = """#!/bin/bash
+# stand-in for the `hdfs dfs` command line of a YARN container: hdfs://nn/<p> lives under $FAKE_HDFS_ROOT/<p>
+shift
+map() { echo "${1/hdfs:\\/\\/nn/$FAKE_HDFS_ROOT}"; }
+case "$1" in
+  -cat) cat "$(map "$2")" ;;
+  -test) [ -e "$(map "$3")" ] ;;
+  -get) cp -r "$(map "$3")" "$4" ;;
+  -rm) rm -rf "$(map "$4")" ;;
+  -mkdir) mkdir -p "$(map "$3")" ;;
+  -put) rm -rf "$(map "$4")"; cp -r "$3" "$(map "$4")" ;;
+  *) echo "unsupported $1" >&2; exit 2 ;;
+esac
+"""
+
+
+def test_worker_reads_and_writes_scheme_paths_through_the_hdfs_cli(sb, tmp_path, fake_trainer, monkeypatch):
+    """the stock AM hands out hdfs:// URIs (TrainingDataSet.java:74) and HDFS model paths, which the reference reads with
+    tf.gfile: training files are fetched with `hdfs dfs -cat`, checkpoint and SavedModel are staged locally and uploaded;
+    without the CLI the worker fails fast with a message that says so"""
+    from shifu_tensorflow_b200 import trainer as tr
+    root = tmp_path / "hdfs_root"
+    (root / "data").mkdir(parents=True)
+    cli = tmp_path / "hdfs"
+    cli.write_text(_FAKE_HDFS); cli.chmod(0o755)
+    monkeypatch.setenv("FAKE_HDFS_ROOT", str(root))
+    monkeypatch.setattr(tr._Fs, "CLI", str(cli))
+    work = tmp_path / "w"; work.mkdir()
+    rc, lines, env, (X, y, w, F, conf) = _run_worker(sb, work, 400, 2, {}, env_extra={"SB_HOST_LOADER": "1"})   # writes the gz file
+    os.replace(env["TRAINING_DATA_PATH"], root / "data" / "part-00000.gz")
+    fake_trainer.instances.clear()
+    work2 = tmp_path / "w2"; work2.mkdir()
+    extra = {"SB_HOST_LOADER": "1", "TRAINING_DATA_PATH": "hdfs://nn/data/part-00000.gz", "TMP_MODEL_PATH": "hdfs://nn/tmp_model",
+             "FINAL_MODEL_PATH": "hdfs://nn/final_model"}
+
+    real_run = _run_worker.__globals__["_write_gz"]
+    _run_worker.__globals__["_write_gz"] = lambda *a, **k: None      # the data already lives on "HDFS"
+    try:
+        rc, lines, env, _ = _run_worker(sb, work2, 400, 2, {}, env_extra=extra)
+    finally:
+        _run_worker.__globals__["_write_gz"] = real_run
+    assert rc == 0 and len(lines) >= 2
+    t = fake_trainer.instances[0]
+    assert t.n_rows > 0 and ("init_xavier", 11) in t.calls
+    assert (root / "tmp_model" / "model.ckpt").read_text() == "ckpt"           # staged locally, uploaded
+    assert (root / "final_model").is_dir()
+    assert not os.path.exists(work2 / "hdfs:")                                  # nothing written into a local 'hdfs:' directory
+    # second run: the checkpoint on "HDFS" is fetched and restored by worker 0
+    fake_trainer.instances.clear()
+    _run_worker.__globals__["_write_gz"] = lambda *a, **k: None
+    try:
+        rc, _, _, _ = _run_worker(sb, tmp_path / "w2", 400, 2, {}, env_extra=extra)
+    finally:
+        _run_worker.__globals__["_write_gz"] = real_run
+    assert rc == 0 and [c for c in fake_trainer.instances[0].calls if c[0] == "load_checkpoint"]
+    # no CLI -> clear failure
+    monkeypatch.setattr(tr._Fs, "CLI", str(tmp_path / "no_such_hdfs"))
+    with pytest.raises(RuntimeError, match="needs the"):
+        tr._Fs.read_bytes("hdfs://nn/data/part-00000.gz")
