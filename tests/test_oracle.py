@@ -112,3 +112,33 @@ def test_torch_cpu_worker_equals_numpy_oracle(optimizer):
         gl = wk.step(torch.from_numpy(X), torch.from_numpy(y), torch.from_numpy(w))
         assert abs(gl - rl) < 1e-6
     assert np.abs(wk.flat_params() - ref.theta).max() < 2e-6
+
+
+def test_oracle_matches_tf_golden():
+    """When somebody has run oracle/tf_golden.py on a machine WITH TensorFlow and committed tests/golden/tf_golden.npz, the
+    oracle is pinned to real TF output here (forward, both losses, all gradients, three steps of all four optimizers,
+    including the ApplyAdadelta evaluation order).  Until then this test is skipped and parity stays 'unpinned'."""
+    import os
+    import pytest
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tf_golden.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/tf_golden.npz absent: no TensorFlow was available to write it (oracle/tf_golden.py)")
+    G = np.load(path)
+    net = so.NetDesc(int(G["F"]), [int(h) for h in G["hidden"]], [int(a) for a in G["acts"]])
+    params = [G["param%d" % i] for i in range(2 * len(net.acts) + 2)]
+    X, y, w = G["X"], G["y"], G["w"]
+    kinds = {"adadelta": so.OptConfig(kind=so.OPT_ADADELTA, lr=0.5), "adam": so.OptConfig(kind=so.OPT_ADAM, lr=0.01),
+             "sgd": so.OptConfig(kind=so.OPT_SGD, lr=0.1), "momentum": so.OptConfig(kind=so.OPT_MOMENTUM, lr=0.1, momentum=0.9)}
+    for loss_name, loss_id in (("mse", so.LOSS_MSE), ("ce", so.LOSS_SIGMOID_CE)):
+        for opt_name, cfg in kinds.items():
+            key = "%s_%s_" % (loss_name, opt_name)
+            L, g, yhat = so.loss_and_grads(net, params, X, y, w, loss_id)
+            assert abs(float(L) - float(G[key + "loss"])) <= 1e-6
+            assert np.abs(yhat - G[key + "yhat"]).max() <= 1e-6
+            for i, gi in enumerate(g):
+                assert np.abs(gi - G[key + "grad%d" % i].reshape(gi.shape)).max() <= 1e-6
+            tr = so.CleanTrainer(net, params, cfg, loss=loss_id)
+            for step in range(3):
+                tr.step([(X, y, w)])
+                for i, p in enumerate(tr.params()):
+                    assert np.abs(p - G[key + "step%d_param%d" % (step + 1, i)].reshape(p.shape)).max() <= 2e-6, (key, step, i)
