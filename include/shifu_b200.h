@@ -93,6 +93,8 @@ int sb_nccl_unique_id(void* out128);
  * (ssgd_monitor.py:110-144, 251-257).  nccl_id may be NULL when world == 1. ---- */
 int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, int rank, int world,
                       sb_trainer_t** out);
+/* (world > 1 with nccl_id == NULL: replicas driven by ONE process; they must be connected with
+ * sb_trainer_set_peer_pointers before the first step, there is no NCCL fallback then.) */
 int sb_trainer_destroy(sb_trainer_t* t);
 /* Optional faster gradient exchange for ranks on one NVLink/NVSwitch node: a two-shot all-reduce kernel over CUDA-IPC
  * peer memory instead of NCCL.  Every rank exports its exchange buffer (64-byte cudaIpcMemHandle_t), the host

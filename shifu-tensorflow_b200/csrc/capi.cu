@@ -8,7 +8,7 @@
 #include "net.cuh"
 #include "gemm_tc_launch.cuh"
 #include "savedmodel.h"
-#include "allreduce_p2p.cuh"
+#include "xchg_p2p.cuh"
 
 using namespace sb;
 
@@ -42,14 +42,22 @@ struct sb_trainer {
   long long ds_rows = 0;
   std::map<std::pair<int, int>, cudaGraphExec_t> graphs;  // (rows, kind * 2 + from_resident) -> captured step
   std::map<int, int> kernels_per_step;
-  // peer-memory gradient exchange (CUDA IPC): xch = [gradient (padded) | P2PFlags] in ONE exported allocation
+  // peer-memory exchange (xchg_p2p.cuh): the net's parameter arena [theta | s1 | s2 | shadows | gradient | P2PFlags] is
+  // ONE exported allocation; `xch` aliases it
   void* xch = nullptr;
-  long long xch_n4 = 0;            // float4 count of the padded gradient (multiple of world)
+  long long xch_n4 = 0;            // float4 count of the padded gradient
+  long long grad_off = 0, flags_off = 0;   // byte offsets of the gradient / flag block inside the arena
   P2PFlags* flags = nullptr;
-  P2PPeers* d_peers = nullptr;     // device table of every rank's gradient / flags pointers
+  P2PPeers* d_peers = nullptr;     // device table of every rank's arena
   std::vector<void*> peer_bases;   // opened IPC mappings (to close)
   bool p2p_ready = false;
+  bool grad_sharded = false;       // the reduced gradient of the last step lives in slices on its owners (sb_trainer_get_grads gathers)
+  bool master_stale = false;       // sharded updates ran since the fp32 master / state were last gathered from their owners
   unsigned int epoch = 0;
+  unsigned int* h_err = nullptr;   // pinned + mapped: a peer that never arrived (xchg_p2p.cuh), 0 = none
+  unsigned int* d_herr = nullptr;
+  unsigned long long xchg_timeout_ns = 300ull * 1000000000ull;
+  int xchg_blocks = 0;             // grid of the exchange kernels (0 = one block per SM)
   // pipelined host-buffer steps (sb_trainer_step_async): second staging slot + copy stream, so the H2D of batch i+1
   // overlaps the compute of batch i
   cudaStream_t copy_stream = nullptr;
@@ -86,18 +94,10 @@ static float lr_for_step(const sb_trainer* t, long long step /*1-based*/) {
 static int enqueue_allreduce(sb_trainer* t, float* buf, long long off = 0, long long count = -1, cudaStream_t st = nullptr) {
   if (t->world <= 1) return SB_OK;
   NcclApi* api = nccl_api();
-  SB_CHECK(t->p2p_ready || (api && t->comm), SB_ERR_NCCL, "no gradient exchange configured (NCCL communicator missing)");
+  SB_CHECK(api && t->comm, SB_ERR_NCCL, "no gradient exchange configured: world = %d but neither an NCCL communicator (nccl_id) nor a "
+           "peer table (sb_trainer_set_peer_handles / _pointers) exists", t->world);
   if (count < 0) count = t->net.n_params;
   if (!st) st = t->net.stream;
-  if (t->p2p_ready && buf == t->grad && off == 0 && count == t->net.n_params) {
-    const int g = t->net.num_sms;
-    if (t->world <= 2) allreduce_p2p_kernel<2><<<g, 512, 0, st>>>(t->d_peers, t->net.desc, t->rank, t->world, t->xch_n4);
-    else if (t->world <= 4) allreduce_p2p_kernel<4><<<g, 512, 0, st>>>(t->d_peers, t->net.desc, t->rank, t->world, t->xch_n4);
-    else if (t->world <= 8) allreduce_p2p_kernel<8><<<g, 512, 0, st>>>(t->d_peers, t->net.desc, t->rank, t->world, t->xch_n4);
-    else allreduce_p2p_kernel<16><<<g, 512, 0, st>>>(t->d_peers, t->net.desc, t->rank, t->world, t->xch_n4);
-    SB_CUDA(cudaGetLastError());
-    return SB_OK;
-  }
   int r = api->AllReduce(buf + off, buf + off, static_cast<size_t>(count), NCCL_FLOAT32, NCCL_SUM, t->comm, st);
   SB_CHECK(r == 0, SB_ERR_NCCL, "ncclAllReduce failed: %s", api->GetErrorString(r));
   return SB_OK;
@@ -111,9 +111,71 @@ static int enqueue_optimizer(sb_trainer* t, const float* g, int w0 = 0, int w1 =
   if (w1 <= w0) return SB_OK;
   // pdl = false: plain dependency (runs after a stream join / on the comm stream)
   SB_TRY(n.launch(optimizer_kernel, dim3(static_cast<unsigned>(w1 - w0)), dim3(256), 0, st, pdl, n.work + w0, n.desc, t->hyper,
-                  n.theta, g, t->s1, t->s2, n.scal, publish_scalars ? t->d_hscal : static_cast<float*>(nullptr),
+                  n.theta, g, n.s1, n.s2, n.scal, publish_scalars ? t->d_hscal : static_cast<float*>(nullptr),
                   n.next_trace(st == n.stream ? "opt" : "opt_side")));
   n.mark("optimizer");
+  return SB_OK;
+}
+
+// segments of the sharded exchange: bit 0 = A (every layer but hidden layer 0), bit 1 = B (hidden layer 0)
+enum { XSEG_A = 1, XSEG_B = 2, XSEG_ALL = 3 };
+
+static XchgParams xchg_params(sb_trainer* t) {
+  Net& n = t->net;
+  XchgParams p;
+  memset(&p, 0, sizeof(p));
+  p.peers = t->d_peers;
+  p.rank = t->rank; p.world = t->world;
+  p.s1_off = static_cast<long long>(n.s1_off); p.s2_off = static_cast<long long>(n.s2_off);
+  p.grad_off = t->grad_off; p.flags_off = t->flags_off;
+  p.work = n.work;
+  p.seg_begin[0] = n.work_end[0]; p.seg_end[0] = n.n_work;     // A: layers 1 .. L (output layer)
+  p.seg_begin[1] = 0; p.seg_end[1] = n.work_end[0];            // B: hidden layer 0
+  p.desc = n.desc;
+  p.hyper = t->hyper;
+  p.host_err = t->d_herr;
+  p.timeout_ns = t->xchg_timeout_ns;
+  return p;
+}
+
+// reduce-scatter -> owner update -> all-gather of the operands for the given segments (xchg_p2p.cuh); `g` must be t->grad
+static int enqueue_xchg(sb_trainer* t, int seg_mask, cudaStream_t st, bool publish_scalars, bool pdl) {
+  Net& n = t->net;
+  XchgParams p = xchg_params(t);
+  p.seg_mask = seg_mask;
+  p.scal = publish_scalars ? n.scal : nullptr;
+  p.host_scal = publish_scalars ? t->d_hscal : nullptr;
+  p.trace = n.next_trace(seg_mask == XSEG_A ? "xchg_A" : (seg_mask == XSEG_B ? "xchg_B" : "xchg"));
+  int runs = 0;
+  for (int sgi = 0; sgi < 2; ++sgi)
+    if ((seg_mask >> sgi) & 1) {
+      const int r = (p.seg_end[sgi] - p.seg_begin[sgi] + t->world - 1) / t->world;
+      if (r > runs) runs = r;
+    }
+  int grid = t->xchg_blocks > 0 ? t->xchg_blocks : n.num_sms;
+  if (grid > runs) grid = runs;
+  if (grid < 1) grid = 1;
+  const dim3 g(static_cast<unsigned>(grid)), b(256);
+  if (t->world <= 2) SB_TRY(n.launch(xchg_update_kernel<2>, g, b, 0, st, pdl, p));
+  else if (t->world <= 4) SB_TRY(n.launch(xchg_update_kernel<4>, g, b, 0, st, pdl, p));
+  else if (t->world <= 8) SB_TRY(n.launch(xchg_update_kernel<8>, g, b, 0, st, pdl, p));
+  else SB_TRY(n.launch(xchg_update_kernel<16>, g, b, 0, st, pdl, p));
+  n.mark("xchg_update");
+  t->master_stale = true;
+  t->grad_sharded = true;
+  return SB_OK;
+}
+
+// before the host reads theta / s1 / s2: pull the runs other ranks own from their owners (no-op unless sharded updates ran)
+static int gather_master(sb_trainer* t) {
+  if (!t->p2p_ready || !t->master_stale || t->world <= 1) return SB_OK;
+  Net& n = t->net;
+  SB_CUDA(cudaStreamSynchronize(n.stream));     // my last exchange kernel has seen every peer's done flag
+  XchgParams p = xchg_params(t);
+  gather_master_kernel<<<n.n_work, 256, 0, n.stream>>>(p, 0);
+  SB_CUDA(cudaGetLastError());
+  SB_CUDA(cudaStreamSynchronize(n.stream));
+  t->master_stale = false;
   return SB_OK;
 }
 
@@ -180,8 +242,11 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   // stream behind the last dA GEMM and is followed (PDL) by the optimizer of layer 0 alone; the side stream updates the
   // other layers right after their dW GEMMs; the two streams only join at the end of the graph.
   static const bool old_sched = getenv("SB_OLD_SCHED") != nullptr;
-  const bool split_tail = !old_sched && kind == G_STEP && t->world == 1 && !pipelined && n.concurrent_bwd && !n.profiling &&
-                          n.side != nullptr && n.precision == SB_PREC_BF16 && n.L > 1;
+  // With the peer-memory exchange (world > 1) the tail has the SAME shape: the two optimizer launches become the two
+  // segment launches of xchg_update_kernel (segment A on the side stream overlaps dW_0, segment B follows dW_0).
+  static const bool one_xchg = getenv("SB_XCHG_ONE") != nullptr;    // experiment: one launch for both segments after a join
+  const bool split_tail = !old_sched && kind == G_STEP && (t->world == 1 || (t->p2p_ready && !one_xchg)) && !pipelined &&
+                          n.concurrent_bwd && !n.profiling && n.side != nullptr && n.precision == SB_PREC_BF16 && n.L > 1;
   // (dW_0 on the main stream also when an exchange or the accumulate kernel follows: it is then joined with the side
   // stream as before)
   n.dw0_on_main = !old_sched && !pipelined && n.concurrent_bwd && !n.profiling && n.side != nullptr &&
@@ -191,20 +256,26 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   n.on_layer_grads = nullptr;
   SB_TRY(bs);
   if (split_tail) {
-    SB_TRY(enqueue_optimizer(t, t->grad, n.work_begin[0], n.work_end[0], n.stream, true, n.use_pdl));
+    if (t->world > 1) SB_TRY(enqueue_xchg(t, XSEG_B, n.stream, true, n.use_pdl));
+    else SB_TRY(enqueue_optimizer(t, t->grad, n.work_begin[0], n.work_end[0], n.stream, true, n.use_pdl));
     // the other layers' shadows are read by the dA GEMMs on the main stream: update them only after the last one
     SB_CUDA(cudaStreamWaitEvent(n.side, n.ev_da_done, 0));
-    SB_TRY(enqueue_optimizer(t, t->grad, n.work_end[0], n.n_work, n.side));
+    if (t->world > 1) SB_TRY(enqueue_xchg(t, XSEG_A, n.side, false, false));
+    else SB_TRY(enqueue_optimizer(t, t->grad, n.work_end[0], n.n_work, n.side));
     SB_CUDA(cudaEventRecord(n.ev_join, n.side));
     SB_CUDA(cudaStreamWaitEvent(n.stream, n.ev_join, 0));
     return SB_OK;
   }
   if (kind == G_STEP) {
     if (pipelined) return SB_OK;
-    SB_TRY(enqueue_allreduce(t, t->grad));
-    if (t->world > 1 && n.profiling) { n.mark("allreduce"); --n.launches; }
-    // directly behind the peer-memory exchange kernel the optimizer is a programmatic dependent (no launch gap)
-    SB_TRY(enqueue_optimizer(t, t->grad, 0, -1, nullptr, true, n.use_pdl && t->world > 1 && t->p2p_ready && !n.profiling));
+    if (t->world > 1 && t->p2p_ready) {
+      // (fp32 mode, one hidden layer, profiling, SB_XCHG_ONE: no split tail) one launch handles both segments
+      SB_TRY(enqueue_xchg(t, XSEG_ALL, n.stream, true, false));
+    } else {
+      SB_TRY(enqueue_allreduce(t, t->grad));
+      if (t->world > 1 && n.profiling) { n.mark("allreduce"); --n.launches; }
+      SB_TRY(enqueue_optimizer(t, t->grad, 0, -1, nullptr, true, false));
+    }
   } else {
     const long long np = n.n_params;
     axpy_kernel<<<static_cast<unsigned>((np + 255) / 256), 256, 0, n.stream>>>(t->acc, t->grad, np, n.scal, t->d_hscal);
@@ -302,9 +373,20 @@ static int poll_nccl(sb_trainer* t) {
   return SB_OK;
 }
 
+// a peer that never arrived at the exchange (xchg_p2p.cuh) left a note in mapped host memory
+static int poll_xchg(sb_trainer* t) {
+  if (!t->h_err) return SB_OK;
+  const unsigned int e = *reinterpret_cast<volatile unsigned int*>(t->h_err);
+  if (e == 0) return SB_OK;
+  return set_error(SB_ERR_NCCL, "gradient exchange timed out on rank %d: rank %u did not reach segment %c of the exchange within %.0f s "
+                   "(peer process dead or stuck); this trainer is no longer usable", t->rank, (e - 1) & 15u, ((e - 1) >> 4) ? 'B' : 'A',
+                   t->xchg_timeout_ns * 1e-9);
+}
+
 static int finish_loss(sb_trainer* t, float* loss_out) {
   SB_CUDA(cudaStreamSynchronize(t->net.stream));
   SB_TRY(poll_nccl(t));
+  SB_TRY(poll_xchg(t));
   if (loss_out) {
     const float nnz = t->h_scal[SCAL_NNZ];
     *loss_out = nnz > 0.f ? t->h_scal[SCAL_LOSS_SUM] / nnz : 0.f;
@@ -365,7 +447,7 @@ int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, 
   *out = nullptr;
   SB_TRY(validate_desc(desc));
   SB_CHECK(world >= 1 && rank >= 0 && rank < world, SB_ERR_INVALID, "bad rank/world %d/%d", rank, world);
-  SB_CHECK(world == 1 || nccl_id != nullptr, SB_ERR_INVALID, "nccl_id required when world > 1");
+  // world > 1 without an NCCL id: the ranks live in one process (sb_trainer_set_peer_pointers is then the only exchange)
   std::unique_ptr<sb_trainer> t(new sb_trainer());
   t->desc = *desc;
   t->rank = rank; t->world = world;
@@ -373,6 +455,13 @@ int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, 
   t->hyper.kind = desc->optimizer;
   t->hyper.rho = desc->rho; t->hyper.eps = desc->epsilon;
   t->hyper.beta1 = desc->beta1; t->hyper.beta2 = desc->beta2; t->hyper.momentum = desc->momentum;
+  {
+    // parameter count is needed for the size of the gradient buffer that lives behind the parameters in the arena
+    long long np = 0; int prev = desc->n_features;
+    for (int l = 0; l <= desc->n_hidden; ++l) { const int out = l < desc->n_hidden ? desc->hidden[l] : 1; np += static_cast<long long>(prev) * out + out; prev = out; }
+    t->xch_n4 = (np + 3) / 4;
+    t->net.arena_extra_bytes = static_cast<size_t>(t->xch_n4) * 16 + sizeof(P2PFlags);
+  }
   int s = t->net.init(desc, device, true);
   if (s != SB_OK) { t->net.destroy(); return s; }
   if (!getenv("SB_NO_CARVEOUT")) {   // see Net::init: no L1 / shared-memory re-partition between the kernels of a step
@@ -381,18 +470,22 @@ int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, 
     cudaFuncSetAttribute(axpy_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }
   Net& n = t->net;
-  {
-    // gradient + exchange flags in one allocation so that a single IPC handle exports both
-    const long long unit = 4ll * world;
-    t->xch_n4 = ((n.n_params + unit - 1) / unit) * world;   // float4 count, a multiple of world (equal slices)
-    const size_t bytes = static_cast<size_t>(t->xch_n4) * 16 + sizeof(P2PFlags);
-    if (cudaMalloc(&t->xch, bytes) != cudaSuccess) { n.destroy(); return set_error(SB_ERR_CUDA, "cudaMalloc(exchange) failed"); }
-    cudaMemset(t->xch, 0, bytes);
-    t->grad = static_cast<float*>(t->xch);
-    t->flags = reinterpret_cast<P2PFlags*>(static_cast<char*>(t->xch) + static_cast<size_t>(t->xch_n4) * 16);
+  // gradient + exchange flags behind the parameters, in the arena a single IPC handle exports
+  t->xch = n.arena;
+  t->grad_off = static_cast<long long>(n.extra_off);
+  t->flags_off = t->grad_off + t->xch_n4 * 16;
+  t->grad = reinterpret_cast<float*>(n.arena + t->grad_off);
+  t->flags = reinterpret_cast<P2PFlags*>(n.arena + t->flags_off);
+  t->s1 = n.s1; t->s2 = n.s2;
+  if ((s = n.dalloc(&t->acc, n.n_params))) { n.destroy(); return s; }
+  if (cudaHostAlloc(reinterpret_cast<void**>(&t->h_err), sizeof(unsigned int) * 4, cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer(reinterpret_cast<void**>(&t->d_herr), t->h_err, 0) != cudaSuccess) {
+    n.destroy();
+    return set_error(SB_ERR_CUDA, "cudaHostAlloc(exchange error word) failed");
   }
-  if ((s = n.dalloc(&t->s1, n.n_params)) || (s = n.dalloc(&t->s2, n.n_params)) ||
-      (s = n.dalloc(&t->acc, n.n_params))) { n.destroy(); return s; }
+  memset(t->h_err, 0, sizeof(unsigned int) * 4);
+  if (const char* e = getenv("SB_XCHG_TIMEOUT_S")) t->xchg_timeout_ns = static_cast<unsigned long long>(atof(e) * 1e9);
+  if (const char* e = getenv("SB_XCHG_BLOCKS")) t->xchg_blocks = atoi(e);
   if (cudaHostAlloc(reinterpret_cast<void**>(&t->h_scal), sizeof(float) * SCAL_COUNT, cudaHostAllocMapped) != cudaSuccess) {
     n.destroy();
     return set_error(SB_ERR_CUDA, "cudaHostAlloc failed");
@@ -419,7 +512,7 @@ int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, 
     t->net.destroy();
     return set_error(SB_ERR_CUDA, "cudaHostGetDevicePointer failed");
   }
-  if (world > 1) {
+  if (world > 1 && nccl_id != nullptr) {
     // The GEMMs are persistent (one CTA per SM, ~200 KB smem each): an NCCL CTA that lands on an SM evicts a GEMM CTA
     // into a second wave.  Keep NCCL to a few CTAs and leave those SMs out of the GEMM grids.
     // (only when the exchange is pipelined behind the backward pass, SB_PIPELINE_AR=1)
@@ -474,12 +567,7 @@ static void close_peer_mappings(sb_trainer* t) {
 static int install_peer_table(sb_trainer* t, void* const* bases) {
   P2PPeers hp;
   memset(&hp, 0, sizeof(hp));
-  const size_t flag_off = static_cast<size_t>(t->xch_n4) * 16;
-  for (int q = 0; q < t->world; ++q) {
-    void* base = (q == t->rank) ? t->xch : bases[q];
-    hp.grad[q] = static_cast<float*>(base);
-    hp.flags[q] = reinterpret_cast<P2PFlags*>(static_cast<char*>(base) + flag_off);
-  }
+  for (int q = 0; q < t->world; ++q) hp.base[q] = static_cast<char*>((q == t->rank) ? t->xch : bases[q]);
   if (!t->d_peers) SB_CUDA(cudaMalloc(&t->d_peers, sizeof(P2PPeers)));
   SB_CUDA(cudaMemcpy(t->d_peers, &hp, sizeof(hp), cudaMemcpyHostToDevice));
   drop_step_graphs(t);
@@ -566,6 +654,7 @@ int sb_trainer_destroy(sb_trainer_t* t) {
   if (t->dsY) cudaFree(t->dsY);
   if (t->dsW) cudaFree(t->dsW);
   if (t->h_scal) cudaFreeHost(t->h_scal);
+  if (t->h_err) cudaFreeHost(t->h_err);
   if (t->h_hist) cudaFreeHost(t->h_hist);
   if (t->copy_stream) cudaStreamDestroy(t->copy_stream);
   if (t->prep) { cudaStreamSynchronize(t->prep); cudaStreamDestroy(t->prep); }
@@ -577,8 +666,7 @@ int sb_trainer_destroy(sb_trainer_t* t) {
   }
   for (void* p : t->peer_bases) cudaIpcCloseMemHandle(p);
   if (t->d_peers) cudaFree(t->d_peers);
-  if (t->xch) cudaFree(t->xch);
-  t->net.destroy();
+  t->net.destroy();      // frees the arena (= xch)
   delete t;
   return SB_OK;
 }
@@ -592,13 +680,14 @@ int sb_trainer_set_params(sb_trainer_t* t, const float* flat, int64_t n) {
   SB_CUDA(cudaMemcpyAsync(t->net.theta, flat, sizeof(float) * n, cudaMemcpyHostToDevice, t->net.stream));
   SB_TRY(t->net.refresh_shadows());
   SB_CUDA(cudaStreamSynchronize(t->net.stream));
-  return SB_OK;
+  return SB_OK;   // (optimizer state is untouched: a sharded trainer keeps each run's state on its owner)
 }
 
 int sb_trainer_get_params(sb_trainer_t* t, float* flat, int64_t n) {
   SB_CHECK(t && flat, SB_ERR_INVALID, "null argument");
   SB_CHECK(n == t->net.n_params, SB_ERR_INVALID, "expected %lld params, got %lld", (long long)t->net.n_params, (long long)n);
   SB_CUDA(cudaSetDevice(t->net.device));
+  SB_TRY(gather_master(t));
   SB_CUDA(cudaMemcpyAsync(flat, t->net.theta, sizeof(float) * n, cudaMemcpyDeviceToHost, t->net.stream));
   SB_CUDA(cudaStreamSynchronize(t->net.stream));
   return SB_OK;
@@ -622,6 +711,13 @@ int sb_trainer_get_grads(sb_trainer_t* t, float* flat, int64_t n) {
   SB_CHECK(t && flat, SB_ERR_INVALID, "null argument");
   SB_CHECK(n == t->net.n_params, SB_ERR_INVALID, "expected %lld grads, got %lld", (long long)t->net.n_params, (long long)n);
   SB_CUDA(cudaSetDevice(t->net.device));
+  if (t->p2p_ready && t->grad_sharded && t->world > 1) {
+    // sharded exchange: every owner kept the reduced gradient of its runs; collect them (overwrites this rank's own
+    // contributions, which the next step clears anyway)
+    SB_CUDA(cudaStreamSynchronize(t->net.stream));
+    gather_master_kernel<<<t->net.n_work, 256, 0, t->net.stream>>>(xchg_params(t), 1);
+    SB_CUDA(cudaGetLastError());
+  }
   SB_CUDA(cudaMemcpyAsync(flat, t->grad, sizeof(float) * n, cudaMemcpyDeviceToHost, t->net.stream));
   SB_CUDA(cudaStreamSynchronize(t->net.stream));
   const float gs = t->grad_out_scale;
@@ -700,8 +796,12 @@ static int apply_accumulated_impl(sb_trainer_t* t, int64_t total_pushes) {
   SB_CUDA(cudaGetLastError());
   // exchange + apply through the (IPC-exported) gradient buffer; it then holds the applied mean for sb_trainer_get_grads
   SB_CUDA(cudaMemcpyAsync(t->grad, t->acc, sizeof(float) * n.n_params, cudaMemcpyDeviceToDevice, n.stream));
-  SB_TRY(enqueue_allreduce(t, t->grad));
-  SB_TRY(enqueue_optimizer(t, t->grad));
+  if (t->world > 1 && t->p2p_ready) {
+    SB_TRY(enqueue_xchg(t, XSEG_ALL, n.stream, false, false));
+  } else {
+    SB_TRY(enqueue_allreduce(t, t->grad));
+    SB_TRY(enqueue_optimizer(t, t->grad));
+  }
   const long long np = n.n_params;
   scale_kernel<<<static_cast<unsigned>((np + 255) / 256), 256, 0, n.stream>>>(t->grad, n.desc, np);
   SB_CUDA(cudaGetLastError());
@@ -955,6 +1055,7 @@ int sb_trainer_sync(sb_trainer_t* t) {
   SB_CHECK(t, SB_ERR_INVALID, "null trainer");
   SB_CUDA(cudaStreamSynchronize(t->net.stream));
   SB_TRY(poll_nccl(t));
+  SB_TRY(poll_xchg(t));
   return SB_OK;
 }
 void* sb_trainer_stream(sb_trainer_t* t) { return t ? reinterpret_cast<void*>(t->net.stream) : nullptr; }
@@ -1004,9 +1105,13 @@ int sb_trainer_profile_step(sb_trainer_t* t, int64_t row_offset, int32_t rows, c
     if (s == SB_OK) s = n.enqueue_hidden_forward(rows, t->grad, &fused_out);
     if (s == SB_OK && !fused_out) s = n.enqueue_out(rows, true, true, nullptr, t->grad);
     if (s == SB_OK) s = n.enqueue_backward(rows, t->grad);
-    if (s == SB_OK) s = enqueue_allreduce(t, t->grad);
-    if (s == SB_OK && t->world > 1) { n.mark("allreduce"); --n.launches; }
-    if (s == SB_OK) s = enqueue_optimizer(t, t->grad);
+    if (t->world > 1 && t->p2p_ready) {
+      if (s == SB_OK) s = enqueue_xchg(t, XSEG_ALL, n.stream, false, false);
+    } else {
+      if (s == SB_OK) s = enqueue_allreduce(t, t->grad);
+      if (s == SB_OK && t->world > 1) { n.mark("allreduce"); --n.launches; }
+      if (s == SB_OK) s = enqueue_optimizer(t, t->grad);
+    }
   }
   n.profiling = false;
   n.from_resident = false;
@@ -1080,6 +1185,7 @@ int sb_trainer_save_checkpoint(sb_trainer_t* t, const char* path) {
   SB_CHECK(t && path, SB_ERR_INVALID, "null argument");
   Net& n = t->net;
   SB_CUDA(cudaSetDevice(n.device));
+  SB_TRY(gather_master(t));
   std::vector<float> buf(static_cast<size_t>(n.n_params) * 3);
   SB_CUDA(cudaMemcpyAsync(buf.data(), n.theta, sizeof(float) * n.n_params, cudaMemcpyDeviceToHost, n.stream));
   SB_CUDA(cudaMemcpyAsync(buf.data() + n.n_params, t->s1, sizeof(float) * n.n_params, cudaMemcpyDeviceToHost, n.stream));

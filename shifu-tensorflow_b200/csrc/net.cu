@@ -176,7 +176,29 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
     prev = ly.out;
   }
   n_params = off;
-  SB_TRY(dalloc(&theta, n_params));
+  const bool bf = precision == SB_PREC_BF16;
+  {
+    auto align256 = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
+    const size_t vec_bytes = align256(static_cast<size_t>(n_params) * sizeof(float) + 64);
+    size_t at = vec_bytes;                       // theta at 0
+    if (training) { s1_off = at; at += vec_bytes; s2_off = at; at += vec_bytes; }
+    shadow_off = at;
+    std::vector<size_t> wn_off(L, 0);
+    if (bf)
+      for (int l = 0; l < L; ++l) { wn_off[l] = at; at += align256(static_cast<size_t>(layers[l].in) * layers[l].ld_out * sizeof(__nv_bfloat16)); }
+    extra_off = at;
+    at += align256(arena_extra_bytes);
+    arena_bytes = at;
+    void* q = nullptr;
+    SB_CUDA(cudaMalloc(&q, arena_bytes));
+    allocs.push_back(q);
+    SB_CUDA(cudaMemsetAsync(q, 0, arena_bytes, stream));
+    arena = static_cast<char*>(q);
+    theta = reinterpret_cast<float*>(arena);
+    if (training) { s1 = reinterpret_cast<float*>(arena + s1_off); s2 = reinterpret_cast<float*>(arena + s2_off); }
+    if (bf)
+      for (int l = 0; l < L; ++l) layers[l].Wn = reinterpret_cast<__nv_bfloat16*>(arena + wn_off[l]);
+  }
   SB_TRY(dalloc(&scal, SCAL_COUNT));
   SB_TRY(dalloc(&desc, 1));
   if (want_trace) SB_TRY(dalloc(&step_trace, 32 * 16));
@@ -187,13 +209,11 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
   SB_TRY(dalloc(&stW, max_batch));
   fill_kernel<<<(max_batch + 255) / 256, 256, 0, stream>>>(ones, 1.f, max_batch);
 
-  const bool bf = precision == SB_PREC_BF16;
   if (bf) {
     SB_TRY(dalloc(&Xb, static_cast<size_t>(max_batch) * ldF));
     A.assign(L, nullptr); dZ.assign(L, nullptr);
     for (int l = 0; l < L; ++l) {
       Layer& ly = layers[l];
-      SB_TRY(dalloc(&ly.Wn, static_cast<size_t>(ly.in) * ly.ld_out));
       SB_TRY(dalloc(&A[l], static_cast<size_t>(max_batch) * ly.ld_out));
       if (training) SB_TRY(dalloc(&dZ[l], static_cast<size_t>(max_batch) * ly.ld_out));
     }

@@ -56,7 +56,14 @@ struct Net {
   int max_batch = 0, ldB = 0, ldF = 0;
   bool training = false;
 
+  // Parameter arena: ONE allocation [theta fp32 | s1 | s2 (training) | bf16 weight shadows | extra], so that a trainer can
+  // export everything the peer-memory exchange touches with a single CUDA-IPC handle (xchg_p2p.cuh).  `arena_extra_bytes`
+  // is set by the trainer BEFORE init(): room for its gradient buffer and flag block behind the parameters.
+  char* arena = nullptr;
+  size_t arena_bytes = 0, arena_extra_bytes = 0;
+  size_t s1_off = 0, s2_off = 0, shadow_off = 0, extra_off = 0;   // byte offsets inside the arena (theta at 0)
   float* theta = nullptr;
+  float *s1 = nullptr, *s2 = nullptr;      // optimizer state (training only)
   // bf16 workspace
   __nv_bfloat16* Xb = nullptr;             // current batch as bf16 [rows, ldF]
   std::vector<__nv_bfloat16*> A, dZ;       // A_l, dZ_l as bf16 [rows, ld_out_l]

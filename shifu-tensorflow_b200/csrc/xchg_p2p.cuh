@@ -1,0 +1,300 @@
+// Sharded gradient exchange + optimizer over NVLink peer memory (CUDA IPC / in-process peers), ONE kernel per segment:
+//
+//     reduce-scatter (P2P loads)  ->  optimizer on the owned slice only  ->  all-gather of the GEMM operands (P2P stores)
+//
+// It replaces, on one NVLink/NVSwitch node, what the reference does with parameter servers: every worker pushes its
+// gradients to the ConditionalAccumulators on the PS tasks, the mean is applied there ONCE per variable, and every worker
+// pulls the new variables (res/ssgd_monitor.py:136-141, 203-206).  Here the "parameter server" of a run of 1024
+// parameters is the rank that owns it:
+//
+//   every rank exports ONE allocation (the parameter arena, net.cuh):  [theta | s1 | s2 | bf16 shadows | gradient | flags]
+//   the flat vector is cut into the optimizer's work runs (<= 1024 parameters each); the runs of a SEGMENT are dealt out
+//   to the ranks in equal contiguous shares.  Two segments: B = hidden layer 0 (its gradient is complete last, after the
+//   dW_0 GEMM), A = every other layer (complete when the side stream's dW GEMMs and the last dA GEMM are done, i.e.
+//   while dW_0 still runs) - one launch per segment, so the exchange of segment A overlaps the dW_0 GEMM.
+//
+//   per launch (flag slot = segment, value = the step's exchange epoch):
+//     arrive   "my gradient of this segment is complete": store epoch into arrive[seg][me] of every peer
+//              (st.release.sys), every block waits until all peers' slots in MY flag block carry it (ld.acquire.sys)
+//     owned runs, 256 threads x 4 parameters each:
+//              g = sum over ranks (fixed order 0..W-1 -> the same bits wherever it is computed) of the peers' gradients,
+//              all W x U 16-byte P2P loads of a thread in flight before the first add;
+//              fp32 master + optimizer state of the run are LOCAL (only the owner ever updates them);
+//              the result is stored to EVERY rank: bf16 into the weight shadow the GEMMs read (8 B per thread - half the
+//              bytes of an fp32 all-gather) or, for runs without a shadow (biases, output layer, fp32 mode), fp32 theta.
+//     done     last block publishes done[seg][me] = epoch to every peer and waits for every peer's: on exit all slices
+//              of my shadows are final and nobody reads my gradient any more.
+//
+// A rank only reads other ranks' gradients of ITS runs and only writes ITS runs of other ranks' operands; the writes
+// happen after every rank has arrived, i.e. after every rank's last reader of those operands in this step (the launch is
+// stream-ordered behind them).  Non-owners keep a stale fp32 master / state for shadow-backed runs: gather_master_kernel
+// refreshes them before anything reads theta on the host side (get_params, checkpoint, export).
+//
+// A lost peer is reported, not trapped: after `timeout_ns` a waiting block records (segment, missing rank) in mapped host
+// memory and every block leaves the kernel; the host turns that into SB_ERR_NCCL at its next wait.
+#pragma once
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace sb {
+
+#define SB_MAX_RANKS 16
+
+struct P2PFlags {                         // at arena + flags_off on every rank
+  unsigned int arrive[2][SB_MAX_RANKS];   // arrive[seg][q] written by rank q
+  unsigned int done[2][SB_MAX_RANKS];     // done[seg][q]   written by rank q
+  unsigned int blocks_done[2];            // local: grid-wide completion counter per segment
+  unsigned int pad[30];
+};
+
+struct P2PPeers {                         // device-resident table, same order on every rank
+  char* base[SB_MAX_RANKS];               // arena of every rank (own entry = own arena)
+};
+
+struct XchgParams {
+  const P2PPeers* peers;
+  int rank, world;
+  long long s1_off, s2_off, grad_off, flags_off;   // byte offsets inside every arena (theta at 0)
+  const OptWork* work;
+  int seg_begin[2], seg_end[2];           // work-table range of segment 0 (A: layers >= 1) and 1 (B: layer 0)
+  int seg_mask;                           // bit s set: this launch handles segment s
+  const BatchDesc* desc;
+  OptHyper hyper;
+  const float* scal;                      // step scalars to publish (nullable)
+  float* host_scal;
+  unsigned int* host_err;                 // mapped pinned: [0] = 0 ok | 1 + 16 * seg + missing rank
+  unsigned long long timeout_ns;          // 0 = wait forever
+  unsigned long long* trace;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_peer_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_peer_f1(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// first work item of rank r's share of [b, e)
+__host__ __device__ inline int xchg_share(int b, int e, int r, int world) {
+  return b + static_cast<int>((static_cast<long long>(e - b) * r) / world);
+}
+
+// Block-wide wait until slots[q] >= epoch for every q < world.  Returns false after a timeout (error recorded).
+__device__ __forceinline__ bool xchg_wait(const unsigned int* slots, int world, unsigned int epoch, const XchgParams& p, int seg,
+                                          unsigned int* sh_fail) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    bool ok = true;
+    if (lane < world) {
+      unsigned long long t0 = 0;
+      unsigned int spins = 0;
+      while (static_cast<int>(ld_acquire_sys(slots + lane) - epoch) < 0) {
+        if ((++spins & 0x3FFu) == 0) {
+          if (*reinterpret_cast<volatile unsigned int*>(sh_fail)) { ok = false; break; }
+          if (p.timeout_ns != 0) {
+            const unsigned long long now = globaltimer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > p.timeout_ns) {
+              if (p.host_err != nullptr) { atomicCAS(p.host_err, 0u, 1u + 16u * seg + lane); __threadfence_system(); }
+              ok = false;
+              break;
+            }
+          }
+        }
+      }
+    }
+    if (!__all_sync(0xffffffffu, ok) && lane == 0) *sh_fail = 1u;
+  }
+  __syncthreads();
+  return *reinterpret_cast<volatile unsigned int*>(sh_fail) == 0u;
+}
+
+// W = compile-time upper bound of `world`; U runs per block iteration, W * U (<= 16) float4 per thread in flight.
+// <= 128 registers per thread (two blocks per SM by register count), so that a block fits beside a persistent GEMM CTA
+// (320 threads x <= 128 registers) - segment A runs while the dW_0 GEMM still occupies every SM.
+template <int W>
+static __global__ void __launch_bounds__(256, 2)
+xchg_update_kernel(const XchgParams p) {
+  constexpr int U = (W <= 4) ? 4 : 16 / W;
+  __shared__ unsigned int sh_fail;
+  __shared__ unsigned int sh_last;
+  if (threadIdx.x == 0) sh_fail = 0u;
+  trace_begin(p.trace, true);
+  pdl_wait();                 // the gradient of this segment is complete (programmatic dependent of the last GEMM)
+  pdl_launch_dependents();
+  trace_begin(p.trace, false);
+  __syncthreads();
+  const unsigned int epoch = p.desc->epoch;
+  char* pb[W];                // every rank's arena (entries >= world alias the own arena and are never used)
+#pragma unroll
+  for (int q = 0; q < W; ++q) pb[q] = p.peers->base[q < p.world ? q : p.rank];
+  char* const my_base = p.peers->base[p.rank];
+  float* const theta = reinterpret_cast<float*>(my_base);
+  P2PFlags* mine = reinterpret_cast<P2PFlags*>(my_base + p.flags_off);
+  if (p.host_scal != nullptr && blockIdx.x == 0 && threadIdx.x < SCAL_COUNT) {
+    p.host_scal[threadIdx.x] = p.scal[threadIdx.x];     // loss sum / n_nz of this rank's mini-batch (see optimizer_kernel)
+    if (threadIdx.x == 0 && p.desc->hist != nullptr) *p.desc->hist = make_float2(p.scal[SCAL_LOSS_SUM], p.scal[SCAL_NNZ]);
+    __threadfence_system();
+  }
+  const float lr_t = p.desc->lr_t, gs = p.desc->gscale;
+  const bool use_s1 = p.hyper.kind != SB_OPT_SGD;
+  const bool use_s2 = p.hyper.kind == SB_OPT_ADAM || p.hyper.kind == SB_OPT_ADADELTA;
+  float* const s1 = reinterpret_cast<float*>(my_base + p.s1_off);
+  float* const s2 = reinterpret_cast<float*>(my_base + p.s2_off);
+  bool alive = true;
+#pragma unroll 1
+  for (int seg = 0; seg < 2; ++seg) {
+    if (!((p.seg_mask >> seg) & 1)) continue;
+    // ---- arrive ----
+    if (blockIdx.x == 0 && threadIdx.x < p.world)
+      st_release_sys(&reinterpret_cast<P2PFlags*>(p.peers->base[threadIdx.x] + p.flags_off)->arrive[seg][p.rank], epoch);
+    if (alive) alive = xchg_wait(mine->arrive[seg], p.world, epoch, p, seg, &sh_fail);
+    // ---- owned runs ----
+    const int w0 = xchg_share(p.seg_begin[seg], p.seg_end[seg], p.rank, p.world);
+    const int w1 = xchg_share(p.seg_begin[seg], p.seg_end[seg], p.rank + 1, p.world);
+    if (alive) {
+      for (int wb = w0 + static_cast<int>(blockIdx.x) * U; wb < w1; wb += static_cast<int>(gridDim.x) * U) {
+        OptWork wk[U];
+        bool vec[U];
+        float4 g[U][W];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int w = wb + u;
+          if (w < w1) wk[u] = p.work[w]; else { wk[u].count = 0; wk[u].off = 0; wk[u].Wn = nullptr; wk[u].out_dim = 0; wk[u].mat_off = 0; wk[u].ld_out = 0; }
+          vec[u] = (wk[u].off & 3) == 0 && (wk[u].count & 3) == 0 &&
+                   (wk[u].Wn == nullptr || ((wk[u].out_dim & 3) == 0 && ((wk[u].off - wk[u].mat_off) & 3) == 0 && (wk[u].ld_out & 3) == 0));
+          const int e = threadIdx.x * 4;
+#pragma unroll
+          for (int q = 0; q < W; ++q)
+            g[u][q] = (vec[u] && q < p.world && e < wk[u].count) ? ld_peer_f4(reinterpret_cast<const float*>(pb[q] + p.grad_off) + wk[u].off + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (wk[u].count == 0) continue;
+          const long long shadow_rel = wk[u].Wn != nullptr ? reinterpret_cast<char*>(wk[u].Wn) - my_base : 0;
+          if (vec[u]) {
+            const int e = threadIdx.x * 4;
+            if (e < wk[u].count) {
+              float4 acc = g[u][0];               // fixed rank order
+#pragma unroll
+              for (int q = 1; q < W; ++q) { acc.x += g[u][q].x; acc.y += g[u][q].y; acc.z += g[u][q].z; acc.w += g[u][q].w; }
+              const long long idx = wk[u].off + e;
+              const float4 th = *reinterpret_cast<const float4*>(theta + idx);
+              float4 a = use_s1 ? *reinterpret_cast<const float4*>(s1 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+              float4 b = use_s2 ? *reinterpret_cast<const float4*>(s2 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+              float4 t;
+              t.x = opt_update(p.hyper, lr_t, th.x, acc.x * gs, a.x, b.x);
+              t.y = opt_update(p.hyper, lr_t, th.y, acc.y * gs, a.y, b.y);
+              t.z = opt_update(p.hyper, lr_t, th.z, acc.z * gs, a.z, b.z);
+              t.w = opt_update(p.hyper, lr_t, th.w, acc.w * gs, a.w, b.w);
+              *reinterpret_cast<float4*>(theta + idx) = t;
+              // the owner keeps the reduced gradient of its runs (nobody else reads this part of my buffer): parity hook
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(my_base + p.grad_off) + idx) = acc;
+              if (use_s1) *reinterpret_cast<float4*>(s1 + idx) = a;
+              if (use_s2) *reinterpret_cast<float4*>(s2 + idx) = b;
+              if (wk[u].Wn != nullptr) {
+                const long long m = idx - wk[u].mat_off;
+                const long long r = m / wk[u].out_dim;     // 4 consecutive elements never straddle a row
+                const long long rel = shadow_rel + (r * wk[u].ld_out + (m - r * wk[u].out_dim)) * 2;
+                uint2 o;
+                o.x = pack_bf16x2(t.x, t.y); o.y = pack_bf16x2(t.z, t.w);
+#pragma unroll
+                for (int q = 0; q < W; ++q)
+                  if (q < p.world) *reinterpret_cast<uint2*>(pb[q] + rel) = o;
+              } else {
+#pragma unroll
+                for (int q = 0; q < W; ++q)
+                  if (q < p.world && q != p.rank) *reinterpret_cast<float4*>(pb[q] + idx * 4) = t;
+              }
+            }
+          } else {
+            // unaligned run (odd widths): scalar path, 4 elements per thread strided by 256
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int e = threadIdx.x + 256 * i;
+              if (e < wk[u].count) {
+                const long long idx = wk[u].off + e;
+                float acc = 0.f;
+                for (int q = 0; q < p.world; ++q) acc += ld_peer_f1(reinterpret_cast<const float*>(p.peers->base[q] + p.grad_off) + idx);
+                float a = use_s1 ? s1[idx] : 0.f, b = use_s2 ? s2[idx] : 0.f;
+                const float t = opt_update(p.hyper, lr_t, theta[idx], acc * gs, a, b);
+                theta[idx] = t;
+                reinterpret_cast<float*>(my_base + p.grad_off)[idx] = acc;
+                if (use_s1) s1[idx] = a;
+                if (use_s2) s2[idx] = b;
+                if (wk[u].Wn != nullptr) {
+                  const long long m = idx - wk[u].mat_off;
+                  const long long r = m / wk[u].out_dim;
+                  const long long rel = shadow_rel + (r * wk[u].ld_out + (m - r * wk[u].out_dim)) * 2;
+                  const __nv_bfloat16 hv = __float2bfloat16_rn(t);
+                  for (int q = 0; q < p.world; ++q) *reinterpret_cast<__nv_bfloat16*>(p.peers->base[q] + rel) = hv;
+                } else {
+                  for (int q = 0; q < p.world; ++q)
+                    if (q != p.rank) reinterpret_cast<float*>(p.peers->base[q])[idx] = t;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    // ---- done ----
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) sh_last = (atomicAdd(&mine->blocks_done[seg], 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (sh_last) {
+      if (threadIdx.x == 0) mine->blocks_done[seg] = 0;
+      __threadfence_system();
+      if (threadIdx.x < p.world)
+        st_release_sys(&reinterpret_cast<P2PFlags*>(p.peers->base[threadIdx.x] + p.flags_off)->done[seg][p.rank], epoch);
+      if (alive) alive = xchg_wait(mine->done[seg], p.world, epoch, p, seg, &sh_fail);
+    }
+    __syncthreads();
+  }
+  trace_end(p.trace);
+}
+
+// Refresh the stale parts of a non-owner's fp32 master and optimizer state from the owners (before the host reads them);
+// what = 1: the reduced gradient instead (each owner kept the sum of its runs).
+// Every run is pulled from its owner unless this rank owns it.  One block per work item.
+static __global__ void __launch_bounds__(256)
+gather_master_kernel(const XchgParams p, int what) {
+  const int w = blockIdx.x;
+  float* const theta = reinterpret_cast<float*>(p.peers->base[p.rank]);
+  int owner = -1;
+  for (int seg = 0; seg < 2; ++seg) {
+    if (w >= p.seg_begin[seg] && w < p.seg_end[seg]) {
+      for (int r = 0; r < p.world; ++r)
+        if (w >= xchg_share(p.seg_begin[seg], p.seg_end[seg], r, p.world) && w < xchg_share(p.seg_begin[seg], p.seg_end[seg], r + 1, p.world)) owner = r;
+    }
+  }
+  if (owner < 0 || owner == p.rank) return;
+  const OptWork wk = p.work[w];
+  char* const my_base = p.peers->base[p.rank];
+  const char* ob = p.peers->base[owner];
+  for (int e = threadIdx.x; e < wk.count; e += 256) {
+    const long long idx = wk.off + e;
+    if (what == 1) {
+      reinterpret_cast<float*>(my_base + p.grad_off)[idx] = ld_peer_f1(reinterpret_cast<const float*>(ob + p.grad_off) + idx);
+      continue;
+    }
+    theta[idx] = ld_peer_f1(reinterpret_cast<const float*>(ob) + idx);
+    reinterpret_cast<float*>(my_base + p.s1_off)[idx] = ld_peer_f1(reinterpret_cast<const float*>(ob + p.s1_off) + idx);
+    reinterpret_cast<float*>(my_base + p.s2_off)[idx] = ld_peer_f1(reinterpret_cast<const float*>(ob + p.s2_off) + idx);
+  }
+}
+
+}  // namespace sb

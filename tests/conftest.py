@@ -4,6 +4,10 @@ import sys
 import numpy as np
 import pytest
 
+# several replicas on ONE GPU (tests/test_data_parallel_one_gpu.py) wait for each other inside kernels: every stream needs its
+# own hardware queue, otherwise a kernel can be queued behind the one that waits for it (must be set before CUDA initialises)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -1,0 +1,168 @@
+"""Data-parallel parity on EXACTLY the multi-GPU path bench.py times, runnable on ONE GPU:
+
+    sb_trainer_load_dataset + sb_trainer_run_resident + the peer-memory exchange kernels (xchg_update_kernel: reduce-scatter
+    by P2P loads -> optimizer on the owned runs -> all-gather of the bf16 weight shadows by P2P stores, segment A on the
+    side stream / segment B PDL-chained behind dW_0)
+
+W replicas (ranks) live in this process on the SAME device, each with its own streams and its own parameter arena; the
+peer table of every replica points at the others' arenas (sb_trainer_set_peer_pointers - the in-process twin of the
+CUDA-IPC handle exchange), so the same kernels run with peer pointers that happen to be local.  Checked against
+oracle.CleanTrainer.step([shard_0, .., shard_{W-1}]) (mean over ranks of per-rank mini-batch gradients,
+ssgd_monitor.py:136-141) in fp32 mode and oracle.Bf16Trainer in bf16 mode; replicas must stay bit-identical.
+
+The exchange kernels spin until every replica has arrived, so on one device they must not occupy every SM: these tests
+create the trainers with SB_XCHG_BLOCKS=8."""
+import numpy as np
+import pytest
+
+from oracle import shifu_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(sb, W, F, hidden, acts, B, prec, opt, lr, monkeypatch, seed=4):
+    monkeypatch.setenv("SB_XCHG_BLOCKS", "8")
+    monkeypatch.setenv("SB_XCHG_TIMEOUT_S", "60")
+    net = so.NetDesc(F, hidden, acts)
+    params = so.xavier_init(net, seed)
+    desc = sb.make_desc(F, hidden, acts, loss=sb.LOSS_MSE, optimizer=opt, learning_rate=lr, max_batch=B, precision=prec)
+    ts = [sb.Trainer(desc, device=0, nccl_id=None, rank=r, world=W) for r in range(W)]
+    bases = [t.exchange_base for t in ts]
+    for t in ts:
+        t.set_peer_pointers(bases)
+        t.set_params(so.flatten_params(params))
+    return net, params, ts
+
+
+def _shards(W, n_batches, B, F, seed):
+    """per-rank resident sets: rank r holds n_batches mini-batches of B rows with its own n_nz"""
+    out = []
+    for r in range(W):
+        X, y, w = so.synth_batch(n_batches * B, F, seed + 17 * r, weights="mixed")
+        rng = np.random.RandomState(seed + r)
+        beta = rng.randn(F).astype(np.float32) / np.sqrt(F)
+        y = (rng.uniform(size=(len(X), 1)) < 1 / (1 + np.exp(-2 * (X @ beta).reshape(-1, 1)))).astype(np.float32)
+        out.append((X, y, w))
+    return out
+
+
+def _run_all(ts, shards, n_steps, B, n_batches, chunk=4):
+    for t, (X, y, w) in zip(ts, shards):
+        t.load_dataset(X, y, w)
+    # queue the same steps on every replica, a few at a time (everything is asynchronous; a replica's exchange kernel waits
+    # on the device until the others arrive)
+    for s0 in range(0, n_steps, chunk):
+        offs = [((s0 + k) % n_batches) * B for k in range(min(chunk, n_steps - s0))]
+        for t in ts:
+            t.run_resident(offs, B)
+    for t in ts:
+        t.sync()
+
+
+@pytest.mark.parametrize("W", [2, 4])
+@pytest.mark.parametrize("prec", [0, 1])
+def test_replicas_on_one_gpu_match_the_data_parallel_oracle(sb, monkeypatch, W, prec):
+    F, hidden, acts, B, n_batches, n_steps = 256, [192, 128, 64], [so.ACT_RELU, so.ACT_TANH, so.ACT_LEAKYRELU], 512, 3, 10
+    net, params, ts = _make(sb, W, F, hidden, acts, B, prec, so.OPT_ADAM, 0.003, monkeypatch)
+    shards = _shards(W, n_batches, B, F, 100)
+    _run_all(ts, shards, n_steps, B, n_batches)
+    cfg = so.OptConfig(kind=so.OPT_ADAM, lr=0.003)
+    ref = so.CleanTrainer(net, params, cfg) if prec == 0 else so.Bf16Trainer(net, params, cfg, fused_out=hidden[-1] <= 128)
+    want = []
+    for s in range(n_steps):
+        o = (s % n_batches) * B
+        want.append(ref.step([(X[o:o + B], y[o:o + B], w[o:o + B]) for (X, y, w) in shards]))
+    want = np.array(want, dtype=np.float64)                       # [step, rank]
+    got = np.stack([t.loss_history(1, n_steps) for t in ts], axis=1)
+    thetas = [t.get_params() for t in ts]
+    grads = [t.get_grads() for t in ts]
+    Xp = shards[0][0][:300]
+    preds = [t.predict(Xp) for t in ts]
+    for t in ts:
+        t.close()
+    for r in range(1, W):
+        np.testing.assert_array_equal(thetas[0], thetas[r])       # one owner per run -> every replica reads the same bits
+        np.testing.assert_array_equal(grads[0], grads[r])
+        np.testing.assert_array_equal(preds[0], preds[r])         # the bf16 shadows / biases the forward reads are identical
+    tol_l, tol_p = (1e-4, 1e-4) if prec == 0 else (1e-3, 5e-3)
+    assert np.abs(got - want).max() <= tol_l, (got, want)
+    assert np.abs(thetas[0] - ref.theta).max() <= tol_p
+    assert np.abs(grads[0] - ref.last_grads).max() <= (1e-5 if prec == 0 else 2e-3 * np.abs(ref.last_grads).max())
+
+
+def test_cfg2_shape_two_replicas_bf16(sb, monkeypatch):
+    """the benchmarked config itself: 2000 cols x 8192 rows per rank, [1024, 512, 256], momentum, bf16, W = 2 on one GPU"""
+    F, hidden, B, n_batches, n_steps = 2000, [1024, 512, 256], 8192, 2, 6
+    acts = [so.ACT_RELU] * 3
+    net, params, ts = _make(sb, 2, F, hidden, acts, B, 1, so.OPT_MOMENTUM, 0.01, monkeypatch)
+    shards = _shards(2, n_batches, B, F, 7)
+    _run_all(ts, shards, n_steps, B, n_batches)
+    ref = so.Bf16Trainer(net, params, so.OptConfig(kind=so.OPT_MOMENTUM, lr=0.01), fused_out=False)
+    want = []
+    for s in range(n_steps):
+        o = (s % n_batches) * B
+        want.append(ref.step([(X[o:o + B], y[o:o + B], w[o:o + B]) for (X, y, w) in shards]))
+    got = np.stack([t.loss_history(1, n_steps) for t in ts], axis=1)
+    thetas = [t.get_params() for t in ts]
+    for t in ts:
+        t.close()
+    np.testing.assert_array_equal(thetas[0], thetas[1])
+    assert np.abs(got - np.array(want)).max() <= 1e-3
+    assert np.abs(thetas[0] - ref.theta).max() <= 5e-3
+
+
+def test_epoch_sync_schedule_over_the_exchange(sb, monkeypatch):
+    """accumulate + apply_accumulated(total pushes) through the exchange kernels: mean of all accepted mini-batch gradients of
+    all ranks, one update (SyncReplicasOptimizer's take_grad, ssgd_monitor.py:136-141)"""
+    F, hidden, acts, B = 64, [48, 24], [so.ACT_TANH, so.ACT_RELU], 96
+    net, params, ts = _make(sb, 2, F, hidden, acts, B, 0, so.OPT_ADADELTA, 1.0, monkeypatch)
+    shards = _shards(2, 3, B, F, 5)
+    for t, (X, y, w) in zip(ts, shards):
+        t.load_dataset(X, y, w)
+    # rank 0 accepted 3 pushes, rank 1 only 2 (one was stale): divisor = 5
+    for k in range(3):
+        ts[0].accumulate_resident(k * B, B)
+    for k in range(2):
+        ts[1].accumulate_resident(k * B, B)
+    import threading
+    th = [threading.Thread(target=t.apply_accumulated, args=(5,)) for t in ts]     # apply waits for the device: one host thread per rank
+    [x.start() for x in th]; [x.join(120) for x in th]
+    P = params
+    gsum = np.zeros(net.n_params(), np.float32)
+    for r, n_acc in ((0, 3), (1, 2)):
+        X, y, w = shards[r]
+        for k in range(n_acc):
+            gsum += so.flatten_params(so.loss_and_grads(net, P, X[k * B:(k + 1) * B], y[k * B:(k + 1) * B], w[k * B:(k + 1) * B])[1])
+    opt = so.Optimizer(so.OptConfig(kind=so.OPT_ADADELTA, lr=1.0), gsum.size)
+    want = opt.apply(so.flatten_params(params), gsum / np.float32(5))
+    thetas = [t.get_params() for t in ts]
+    for t in ts:
+        t.close()
+    np.testing.assert_array_equal(thetas[0], thetas[1])
+    assert np.abs(thetas[0] - want).max() <= 2e-5
+
+
+def test_missing_peer_is_an_error_not_a_hang(sb, monkeypatch):
+    """a rank whose peer never reaches the exchange gets SB_ERR_NCCL naming the missing rank after the timeout (the kernel
+    leaves instead of trapping or spinning forever)"""
+    monkeypatch.setenv("SB_XCHG_BLOCKS", "8")
+    monkeypatch.setenv("SB_XCHG_TIMEOUT_S", "1.5")
+    F, hidden, acts, B = 64, [48, 24], [so.ACT_TANH, so.ACT_RELU], 96
+    desc = sb.make_desc(F, hidden, acts, optimizer=so.OPT_SGD, learning_rate=0.1, max_batch=B, precision=1)
+    ts = [sb.Trainer(desc, device=0, nccl_id=None, rank=r, world=2) for r in range(2)]
+    for t in ts:
+        t.set_peer_pointers([x.exchange_base for x in ts])
+        t.init_xavier(3)
+    X, y, w = so.synth_batch(B, F, 1)
+    ts[0].load_dataset(X, y, w)
+    ts[0].step_resident_async(0, B)          # rank 1 never steps
+    with pytest.raises(sb.capi.ShifuB200Error, match="rank 1 did not reach"):
+        ts[0].sync()
+    for t in ts:
+        t.close()
+    # no exchange configured at all is refused up front
+    t = sb.Trainer(desc, device=0, nccl_id=None, rank=0, world=2)
+    t.init_xavier(3); t.load_dataset(X, y, w)
+    with pytest.raises(sb.capi.ShifuB200Error, match="no gradient exchange configured"):
+        t.step_resident(0, B)
+    t.close()
