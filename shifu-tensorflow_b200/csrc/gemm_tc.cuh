@@ -334,7 +334,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // warps idle during the main loop): per-row label / weight / n_nz / b_o of the fused output layer, and the first
       // chunk of A_{l-1} of the dA epilogue (the next chunk's is fetched while the current one is processed)
       float pre_y = 0.f, pre_w = 0.f, pre_nnz = 0.f, pre_bo = 0.f;
-      uint4 aux_nxt[4];
+      // dA epilogue: A_{l-1} of EVERY chunk this warp will handle is fetched before the accumulator wait (the loads do not
+      // depend on it) and kept in registers as a shift queue, so that one L2 / HBM latency is paid per tile instead of one
+      // per 32-column chunk (the chunk-ahead prefetch left this epilogue latency bound: 5 us per 256 x 256 tile at cfg2)
+      constexpr int AUXQ = (EPI == EPI_DA) ? (BN / 64 > 0 ? BN / 64 : 1) : 1;
+      uint4 aux_q[AUXQ][4];
       const int row_base = tm * TILE_M + static_cast<int>(rank) * BM + quarter * 32;   // first row of this warp's 32
       // store a 32 x 64 B tile held one-row-per-thread (4 pieces each) to a row-major bf16 matrix, coalesced
       auto store_rows_bf16 = [&](const uint4 (&mine)[4], __nv_bfloat16* base, int ld, int col0_, bool all_cols) {
@@ -366,7 +370,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         pre_nnz = p.scal[SCAL_NNZ];
         pre_bo = __ldg(p.bo);
       }
-      if constexpr (EPI == EPI_DA) load_aux(half, aux_nxt);
+      if constexpr (EPI == EPI_DA) {
+#pragma unroll
+        for (int i = 0; i < AUXQ; ++i) load_aux(half + 2 * i, aux_q[i]);
+      }
       const uint32_t sm_bias = sm_vec + static_cast<uint32_t>(it & 1) * (BN * 4u);   // EPI_FWD: this tile's bias, double-buffered
       if constexpr (EPI == EPI_FWD) {
         // (a warp reaches this barrier only after finishing the previous tile, so buffer it & 1 is no longer read)
@@ -523,8 +530,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else if constexpr (EPI == EPI_DA) {
           // multiply by act'(A_{l-1}[row, col]) read as bf16 (64 B per thread per chunk, fetched one chunk ahead)
           uint4 a4[4];
-          lanes_to_row(aux_nxt, a4);
-          load_aux(c + 2, aux_nxt);
+          lanes_to_row(aux_q[0], a4);
+#pragma unroll
+          for (int i = 0; i + 1 < AUXQ; ++i) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) aux_q[i][k] = aux_q[i + 1][k];
+          }
           const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(a4);
           switch (act_sel) {
             case SB_ACT_RELU: epi_da_chunk<SB_ACT_RELU>(v, ah); break;

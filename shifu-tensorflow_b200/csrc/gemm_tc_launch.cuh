@@ -31,7 +31,7 @@ static int launch_gemm_tc_one(const GemmPlan& pl, const CUtensorMap& a, const CU
   return SB_OK;
 }
 
-// EPI_FWD_OUT: one instantiation per (tile width 64 | 128, activation), single CTAs only
+// EPI_FWD_OUT: one instantiation per (tile width 64 | 128 | 256, activation), single CTAs only
 template <int BN, bool A_MN, bool B_MN>
 static int launch_fwd_out_act(const GemmPlan& pl, const CUtensorMap& a, const CUtensorMap& b, const GemmTcParams& p, cudaStream_t st,
                               bool pdl) {
@@ -51,6 +51,7 @@ int launch_gemm_tc(const GemmPlan& pl, const CUtensorMap& a, const CUtensorMap& 
   if constexpr (EPI == EPI_FWD_OUT) {
     if (pl.cg == 1 && pl.bn == 64) return launch_fwd_out_act<64, A_MN, B_MN>(pl, a, b, p, st, pdl);
     if (pl.cg == 1 && pl.bn == 128) return launch_fwd_out_act<128, A_MN, B_MN>(pl, a, b, p, st, pdl);
+    if (pl.cg == 1 && pl.bn == 256) return launch_fwd_out_act<256, A_MN, B_MN>(pl, a, b, p, st, pdl);
     return set_error(SB_ERR_INVALID, "fused output layer: no instantiation for cg=%d bn=%d", pl.cg, pl.bn);
   } else {
   if (pl.cg == 1 && pl.bn == 64) return launch_gemm_tc_one<64, EPI, A_MN, B_MN, 1>(pl, a, b, p, st, pdl);
@@ -70,7 +71,7 @@ int set_gemm_tc_attrs() {
                                GemmTcCfg<BN, 1>::SMEM_BYTES))
 #define SB_ATTR_ALL(BN) SB_ATTR_ACT(BN, SB_ACT_NONE); SB_ATTR_ACT(BN, SB_ACT_SIGMOID); SB_ATTR_ACT(BN, SB_ACT_TANH); \
                         SB_ATTR_ACT(BN, SB_ACT_RELU); SB_ATTR_ACT(BN, SB_ACT_LEAKYRELU)
-    SB_ATTR_ALL(64); SB_ATTR_ALL(128);
+    SB_ATTR_ALL(64); SB_ATTR_ALL(128); SB_ATTR_ALL(256);
 #undef SB_ATTR_ALL
 #undef SB_ATTR_ACT
     return SB_OK;

@@ -134,6 +134,7 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
   if (const char* e = getenv("SB_NO_PDL")) use_pdl = !(e[0] == '1');
   if (const char* e = getenv("SB_NO_FORK")) concurrent_bwd = !(e[0] == '1');
   if (const char* e = getenv("SB_NO_FUSE_OUT")) fuse_out_layer = !(e[0] == '1');
+  if (const char* e = getenv("SB_FUSE_OUT_MAX")) fuse_out_max = atoi(e);   // experiment: 128 restores the round-1 rule
   const bool want_trace = getenv("SB_STEP_TRACE") != nullptr;
   gemm_sms = num_sms;
   SB_CUDA(cudaSetDevice(device));
@@ -335,13 +336,15 @@ int Net::enqueue_hidden_forward(int rows, float* grad, bool* fused_out) {
       p.bias = theta + ly.b_off; p.act = ly.act;
       p.out = A[l]; p.ld_out = ly.ld_out;
       p.a_rows = res0 ? desc : nullptr;
-      if (l == L - 1 && grad != nullptr && fuse_out_layer && training && ly.out <= 128) {
+      if (l == L - 1 && grad != nullptr && fuse_out_layer && training && ly.out <= fuse_out_max) {
         // K2 + K3 + K4 + output backward in one kernel: one n-tile must cover the whole layer width
         GemmPlan fp = pl;
         fp.split_k = 1; fp.kb_per_split = (ly.in + 63) / 64;
-        // (the 256-wide pair tile works too, but at h_L = 256 it measured slower than GEMM + out_layer kernel)
+        // (a 256-wide PAIR tile measured slower than GEMM + out_layer kernel in round 1; the single-CTA 128 x 256 tile keeps
+        // whole rows of A_L in one CTA's TMEM - 2 x 256 columns, double-buffered - and needs no second kernel)
         if (ly.out <= 64) { fp.cg = 1; fp.bn = 64; }
-        else { fp.cg = 1; fp.bn = 128; }
+        else if (ly.out <= 128) { fp.cg = 1; fp.bn = 128; }
+        else { fp.cg = 1; fp.bn = 256; }
         const int slots = gemm_sms / fp.cg;
         const int tiles = (rows + 128 * fp.cg - 1) / (128 * fp.cg);
         fp.grid = (tiles < slots ? tiles : slots) * fp.cg;

@@ -131,6 +131,7 @@ struct Net {
   // backward in its epilogue when h_L <= 128; *fused_out tells the caller whether enqueue_out is still needed
   int enqueue_hidden_forward(int rows, float* grad = nullptr, bool* fused_out = nullptr);
   bool fuse_out_layer = true;
+  int fuse_out_max = 256;                    // widest last hidden layer whose GEMM also runs the output layer (one n-tile)
   // bf16 HBM-resident training set (trainer): when `from_resident` is set while enqueueing, layer 0's GEMMs read their A
   // operand from it by TMA at row offset desc->row0 and no load_batch kernel runs
   const __nv_bfloat16* resident_Xb = nullptr;

@@ -67,7 +67,7 @@ def test_replicas_on_one_gpu_match_the_data_parallel_oracle(sb, monkeypatch, W, 
     shards = _shards(W, n_batches, B, F, 100)
     _run_all(ts, shards, n_steps, B, n_batches)
     cfg = so.OptConfig(kind=so.OPT_ADAM, lr=0.003)
-    ref = so.CleanTrainer(net, params, cfg) if prec == 0 else so.Bf16Trainer(net, params, cfg, fused_out=hidden[-1] <= 128)
+    ref = so.CleanTrainer(net, params, cfg) if prec == 0 else so.Bf16Trainer(net, params, cfg, fused_out=hidden[-1] <= 256)
     want = []
     for s in range(n_steps):
         o = (s % n_batches) * B
@@ -97,7 +97,7 @@ def test_cfg2_shape_two_replicas_bf16(sb, monkeypatch):
     net, params, ts = _make(sb, 2, F, hidden, acts, B, 1, so.OPT_MOMENTUM, 0.01, monkeypatch)
     shards = _shards(2, n_batches, B, F, 7)
     _run_all(ts, shards, n_steps, B, n_batches)
-    ref = so.Bf16Trainer(net, params, so.OptConfig(kind=so.OPT_MOMENTUM, lr=0.01), fused_out=False)
+    ref = so.Bf16Trainer(net, params, so.OptConfig(kind=so.OPT_MOMENTUM, lr=0.01), fused_out=True)
     want = []
     for s in range(n_steps):
         o = (s % n_batches) * B

@@ -82,7 +82,7 @@ def _bf16_case(sb, F, hidden, acts, rows, loss, weights, seed=3):
                                        precision=sb.PREC_BF16)
     X, y, w = so.synth_batch(rows, F, seed, weights=weights)
     L32, g32, _ = so.loss_and_grads(net, params, X, y, w, loss)
-    Lb, gb, _ = so.loss_and_grads_bf16(net, params, X, y, w, loss, fused_out=hidden[-1] <= 128)
+    Lb, gb, _ = so.loss_and_grads_bf16(net, params, X, y, w, loss, fused_out=hidden[-1] <= 256)
     with sb.Trainer(desc) as t:
         t.set_params(so.flatten_params(params))
         return net, L32, so.flatten_params(g32), Lb, so.flatten_params(gb), t.step(X, y, w), t.get_grads()
