@@ -51,10 +51,15 @@ typedef enum { SB_ACT_SIGMOID = 0, SB_ACT_TANH = 1, SB_ACT_RELU = 2, SB_ACT_LEAK
 typedef enum { SB_LOSS_MSE = 0, SB_LOSS_SIGMOID_CE = 1 } sb_loss;
 /* ADADELTA: ssgd_monitor.py:138; ADAM: ssgd.py:57; SGD: ssgd_monitor_bk.py:81; MOMENTUM: north star */
 typedef enum { SB_OPT_ADADELTA = 0, SB_OPT_ADAM = 1, SB_OPT_SGD = 2, SB_OPT_MOMENTUM = 3 } sb_optimizer;
-/* SB_PREC_FP32: fp32 operands and fp32 accumulation end to end (what TF-CPU computes) - parity mode.
+/* SB_PREC_FP32: fp32 operands and fp32 accumulation end to end (what TF-CPU computes) - parity mode (CUDA cores).
  * SB_PREC_BF16: bf16 operands on tcgen05 tensor cores, fp32 accumulation in TMEM, fp32 master
- *               weights and optimizer state - performance mode. */
-typedef enum { SB_PREC_FP32 = 0, SB_PREC_BF16 = 1 } sb_precision;
+ *               weights and optimizer state - performance mode.
+ * SB_PREC_FP32_TC: fp32-class accuracy ON the tensor cores: every fp32 operand value is split into three bf16 parts
+ *               (v = p0 + p1 + p2, exact to ~2^-24), the six part products with i + j < 3 accumulate in fp32 TMEM.  Same
+ *               kernels as SB_PREC_BF16 over a six times longer K axis; meets the fp32 tolerances (loss / gradients
+ *               1e-4, scores 1e-5).  Parity mode that is not a CUDA-core program.
+ * SB_PREC_BF16X2: two parts, three products (~2^-17 relative per product): half the cost of FP32_TC. */
+typedef enum { SB_PREC_FP32 = 0, SB_PREC_BF16 = 1, SB_PREC_FP32_TC = 2, SB_PREC_BF16X2 = 3 } sb_precision;
 
 typedef struct {
   int32_t n_features;              /* FEATURE_COUNT = len(SELECTED_COLUMN_NUMS), ssgd_monitor.py:43-44 */
@@ -262,6 +267,10 @@ int sb_debug_gemm_bf16_ex(const float* A, const float* B, float* D, int32_t M, i
  * 256 x cfg_bn tile, tcgen05 cta_group::2, cfg_bn 128|256); cfg_cg = 0 lets the planner choose. */
 int sb_debug_gemm_bf16_cfg(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K,
                            int32_t split_k, int32_t a_mn, int32_t b_mn, int32_t cfg_cg, int32_t cfg_bn, int device);
+
+/* D = A B^T with every fp32 operand value held as np bf16 parts (np = 2: three part products, 3: six; see sb_precision):
+ * the tensor-core parity GEMM behind SB_PREC_FP32_TC / SB_PREC_BF16X2. */
+int sb_debug_gemm_split(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t np, int device);
 
 /* micro-benchmark of one tile configuration: average device milliseconds per launch over `iters` back-to-back launches
  * (CUDA events on the launching stream, operands L2-warm) */

@@ -19,7 +19,7 @@ SB_NCCL_ID_BYTES = 128
 ACT_SIGMOID, ACT_TANH, ACT_RELU, ACT_LEAKYRELU, ACT_NONE = 0, 1, 2, 3, -1
 LOSS_MSE, LOSS_SIGMOID_CE = 0, 1
 OPT_ADADELTA, OPT_ADAM, OPT_SGD, OPT_MOMENTUM = 0, 1, 2, 3
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_FP32_TC, PREC_BF16X2 = 0, 1, 2, 3
 SB_OK, SB_ERR_INVALID, SB_ERR_CUDA, SB_ERR_NCCL, SB_ERR_IO, SB_ERR_STATE, SB_ERR_FORMAT = 0, -1, -2, -3, -4, -5, -6
 
 
@@ -130,6 +130,7 @@ PROTOTYPES = {
                                            C.c_int64, _P(C.c_int64), _P(CellFlag), C.c_int64, _P(C.c_int64)]),
     "sb_savedmodel_write": (C.c_int, [_cp, _P(NetDesc), _f32p, C.c_int64]),
     "sb_savedmodel_read": (C.c_int, [_cp, _cp, _cp, _cp, _P(NetDesc), _P(C.c_int32), _f32p, C.c_int64, _P(C.c_int64)]),
+    "sb_debug_gemm_split": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
     "sb_debug_gemm_bf16": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
     "sb_debug_gemm_bf16_ex": (C.c_int, [_f32p, _f32p, _f32p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int]),
     "sb_debug_step_trace": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.c_int32, C.c_char_p, C.c_int32, C.POINTER(C.c_int32)]),
@@ -476,6 +477,17 @@ def debug_gemm_bf16(A: np.ndarray, B: np.ndarray, split_k: int = 1, device: int 
     assert K == K2
     D = np.zeros((M, N), np.float32)
     check(lib().sb_debug_gemm_bf16_cfg(_ptr(A), _ptr(B), _ptr(D), M, N, K, split_k, int(a_mn), int(b_mn), cg, bn, device))
+    return D
+
+
+def debug_gemm_split(A: np.ndarray, B: np.ndarray, np_parts: int, device: int = 0) -> np.ndarray:
+    """D[M,N] = A[M,K] B[N,K]^T on the tcgen05 path with every fp32 value split into np_parts bf16 parts"""
+    A, B = _f32(A), _f32(B)
+    M, K = A.shape
+    N, K2 = B.shape
+    assert K == K2
+    D = np.zeros((M, N), np.float32)
+    check(lib().sb_debug_gemm_split(_ptr(A), _ptr(B), _ptr(D), M, N, K, np_parts, device))
     return D
 
 

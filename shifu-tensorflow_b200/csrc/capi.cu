@@ -185,7 +185,7 @@ static bool step_is_pipelined(const sb_trainer* t, int kind) {
   static const bool want_pipeline = getenv("SB_PIPELINE_AR") != nullptr;
   const Net& n = t->net;
   return want_pipeline && kind == G_STEP && n.concurrent_bwd && !n.profiling && n.side != nullptr &&
-         n.precision == SB_PREC_BF16;
+         n.tc();
 }
 
 // the body of one step as a sequence of stream operations (captured into a CUDA graph)
@@ -246,11 +246,11 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   // segment launches of xchg_update_kernel (segment A on the side stream overlaps dW_0, segment B follows dW_0).
   static const bool one_xchg = getenv("SB_XCHG_ONE") != nullptr;    // experiment: one launch for both segments after a join
   const bool split_tail = !old_sched && kind == G_STEP && (t->world == 1 || (t->p2p_ready && !one_xchg)) && !pipelined &&
-                          n.concurrent_bwd && !n.profiling && n.side != nullptr && n.precision == SB_PREC_BF16 && n.L > 1;
+                          n.concurrent_bwd && !n.profiling && n.side != nullptr && n.tc() && n.L > 1;
   // (dW_0 on the main stream also when an exchange or the accumulate kernel follows: it is then joined with the side
   // stream as before)
   n.dw0_on_main = !old_sched && !pipelined && n.concurrent_bwd && !n.profiling && n.side != nullptr &&
-                  n.precision == SB_PREC_BF16 && n.L > 1;
+                  n.tc() && n.L > 1;
   n.defer_join = split_tail;
   int bs = n.enqueue_backward(rows, t->grad);
   n.on_layer_grads = nullptr;
@@ -837,11 +837,14 @@ int sb_trainer_load_dataset(sb_trainer_t* t, const float* X, const float* y, con
     fill_kernel<<<static_cast<unsigned>((n_rows + 255) / 256), 256, 0, n.stream>>>(t->dsW, 1.f, n_rows);
     SB_CUDA(cudaGetLastError());
   }
-  if (n.precision == SB_PREC_BF16) {
-    // keep the set in HBM in the form the layer-0 GEMMs consume (bf16, row pitch ldF): converted once here, read by
-    // TMA every step.  Converted through a bounded fp32 window so a 100+ GB set never needs a second full copy.
-    SB_CUDA(cudaMalloc(&t->dsXb, sizeof(__nv_bfloat16) * static_cast<size_t>(n_rows) * n.ldF));
-    SB_CUDA(cudaMemsetAsync(t->dsXb, 0, sizeof(__nv_bfloat16) * static_cast<size_t>(n_rows) * n.ldF, n.stream));
+  if (n.tc()) {
+    // keep the set in HBM in the form the layer-0 GEMMs consume (bf16, row pitch ldF; split modes: nparts such arrays):
+    // converted once here, read by TMA every step.  Converted through a bounded fp32 window so a 100+ GB set never needs
+    // a second full copy.
+    const size_t part_elems = static_cast<size_t>(n_rows) * n.ldF;
+    SB_CUDA(cudaMalloc(&t->dsXb, sizeof(__nv_bfloat16) * part_elems * n.nparts));
+    SB_CUDA(cudaMemsetAsync(t->dsXb, 0, sizeof(__nv_bfloat16) * part_elems * n.nparts, n.stream));
+    n.resident_ps = static_cast<long long>(part_elems);
     const int64_t win = 32768;
     float* tmp = nullptr;
     SB_CUDA(cudaMalloc(&tmp, sizeof(float) * static_cast<size_t>(win < n_rows ? win : n_rows) * n.F));
@@ -849,7 +852,8 @@ int sb_trainer_load_dataset(sb_trainer_t* t, const float* X, const float* y, con
       const int64_t c = n_rows - r0 < win ? n_rows - r0 : win;
       SB_CUDA(cudaMemcpyAsync(tmp, X + r0 * n.F, sizeof(float) * c * n.F, cudaMemcpyHostToDevice, n.stream));
       cast_bf16_kernel<<<static_cast<unsigned>((c * n.F + 255) / 256), 256, 0, n.stream>>>(tmp, static_cast<int>(c), n.F,
-                                                                                           t->dsXb + r0 * n.ldF, n.ldF);
+                                                                                           t->dsXb + r0 * n.ldF, n.ldF, n.nparts,
+                                                                                           n.resident_ps);
       SB_CUDA(cudaGetLastError());
       SB_CUDA(cudaStreamSynchronize(n.stream));   // X may be pageable: the window is reused
     }
@@ -1252,7 +1256,7 @@ static const int MODEL_CHUNK_ROWS = 16384;        // fp32 parity mode
 static const int MODEL_CHUNK_ROWS_BF16 = 65536;   // bf16: bigger GEMMs per launch (workspace ~0.8 GB at 2000 cols)
 
 static int model_from_desc(sb_net_desc d, const float* flat, int64_t n, int device, sb_model_t** out) {
-  d.max_batch = d.precision == SB_PREC_BF16 ? MODEL_CHUNK_ROWS_BF16 : MODEL_CHUNK_ROWS;
+  d.max_batch = d.precision == SB_PREC_FP32 ? MODEL_CHUNK_ROWS : (d.precision == SB_PREC_BF16 ? MODEL_CHUNK_ROWS_BF16 : MODEL_CHUNK_ROWS_BF16 / 2);
   std::unique_ptr<sb_model> m(new sb_model());
   m->desc = d;
   int s = m->net.init(&d, device, false);
@@ -1440,17 +1444,17 @@ static int debug_gemm_impl(const float* A, const float* B, float* D, int32_t M, 
     const int work = tiles * pl.split_k;
     pl.grid = (work < slots ? work : slots) * pl.cg;
   }
-  CUtensorMap ta, tb;
-  int s = make_tmap_bf16(&ta, dA, a_rows, a_cols, lda, a_mn ? 64 : 128);
-  if (s == SB_OK) s = make_tmap_bf16(&tb, dB, b_rows, b_cols, ldb, b_mn ? 64 : plan_box_rows_b(pl));
+  TmapSet tms;
+  int s = make_tmap_bf16(&tms.a[0], dA, a_rows, a_cols, lda, a_mn ? 64 : 128);
+  if (s == SB_OK) s = make_tmap_bf16(&tms.b[0], dB, b_rows, b_cols, ldb, b_mn ? 64 : plan_box_rows_b(pl));
   if (s == SB_OK) {
     GemmTcParams p = {};
     p.M = M; p.N = N; p.K = K;
     p.accum = dD; p.ld_acc = N;
     auto launch = [&]() -> int {
-      if (!a_mn && !b_mn) return launch_gemm_tc<EPI_F32, false, false>(pl, ta, tb, p, 0);
-      if (!a_mn) return launch_gemm_tc<EPI_F32, false, true>(pl, ta, tb, p, 0);
-      return launch_gemm_tc<EPI_F32, true, true>(pl, ta, tb, p, 0);
+      if (!a_mn && !b_mn) return launch_gemm_tc<EPI_F32, false, false>(pl, tms, p, 0);
+      if (!a_mn) return launch_gemm_tc<EPI_F32, false, true>(pl, tms, p, 0);
+      return launch_gemm_tc<EPI_F32, true, true>(pl, tms, p, 0);
     };
     if (!a_mn && !b_mn) s = set_gemm_tc_attrs<EPI_F32, false, false>();
     else if (!a_mn) s = set_gemm_tc_attrs<EPI_F32, false, true>();
@@ -1472,9 +1476,9 @@ static int debug_gemm_impl(const float* A, const float* B, float* D, int32_t M, 
       q.acc_vec4 = (N % 4 == 0) ? 1 : 0;
       const bool bench_pdl = getenv("SB_BENCH_PDL") != nullptr;
       auto real = [&]() -> int {
-        if (!a_mn && !b_mn) return launch_gemm_tc<EPI_DA, false, false>(pl, ta, tb, q, 0, bench_pdl);
-        if (!a_mn) return launch_gemm_tc<EPI_FWD, false, true>(pl, ta, tb, q, 0, bench_pdl);
-        return launch_gemm_tc<EPI_DW, true, true>(pl, ta, tb, q, 0, bench_pdl);
+        if (!a_mn && !b_mn) return launch_gemm_tc<EPI_DA, false, false>(pl, tms, q, 0, bench_pdl);
+        if (!a_mn) return launch_gemm_tc<EPI_FWD, false, true>(pl, tms, q, 0, bench_pdl);
+        return launch_gemm_tc<EPI_DW, true, true>(pl, tms, q, 0, bench_pdl);
       };
       if (!a_mn && !b_mn) s = set_gemm_tc_attrs<EPI_DA, false, false>();
       else if (!a_mn) s = set_gemm_tc_attrs<EPI_FWD, false, true>();
@@ -1530,6 +1534,50 @@ static int debug_gemm_impl(const float* A, const float* B, float* D, int32_t M, 
 }
 
 extern "C" {
+
+// D[M,N] = A[M,K] B[N,K]^T with every fp32 operand value split into `np` bf16 parts (np = 1: plain bf16)
+int sb_debug_gemm_split(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t np, int device) {
+  SB_CHECK(A && B && D && M > 0 && N > 0 && K > 0 && np >= 1 && np <= 3, SB_ERR_INVALID, "bad argument");
+  int n_dev = 0;
+  SB_CHECK(cudaGetDeviceCount(&n_dev) == cudaSuccess && n_dev > 0, SB_ERR_CUDA, "no CUDA device available");
+  cudaDeviceProp prop;
+  SB_CUDA(cudaGetDeviceProperties(&prop, device));
+  SB_CHECK(prop.major == 10, SB_ERR_CUDA, "device is sm_%d%d, need sm_100", prop.major, prop.minor);
+  SB_CUDA(cudaSetDevice(device));
+  const int ld = round_up(K, 8);
+  const long long a_ps = static_cast<long long>(M) * ld, b_ps = static_cast<long long>(N) * ld;
+  float *dA32 = nullptr, *dB32 = nullptr, *dD = nullptr;
+  __nv_bfloat16 *dA = nullptr, *dB = nullptr;
+  SB_CUDA(cudaMalloc(&dA32, sizeof(float) * M * K));
+  SB_CUDA(cudaMalloc(&dB32, sizeof(float) * N * K));
+  SB_CUDA(cudaMalloc(&dD, sizeof(float) * M * N));
+  SB_CUDA(cudaMalloc(&dA, sizeof(__nv_bfloat16) * a_ps * np));
+  SB_CUDA(cudaMalloc(&dB, sizeof(__nv_bfloat16) * b_ps * np));
+  SB_CUDA(cudaMemset(dA, 0, sizeof(__nv_bfloat16) * a_ps * np));
+  SB_CUDA(cudaMemset(dB, 0, sizeof(__nv_bfloat16) * b_ps * np));
+  SB_CUDA(cudaMemset(dD, 0, sizeof(float) * M * N));
+  SB_CUDA(cudaMemcpy(dA32, A, sizeof(float) * M * K, cudaMemcpyHostToDevice));
+  SB_CUDA(cudaMemcpy(dB32, B, sizeof(float) * N * K, cudaMemcpyHostToDevice));
+  cast_bf16_kernel<<<static_cast<unsigned>((static_cast<long long>(M) * K + 255) / 256), 256>>>(dA32, M, K, dA, ld, np, a_ps);
+  cast_bf16_kernel<<<static_cast<unsigned>((static_cast<long long>(N) * K + 255) / 256), 256>>>(dB32, N, K, dB, ld, np, b_ps);
+  GemmTcParams p = {};
+  set_part_pairs(&p, np);
+  p.M = M; p.N = N; p.K = K;
+  p.accum = dD; p.ld_acc = N;
+  const GemmPlan pl = plan_gemm(M, N, round_up(K, 64) * p.n_pairs, prop.multiProcessorCount, false);
+  TmapSet tms;
+  int s = make_tmaps_bf16(tms.a, dA, a_ps, np, M, K, ld, 128);
+  if (s == SB_OK) s = make_tmaps_bf16(tms.b, dB, b_ps, np, N, K, ld, plan_box_rows_b(pl));
+  if (s == SB_OK) s = set_gemm_tc_attrs<EPI_F32, false, false>();
+  if (s == SB_OK) s = launch_gemm_tc<EPI_F32, false, false>(pl, tms, p, 0);
+  if (s == SB_OK) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) s = set_error(SB_ERR_CUDA, "gemm_tc_kernel (split) failed: %s", cudaGetErrorString(e));
+    else if (cudaMemcpy(D, dD, sizeof(float) * M * N, cudaMemcpyDeviceToHost) != cudaSuccess) s = set_error(SB_ERR_CUDA, "D2H failed");
+  }
+  cudaFree(dA32); cudaFree(dB32); cudaFree(dD); cudaFree(dA); cudaFree(dB);
+  return s;
+}
 
 int sb_debug_gemm_bf16_ex(const float* A, const float* B, float* D, int32_t M, int32_t N, int32_t K, int32_t split_k,
                           int32_t a_mn, int32_t b_mn, int device) {

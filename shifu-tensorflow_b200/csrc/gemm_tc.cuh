@@ -73,6 +73,22 @@ struct GemmTcParams {
   float4* zero_buf;
   long long zero_n4;
   unsigned long long* trace;  // debug: CTA 0 writes %globaltimer stamps of its pipeline milestones (nullable)
+  // Split-precision modes (SB_PREC_FP32_TC / SB_PREC_BF16X2, net.cuh): every fp32 operand value is held as np bf16 PARTS
+  // v = p0 + p1 (+ p2) in np equally shaped arrays; the contraction is then a plain bf16 GEMM over an EXTENDED K axis that
+  // walks the part pairs (a_i, b_j) with i + j < np one after the other, all accumulating into the same fp32 TMEM tile:
+  //   np = 2 : a0b0 + a0b1 + a1b0                        (relative error ~2^-17 per product)
+  //   np = 3 : a0b0 + a0b1 + a1b0 + a0b2 + a1b1 + a2b0   (~2^-24: fp32-class, what TF-CPU's fp32 GEMM delivers)
+  // The MMA issuer does not know about it; the TMA producer picks the pair's tensor maps per k-block.
+  int np;                     // parts per value in `out` / `aux` (1 = plain bf16)
+  int n_pairs;                // part pairs accumulated (1, 3 or 6); 0 is read as 1
+  unsigned char pair_a[6], pair_b[6];
+  long long out_ps, aux_ps;   // element stride between consecutive parts of `out` / `aux`
+};
+
+// tensor maps of the parts of both operands (one kernel parameter, 768 B)
+struct TmapSet {
+  CUtensorMap a[3];
+  CUtensorMap b[3];
 };
 
 template <int BN, int CG>
@@ -114,7 +130,7 @@ constexpr int SB_ACT_AT_RUNTIME = -100;
 
 template <int BN, int EPI, bool A_MN, bool B_MN, int CG, int ACT_T = SB_ACT_AT_RUNTIME>
 __global__ void __launch_bounds__(GemmTcCfg<BN, CG>::THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmTcParams p) {
+gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
   using Cfg = GemmTcCfg<BN, CG>;
   const int act_sel = (ACT_T == SB_ACT_AT_RUNTIME) ? p.act : ACT_T;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES, TILE_M = Cfg::TILE_M, BN_CTA = Cfg::BN_CTA;
@@ -140,9 +156,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // CTA rank inside the pair
   const bool leader = rank == 0;
 
+  const int n_pairs = p.n_pairs > 0 ? p.n_pairs : 1;
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmA);
-    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tms.a[0]);
+    tma_prefetch_desc(&tms.b[0]);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -177,7 +194,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tiles_n = (p.N + BN - 1) / BN;
   const int n_tiles = tiles_m * tiles_n;
   const int n_work = n_tiles * p.split_k;
-  const int total_kb = (p.K + BK - 1) / BK;
+  const int part_kb = (p.K + BK - 1) / BK;         // k-blocks of ONE part pair
+  const int total_kb = part_kb * n_pairs;          // extended K axis: the pairs one after the other
   const int w_first = (CG == 2) ? (blockIdx.x >> 1) : blockIdx.x;   // work items are per CTA (CG=1) or per pair (CG=2)
   const int w_step = (CG == 2) ? (gridDim.x >> 1) : gridDim.x;
 
@@ -194,7 +212,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int kb1 = min(total_kb, kb0 + p.kb_per_split);
         const int m0 = tm * TILE_M + static_cast<int>(rank) * BM;      // this CTA's rows of A
         const int n0 = tn * BN + static_cast<int>(rank) * BN_CTA;      // this CTA's share of the B tile
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kbx = kb0; kbx < kb1; ++kbx) {
+          const int pp = (n_pairs > 1) ? kbx / part_kb : 0;     // which part pair this k-block belongs to
+          const int kb = kbx - pp * part_kb;
+          const CUtensorMap* tmA = &tms.a[n_pairs > 1 ? p.pair_a[pp] : 0];
+          const CUtensorMap* tmB = &tms.b[n_pairs > 1 ? p.pair_b[pp] : 0];
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t fb = full_bar(stage);
           if (leader) mbar_arrive_expect_tx(fb, Cfg::STAGE_BYTES * CG);
@@ -205,21 +227,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if constexpr (A_MN) {
 #pragma unroll
             for (int i = 0; i < BM / 64; ++i)  // 64(MN) x 64(K) boxes, 8 KB each, side by side along MN
-              load(smem_a(stage) + i * 8192, &tmA, m0 + i * 64, kb * BK + a_row0);   // rows of the set = K here
+              load(smem_a(stage) + i * 8192, tmA, m0 + i * 64, kb * BK + a_row0);   // rows of the set = K here
           } else {
-            load(smem_a(stage), &tmA, kb * BK, m0 + a_row0);
+            load(smem_a(stage), tmA, kb * BK, m0 + a_row0);
           }
           if constexpr (B_MN) {
 #pragma unroll
             for (int i = 0; i < BN_CTA / 64; ++i)
-              load(smem_b(stage) + i * 8192, &tmB, n0 + i * 64, kb * BK);
+              load(smem_b(stage) + i * 8192, tmB, n0 + i * 64, kb * BK);
           } else {
-            load(smem_b(stage), &tmB, kb * BK, n0);
+            load(smem_b(stage), tmB, kb * BK, n0);
           }
           if constexpr (CG == 2) {
             if (!leader) mbar_arrive_cluster(fb, 0);  // second arrival on the leader's full barrier
           }
-          if (kb == kb0 && w == w_first) stamp(3);  // first TMA issued
+          if (kbx == kb0 && w == w_first) stamp(3);  // first TMA issued
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -353,7 +375,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       };
-      auto load_aux = [&](int c, uint4 (&a)[4]) {   // lane-coalesced fetch of chunk c of A_{l-1}; zeros outside
+      // split-precision output: part 0 = bf16(v), part k = bf16(v - sum of the previous parts); np = 1 is the plain store.
+      // x is left untouched (the residual of part k is re-derived from x: at most two extra cvt + sub per element).
+      auto store_parts = [&](const float (&x)[32], __nv_bfloat16* base, long long ps, int ld, int col0_, bool all_cols) {
+        for (int part = 0; part < p.np; ++part) {
+          auto res = [&](float r) {
+            for (int i = 0; i < part; ++i) r -= __bfloat162float(__float2bfloat16_rn(r));
+            return r;
+          };
+          uint4 o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            o[q].x = pack_bf16x2(res(x[q * 8 + 0]), res(x[q * 8 + 1]));
+            o[q].y = pack_bf16x2(res(x[q * 8 + 2]), res(x[q * 8 + 3]));
+            o[q].z = pack_bf16x2(res(x[q * 8 + 4]), res(x[q * 8 + 5]));
+            o[q].w = pack_bf16x2(res(x[q * 8 + 6]), res(x[q * 8 + 7]));
+          }
+          store_rows_bf16(o, base + part * ps, ld, col0_, all_cols);
+        }
+      };
+      auto load_aux = [&](int c, uint4 (&a)[4], int part = 0) {   // lane-coalesced fetch of chunk c of A_{l-1}; zeros outside
 #pragma unroll
         for (int i = 0; i < 4; ++i) a[i] = make_uint4(0, 0, 0, 0);
         const int gc = tn * BN + c * 32 + 8 * lpc;
@@ -361,7 +402,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int gr = row_base + 8 * i + lrow;
-            if (gr < p.M) a[i] = __ldg(reinterpret_cast<const uint4*>(p.aux + static_cast<size_t>(gr) * p.ld_aux + gc));
+            if (gr < p.M) a[i] = __ldg(reinterpret_cast<const uint4*>(p.aux + part * p.aux_ps + static_cast<size_t>(gr) * p.ld_aux + gc));
           }
         }
       };
@@ -476,19 +517,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             default: SB_G(SB_ACT_NONE) break;
 #undef SB_G
           }
-          {
-            uint4 o[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              o[q].x = pack_bf16x2(g[q * 8 + 0], g[q * 8 + 1]);
-              o[q].y = pack_bf16x2(g[q * 8 + 2], g[q * 8 + 3]);
-              o[q].z = pack_bf16x2(g[q * 8 + 4], g[q * 8 + 5]);
-              o[q].w = pack_bf16x2(g[q * 8 + 6], g[q * 8 + 7]);
-            }
-            store_rows_bf16(o, p.out, p.ld_out, col0, false);
-          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] *= dz;          // dz * a  -> dw_o contributions (0 for rows >= M)
+          store_parts(g, p.out, p.out_ps, p.ld_out, col0, false);       // dZ_L (bf16, or its parts)
           const float sb_ = warp_colsum_32x32(g, lane);
           const float sw_ = warp_colsum_32x32(v, lane);
           if (col0 + lane < p.N) { red_add_f32(p.g_bL + col0 + lane, sb_); red_add_f32(p.g_wo + col0 + lane, sw_); }
@@ -536,7 +567,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < 4; ++k) aux_q[i][k] = aux_q[i + 1][k];
           }
-          const __nv_bfloat16* ah = reinterpret_cast<const __nv_bfloat16*>(a4);
+          __nv_bfloat16* ah = reinterpret_cast<__nv_bfloat16*>(a4);
+          if (p.np > 1 && (act_sel == SB_ACT_SIGMOID || act_sel == SB_ACT_TANH)) {
+            // act' needs the VALUE of A_{l-1}: add the lower parts (fetched here, not prefetched: the split modes are the
+            // parity modes).  relu / leaky relu only look at the sign, which part 0 carries.
+            float af[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) af[j] = __bfloat162float(ah[j]);
+            for (int part = 1; part < p.np; ++part) {
+              uint4 lo_l[4], lo_r[4];
+              load_aux(c, lo_l, part);
+              lanes_to_row(lo_l, lo_r);
+              const __nv_bfloat16* lh = reinterpret_cast<const __nv_bfloat16*>(lo_r);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) af[j] += __bfloat162float(lh[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= act_grad_from_out(af[j], act_sel);
+          } else
           switch (act_sel) {
             case SB_ACT_RELU: epi_da_chunk<SB_ACT_RELU>(v, ah); break;
             case SB_ACT_SIGMOID: epi_da_chunk<SB_ACT_SIGMOID>(v, ah); break;
@@ -552,18 +600,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
 
         if constexpr (EPI == EPI_FWD || EPI == EPI_DA) {
-          {
-            // row-major bf16 (ld_out is a multiple of 8, pad columns belong to the buffer)
-            uint4 o[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              o[q].x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-              o[q].y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-              o[q].z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-              o[q].w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-            }
-            store_rows_bf16(o, p.out, p.ld_out, col0, full);
-          }
+          // row-major bf16 (ld_out is a multiple of 8, pad columns belong to the buffer); split modes: np part arrays
+          store_parts(v, p.out, p.out_ps, p.ld_out, col0, full);
           if constexpr (EPI == EPI_DA) {
             if (p.colsum != nullptr) {
               // bias gradient: per-column sum over this warp's 32 rows, one atomic per column per warp
@@ -647,6 +685,10 @@ PFN_encodeTiled get_encode_tiled();
 // them), ld*2 must be a multiple of 16 bytes.  K-major operand: box_rows = rows one CTA stages (128 for A,
 // BN / CG for B); MN-major operand: 64.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int cols, int ld, int box_rows);
+// the same map for each of np part arrays that lie part_stride ELEMENTS apart (np = 1: just the one)
+int make_tmaps_bf16(CUtensorMap* out3, const void* base, long long part_stride, int np, int rows, int cols, int ld, int box_rows);
+// fills n_pairs / pair_a / pair_b of p for np parts per operand
+void set_part_pairs(GemmTcParams* p, int np);
 
 // Tile configuration chosen per problem.
 struct GemmPlan {

@@ -5,7 +5,7 @@
 namespace sb {
 
 template <int BN, int EPI, bool A_MN, bool B_MN, int CG, int ACT_T = SB_ACT_AT_RUNTIME>
-static int launch_gemm_tc_one(const GemmPlan& pl, const CUtensorMap& a, const CUtensorMap& b, const GemmTcParams& p, cudaStream_t st,
+static int launch_gemm_tc_one(const GemmPlan& pl, const TmapSet& tms, const GemmTcParams& p, cudaStream_t st,
                               bool pdl) {
   using Cfg = GemmTcCfg<BN, CG>;
   cudaLaunchConfig_t cfg = {};
@@ -27,37 +27,39 @@ static int launch_gemm_tc_one(const GemmPlan& pl, const CUtensorMap& a, const CU
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  SB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, A_MN, B_MN, CG, ACT_T>, a, b, p));
+  SB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, A_MN, B_MN, CG, ACT_T>, tms, p));
   return SB_OK;
 }
 
 // EPI_FWD_OUT: one instantiation per (tile width 64 | 128 | 256, activation), single CTAs only
 template <int BN, bool A_MN, bool B_MN>
-static int launch_fwd_out_act(const GemmPlan& pl, const CUtensorMap& a, const CUtensorMap& b, const GemmTcParams& p, cudaStream_t st,
+static int launch_fwd_out_act(const GemmPlan& pl, const TmapSet& tms, const GemmTcParams& p, cudaStream_t st,
                               bool pdl) {
   switch (p.act) {
-    case SB_ACT_SIGMOID: return launch_gemm_tc_one<BN, EPI_FWD_OUT, A_MN, B_MN, 1, SB_ACT_SIGMOID>(pl, a, b, p, st, pdl);
-    case SB_ACT_TANH: return launch_gemm_tc_one<BN, EPI_FWD_OUT, A_MN, B_MN, 1, SB_ACT_TANH>(pl, a, b, p, st, pdl);
-    case SB_ACT_RELU: return launch_gemm_tc_one<BN, EPI_FWD_OUT, A_MN, B_MN, 1, SB_ACT_RELU>(pl, a, b, p, st, pdl);
-    case SB_ACT_LEAKYRELU: return launch_gemm_tc_one<BN, EPI_FWD_OUT, A_MN, B_MN, 1, SB_ACT_LEAKYRELU>(pl, a, b, p, st, pdl);
-    default: return launch_gemm_tc_one<BN, EPI_FWD_OUT, A_MN, B_MN, 1, SB_ACT_NONE>(pl, a, b, p, st, pdl);
+    case SB_ACT_SIGMOID: return launch_gemm_tc_one<BN, EPI_FWD_OUT, A_MN, B_MN, 1, SB_ACT_SIGMOID>(pl, tms, p, st, pdl);
+    case SB_ACT_TANH: return launch_gemm_tc_one<BN, EPI_FWD_OUT, A_MN, B_MN, 1, SB_ACT_TANH>(pl, tms, p, st, pdl);
+    case SB_ACT_RELU: return launch_gemm_tc_one<BN, EPI_FWD_OUT, A_MN, B_MN, 1, SB_ACT_RELU>(pl, tms, p, st, pdl);
+    case SB_ACT_LEAKYRELU: return launch_gemm_tc_one<BN, EPI_FWD_OUT, A_MN, B_MN, 1, SB_ACT_LEAKYRELU>(pl, tms, p, st, pdl);
+    default: return launch_gemm_tc_one<BN, EPI_FWD_OUT, A_MN, B_MN, 1, SB_ACT_NONE>(pl, tms, p, st, pdl);
   }
 }
 
 template <int EPI, bool A_MN, bool B_MN>
-int launch_gemm_tc(const GemmPlan& pl, const CUtensorMap& a, const CUtensorMap& b, GemmTcParams p, cudaStream_t st, bool pdl = false) {
+int launch_gemm_tc(const GemmPlan& pl, const TmapSet& tms, GemmTcParams p, cudaStream_t st, bool pdl = false) {
+  if (p.np < 1) p.np = 1;
+  if (p.n_pairs < 1) p.n_pairs = 1;
   p.split_k = pl.split_k;
   p.kb_per_split = pl.kb_per_split;
   if constexpr (EPI == EPI_FWD_OUT) {
-    if (pl.cg == 1 && pl.bn == 64) return launch_fwd_out_act<64, A_MN, B_MN>(pl, a, b, p, st, pdl);
-    if (pl.cg == 1 && pl.bn == 128) return launch_fwd_out_act<128, A_MN, B_MN>(pl, a, b, p, st, pdl);
-    if (pl.cg == 1 && pl.bn == 256) return launch_fwd_out_act<256, A_MN, B_MN>(pl, a, b, p, st, pdl);
+    if (pl.cg == 1 && pl.bn == 64) return launch_fwd_out_act<64, A_MN, B_MN>(pl, tms, p, st, pdl);
+    if (pl.cg == 1 && pl.bn == 128) return launch_fwd_out_act<128, A_MN, B_MN>(pl, tms, p, st, pdl);
+    if (pl.cg == 1 && pl.bn == 256) return launch_fwd_out_act<256, A_MN, B_MN>(pl, tms, p, st, pdl);
     return set_error(SB_ERR_INVALID, "fused output layer: no instantiation for cg=%d bn=%d", pl.cg, pl.bn);
   } else {
-  if (pl.cg == 1 && pl.bn == 64) return launch_gemm_tc_one<64, EPI, A_MN, B_MN, 1>(pl, a, b, p, st, pdl);
-  if (pl.cg == 1 && pl.bn == 128) return launch_gemm_tc_one<128, EPI, A_MN, B_MN, 1>(pl, a, b, p, st, pdl);
-  if (pl.cg == 2 && pl.bn == 128) return launch_gemm_tc_one<128, EPI, A_MN, B_MN, 2>(pl, a, b, p, st, pdl);
-  if (pl.cg == 2 && pl.bn == 256) return launch_gemm_tc_one<256, EPI, A_MN, B_MN, 2>(pl, a, b, p, st, pdl);
+  if (pl.cg == 1 && pl.bn == 64) return launch_gemm_tc_one<64, EPI, A_MN, B_MN, 1>(pl, tms, p, st, pdl);
+  if (pl.cg == 1 && pl.bn == 128) return launch_gemm_tc_one<128, EPI, A_MN, B_MN, 1>(pl, tms, p, st, pdl);
+  if (pl.cg == 2 && pl.bn == 128) return launch_gemm_tc_one<128, EPI, A_MN, B_MN, 2>(pl, tms, p, st, pdl);
+  if (pl.cg == 2 && pl.bn == 256) return launch_gemm_tc_one<256, EPI, A_MN, B_MN, 2>(pl, tms, p, st, pdl);
   return set_error(SB_ERR_INVALID, "no gemm_tc instantiation for cg=%d bn=%d", pl.cg, pl.bn);
   }
 }

@@ -33,6 +33,13 @@ static __global__ void set_batch_kernel(BatchDesc* d, const float* X, const floa
   }
 }
 
+// Split-precision modes: the value whose bf16 rounding is part `part` of x (part 0: x itself; part k: x minus the first k
+// parts).  x = bf16(r_0) + bf16(r_1) + ... with r_0 = x, r_{k+1} = r_k - bf16(r_k).
+__device__ __forceinline__ float bf16_residual(float x, int part) {
+  for (int i = 0; i < part; ++i) x -= __bfloat162float(__float2bfloat16_rn(x));
+  return x;
+}
+
 // step scalars (device): [0] = sum_i w_i * per-row loss, [1] = n_nz (count of non-zero weights)
 enum { SCAL_LOSS_SUM = 0, SCAL_NNZ = 1, SCAL_COUNT = 4 };
 
@@ -47,7 +54,8 @@ enum { SCAL_LOSS_SUM = 0, SCAL_NNZ = 1, SCAL_COUNT = 4 };
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 load_batch_kernel(const BatchDesc* __restrict__ desc, int rows, int F, __nv_bfloat16* __restrict__ Xb, int ldF,
-                  float* __restrict__ Xf, float* __restrict__ scal, float* __restrict__ zero_buf, long long zero_n) {
+                  float* __restrict__ Xf, float* __restrict__ scal, float* __restrict__ zero_buf, long long zero_n,
+                  int np = 1, long long part_stride = 0) {
   pdl_wait();
   pdl_launch_dependents();
   // the step's gradient buffer is accumulated with atomics: clear it here (replaces a memset node in the graph)
@@ -68,10 +76,14 @@ load_batch_kernel(const BatchDesc* __restrict__ desc, int rows, int F, __nv_bflo
       for (int j = 0; j < 8; ++j) v[j] = (c + j < F) ? __ldg(X + static_cast<size_t>(r) * F + c + j) : 0.f;
     }
     if constexpr (BF16) {
-      uint4 o;
-      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(Xb + static_cast<size_t>(r) * ldF + c) = o;
+      for (int part = 0; part < np; ++part) {      // np > 1: split-precision parts (bf16_residual)
+        uint4 o;
+        o.x = pack_bf16x2(bf16_residual(v[0], part), bf16_residual(v[1], part));
+        o.y = pack_bf16x2(bf16_residual(v[2], part), bf16_residual(v[3], part));
+        o.z = pack_bf16x2(bf16_residual(v[4], part), bf16_residual(v[5], part));
+        o.w = pack_bf16x2(bf16_residual(v[6], part), bf16_residual(v[7], part));
+        *reinterpret_cast<uint4*>(Xb + part * part_stride + static_cast<size_t>(r) * ldF + c) = o;
+      }
     } else {
       if (vec) {
         *reinterpret_cast<float4*>(Xf + static_cast<size_t>(r) * F + c) = make_float4(v[0], v[1], v[2], v[3]);
@@ -121,6 +133,8 @@ struct OutLayerParams {
   void* dZ; int ld_dZ;       // [rows, ld_dZ] bf16 or fp32
   float* g_wo; float* g_bo; float* g_bL;  // gradient slots (atomic accumulate)
   unsigned long long* trace;              // debug timeline (nullable): [0] entry, [2] deps resolved (block 0), [10] last exit
+  int np;                                 // bf16 parts per value of A / dZ (split-precision modes; 0 or 1 = plain)
+  long long a_ps, dz_ps;                  // element stride between parts
 };
 
 // in-graph kernel span for the step timeline: begin = block 0's stamp after griddepcontrol.wait, end = atomicMax over blocks
@@ -161,7 +175,11 @@ out_layer_kernel(const OutLayerParams p) {
     float z = 0.f;
     if (r < p.rows) {
       const T* ar = A + static_cast<size_t>(r) * p.ldA;
-      for (int j = lane; j < p.H; j += 32) z = fmaf(ld_as_float<T>(ar + j), __ldg(p.wo + j), z);
+      for (int j = lane; j < p.H; j += 32) {
+        float a = ld_as_float<T>(ar + j);
+        for (int part = 1; part < p.np; ++part) a += ld_as_float<T>(ar + part * p.a_ps + j);
+        z = fmaf(a, __ldg(p.wo + j), z);
+      }
     }
     z = warp_sum(z) + bo;
     if (lane == 0) {
@@ -212,12 +230,15 @@ out_layer_kernel(const OutLayerParams p) {
       const int rl = rh * 16 + i, r = r0 + rl;
       float g = 0.f;
       if (r < p.rows && j < p.H) {
-        const float a = ld_as_float<T>(A + static_cast<size_t>(r) * p.ldA + j);
+        float a = ld_as_float<T>(A + static_cast<size_t>(r) * p.ldA + j);
+        for (int part = 1; part < p.np; ++part) a += ld_as_float<T>(A + part * p.a_ps + static_cast<size_t>(r) * p.ldA + j);
         const float dz = dz_row[rl];
         g = dz * woj * act_grad_from_out(a, p.act);
         s_dw = fmaf(dz, a, s_dw);
         s_db += g;
         st_from_float<T>(dZ + static_cast<size_t>(r) * p.ld_dZ + j, g);
+        for (int part = 1; part < p.np; ++part)
+          st_from_float<T>(dZ + part * p.dz_ps + static_cast<size_t>(r) * p.ld_dZ + j, bf16_residual(g, part));
       }
     }
     if (j < p.H) {
@@ -271,10 +292,16 @@ out_layer_rows_kernel(const OutLayerParams p, int rows_per_block) {
       if (col0 < p.ldA && col0 < p.H) raw = *reinterpret_cast<const uint4*>(A + static_cast<size_t>(r) * p.ldA + col0);
       const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        a[c][k] = (col0 + k < p.H) ? __bfloat162float(h[k]) : 0.f;   // pad columns of A_L hold act(0), not 0
-        z = fmaf(a[c][k], wo[c][k], z);
+      for (int k = 0; k < 8; ++k) a[c][k] = (col0 + k < p.H) ? __bfloat162float(h[k]) : 0.f;   // pad columns of A_L hold act(0), not 0
+      for (int part = 1; part < p.np; ++part) {       // split-precision modes: add the lower parts
+        uint4 lo = make_uint4(0, 0, 0, 0);
+        if (col0 < p.ldA && col0 < p.H) lo = *reinterpret_cast<const uint4*>(A + part * p.a_ps + static_cast<size_t>(r) * p.ldA + col0);
+        const __nv_bfloat16* hl = reinterpret_cast<const __nv_bfloat16*>(&lo);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[c][k] += (col0 + k < p.H) ? __bfloat162float(hl[k]) : 0.f;
       }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) z = fmaf(a[c][k], wo[c][k], z);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
@@ -306,10 +333,15 @@ out_layer_rows_kernel(const OutLayerParams p, int rows_per_block) {
           s_dw[c][k] = fmaf(dz, a[c][k], s_dw[c][k]);
         }
         if (col0 < p.ld_dZ && col0 < p.H) {
-          uint4 o;
-          o.x = pack_bf16x2(g[0], g[1]); o.y = pack_bf16x2(g[2], g[3]);
-          o.z = pack_bf16x2(g[4], g[5]); o.w = pack_bf16x2(g[6], g[7]);
-          *reinterpret_cast<uint4*>(dZ + static_cast<size_t>(r) * p.ld_dZ + col0) = o;
+          const int np = p.np > 1 ? p.np : 1;
+          for (int part = 0; part < np; ++part) {
+            uint4 o;
+            o.x = pack_bf16x2(bf16_residual(g[0], part), bf16_residual(g[1], part));
+            o.y = pack_bf16x2(bf16_residual(g[2], part), bf16_residual(g[3], part));
+            o.z = pack_bf16x2(bf16_residual(g[4], part), bf16_residual(g[5], part));
+            o.w = pack_bf16x2(bf16_residual(g[6], part), bf16_residual(g[7], part));
+            *reinterpret_cast<uint4*>(dZ + part * p.dz_ps + static_cast<size_t>(r) * p.ld_dZ + col0) = o;
+          }
         }
       }
     }
@@ -384,7 +416,22 @@ struct OptWork {
   long long mat_off;      // flat offset of that matrix
   __nv_bfloat16* Wn;      // shadow base (nullptr: no shadow)
   int ld_out;
+  int np;                 // bf16 parts of the shadow (split-precision modes; 1 = plain)
+  long long part_stride;  // elements between parts
 };
+
+// store 4 / 1 updated weights into the bf16 shadow (all of its parts)
+__device__ __forceinline__ void shadow_store4(const OptWork& wk, long long at, const float4& t) {
+  for (int part = 0; part < wk.np; ++part) {
+    uint2 o;
+    o.x = pack_bf16x2(bf16_residual(t.x, part), bf16_residual(t.y, part));
+    o.y = pack_bf16x2(bf16_residual(t.z, part), bf16_residual(t.w, part));
+    *reinterpret_cast<uint2*>(wk.Wn + part * wk.part_stride + at) = o;
+  }
+}
+__device__ __forceinline__ void shadow_store1(const OptWork& wk, long long at, float t) {
+  for (int part = 0; part < wk.np; ++part) wk.Wn[part * wk.part_stride + at] = __float2bfloat16_rn(bf16_residual(t, part));
+}
 
 static __global__ void __launch_bounds__(256)
 optimizer_kernel(const OptWork* __restrict__ work, const BatchDesc* __restrict__ desc, OptHyper h,
@@ -427,9 +474,7 @@ optimizer_kernel(const OptWork* __restrict__ work, const BatchDesc* __restrict__
       if (wk.Wn != nullptr) {
         const long long m = idx - wk.mat_off;
         const long long r = m / wk.out_dim;     // 4 consecutive elements never straddle a row (out_dim % 4 == 0)
-        uint2 o;
-        o.x = pack_bf16x2(t.x, t.y); o.y = pack_bf16x2(t.z, t.w);
-        *reinterpret_cast<uint2*>(wk.Wn + r * wk.ld_out + (m - r * wk.out_dim)) = o;
+        shadow_store4(wk, r * wk.ld_out + (m - r * wk.out_dim), t);
       }
     }
     trace_end(trace);
@@ -448,7 +493,7 @@ optimizer_kernel(const OptWork* __restrict__ work, const BatchDesc* __restrict__
       if (wk.Wn != nullptr) {
         const long long m = idx - wk.mat_off;
         const long long r = m / wk.out_dim;
-        wk.Wn[r * wk.ld_out + (m - r * wk.out_dim)] = __float2bfloat16_rn(t);
+        shadow_store1(wk, r * wk.ld_out + (m - r * wk.out_dim), t);
       }
     }
   }
@@ -467,7 +512,7 @@ shadow_refresh_kernel(const OptWork* __restrict__ work, const float* __restrict_
       const long long idx = wk.off + e;
       const long long m = idx - wk.mat_off;
       const long long r = m / wk.out_dim;
-      wk.Wn[r * wk.ld_out + (m - r * wk.out_dim)] = __float2bfloat16_rn(theta[idx]);
+      shadow_store1(wk, r * wk.ld_out + (m - r * wk.out_dim), theta[idx]);
     }
   }
 }
@@ -498,11 +543,13 @@ static __global__ void fill_kernel(float* __restrict__ p, float v, long long n) 
   if (i < n) p[i] = v;
 }
 // f32 -> bf16 with arbitrary leading dims (test hook operand staging)
-static __global__ void cast_bf16_kernel(const float* __restrict__ src, int rows, int cols, __nv_bfloat16* __restrict__ dst, int ld) {
+static __global__ void cast_bf16_kernel(const float* __restrict__ src, int rows, int cols, __nv_bfloat16* __restrict__ dst, int ld,
+                                        int np = 1, long long part_stride = 0) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i < static_cast<long long>(rows) * cols) {
     const int r = static_cast<int>(i / cols), c = static_cast<int>(i % cols);
-    dst[static_cast<size_t>(r) * ld + c] = __float2bfloat16_rn(src[i]);
+    for (int part = 0; part < np; ++part)
+      dst[part * part_stride + static_cast<size_t>(r) * ld + c] = __float2bfloat16_rn(bf16_residual(src[i], part));
   }
 }
 

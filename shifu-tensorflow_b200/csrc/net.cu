@@ -35,6 +35,21 @@ PFN_encodeTiled get_encode_tiled() {
   return fn;
 }
 
+int make_tmaps_bf16(CUtensorMap* out3, const void* base, long long part_stride, int np, int rows, int cols, int ld, int box_rows) {
+  for (int k = 0; k < (np > 1 ? np : 1); ++k)
+    SB_TRY(make_tmap_bf16(out3 + k, static_cast<const __nv_bfloat16*>(base) + k * part_stride, rows, cols, ld, box_rows));
+  return SB_OK;
+}
+
+void set_part_pairs(GemmTcParams* p, int np) {
+  p->np = np > 1 ? np : 1;
+  int n = 0;
+  // smallest products first: they are added to a still small accumulator
+  for (int sum = p->np - 1; sum >= 0; --sum)
+    for (int i = 0; i <= sum; ++i) { p->pair_a[n] = static_cast<unsigned char>(i); p->pair_b[n] = static_cast<unsigned char>(sum - i); ++n; }
+  p->n_pairs = n;
+}
+
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rows, int cols, int ld, int box_rows) {
   PFN_encodeTiled enc = get_encode_tiled();
   SB_CHECK(enc != nullptr, SB_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
@@ -96,6 +111,8 @@ GemmPlan plan_gemm(int M, int N, int K, int num_sms, bool allow_split) {
   return pl;
 }
 
+static inline int pairs_of(int np) { return np == 3 ? 6 : (np == 2 ? 3 : 1); }
+
 int validate_desc(const sb_net_desc* d) {
   SB_CHECK(d != nullptr, SB_ERR_INVALID, "net desc is null");
   SB_CHECK(d->n_features > 0, SB_ERR_INVALID, "n_features must be > 0 (got %d)", d->n_features);
@@ -106,7 +123,7 @@ int validate_desc(const sb_net_desc* d) {
     SB_CHECK(d->acts[l] >= SB_ACT_NONE && d->acts[l] <= SB_ACT_LEAKYRELU, SB_ERR_INVALID, "acts[%d] invalid", l);
   }
   SB_CHECK(d->max_batch > 0, SB_ERR_INVALID, "max_batch must be > 0");
-  SB_CHECK(d->precision == SB_PREC_FP32 || d->precision == SB_PREC_BF16, SB_ERR_INVALID, "precision invalid");
+  SB_CHECK(d->precision >= SB_PREC_FP32 && d->precision <= SB_PREC_BF16X2, SB_ERR_INVALID, "precision invalid");
   SB_CHECK(d->loss == SB_LOSS_MSE || d->loss == SB_LOSS_SIGMOID_CE, SB_ERR_INVALID, "loss invalid");
   SB_CHECK(d->optimizer >= SB_OPT_ADADELTA && d->optimizer <= SB_OPT_MOMENTUM, SB_ERR_INVALID, "optimizer invalid");
   return SB_OK;
@@ -158,6 +175,7 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
   F = d->n_features;
   L = d->n_hidden;
   precision = d->precision;
+  nparts = precision == SB_PREC_FP32_TC ? 3 : (precision == SB_PREC_BF16X2 ? 2 : 1);
   loss = d->loss;
   max_batch = d->max_batch;
   ldB = round_up(max_batch, 8);
@@ -177,7 +195,7 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
     prev = ly.out;
   }
   n_params = off;
-  const bool bf = precision == SB_PREC_BF16;
+  const bool bf = tc();
   {
     auto align256 = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
     const size_t vec_bytes = align256(static_cast<size_t>(n_params) * sizeof(float) + 64);
@@ -185,8 +203,13 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
     if (training) { s1_off = at; at += vec_bytes; s2_off = at; at += vec_bytes; }
     shadow_off = at;
     std::vector<size_t> wn_off(L, 0);
+    Wn_ps.assign(L, 0);
     if (bf)
-      for (int l = 0; l < L; ++l) { wn_off[l] = at; at += align256(static_cast<size_t>(layers[l].in) * layers[l].ld_out * sizeof(__nv_bfloat16)); }
+      for (int l = 0; l < L; ++l) {
+        const size_t part = align256(static_cast<size_t>(layers[l].in) * layers[l].ld_out * sizeof(__nv_bfloat16));
+        wn_off[l] = at; at += part * nparts;
+        Wn_ps[l] = static_cast<long long>(part / sizeof(__nv_bfloat16));
+      }
     extra_off = at;
     at += align256(arena_extra_bytes);
     arena_bytes = at;
@@ -211,12 +234,14 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
   fill_kernel<<<(max_batch + 255) / 256, 256, 0, stream>>>(ones, 1.f, max_batch);
 
   if (bf) {
-    SB_TRY(dalloc(&Xb, static_cast<size_t>(max_batch) * ldF));
-    A.assign(L, nullptr); dZ.assign(L, nullptr);
+    Xb_ps = static_cast<long long>(max_batch) * ldF;
+    SB_TRY(dalloc(&Xb, static_cast<size_t>(Xb_ps) * nparts));
+    A.assign(L, nullptr); dZ.assign(L, nullptr); A_ps.assign(L, 0);
     for (int l = 0; l < L; ++l) {
       Layer& ly = layers[l];
-      SB_TRY(dalloc(&A[l], static_cast<size_t>(max_batch) * ly.ld_out));
-      if (training) SB_TRY(dalloc(&dZ[l], static_cast<size_t>(max_batch) * ly.ld_out));
+      A_ps[l] = static_cast<long long>(max_batch) * ly.ld_out;
+      SB_TRY(dalloc(&A[l], static_cast<size_t>(A_ps[l]) * nparts));
+      if (training) SB_TRY(dalloc(&dZ[l], static_cast<size_t>(A_ps[l]) * nparts));
     }
   } else {
     SB_TRY(dalloc(&Xf, static_cast<size_t>(max_batch) * F));
@@ -233,7 +258,11 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
     for (long long s = 0; s < n; s += 1024) {
       OptWork w = {};
       w.off = o + s; w.count = static_cast<int>(n - s < 1024 ? n - s : 1024);
-      if (mat) { w.out_dim = mat->out; w.mat_off = mat->w_off; w.Wn = mat->Wn; w.ld_out = mat->ld_out; }
+      w.np = 1;
+      if (mat) {
+        w.out_dim = mat->out; w.mat_off = mat->w_off; w.Wn = mat->Wn; w.ld_out = mat->ld_out;
+        w.np = nparts; w.part_stride = Wn_ps[static_cast<size_t>(mat - layers.data())];
+      }
       wk.push_back(w);
     }
   };
@@ -296,7 +325,7 @@ void Net::destroy() {
 }
 
 int Net::refresh_shadows() {
-  if (precision != SB_PREC_BF16) return SB_OK;
+  if (!tc()) return SB_OK;
   shadow_refresh_kernel<<<n_work, 256, 0, stream>>>(work, theta);
   SB_CUDA(cudaGetLastError());
   return SB_OK;
@@ -309,12 +338,14 @@ int Net::enqueue_load(int rows, float* zero_buf, long long zero_n) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   // first kernel of the step: its stream predecessor is set_batch_kernel (a kernel), so PDL applies here too
-  if (precision == SB_PREC_BF16)
+  if (tc())
     SB_TRY(launch(load_batch_kernel<true>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, use_pdl,
-                  static_cast<const BatchDesc*>(desc), rows, F, Xb, ldF, static_cast<float*>(nullptr), scal, zero_buf, zero_n));
+                  static_cast<const BatchDesc*>(desc), rows, F, Xb, ldF, static_cast<float*>(nullptr), scal, zero_buf, zero_n,
+                  nparts, Xb_ps));
   else
     SB_TRY(launch(load_batch_kernel<false>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, use_pdl,
-                  static_cast<const BatchDesc*>(desc), rows, F, static_cast<__nv_bfloat16*>(nullptr), ldF, Xf, scal, zero_buf, zero_n));
+                  static_cast<const BatchDesc*>(desc), rows, F, static_cast<__nv_bfloat16*>(nullptr), ldF, Xf, scal, zero_buf, zero_n,
+                  1, 0ll));
   mark("load_batch");
   return SB_OK;
 }
@@ -323,23 +354,25 @@ int Net::enqueue_hidden_forward(int rows, float* grad, bool* fused_out) {
   if (fused_out) *fused_out = false;
   for (int l = 0; l < L; ++l) {
     Layer& ly = layers[l];
-    if (precision == SB_PREC_BF16) {
+    if (tc()) {
       // Z = A_{l-1}[rows,in] (K-major) x W_l[in,out] (MN-major B operand: n contiguous)
-      const GemmPlan pl = plan_gemm(rows, ly.out, ly.in, gemm_sms, false);
-      CUtensorMap ta, tb;
+      const GemmPlan pl = plan_gemm(rows, ly.out, round_up(ly.in, 64) * pairs_of(nparts), gemm_sms, false);
+      TmapSet tm;
       const bool res0 = (l == 0) && from_resident;
       const __nv_bfloat16* src = (l == 0) ? (res0 ? resident_Xb : Xb) : A[l - 1];
-      SB_TRY(make_tmap_bf16(&ta, src, res0 ? static_cast<int>(resident_rows) : rows, ly.in, ly.ld_in, 128));
-      SB_TRY(make_tmap_bf16(&tb, ly.Wn, ly.in, ly.out, ly.ld_out, 64));
+      const long long src_ps = (l == 0) ? (res0 ? resident_ps : Xb_ps) : A_ps[l - 1];
+      SB_TRY(make_tmaps_bf16(tm.a, src, src_ps, nparts, res0 ? static_cast<int>(resident_rows) : rows, ly.in, ly.ld_in, 128));
+      SB_TRY(make_tmaps_bf16(tm.b, ly.Wn, Wn_ps[l], nparts, ly.in, ly.out, ly.ld_out, 64));
       GemmTcParams p = {};
+      set_part_pairs(&p, nparts);
       p.M = rows; p.N = ly.out; p.K = ly.in;
       p.bias = theta + ly.b_off; p.act = ly.act;
-      p.out = A[l]; p.ld_out = ly.ld_out;
+      p.out = A[l]; p.ld_out = ly.ld_out; p.out_ps = A_ps[l];
       p.a_rows = res0 ? desc : nullptr;
       if (l == L - 1 && grad != nullptr && fuse_out_layer && training && ly.out <= fuse_out_max) {
         // K2 + K3 + K4 + output backward in one kernel: one n-tile must cover the whole layer width
         GemmPlan fp = pl;
-        fp.split_k = 1; fp.kb_per_split = (ly.in + 63) / 64;
+        fp.split_k = 1; fp.kb_per_split = ((ly.in + 63) / 64) * pairs_of(nparts);
         // (a 256-wide PAIR tile measured slower than GEMM + out_layer kernel in round 1; the single-CTA 128 x 256 tile keeps
         // whole rows of A_L in one CTA's TMEM - 2 x 256 columns, double-buffered - and needs no second kernel)
         if (ly.out <= 64) { fp.cg = 1; fp.bn = 64; }
@@ -354,7 +387,7 @@ int Net::enqueue_hidden_forward(int rows, float* grad, bool* fused_out) {
         p.desc = desc; p.scal = scal; p.loss = loss;
         p.g_wo = grad + ol.w_off; p.g_bo = grad + ol.b_off; p.g_bL = grad + ly.b_off;
         p.trace = next_trace("fwd_out");
-        SB_TRY((launch_gemm_tc<EPI_FWD_OUT, false, true>(fp, ta, tb, p, stream, use_pdl)));
+        SB_TRY((launch_gemm_tc<EPI_FWD_OUT, false, true>(fp, tm, p, stream, use_pdl)));
         if (fused_out) *fused_out = true;
         mark("gemm_fwd_out");
         continue;
@@ -364,7 +397,7 @@ int Net::enqueue_hidden_forward(int rows, float* grad, bool* fused_out) {
         zero_buf = nullptr;
       }
       p.trace = next_trace("fwd");
-      SB_TRY((launch_gemm_tc<EPI_FWD, false, true>(pl, ta, tb, p, stream, use_pdl)));
+      SB_TRY((launch_gemm_tc<EPI_FWD, false, true>(pl, tm, p, stream, use_pdl)));
     } else {
       GemmF32Params p = {};
       p.M = rows; p.N = ly.out; p.K = ly.in;
@@ -394,8 +427,9 @@ int Net::enqueue_out(int rows, bool do_loss, bool do_bwd, float* yhat_dst, float
   }
   const int grid = (rows + 31) / 32;
   static const bool old_out = getenv("SB_OLD_OUT") != nullptr;
-  if (precision == SB_PREC_BF16) {
+  if (tc()) {
     p.A = A[L - 1]; p.ldA = hl.ld_out;
+    p.np = nparts; p.a_ps = A_ps[L - 1]; p.dz_ps = A_ps[L - 1];
     if (do_bwd) { p.dZ = dZ[L - 1]; p.ld_dZ = hl.ld_out; }
     if (hl.out <= 1024 && !old_out) {
       // one-pass kernel: rows per block sized for ~2 blocks per SM, at least one row per warp
@@ -422,7 +456,7 @@ int Net::enqueue_out(int rows, bool do_loss, bool do_bwd, float* yhat_dst, float
 int Net::enqueue_backward(int rows, float* grad) {
   // dW_l and dA_l both consume dZ_l and are independent of each other: the dW GEMMs go to the side stream and
   // overlap the dA chain (they are each well under one wave at cfg1 sizes).  Not while profiling (clean times).
-  const bool fork = concurrent_bwd && !profiling && side != nullptr && precision == SB_PREC_BF16;
+  const bool fork = concurrent_bwd && !profiling && side != nullptr && tc();
   // dW_1 (side stream) and dW_0 (main stream) run at the same time, one CTA per SM each.  If their natural grids do not
   // fit the machine together, dW_1's second wave only starts when dW_0's CTAs exit (measured: the side optimizer then
   // finishes 4 us after the main one, scripts/step_timeline.py).  Compare, in k-blocks per CTA, "natural grids, dW_1
@@ -430,11 +464,12 @@ int Net::enqueue_backward(int rows, float* grad) {
   int dw_sms[2] = {gemm_sms, gemm_sms};
   static const bool no_budget = getenv("SB_NO_DW_BUDGET") != nullptr;
   if (fork && dw0_on_main && L > 1 && !on_layer_grads && !no_budget) {
-    const GemmPlan n0 = plan_gemm(layers[0].in, layers[0].out, rows, gemm_sms, true);
-    const GemmPlan n1 = plan_gemm(layers[1].in, layers[1].out, rows, gemm_sms, true);
+    const int kx = round_up(rows, 64) * pairs_of(nparts);
+    const GemmPlan n0 = plan_gemm(layers[0].in, layers[0].out, kx, gemm_sms, true);
+    const GemmPlan n1 = plan_gemm(layers[1].in, layers[1].out, kx, gemm_sms, true);
     if (n0.grid + n1.grid > gemm_sms) {
-      const GemmPlan b1 = plan_gemm(layers[1].in, layers[1].out, rows, gemm_sms / 3, true);
-      const GemmPlan b0 = plan_gemm(layers[0].in, layers[0].out, rows, gemm_sms - b1.grid, true);
+      const GemmPlan b1 = plan_gemm(layers[1].in, layers[1].out, kx, gemm_sms / 3, true);
+      const GemmPlan b0 = plan_gemm(layers[0].in, layers[0].out, kx, gemm_sms - b1.grid, true);
       auto waves = [&](const GemmPlan& pl, int M, int N, int sms) {   // k-blocks one CTA works through
         const int tiles = ((M + 128 * pl.cg - 1) / (128 * pl.cg)) * ((N + pl.bn - 1) / pl.bn) * pl.split_k;
         const int slots = sms / pl.cg;
@@ -448,7 +483,7 @@ int Net::enqueue_backward(int rows, float* grad) {
   }
   for (int l = L - 1; l >= 0; --l) {
     Layer& ly = layers[l];
-    if (precision == SB_PREC_BF16) {
+    if (tc()) {
       // dW_l[in,out] += sum_rows A_{l-1}[rows,in] (MN-major A) * dZ_l[rows,out] (MN-major B), split-K over rows.
       // With a gradient exchange behind it, a big layer is cut into row chunks of W_l (each a contiguous slice of the
       // flat gradient) so that the all-reduce of chunk c overlaps the GEMM of chunk c+1.
@@ -469,21 +504,23 @@ int Net::enqueue_backward(int rows, float* grad) {
         }
         const bool res0 = (l == 0) && from_resident;
         const __nv_bfloat16* ap = (l == 0) ? (res0 ? resident_Xb : Xb) : A[l - 1];
+        const long long ap_ps = (l == 0) ? (res0 ? resident_ps : Xb_ps) : A_ps[l - 1];
         for (int r0 = 0; r0 < ly.in; r0 += chunk_rows) {
           const int r1 = (r0 + chunk_rows < ly.in) ? r0 + chunk_rows : ly.in;
-          const GemmPlan pl = plan_gemm(r1 - r0, ly.out, rows, l < 2 ? dw_sms[l] : gemm_sms, true);
-          CUtensorMap ta, tb;
+          const GemmPlan pl = plan_gemm(r1 - r0, ly.out, round_up(rows, 64) * pairs_of(nparts), l < 2 ? dw_sms[l] : gemm_sms, true);
+          TmapSet tm;
           // resident set: rows past the batch end are real rows of other batches; the B operand (dZ_l, extent = rows) is
           // zero-filled there, so they contribute nothing
-          SB_TRY(make_tmap_bf16(&ta, ap + r0, res0 ? static_cast<int>(resident_rows) : rows, r1 - r0, ly.ld_in, 64));
-          SB_TRY(make_tmap_bf16(&tb, dZ[l], rows, ly.out, ly.ld_out, 64));
+          SB_TRY(make_tmaps_bf16(tm.a, ap + r0, ap_ps, nparts, res0 ? static_cast<int>(resident_rows) : rows, r1 - r0, ly.ld_in, 64));
+          SB_TRY(make_tmaps_bf16(tm.b, dZ[l], A_ps[l], nparts, rows, ly.out, ly.ld_out, 64));
           GemmTcParams p = {};
+          set_part_pairs(&p, nparts);
           p.M = r1 - r0; p.N = ly.out; p.K = rows;
           p.a_rows = res0 ? desc : nullptr;
           p.accum = grad + ly.w_off + static_cast<long long>(r0) * ly.out; p.ld_acc = ly.out;
           p.acc_vec4 = (ly.out % 4 == 0 && ly.w_off % 4 == 0) ? 1 : 0;
           p.trace = next_trace("dW");
-          SB_TRY((launch_gemm_tc<EPI_DW, true, true>(pl, ta, tb, p, on_main ? stream : side, use_pdl && on_main)));
+          SB_TRY((launch_gemm_tc<EPI_DW, true, true>(pl, tm, p, on_main ? stream : side, use_pdl && on_main)));
           mark("gemm_dw");
           if (fork && on_layer_grads) {
             const long long e0 = static_cast<long long>(r0) * ly.out, e1 = static_cast<long long>(r1) * ly.out;
@@ -497,18 +534,19 @@ int Net::enqueue_backward(int rows, float* grad) {
       if (l > 0) {
         // dZ_{l-1}[rows,in] = (dZ_l[rows,out] (K-major) x W_l[in,out] (K-major B: k = out contiguous)) .* act'(A_{l-1})
         Layer& pl = layers[l - 1];
-        const GemmPlan gp = plan_gemm(rows, ly.in, ly.out, gemm_sms, false);
-        CUtensorMap ta, tb;
-        SB_TRY(make_tmap_bf16(&ta, dZ[l], rows, ly.out, ly.ld_out, 128));
-        SB_TRY(make_tmap_bf16(&tb, ly.Wn, ly.in, ly.out, ly.ld_out, plan_box_rows_b(gp)));
+        const GemmPlan gp = plan_gemm(rows, ly.in, round_up(ly.out, 64) * pairs_of(nparts), gemm_sms, false);
+        TmapSet tm;
+        SB_TRY(make_tmaps_bf16(tm.a, dZ[l], A_ps[l], nparts, rows, ly.out, ly.ld_out, 128));
+        SB_TRY(make_tmaps_bf16(tm.b, ly.Wn, Wn_ps[l], nparts, ly.in, ly.out, ly.ld_out, plan_box_rows_b(gp)));
         GemmTcParams p = {};
+        set_part_pairs(&p, nparts);
         p.M = rows; p.N = ly.in; p.K = ly.out;
         p.act = pl.act;
-        p.aux = A[l - 1]; p.ld_aux = pl.ld_out;
-        p.out = dZ[l - 1]; p.ld_out = pl.ld_out;
+        p.aux = A[l - 1]; p.ld_aux = pl.ld_out; p.aux_ps = A_ps[l - 1];
+        p.out = dZ[l - 1]; p.ld_out = pl.ld_out; p.out_ps = A_ps[l - 1];
         p.colsum = grad + pl.b_off;
         p.trace = next_trace("dA");
-        SB_TRY((launch_gemm_tc<EPI_DA, false, false>(gp, ta, tb, p, stream, use_pdl)));
+        SB_TRY((launch_gemm_tc<EPI_DA, false, false>(gp, tm, p, stream, use_pdl)));
         mark("gemm_da");
         if (l == 1 && fork && defer_join) SB_CUDA(cudaEventRecord(ev_da_done, stream));
       }

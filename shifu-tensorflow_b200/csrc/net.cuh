@@ -53,6 +53,13 @@ struct Net {
   std::vector<Layer> layers;    // L hidden + 1 output (out = 1)
   long long n_params = 0;
   int precision = SB_PREC_FP32, loss = SB_LOSS_MSE;
+  // tensor-core modes keep every GEMM operand as `nparts` bf16 arrays (1 = plain bf16; 3 = SB_PREC_FP32_TC; 2 = BF16X2),
+  // see GemmTcParams in gemm_tc.cuh.  Part k of a buffer lies k * <buffer>_ps elements behind part 0.
+  int nparts = 1;
+  bool tc() const { return precision != SB_PREC_FP32; }
+  long long Xb_ps = 0;                       // part strides (elements)
+  std::vector<long long> A_ps, Wn_ps;        // A_ps[l] also applies to dZ[l]
+  long long resident_ps = 0;
   int max_batch = 0, ldB = 0, ldF = 0;
   bool training = false;
 

@@ -172,7 +172,7 @@ xchg_update_kernel(const XchgParams p) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int w = wb + u;
-          if (w < w1) wk[u] = p.work[w]; else { wk[u].count = 0; wk[u].off = 0; wk[u].Wn = nullptr; wk[u].out_dim = 0; wk[u].mat_off = 0; wk[u].ld_out = 0; }
+          if (w < w1) wk[u] = p.work[w]; else { wk[u].count = 0; wk[u].off = 0; wk[u].Wn = nullptr; wk[u].out_dim = 0; wk[u].mat_off = 0; wk[u].ld_out = 0; wk[u].np = 1; wk[u].part_stride = 0; }
           vec[u] = (wk[u].off & 3) == 0 && (wk[u].count & 3) == 0 &&
                    (wk[u].Wn == nullptr || ((wk[u].out_dim & 3) == 0 && ((wk[u].off - wk[u].mat_off) & 3) == 0 && (wk[u].ld_out & 3) == 0));
           const int e = threadIdx.x * 4;
@@ -208,11 +208,15 @@ xchg_update_kernel(const XchgParams p) {
                 const long long m = idx - wk[u].mat_off;
                 const long long r = m / wk[u].out_dim;     // 4 consecutive elements never straddle a row
                 const long long rel = shadow_rel + (r * wk[u].ld_out + (m - r * wk[u].out_dim)) * 2;
-                uint2 o;
-                o.x = pack_bf16x2(t.x, t.y); o.y = pack_bf16x2(t.z, t.w);
+                for (int part = 0; part < wk[u].np; ++part) {      // split-precision modes: every part of the shadow
+                  uint2 o;
+                  o.x = pack_bf16x2(bf16_residual(t.x, part), bf16_residual(t.y, part));
+                  o.y = pack_bf16x2(bf16_residual(t.z, part), bf16_residual(t.w, part));
+                  const long long prel = rel + part * wk[u].part_stride * 2;
 #pragma unroll
-                for (int q = 0; q < W; ++q)
-                  if (q < p.world) *reinterpret_cast<uint2*>(pb[q] + rel) = o;
+                  for (int q = 0; q < W; ++q)
+                    if (q < p.world) *reinterpret_cast<uint2*>(pb[q] + prel) = o;
+                }
               } else {
 #pragma unroll
                 for (int q = 0; q < W; ++q)
@@ -238,8 +242,11 @@ xchg_update_kernel(const XchgParams p) {
                   const long long m = idx - wk[u].mat_off;
                   const long long r = m / wk[u].out_dim;
                   const long long rel = shadow_rel + (r * wk[u].ld_out + (m - r * wk[u].out_dim)) * 2;
-                  const __nv_bfloat16 hv = __float2bfloat16_rn(t);
-                  for (int q = 0; q < p.world; ++q) *reinterpret_cast<__nv_bfloat16*>(p.peers->base[q] + rel) = hv;
+                  for (int part = 0; part < wk[u].np; ++part) {
+                    const __nv_bfloat16 hv = __float2bfloat16_rn(bf16_residual(t, part));
+                    for (int q = 0; q < p.world; ++q)
+                      *reinterpret_cast<__nv_bfloat16*>(p.peers->base[q] + rel + part * wk[u].part_stride * 2) = hv;
+                  }
                 } else {
                   for (int q = 0; q < p.world; ++q)
                     if (q != p.rank) reinterpret_cast<float*>(p.peers->base[q])[idx] = t;

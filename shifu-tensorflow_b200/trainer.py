@@ -20,7 +20,8 @@ periods and the 5 s sleep per epoch are not reproduced.
 Optional ModelConfig train.params the reference does not have (defaults = reference behaviour):
   Optimizer  "adadelta" (default) | "adam" | "sgd" | "momentum"
   Loss       "squared" (default: MSE on the sigmoid output, ssgd_monitor.py:129) | "log" (sigmoid cross-entropy)
-  Precision  "bf16" (default) | "fp32"
+  Precision  "bf16" (default) | "fp32" (CUDA-core parity mode) | "fp32_tc" (fp32-class accuracy on the tensor cores:
+             three bf16 parts per value) | "bf16x2" (two parts)
   MiniBatchs mini-batch rows (default BATCH_SIZE = 100, ssgd_monitor.py:33)
   Schedule   "sync_replicas" (default; "epoch" is accepted as an alias): the reference's SyncReplicasOptimizer schedule
              (ssgd_monitor.py:136-141,218,259-260) - every run pushes its mini-batch gradient, a push tagged with a stale
@@ -103,7 +104,8 @@ def model(feature_count: int, model_conf: Optional[dict], max_batch: int) -> cap
         learning_rate = 0.003
     opt = _OPT[str(params.get('Optimizer', 'adadelta')).lower()]
     loss = _LOSS[str(params.get('Loss', 'squared')).lower()]
-    prec = capi.PREC_FP32 if str(params.get('Precision', 'bf16')).lower() == 'fp32' else capi.PREC_BF16
+    prec = {'fp32': capi.PREC_FP32, 'fp32_tc': capi.PREC_FP32_TC, 'bf16x2': capi.PREC_BF16X2}.get(
+        str(params.get('Precision', 'bf16')).lower(), capi.PREC_BF16)
     return capi.make_desc(feature_count, hidden, acts, loss=loss, optimizer=opt, learning_rate=learning_rate,
                           max_batch=max_batch, precision=prec)
 

@@ -12,8 +12,10 @@ GOLDEN_HEAD = os.path.join(os.path.dirname(__file__), "golden", "dummydl_head.np
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("precision,tol", [(0, 1e-5), (1, 2e-2)])
+@pytest.mark.parametrize("precision,tol", [(0, 1e-5), (2, 1e-5), (3, 1e-5), (1, 2e-2)])
 def test_model_score_matches_oracle(sb, precision, tol):
+    """1e-5 (north star) must hold in both parity modes: fp32 on the CUDA cores (0) and fp32-class on the tensor cores
+    (2 = three bf16 parts); the two-part mode (3) meets it as well on this net; plain bf16 (1) is the performance mode."""
     net, params, cfg, desc = make_pair(sb, 200, [100, 50], [so.ACT_RELU, so.ACT_TANH], precision=precision)
     X, _, _ = so.synth_batch(1000, 200, 3)
     m = sb.Model.create(desc, so.flatten_params(params))
@@ -51,10 +53,24 @@ def test_scorer_on_reference_fixture_weights(sb):
     g = np.load(GOLDEN_HEAD)
     hidden = [g["W0"].shape[1], g["W1"].shape[1], g["W2"].shape[1]]
     flat = np.concatenate([np.concatenate([g["W%d" % i].ravel(), g["b%d" % i].ravel()]) for i in range(4)])
-    desc = sb.make_desc(1522, hidden, [so.ACT_RELU] * 3)
-    m = sb.Model.create(desc, flat)
-    assert np.abs(m.score(g["X"]) - g["Y"].ravel()).max() <= 1e-5
+    for prec in (sb.PREC_FP32, sb.PREC_FP32_TC):
+        desc = sb.make_desc(1522, hidden, [so.ACT_RELU] * 3, precision=prec)
+        m = sb.Model.create(desc, flat)
+        assert np.abs(m.score(g["X"]) - g["Y"].ravel()).max() <= 1e-5
+        m.close()
+
+
+@pytest.mark.gpu
+def test_cfg2_net_scores_within_1e5_on_tensor_cores(sb):
+    """the eval-path net (BASELINE config 5: 2000 cols, [1024, 512, 256]) scored in SB_PREC_FP32_TC: <= 1e-5 from the oracle"""
+    net, params, cfg, desc = make_pair(sb, 2000, [1024, 512, 256], [so.ACT_RELU] * 3, precision=sb.PREC_FP32_TC)
+    X, _, _ = so.synth_batch(4096, 2000, 3)
+    m = sb.Model.create(desc, so.flatten_params(params))
+    got = m.score(X)
+    want = so.score_rows(net, params, X.astype(np.float64))
+    err = np.abs(got - want).max()
     m.close()
+    assert err <= 1e-5, err
 
 
 @pytest.mark.gpu

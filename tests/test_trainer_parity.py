@@ -23,12 +23,18 @@ def _one_step(sb, n_features, hidden, acts, rows, loss, optimizer, precision, we
         return ref_loss, ref.last_grads, ref.theta, got_loss, t.get_grads(), t.get_params()
 
 
+# the two parity modes: fp32 FFMA on the CUDA cores, and fp32-class accuracy on the tensor cores (three bf16 parts per value,
+# six tcgen05 products per contraction) - both must meet the north star's fp32 tolerances
+FP32_MODES = [0, 2]     # sb.PREC_FP32, sb.PREC_FP32_TC
+
+
 @pytest.mark.gpu
+@pytest.mark.parametrize("prec", FP32_MODES)
 @pytest.mark.parametrize("act", [0, 1, 2, 3])
 @pytest.mark.parametrize("loss", [so.LOSS_MSE, so.LOSS_SIGMOID_CE])
-def test_fp32_step_cfg0_all_activations(sb, act, loss):
+def test_fp32_step_cfg0_all_activations(sb, act, loss, prec):
     """cfg0: 200 cols, [100, 50], B=100 (the reference's hard-coded BATCH_SIZE, ssgd_monitor.py:33)."""
-    rl, rg, rt, gl, gg, gt = _one_step(sb, 200, [100, 50], [act, act], 100, loss, so.OPT_SGD, sb.PREC_FP32)
+    rl, rg, rt, gl, gg, gt = _one_step(sb, 200, [100, 50], [act, act], 100, loss, so.OPT_SGD, prec)
     assert abs(gl - rl) <= 1e-4
     assert np.abs(gg - rg).max() <= 1e-4
     # in practice fp32 vs fp32 agrees far tighter than the contract; keep a regression guard too
@@ -37,10 +43,11 @@ def test_fp32_step_cfg0_all_activations(sb, act, loss):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("prec", FP32_MODES)
 @pytest.mark.parametrize("optimizer", [so.OPT_ADADELTA, so.OPT_ADAM, so.OPT_SGD, so.OPT_MOMENTUM])
-def test_fp32_three_steps_each_optimizer(sb, optimizer):
+def test_fp32_three_steps_each_optimizer(sb, optimizer, prec):
     net, params, cfg, desc = make_pair(sb, 64, [48, 24], [so.ACT_TANH, so.ACT_RELU], optimizer=optimizer, lr=0.05,
-                                       max_batch=96, precision=sb.PREC_FP32)
+                                       max_batch=96, precision=prec)
     ref = so.CleanTrainer(net, params, cfg)
     with sb.Trainer(desc) as t:
         t.set_params(so.flatten_params(params))
@@ -54,11 +61,12 @@ def test_fp32_three_steps_each_optimizer(sb, optimizer):
 
 
 @pytest.mark.gpu
-def test_fp32_ragged_shapes_and_zero_weights(sb):
+@pytest.mark.parametrize("prec", FP32_MODES)
+def test_fp32_ragged_shapes_and_zero_weights(sb, prec):
     """odd widths (not multiples of 4/8/32), rows not a multiple of 32, and an all-zero weight batch
     (loss must be 0 and no update must happen: _safe_div in SUM_BY_NONZERO_WEIGHTS)."""
     net, params, cfg, desc = make_pair(sb, 37, [19, 7], [so.ACT_LEAKYRELU, so.ACT_SIGMOID], optimizer=so.OPT_SGD,
-                                       max_batch=101, precision=sb.PREC_FP32)
+                                       max_batch=101, precision=prec)
     X, y, w = so.synth_batch(101, 37, 5, weights="mixed")
     ref = so.CleanTrainer(net, params, cfg)
     rl = ref.step([(X, y, w)])[0]
