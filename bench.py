@@ -231,7 +231,11 @@ def step_timeline(names, stamps, B, F, hidden):
                 role += "+out"
         elif nm in ("dW", "dA"):
             role, M, N, K = next(bi); flops = 2 * M * N * K
-        rows.append({"kernel": role, "entry": int(st[0]), "begin": begin, "end": end, "flops": flops})
+        cta0 = None
+        if flops and st[3] and st[6]:      # CTA 0's pipeline milestones (us after its dependencies resolved)
+            cta0 = {"first_tma": (int(st[3]) - begin) / 1e3, "first_acc": (int(st[6]) - begin) / 1e3,
+                    "first_epilogue": (int(st[7]) - begin) / 1e3 if st[7] else None, "exit": (int(st[8]) - begin) / 1e3 if st[8] else None}
+        rows.append({"kernel": role, "entry": int(st[0]), "begin": begin, "end": end, "flops": flops, "cta0": cta0})
     if not rows:
         return None
     t0 = min(r["begin"] for r in rows)
@@ -420,7 +424,9 @@ def main():
                                           "frac": sum(k["flops"] for k in gem) / (sum_us * 1e-6) / 1e12 / peak_tf},
                             "step_span_us": tl["span_us"], "step_busy_us": tl["busy_us"], "step_idle_us": tl["idle_us"],
                             "step_fraction_of_peak": (value / world * f_train / 1e12) / peak_tf,
-                            "kernels": [{k2: (round(v, 3) if isinstance(v, float) else v) for k2, v in k.items()} for k in tl["kernels"]]}
+                            "kernels": [{k2: (round(v, 3) if isinstance(v, float) else
+                                              ({a_: (round(b_, 2) if b_ is not None else None) for a_, b_ in v.items()} if isinstance(v, dict) else v))
+                                         for k2, v in k.items()} for k in tl["kernels"]]}
         if roofline is None:
             roofline = {"bound": "tensor", "achieved": value / world * f_train / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
                         "frac": (value / world * f_train / 1e12) / peak_tf, "traffic": None, "peak_source": peak_src,

@@ -131,6 +131,17 @@ int sb_trainer_get_grads(sb_trainer_t* t, float* flat, int64_t n);
 int sb_trainer_step(sb_trainer_t* t, const float* X, const float* y, const float* w, int32_t rows,
                     float* loss_out);
 
+/* Wide+deep (BASELINE.json configs[3]; the reference only plumbs the numeric / categorical column lists,
+ * TensorflowTaskExecutor.java:213-223, and has no sparse model - spec in oracle/wide_deep.py): the first hidden layer's
+ * n_features = n_dense + n_onehot inputs are n_dense numeric columns followed by the one-hot expansion of n_cat categorical
+ * columns.  A sparse step feeds the dense block Xd [rows, n_dense] and idx [rows, n_cat] (global one-hot column of each
+ * categorical value, -1 = missing) and evaluates the one-hot block as an embedding gather (forward) / scatter-add
+ * (gradient) - the SAME parameters, loss and update as sb_trainer_step on the materialised one-hot matrix. */
+int sb_trainer_set_sparse(sb_trainer_t* t, int32_t n_dense, int32_t n_onehot, int32_t n_cat);
+int sb_trainer_step_sparse(sb_trainer_t* t, const float* Xd, const int32_t* idx, const float* y, const float* w,
+                           int32_t rows, float* loss_out);
+int sb_trainer_predict_sparse(sb_trainer_t* t, const float* Xd, const int32_t* idx, int64_t rows, float* out);
+
 /* Same step, pipelined: returns as soon as the work is queued.  The H2D copy of this batch goes through a second
  * staging slot on a copy stream and overlaps the previous step's compute; the loss of the most recent step is read
  * with sb_trainer_last_loss (which waits).  X / y / w must be pinned (sb_host_alloc or equivalent) for the copy to be

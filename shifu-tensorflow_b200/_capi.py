@@ -91,6 +91,9 @@ PROTOTYPES = {
     "sb_trainer_init_xavier": (C.c_int, [_vp, C.c_uint64]),
     "sb_trainer_get_grads": (C.c_int, [_vp, _f32p, C.c_int64]),
     "sb_trainer_step": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_int32, _f32p]),
+    "sb_trainer_set_sparse": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32]),
+    "sb_trainer_step_sparse": (C.c_int, [_vp, _f32p, _P(C.c_int32), _f32p, _f32p, C.c_int32, _f32p]),
+    "sb_trainer_predict_sparse": (C.c_int, [_vp, _f32p, _P(C.c_int32), C.c_int64, _f32p]),
     "sb_trainer_step_async": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_int32]),
     "sb_trainer_accumulate": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_int32, _f32p]),
     "sb_trainer_apply_accumulated": (C.c_int, [_vp]),
@@ -261,6 +264,34 @@ class Trainer:
         loss = C.c_float()
         check(lib().sb_trainer_step(self._h, _ptr(X), _ptr(y), _ptr(w), rows, C.byref(loss)))
         return float(loss.value)
+
+    # ---- wide+deep: dense block + index matrix (oracle/wide_deep.py) ----
+    def set_sparse(self, n_dense: int, n_onehot: int, n_cat: int):
+        check(lib().sb_trainer_set_sparse(self._h, n_dense, n_onehot, n_cat))
+        self._sparse = (n_dense, n_cat)
+
+    def _xd_idx(self, Xd, idx):
+        n_dense, n_cat = self._sparse
+        Xd = _f32(Xd)
+        idx = np.ascontiguousarray(idx, dtype=np.int32)
+        if Xd.ndim != 2 or Xd.shape[1] != n_dense or idx.shape != (Xd.shape[0], n_cat):
+            raise ValueError("Xd must be [rows, %d], idx [rows, %d]" % (n_dense, n_cat))
+        return Xd, idx
+
+    def step_sparse(self, Xd, idx, y, w=None) -> float:
+        Xd, idx = self._xd_idx(Xd, idx)
+        y = _f32(y).reshape(-1)
+        w = None if w is None else _f32(w).reshape(-1)
+        loss = C.c_float()
+        check(lib().sb_trainer_step_sparse(self._h, _ptr(Xd), idx.ctypes.data_as(_P(C.c_int32)), _ptr(y), _ptr(w), Xd.shape[0],
+                                           C.byref(loss)))
+        return float(loss.value)
+
+    def predict_sparse(self, Xd, idx) -> np.ndarray:
+        Xd, idx = self._xd_idx(Xd, idx)
+        out = np.empty(Xd.shape[0], np.float32)
+        check(lib().sb_trainer_predict_sparse(self._h, _ptr(Xd), idx.ctypes.data_as(_P(C.c_int32)), Xd.shape[0], _ptr(out)))
+        return out
 
     def step_async(self, X, y, w=None) -> None:
         """queue one step on HOST buffers without waiting (X/y/w should be pinned and not reused for two more steps)"""

@@ -51,6 +51,7 @@ struct sb_trainer {
   P2PPeers* d_peers = nullptr;     // device table of every rank's arena
   std::vector<void*> peer_bases;   // opened IPC mappings (to close)
   bool p2p_ready = false;
+  bool peers_share_device = false; // in-process replicas on this device (tests): see XchgParams::early_dependents
   bool grad_sharded = false;       // the reduced gradient of the last step lives in slices on its owners (sb_trainer_get_grads gathers)
   bool master_stale = false;       // sharded updates ran since the fp32 master / state were last gathered from their owners
   unsigned int epoch = 0;
@@ -135,6 +136,7 @@ static XchgParams xchg_params(sb_trainer* t) {
   p.hyper = t->hyper;
   p.host_err = t->d_herr;
   p.timeout_ns = t->xchg_timeout_ns;
+  p.early_dependents = t->peers_share_device ? 0 : 1;
   return p;
 }
 
@@ -189,10 +191,11 @@ static bool step_is_pipelined(const sb_trainer* t, int kind) {
 }
 
 // the body of one step as a sequence of stream operations (captured into a CUDA graph)
-static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = false) {
+static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = false, bool sparse = false) {
   Net& n = t->net;
-  struct Scope { Net& n; ~Scope() { n.from_resident = false; n.zero_buf = nullptr; n.dw0_on_main = n.defer_join = false; } } scope{n};
+  struct Scope { Net& n; ~Scope() { n.from_resident = false; n.zero_buf = nullptr; n.dw0_on_main = n.defer_join = false; n.sparse_step = false; } } scope{n};
   n.from_resident = resident;
+  n.sparse_step = sparse;
   n.trace_k = 0;
   if (resident) {
     // no load kernel: the batch is read by TMA from the bf16 resident set; set_batch_kernel already published n_nz.
@@ -285,15 +288,15 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   return SB_OK;
 }
 
-static int get_graph(sb_trainer* t, int rows, int kind, bool resident, int pair, cudaGraphExec_t* out) {
-  auto key = std::make_pair(rows, kind * 4 + (resident ? 2 : 0) + pair);
+static int get_graph(sb_trainer* t, int rows, int kind, bool resident, int pair, cudaGraphExec_t* out, bool sparse = false) {
+  auto key = std::make_pair(rows, kind * 8 + (sparse ? 4 : 0) + (resident ? 2 : 0) + pair);
   auto it = t->graphs.find(key);
   if (it != t->graphs.end()) { *out = it->second; return SB_OK; }
   Net& n = t->net;
   n.launches = 0;
   cudaGraph_t g = nullptr;
   SB_CUDA(cudaStreamBeginCapture(n.stream, cudaStreamCaptureModeThreadLocal));
-  int s = enqueue_step_body(t, rows, kind, resident);
+  int s = enqueue_step_body(t, rows, kind, resident, sparse);
   cudaError_t e = cudaStreamEndCapture(n.stream, &g);
   if (s != SB_OK) { if (g) cudaGraphDestroy(g); return s; }
   SB_CHECK(e == cudaSuccess, SB_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
@@ -301,13 +304,14 @@ static int get_graph(sb_trainer* t, int rows, int kind, bool resident, int pair,
   SB_CUDA(cudaGraphInstantiate(&ge, g, 0));
   cudaGraphDestroy(g);
   t->graphs[key] = ge;
-  if (kind == G_STEP && (resident || !t->dsXb)) t->kernels_per_step[rows] = n.launches + 1;  // + set_batch_kernel
+  if (kind == G_STEP && !sparse && (resident || !t->dsXb)) t->kernels_per_step[rows] = n.launches + 1;  // + set_batch_kernel
   *out = ge;
   return SB_OK;
 }
 
 // X, y, w are DEVICE pointers here
-static int run_step(sb_trainer* t, const float* X, const float* y, const float* w, int rows, int kind, long long resident_row0 = -1) {
+static int run_step(sb_trainer* t, const float* X, const float* y, const float* w, int rows, int kind, long long resident_row0 = -1,
+                    bool sparse = false) {
   Net& n = t->net;
   SB_CHECK(rows > 0 && rows <= n.max_batch, SB_ERR_INVALID, "rows=%d outside (0, max_batch=%d]", rows, n.max_batch);
   SB_CUDA(cudaSetDevice(n.device));
@@ -320,7 +324,7 @@ static int run_step(sb_trainer* t, const float* X, const float* y, const float* 
   n.desc = t->descs[pair];
   n.scal = t->scals[pair];
   cudaGraphExec_t ge = nullptr;
-  if (!no_graph) SB_TRY(get_graph(t, rows, kind, resident, pair, &ge));
+  if (!no_graph) SB_TRY(get_graph(t, rows, kind, resident, pair, &ge, sparse));
   float lr_t = t->lr, gscale = 1.f / static_cast<float>(t->world);
   if (kind == G_STEP) {
     ++t->global_step;
@@ -351,7 +355,7 @@ static int run_step(sb_trainer* t, const float* X, const float* y, const float* 
                                                kind == G_STEP ? t->hist_slot(t->global_step) : nullptr);
   }
   SB_CUDA(cudaGetLastError());
-  if (no_graph) SB_TRY(enqueue_step_body(t, rows, kind, resident));
+  if (no_graph) SB_TRY(enqueue_step_body(t, rows, kind, resident, sparse));
   else SB_CUDA(cudaGraphLaunch(ge, n.stream));
   // the step's tail kernel (optimizer / accumulate) wrote (loss sum, n_nz) into h_scal; visible after a stream sync
   if (step_is_pipelined(t, kind))
@@ -624,6 +628,7 @@ int sb_trainer_set_peer_pointers(sb_trainer_t* t, void* const* bases, int32_t n)
     cudaPointerAttributes at;
     SB_CUDA(cudaPointerGetAttributes(&at, bases[q]));
     SB_CHECK(at.type == cudaMemoryTypeDevice, SB_ERR_INVALID, "pointer of rank %d is not device memory", q);
+    if (at.device == t->net.device) t->peers_share_device = true;
     if (at.device != t->net.device) {
       int can = 0;
       SB_CUDA(cudaDeviceCanAccessPeer(&can, t->net.device, at.device));
@@ -730,6 +735,53 @@ int sb_trainer_step(sb_trainer_t* t, const float* X, const float* y, const float
   SB_TRY(stage_host_batch(t, X, y, w, rows));
   SB_TRY(run_step(t, t->net.stX, t->net.stY, w ? t->net.stW : nullptr, rows, G_STEP));
   return finish_loss(t, loss_out);
+}
+
+// ---- wide+deep (BASELINE config 4): hidden layer 0 = [dense | one-hot]; the step feeds (dense block, index matrix) ----
+int sb_trainer_set_sparse(sb_trainer_t* t, int32_t n_dense, int32_t n_onehot, int32_t n_cat) {
+  SB_CHECK(t, SB_ERR_INVALID, "null trainer");
+  return t->net.set_sparse(n_dense, n_onehot, n_cat);
+}
+
+static int stage_sparse_batch(Net& n, const float* Xd, const int32_t* idx, const float* y, const float* w, int rows) {
+  SB_CHECK(n.n_cat > 0, SB_ERR_STATE, "sb_trainer_set_sparse has not been called");
+  SB_CHECK(Xd && idx, SB_ERR_INVALID, "Xd and idx must not be null");
+  SB_CHECK(rows > 0 && rows <= n.max_batch, SB_ERR_INVALID, "rows=%d outside (0, max_batch=%d]", rows, n.max_batch);
+  for (long long i = 0; i < static_cast<long long>(rows) * n.n_cat; ++i)
+    SB_CHECK(idx[i] < n.n_onehot, SB_ERR_INVALID, "idx[%lld] = %d outside [-1, n_onehot=%d)", i, idx[i], n.n_onehot);
+  SB_CUDA(cudaSetDevice(n.device));
+  SB_CUDA(cudaMemcpyAsync(n.stX, Xd, sizeof(float) * rows * static_cast<size_t>(n.n_dense), cudaMemcpyHostToDevice, n.stream));
+  SB_CUDA(cudaMemcpyAsync(n.idx, idx, sizeof(int32_t) * rows * static_cast<size_t>(n.n_cat), cudaMemcpyHostToDevice, n.stream));
+  if (y) SB_CUDA(cudaMemcpyAsync(n.stY, y, sizeof(float) * rows, cudaMemcpyHostToDevice, n.stream));
+  if (w) SB_CUDA(cudaMemcpyAsync(n.stW, w, sizeof(float) * rows, cudaMemcpyHostToDevice, n.stream));
+  return SB_OK;
+}
+
+int sb_trainer_step_sparse(sb_trainer_t* t, const float* Xd, const int32_t* idx, const float* y, const float* w, int32_t rows,
+                           float* loss_out) {
+  SB_CHECK(t && y, SB_ERR_INVALID, "null argument");
+  SB_TRY(stage_sparse_batch(t->net, Xd, idx, y, w, rows));
+  SB_TRY(run_step(t, t->net.stX, t->net.stY, w ? t->net.stW : nullptr, rows, G_STEP, -1, true));
+  return finish_loss(t, loss_out);
+}
+
+int sb_trainer_predict_sparse(sb_trainer_t* t, const float* Xd, const int32_t* idx, int64_t rows, float* out) {
+  SB_CHECK(t && out, SB_ERR_INVALID, "null argument");
+  Net& n = t->net;
+  struct Scope { Net& n; ~Scope() { n.sparse_step = false; } } scope{n};
+  for (int64_t r0 = 0; r0 < rows; r0 += n.max_batch) {
+    const int c = static_cast<int>(rows - r0 < n.max_batch ? rows - r0 : n.max_batch);
+    SB_TRY(stage_sparse_batch(n, Xd + r0 * n.n_dense, idx + r0 * n.n_cat, nullptr, nullptr, c));
+    set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, n.stX, n.stY, n.ones, 0.f, 1.f);
+    n.sparse_step = true;
+    SB_TRY(n.enqueue_load(c));
+    SB_TRY(n.enqueue_hidden_forward(c));
+    n.sparse_step = false;
+    SB_TRY(n.enqueue_out(c, false, false, n.yhat, nullptr));
+    SB_CUDA(cudaMemcpyAsync(out + r0, n.yhat, sizeof(float) * c, cudaMemcpyDeviceToHost, n.stream));
+    SB_CUDA(cudaStreamSynchronize(n.stream));
+  }
+  return SB_OK;
 }
 
 int sb_trainer_step_async(sb_trainer_t* t, const float* X, const float* y, const float* w, int32_t rows) {

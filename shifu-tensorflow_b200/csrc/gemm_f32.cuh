@@ -18,6 +18,7 @@ struct GemmF32Params {
   const float* aux; int ld_aux;
   float* colsum;
   float* accum; int ld_acc;
+  const float* addend; int ld_add;   // EPI_FWD, nullable: added to the pre-activation (wide+deep: the embedding sum)
 };
 
 template <int EPI>
@@ -88,6 +89,7 @@ gemm_f32_kernel(const GemmF32Params p) {
       if (gm >= p.M || gn >= p.N) continue;
       float v = acc[i][j];
       if constexpr (EPI == EPI_FWD) {
+        if (p.addend != nullptr) v += __ldg(p.addend + static_cast<size_t>(gm) * p.ld_add + gn);
         v = act_apply(v + __ldg(p.bias + gn), p.act);
         p.out[static_cast<size_t>(gm) * p.ld_out + gn] = v;
       } else if constexpr (EPI == EPI_DA) {

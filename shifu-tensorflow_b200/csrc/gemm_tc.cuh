@@ -83,6 +83,11 @@ struct GemmTcParams {
   int n_pairs;                // part pairs accumulated (1, 3 or 6); 0 is read as 1
   unsigned char pair_a[6], pair_b[6];
   long long out_ps, aux_ps;   // element stride between consecutive parts of `out` / `aux`
+  // EPI_FWD, nullable: fp32 [M, ld_add] added to the pre-activation before bias + activation.  Wide+deep first layer:
+  // the sum of the embedding rows of the row's categorical values, i.e. the one-hot block of Z_0 = X W_0 evaluated as a
+  // gather (oracle/wide_deep.py) while this GEMM contracts only the dense columns.
+  const float* addend;
+  int ld_add;
 };
 
 // tensor maps of the parts of both operands (one kernel parameter, 768 B)
@@ -106,7 +111,8 @@ struct GemmTcCfg {
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*epilogue scratch*/ +
-                                    2048 /*bias (+ w_o) of the tile*/ + 8 * 2048 /*per-warp transpose tile*/;
+                                    2048 /*bias (+ w_o) of the tile*/ + 8 * 2048 /*per-warp transpose tile*/ +
+                                    4096 /*column-sum accumulators of the tile (db, dw_o), double-buffered*/;
   static constexpr int EPI_WARPS = 8;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
@@ -308,6 +314,34 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
     // sides): on the global side lane l handles piece (l & 3) of rows 8 i + (l >> 2), i = 0..3, i.e. four lanes cover
     // 64 contiguous bytes of a row and one instruction touches 8 rows instead of 32.
     const uint32_t sm_stage = sm_vec + 2048u + static_cast<uint32_t>(warp - 2) * 2048u;
+    // Column sums (bias gradients; dw_o of the fused output layer) are accumulated per CTA in shared memory and flushed to
+    // the flat gradient ONCE per tile and column: one red.global per column per 128 rows instead of one per 32 rows.  With
+    // one red per warp and chunk, the 8192 x 1024 dA GEMM of cfg2 sent 262 k reds to 32 cache lines and spent 3/4 of its time
+    // waiting for the L2 atomic units (tensor pipe 25 % active, profiles/ncu_r01_cfg2_gemm_full.txt).
+    // layout: [buffer (tile parity)][array 0: db | array 1: dw_o][BN] floats
+    const uint32_t sm_col = sm_vec + 2048u + 8u * 2048u;
+    auto col_slot = [&](int buf, int arr, int j) { return sm_col + static_cast<uint32_t>(((buf * 2 + arr) * BN + j) * 4); };
+    auto red_shared = [](uint32_t a, float v) { asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); };
+    if constexpr (EPI == EPI_DA || EPI == EPI_FWD_OUT) {
+      for (int j = et; j < 4 * BN; j += 256) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sm_col + static_cast<uint32_t>(j) * 4u), "f"(0.f) : "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    // after every epilogue warp has added its sums of tile `it`: one thread per column flushes and clears buffer it & 1
+    auto flush_cols = [&](int it_, int tn_, float* dst0, float* dst1) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int j = et; j < BN; j += 256) {
+        const int col = tn_ * BN + j;
+#pragma unroll
+        for (int arr = 0; arr < 2; ++arr) {
+          float* dst = arr == 0 ? dst0 : dst1;
+          if (dst == nullptr) continue;
+          float vsum;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(vsum) : "r"(col_slot(it_ & 1, arr, j)) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(col_slot(it_ & 1, arr, j)), "f"(0.f) : "memory");
+          if (col < p.N && vsum != 0.f) red_add_f32(dst + col, vsum);
+        }
+      }
+    };
     const int lrow = lane >> 2, lpc = lane & 3;
     auto stg = [&](int r, int pc) { return sm_stage + static_cast<uint32_t>(r) * 64u + static_cast<uint32_t>((pc ^ ((r >> 1) & 3)) << 4); };
     auto sts4 = [](uint32_t a, const uint4& v) {
@@ -522,7 +556,8 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
           store_parts(g, p.out, p.out_ps, p.ld_out, col0, false);       // dZ_L (bf16, or its parts)
           const float sb_ = warp_colsum_32x32(g, lane);
           const float sw_ = warp_colsum_32x32(v, lane);
-          if (col0 + lane < p.N) { red_add_f32(p.g_bL + col0 + lane, sb_); red_add_f32(p.g_wo + col0 + lane, sw_); }
+          red_shared(col_slot(it & 1, 0, col0 + lane), sb_);       // columns beyond N carry zeros
+          red_shared(col_slot(it & 1, 1, col0 + lane), sw_);
         }
         tcgen05_fence_before();
         __syncwarp();
@@ -530,6 +565,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
           if constexpr (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
           else mbar_arrive(tempty_bar(acc));
         }
+        flush_cols(it, 0, p.g_bL, p.g_wo);
         continue;
       }
 #pragma unroll 1
@@ -545,6 +581,20 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
         const bool full = col0 + 32 <= p.N;  // warp-uniform fast path
 
         if constexpr (EPI == EPI_FWD) {
+          if (p.addend != nullptr && row_ok) {
+            const float* ad = p.addend + static_cast<size_t>(row) * p.ld_add + col0;
+            if (full && (p.ld_add & 3) == 0) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(ad) + q);
+                v[4 * q] += a4.x; v[4 * q + 1] += a4.y; v[4 * q + 2] += a4.z; v[4 * q + 3] += a4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) v[j] += __ldg(ad + j);
+            }
+          }
           float b[32];   // staged before the accumulator wait (0 beyond N)
 #pragma unroll
           for (int q = 0; q < 8; ++q)
@@ -606,7 +656,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
             if (p.colsum != nullptr) {
               // bias gradient: per-column sum over this warp's 32 rows, one atomic per column per warp
               const float s = warp_colsum_32x32(v, lane);
-              if (col0 + lane < p.N) red_add_f32(p.colsum + col0 + lane, s);
+              red_shared(col_slot(it & 1, 0, c * 32 + lane), s);     // columns beyond N / rows beyond M were zeroed above
             }
           }
         } else if constexpr (EPI == EPI_DW) {
@@ -656,6 +706,9 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
       if (lane == 0) {
         if constexpr (CG == 2) mbar_arrive_cluster(tempty_bar(acc), 0);
         else mbar_arrive(tempty_bar(acc));
+      }
+      if constexpr (EPI == EPI_DA) {
+        if (p.colsum != nullptr) flush_cols(it, tn, p.colsum, nullptr);
       }
       if (w == w_first && warp == 2 && lane == 0) stamp(7);  // first tile's epilogue done
     }

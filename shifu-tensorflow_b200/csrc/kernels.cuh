@@ -517,6 +517,94 @@ shadow_refresh_kernel(const OptWork* __restrict__ work, const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Wide+deep first layer (BASELINE config 4; spec + CPU oracle in oracle/wide_deep.py): Shifu's one-hot normalisation turns
+// C categorical columns into n_onehot 0/1 columns of the reference's first dense layer (res/ssgd_monitor.py:57-71).  With
+// idx[r, c] = the global one-hot column that is 1 for categorical column c of row r (-1 = missing), the one-hot block of
+//     Z_0 = [X_dense | X_onehot] W_0 + b_0
+// is a gather-sum of rows of W_e = W_0[n_dense:], and its gradient a scatter-add of dZ_0 rows.  Both read the SAME operand
+// precision as the dense path (bf16 shadow / its parts, or fp32), so the sparse evaluation equals the dense layer on the
+// materialised one-hot matrix up to fp32 summation order.  HBM/L2-bound: one warp per row, 16-byte accesses.
+// ------------------------------------------------------------------------------------------------
+struct EmbedParams {
+  int rows, n_cat, H;              // H = width of hidden layer 0
+  const int* idx;                  // [rows, n_cat]
+  const __nv_bfloat16* We;         // bf16 modes: shadow rows of W_e [n_onehot, ldW] (part 0); nullptr in fp32 mode
+  long long We_ps; int np;         // parts
+  const float* We32;               // fp32 mode: master rows [n_onehot, ldW]
+  int ldW;
+  float* E; int ldE;               // gather: out [rows, ldE] fp32
+  const __nv_bfloat16* dZ; long long dZ_ps; int ld_dZ;   // scatter: dZ_0 (bf16 modes) ...
+  const float* dZ32;               // ... or fp32
+  float* gWe;                      // scatter: gradient rows of W_e [n_onehot, H] fp32 (flat gradient, ld = H)
+};
+
+static __global__ void __launch_bounds__(256) embed_gather_kernel(const EmbedParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= p.rows) return;
+  for (int c0 = lane * 8; c0 < p.H; c0 += 256) {       // 8 columns per lane per pass
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int c = 0; c < p.n_cat; ++c) {
+      const int j = __ldg(p.idx + static_cast<size_t>(r) * p.n_cat + c);
+      if (j < 0) continue;
+      if (p.We != nullptr) {
+        for (int part = 0; part < p.np; ++part) {
+          const __nv_bfloat16* src = p.We + part * p.We_ps + static_cast<size_t>(j) * p.ldW + c0;
+          if (c0 + 8 <= p.H && (p.ldW & 7) == 0) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(src));
+            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] += __bfloat162float(h[k]);
+          } else {
+            for (int k = 0; k < 8; ++k)
+              if (c0 + k < p.H) acc[k] += __bfloat162float(src[k]);
+          }
+        }
+      } else {
+        const float* src = p.We32 + static_cast<size_t>(j) * p.ldW + c0;
+        for (int k = 0; k < 8; ++k)
+          if (c0 + k < p.H) acc[k] += __ldg(src + k);
+      }
+    }
+    float* dst = p.E + static_cast<size_t>(r) * p.ldE + c0;
+    for (int k = 0; k < 8; ++k)
+      if (c0 + k < p.H) dst[k] = acc[k];
+  }
+}
+
+static __global__ void __launch_bounds__(256) embed_scatter_kernel(const EmbedParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= p.rows) return;
+  for (int c0 = lane * 4; c0 < p.H; c0 += 128) {       // 4 columns per lane per pass -> red.global.add.v4.f32
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < 4; ++k) {
+      if (c0 + k >= p.H) break;
+      if (p.dZ != nullptr) {
+        for (int part = 0; part < p.np; ++part) g[k] += __bfloat162float(p.dZ[part * p.dZ_ps + static_cast<size_t>(r) * p.ld_dZ + c0 + k]);
+      } else {
+        g[k] = p.dZ32[static_cast<size_t>(r) * p.ld_dZ + c0 + k];
+      }
+    }
+    for (int c = 0; c < p.n_cat; ++c) {
+      const int j = __ldg(p.idx + static_cast<size_t>(r) * p.n_cat + c);
+      if (j < 0) continue;
+      float* dst = p.gWe + static_cast<size_t>(j) * p.H + c0;
+      if (c0 + 4 <= p.H && (p.H & 3) == 0 && (reinterpret_cast<uintptr_t>(p.gWe) & 15) == 0) red_add_v4_f32(dst, g[0], g[1], g[2], g[3]);
+      else
+        for (int k = 0; k < 4; ++k)
+          if (c0 + k < p.H) red_add_f32(dst + k, g[k]);
+    }
+  }
+}
+
 // acc += g  (epoch-sync schedule: ConditionalAccumulator.apply_grad, res/ssgd_monitor.py:136-141)
 static __global__ void axpy_kernel(float* __restrict__ acc, const float* __restrict__ g, long long n,
                                    const float* __restrict__ scal = nullptr, float* __restrict__ host_scal = nullptr) {

@@ -324,6 +324,41 @@ void Net::destroy() {
   stream = nullptr;
 }
 
+int Net::set_sparse(int n_dense_, int n_onehot_, int n_cat_) {
+  SB_CHECK(n_dense_ >= 1 && n_onehot_ >= 1 && n_cat_ >= 1, SB_ERR_INVALID, "wide+deep needs >= 1 dense, one-hot and categorical column");
+  SB_CHECK(n_dense_ + n_onehot_ == F, SB_ERR_INVALID, "n_dense (%d) + n_onehot (%d) must equal n_features (%d): the sparse path evaluates "
+           "the SAME first layer", n_dense_, n_onehot_, F);
+  SB_CUDA(cudaSetDevice(device));
+  n_dense = n_dense_; n_onehot = n_onehot_; n_cat = n_cat_;
+  ldD = round_up(n_dense, 8);
+  if (!idx) SB_TRY(dalloc(&idx, static_cast<size_t>(max_batch) * n_cat));
+  if (!E) SB_TRY(dalloc(&E, static_cast<size_t>(max_batch) * layers[0].ld_out));
+  SB_CUDA(cudaStreamSynchronize(stream));
+  return SB_OK;
+}
+
+int Net::enqueue_embed(int rows, bool scatter, float* grad, cudaStream_t st) {
+  const Layer& l0 = layers[0];
+  EmbedParams p = {};
+  p.rows = rows; p.n_cat = n_cat; p.H = l0.out;
+  p.idx = idx;
+  p.np = nparts; p.ldW = tc() ? l0.ld_out : l0.out;
+  if (tc()) { p.We = l0.Wn + static_cast<size_t>(n_dense) * l0.ld_out; p.We_ps = Wn_ps[0]; }
+  else p.We32 = theta + l0.w_off + static_cast<long long>(n_dense) * l0.out;
+  p.E = E; p.ldE = l0.ld_out;
+  if (scatter) {
+    if (tc()) { p.dZ = dZ[0]; p.dZ_ps = A_ps[0]; p.ld_dZ = l0.ld_out; }
+    else { p.dZ32 = dZf[0]; p.ld_dZ = l0.out; }
+    p.gWe = grad + l0.w_off + static_cast<long long>(n_dense) * l0.out;
+    SB_TRY(launch(embed_scatter_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, false, p));
+    mark("embed_scatter");
+  } else {
+    SB_TRY(launch(embed_gather_kernel, dim3((rows + 7) / 8), dim3(256), 0, st, false, p));
+    mark("embed_gather");
+  }
+  return SB_OK;
+}
+
 int Net::refresh_shadows() {
   if (!tc()) return SB_OK;
   shadow_refresh_kernel<<<n_work, 256, 0, stream>>>(work, theta);
@@ -332,7 +367,9 @@ int Net::refresh_shadows() {
 }
 
 int Net::enqueue_load(int rows, float* zero_buf, long long zero_n) {
-  const long long units = static_cast<long long>(rows) * (ldF / 8);
+  const int Fx = sparse_step ? n_dense : F;        // a sparse step stages only the dense block
+  const int ldx = sparse_step ? ldD : ldF;
+  const long long units = static_cast<long long>(rows) * (ldx / 8);
   long long blocks = (units + 255) / 256;
   const long long cap = static_cast<long long>(num_sms) * 16;
   if (blocks > cap) blocks = cap;
@@ -340,13 +377,14 @@ int Net::enqueue_load(int rows, float* zero_buf, long long zero_n) {
   // first kernel of the step: its stream predecessor is set_batch_kernel (a kernel), so PDL applies here too
   if (tc())
     SB_TRY(launch(load_batch_kernel<true>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, use_pdl,
-                  static_cast<const BatchDesc*>(desc), rows, F, Xb, ldF, static_cast<float*>(nullptr), scal, zero_buf, zero_n,
+                  static_cast<const BatchDesc*>(desc), rows, Fx, Xb, ldx, static_cast<float*>(nullptr), scal, zero_buf, zero_n,
                   nparts, Xb_ps));
   else
     SB_TRY(launch(load_batch_kernel<false>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream, use_pdl,
-                  static_cast<const BatchDesc*>(desc), rows, F, static_cast<__nv_bfloat16*>(nullptr), ldF, Xf, scal, zero_buf, zero_n,
+                  static_cast<const BatchDesc*>(desc), rows, Fx, static_cast<__nv_bfloat16*>(nullptr), ldx, Xf, scal, zero_buf, zero_n,
                   1, 0ll));
   mark("load_batch");
+  if (sparse_step) SB_TRY(enqueue_embed(rows, false, nullptr, stream));
   return SB_OK;
 }
 
@@ -354,25 +392,29 @@ int Net::enqueue_hidden_forward(int rows, float* grad, bool* fused_out) {
   if (fused_out) *fused_out = false;
   for (int l = 0; l < L; ++l) {
     Layer& ly = layers[l];
+    const bool sp0 = (l == 0) && sparse_step;       // wide+deep: contract the dense columns only, add the embedding sums
+    const int k_in = sp0 ? n_dense : ly.in;
+    const int ld_k = sp0 ? ldD : ly.ld_in;
     if (tc()) {
       // Z = A_{l-1}[rows,in] (K-major) x W_l[in,out] (MN-major B operand: n contiguous)
-      const GemmPlan pl = plan_gemm(rows, ly.out, round_up(ly.in, 64) * pairs_of(nparts), gemm_sms, false);
+      const GemmPlan pl = plan_gemm(rows, ly.out, round_up(k_in, 64) * pairs_of(nparts), gemm_sms, false);
       TmapSet tm;
       const bool res0 = (l == 0) && from_resident;
       const __nv_bfloat16* src = (l == 0) ? (res0 ? resident_Xb : Xb) : A[l - 1];
       const long long src_ps = (l == 0) ? (res0 ? resident_ps : Xb_ps) : A_ps[l - 1];
-      SB_TRY(make_tmaps_bf16(tm.a, src, src_ps, nparts, res0 ? static_cast<int>(resident_rows) : rows, ly.in, ly.ld_in, 128));
-      SB_TRY(make_tmaps_bf16(tm.b, ly.Wn, Wn_ps[l], nparts, ly.in, ly.out, ly.ld_out, 64));
+      SB_TRY(make_tmaps_bf16(tm.a, src, src_ps, nparts, res0 ? static_cast<int>(resident_rows) : rows, k_in, ld_k, 128));
+      SB_TRY(make_tmaps_bf16(tm.b, ly.Wn, Wn_ps[l], nparts, k_in, ly.out, ly.ld_out, 64));
       GemmTcParams p = {};
       set_part_pairs(&p, nparts);
-      p.M = rows; p.N = ly.out; p.K = ly.in;
+      p.M = rows; p.N = ly.out; p.K = k_in;
+      if (sp0) { p.addend = E; p.ld_add = ly.ld_out; }
       p.bias = theta + ly.b_off; p.act = ly.act;
       p.out = A[l]; p.ld_out = ly.ld_out; p.out_ps = A_ps[l];
       p.a_rows = res0 ? desc : nullptr;
       if (l == L - 1 && grad != nullptr && fuse_out_layer && training && ly.out <= fuse_out_max) {
         // K2 + K3 + K4 + output backward in one kernel: one n-tile must cover the whole layer width
         GemmPlan fp = pl;
-        fp.split_k = 1; fp.kb_per_split = ((ly.in + 63) / 64) * pairs_of(nparts);
+        fp.split_k = 1; fp.kb_per_split = ((k_in + 63) / 64) * pairs_of(nparts);
         // (a 256-wide PAIR tile measured slower than GEMM + out_layer kernel in round 1; the single-CTA 128 x 256 tile keeps
         // whole rows of A_L in one CTA's TMEM - 2 x 256 columns, double-buffered - and needs no second kernel)
         if (ly.out <= 64) { fp.cg = 1; fp.bn = 64; }
@@ -400,8 +442,9 @@ int Net::enqueue_hidden_forward(int rows, float* grad, bool* fused_out) {
       SB_TRY((launch_gemm_tc<EPI_FWD, false, true>(pl, tm, p, stream, use_pdl)));
     } else {
       GemmF32Params p = {};
-      p.M = rows; p.N = ly.out; p.K = ly.in;
-      p.A = (l == 0) ? Xf : Af[l - 1]; p.sAm = ly.in; p.sAk = 1;
+      p.M = rows; p.N = ly.out; p.K = k_in;
+      p.A = (l == 0) ? Xf : Af[l - 1]; p.sAm = k_in; p.sAk = 1;
+      if (sp0) { p.addend = E; p.ld_add = ly.ld_out; }
       p.B = theta + ly.w_off; p.sBk = ly.out; p.sBn = 1;
       p.bias = theta + ly.b_off; p.act = ly.act;
       p.out = Af[l]; p.ld_out = ly.out;
@@ -503,15 +546,20 @@ int Net::enqueue_backward(int rows, float* grad) {
           SB_CUDA(cudaStreamWaitEvent(side, ev_dz[l], 0));
         }
         const bool res0 = (l == 0) && from_resident;
+        const bool sp0 = (l == 0) && sparse_step;     // wide+deep: dW of the dense rows by GEMM, of the embedding rows by scatter-add
+        const int in_rows = sp0 ? n_dense : ly.in;
+        const int ld_k = sp0 ? ldD : ly.ld_in;
+        if (sp0) chunk_rows = round_up(in_rows, 128);
         const __nv_bfloat16* ap = (l == 0) ? (res0 ? resident_Xb : Xb) : A[l - 1];
         const long long ap_ps = (l == 0) ? (res0 ? resident_ps : Xb_ps) : A_ps[l - 1];
-        for (int r0 = 0; r0 < ly.in; r0 += chunk_rows) {
-          const int r1 = (r0 + chunk_rows < ly.in) ? r0 + chunk_rows : ly.in;
+        if (sp0) SB_TRY(enqueue_embed(rows, true, grad, on_main ? stream : side));
+        for (int r0 = 0; r0 < in_rows; r0 += chunk_rows) {
+          const int r1 = (r0 + chunk_rows < in_rows) ? r0 + chunk_rows : in_rows;
           const GemmPlan pl = plan_gemm(r1 - r0, ly.out, round_up(rows, 64) * pairs_of(nparts), l < 2 ? dw_sms[l] : gemm_sms, true);
           TmapSet tm;
           // resident set: rows past the batch end are real rows of other batches; the B operand (dZ_l, extent = rows) is
           // zero-filled there, so they contribute nothing
-          SB_TRY(make_tmaps_bf16(tm.a, ap + r0, ap_ps, nparts, res0 ? static_cast<int>(resident_rows) : rows, r1 - r0, ly.ld_in, 64));
+          SB_TRY(make_tmaps_bf16(tm.a, ap + r0, ap_ps, nparts, res0 ? static_cast<int>(resident_rows) : rows, r1 - r0, ld_k, 64));
           SB_TRY(make_tmaps_bf16(tm.b, dZ[l], A_ps[l], nparts, rows, ly.out, ly.ld_out, 64));
           GemmTcParams p = {};
           set_part_pairs(&p, nparts);
@@ -557,9 +605,12 @@ int Net::enqueue_backward(int rows, float* grad) {
       }
     } else {
       {
+        const bool sp0 = (l == 0) && sparse_step;
+        const int in_rows = sp0 ? n_dense : ly.in;
+        if (sp0) SB_TRY(enqueue_embed(rows, true, grad, stream));
         GemmF32Params p = {};
-        p.M = ly.in; p.N = ly.out; p.K = rows;
-        p.A = (l == 0) ? Xf : Af[l - 1]; p.sAm = 1; p.sAk = ly.in;
+        p.M = in_rows; p.N = ly.out; p.K = rows;
+        p.A = (l == 0) ? Xf : Af[l - 1]; p.sAm = 1; p.sAk = in_rows;
         p.B = dZf[l]; p.sBk = ly.out; p.sBn = 1;
         p.accum = grad + ly.w_off; p.ld_acc = ly.out;
         const int tiles = ((p.M + 63) / 64) * ((p.N + 63) / 64);

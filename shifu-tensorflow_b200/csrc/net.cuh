@@ -137,6 +137,15 @@ struct Net {
   // grad != nullptr (training step): the last hidden layer's GEMM also runs the output layer, the loss and the output
   // backward in its epilogue when h_L <= 128; *fused_out tells the caller whether enqueue_out is still needed
   int enqueue_hidden_forward(int rows, float* grad = nullptr, bool* fused_out = nullptr);
+  // wide+deep first layer (oracle/wide_deep.py): hidden layer 0 = [n_dense numeric columns | n_onehot one-hot columns of
+  // n_cat categorical columns]; a SPARSE step feeds (dense block, index matrix) and evaluates the one-hot block as an
+  // embedding gather / scatter-add.  F = n_dense + n_onehot, the parameters are those of the dense net.
+  int n_dense = 0, n_onehot = 0, n_cat = 0, ldD = 0;
+  int* idx = nullptr;                        // [max_batch, n_cat] staged indices
+  float* E = nullptr;                        // [max_batch, ld_out_0] embedding sums
+  bool sparse_step = false;                  // set while a sparse step is being enqueued
+  int set_sparse(int n_dense_, int n_onehot_, int n_cat_);
+  int enqueue_embed(int rows, bool scatter, float* grad, cudaStream_t st);
   bool fuse_out_layer = true;
   int fuse_out_max = 256;                    // widest last hidden layer whose GEMM also runs the output layer (one n-tile)
   // bf16 HBM-resident training set (trainer): when `from_resident` is set while enqueueing, layer 0's GEMMs read their A

@@ -64,6 +64,10 @@ struct XchgParams {
   float* host_scal;
   unsigned int* host_err;                 // mapped pinned: [0] = 0 ok | 1 + 16 * seg + missing rank
   unsigned long long timeout_ns;          // 0 = wait forever
+  int early_dependents;                   // 1: let the next kernel of the stream (PDL) become resident while this one still
+                                          // waits for its peers.  0 when the peers share this device (in-process replicas):
+                                          // the next step's persistent GEMM CTAs would take every SM's shared memory while
+                                          // they wait for this kernel, and the replica this kernel waits for could never run
   unsigned long long* trace;
 };
 
@@ -133,7 +137,7 @@ xchg_update_kernel(const XchgParams p) {
   if (threadIdx.x == 0) sh_fail = 0u;
   trace_begin(p.trace, true);
   pdl_wait();                 // the gradient of this segment is complete (programmatic dependent of the last GEMM)
-  pdl_launch_dependents();
+  if (p.early_dependents) pdl_launch_dependents();
   trace_begin(p.trace, false);
   __syncthreads();
   const unsigned int epoch = p.desc->epoch;

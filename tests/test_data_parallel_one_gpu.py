@@ -128,7 +128,7 @@ def test_epoch_sync_schedule_over_the_exchange(sb, monkeypatch):
     th = [threading.Thread(target=t.apply_accumulated, args=(5,)) for t in ts]     # apply waits for the device: one host thread per rank
     [x.start() for x in th]; [x.join(120) for x in th]
     P = params
-    gsum = np.zeros(net.n_params(), np.float32)
+    gsum = np.zeros(so.flatten_params(params).size, np.float32)
     for r, n_acc in ((0, 3), (1, 2)):
         X, y, w = shards[r]
         for k in range(n_acc):
