@@ -26,6 +26,19 @@ class IllegalArgumentException(ValueError):
     """more than one output name (TensorflowModel.java:137-139)."""
 
 
+def check_phase_switch(name: str, value: Any) -> None:
+    """rule for GenericModelConfig inputnames[1:] (see TensorflowModel.init below and java/.../B200Model.java)"""
+    if value is None:
+        return
+    if isinstance(value, (bool, int, float, np.bool_, np.integer, np.floating)):
+        if bool(value):
+            raise IllegalArgumentException("Input %s = %r selects the training branch of the graph; only inference "
+                                           "(false / 0) is supported." % (name, value))
+        return
+    raise IllegalArgumentException("Input %s has unsupported type %s: only boolean / numeric inference-phase switches can be "
+                                   "honoured." % (name, type(value).__name__))
+
+
 class TensorflowModel:
     def __init__(self, device: int = 0, precision: int = capi.PREC_FP32):
         self.properties: Dict[str, Any] = {}
@@ -71,8 +84,12 @@ class TensorflowModel:
         if not self.tags:
             raise RuntimeError("Tags is null")
         # SavedModelBundle.load(modelPath, tags) + feed inputNames[0] / fetch outputNames by op name (:71,85,169).
-        # Extra named inputs (inputNames[1:], e.g. a Keras learning-phase bool taken from `properties`, :73-83) are
-        # inference-time constants: the graph walk of the loader follows the inference branch, so they are not fed.
+        # Extra named inputs (inputNames[1:], fed from `properties` as constants, :73-83 - in the reference's test a Keras
+        # learning-phase bool): the loader walks the INFERENCE branch of the graph, so such an input is honoured only when it
+        # selects that branch.  False / 0 -> accepted (not fed); missing -> skipped like the reference's catch block (:78-80);
+        # True / non-zero (training branch: dropout active) or any other type -> rejected here, at init.
+        for name in self.inputNames[1:]:
+            check_phase_switch(name, self.properties.get(name))
         self._model = capi.Model.load(self.modelPath, self.inputNames[0], self.outputNames, tag=self.tags[0],
                                       device=self._device, precision=self._precision)
         self.initiate = True

@@ -126,6 +126,16 @@ def test_scorer_init_errors_match_tensorflowmodel(sb):
         TensorflowModel().init({"inputnames": [], "properties": base})
     with pytest.raises(IllegalArgumentException):
         TensorflowModel().init({"inputnames": ["a"], "properties": dict(base, outputnames=["o1", "o2"])})
+    # extra named inputs (TensorflowModel.java:73-83; TensorflowModelTest.java:44-47 feeds a Keras learning-phase bool):
+    # accepted when they select the inference branch, rejected when they ask for training or are not a phase switch
+    from shifu_tensorflow_b200.scorer import check_phase_switch
+    for ok in (False, 0, 0.0, None, np.bool_(False)):
+        check_phase_switch("dropout_1/keras_learning_phase", ok)
+    for bad in (True, 1, 0.5, "false", [0]):
+        with pytest.raises(IllegalArgumentException):
+            check_phase_switch("dropout_1/keras_learning_phase", bad)
+    with pytest.raises(IllegalArgumentException, match="training branch"):
+        TensorflowModel().init({"inputnames": ["a", "phase"], "properties": dict(base, phase=True)})
 
 
 def _run_worker(sb, tmp_path, n_rows, epochs, params_extra, seed=5, env_extra=None):
