@@ -163,6 +163,8 @@ int sb_trainer_apply_accumulated_mean(sb_trainer_t* t, int64_t total_pushes);
  * set in RAM and slice mini-batches from it; here the set lives in HBM and each step reads its
  * rows [row_offset, row_offset+rows) from there.  Calling load again replaces the set. */
 int sb_trainer_load_dataset(sb_trainer_t* t, const float* X, const float* y, const float* w, int64_t n_rows);
+/* (X / y / w of sb_trainer_load_dataset, sb_trainer_eval_loss and sb_trainer_predict may be HOST or DEVICE pointers on the
+ * trainer's device: sb_text_parse_device hands the parsed set over without a host round trip.) */
 int sb_trainer_step_resident(sb_trainer_t* t, int64_t row_offset, int32_t rows, float* loss_out);
 /* same, but does not wait for the GPU: the loss of step i is readable after sb_trainer_sync */
 int sb_trainer_step_resident_async(sb_trainer_t* t, int64_t row_offset, int32_t rows);
@@ -252,6 +254,22 @@ typedef struct { int64_t row; int32_t slot; int32_t len; int64_t offset; } sb_ce
 int sb_text_parse(const char* text, int64_t n_bytes, char delim, const int32_t* col_map, int32_t n_map, int32_t n_feat,
                   float* X, float* y, float* w, int64_t max_rows, int64_t* n_rows_out, sb_cell_flag* flags,
                   int64_t flag_cap, int64_t* n_flags_out, int device);
+/* The same parse with the result left ON THE DEVICE: *dX [rows, n_feat], *dy, *dw are cudaMalloc'ed by the library (release
+ * with sb_device_free) and go straight into sb_trainer_load_dataset / sb_trainer_eval_loss; only the flag list (cells for
+ * the caller's float(), patched in with sb_device_patch_f32) and 4 bytes per row (weights, for the n_nz prefix counts) ever
+ * reach the host.  kernel_ms_out (nullable): device time of the three parsing kernels (HBM-bound: text read twice for the
+ * line index, once for the cells; X written once) - bench.py's `ingest` roofline. */
+int sb_text_parse_device(const char* text, int64_t n_bytes, char delim, const int32_t* col_map, int32_t n_map, int32_t n_feat,
+                         float** dX, float** dy, float** dw, int64_t* n_rows_out, sb_cell_flag* flags, int64_t flag_cap,
+                         int64_t* n_flags_out, int device, float* kernel_ms_out);
+int sb_device_alloc_f32(float** out, int64_t n, int device);
+int sb_device_free(void* p);
+int sb_device_patch_f32(float* d_base, int64_t index, float value);
+int sb_device_read_f32(const float* d_src, int64_t n, float* host_out);
+/* d_dst[i, :] = d_src[rows_host[i], :] - the train / valid split of the parsed set (the Bernoulli coins of
+ * ssgd_monitor.py:396 are drawn on the host from the caller's RNG; only the row indices travel) */
+int sb_device_gather_rows(const float* d_src, int32_t n_cols, const int64_t* rows_host, int64_t n, float* d_dst, int device);
+
 /* test hook: the same parsing state machine run on the host (CPU unit tests of the number parser; not a product path) */
 int sb_debug_text_parse_host(const char* text, int64_t n_bytes, char delim, const int32_t* col_map, int32_t n_map,
                              int32_t n_feat, float* X, float* y, float* w, int64_t max_rows, int64_t* n_rows_out,

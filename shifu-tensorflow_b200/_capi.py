@@ -129,6 +129,13 @@ PROTOTYPES = {
     "sb_model_stream": (C.c_void_p, [_vp]),
     "sb_text_parse": (C.c_int, [_cp, C.c_int64, C.c_char, _P(C.c_int32), C.c_int32, C.c_int32, _f32p, _f32p, _f32p, C.c_int64,
                                 _P(C.c_int64), _P(CellFlag), C.c_int64, _P(C.c_int64), C.c_int]),
+    "sb_text_parse_device": (C.c_int, [_cp, C.c_int64, C.c_char, _P(C.c_int32), C.c_int32, C.c_int32, _P(_f32p), _P(_f32p), _P(_f32p),
+                                       _P(C.c_int64), _P(CellFlag), C.c_int64, _P(C.c_int64), C.c_int, _f32p]),
+    "sb_device_alloc_f32": (C.c_int, [_P(_f32p), C.c_int64, C.c_int]),
+    "sb_device_free": (C.c_int, [_vp]),
+    "sb_device_patch_f32": (C.c_int, [_f32p, C.c_int64, C.c_float]),
+    "sb_device_read_f32": (C.c_int, [_f32p, C.c_int64, _f32p]),
+    "sb_device_gather_rows": (C.c_int, [_f32p, C.c_int32, _P(C.c_int64), C.c_int64, _f32p, C.c_int]),
     "sb_debug_text_parse_host": (C.c_int, [_cp, C.c_int64, C.c_char, _P(C.c_int32), C.c_int32, C.c_int32, _f32p, _f32p, _f32p,
                                            C.c_int64, _P(C.c_int64), _P(CellFlag), C.c_int64, _P(C.c_int64)]),
     "sb_savedmodel_write": (C.c_int, [_cp, _P(NetDesc), _f32p, C.c_int64]),
@@ -173,8 +180,58 @@ def _f32(a, shape=None) -> np.ndarray:
     return a
 
 
-def _ptr(a: Optional[np.ndarray]):
-    return None if a is None else a.ctypes.data_as(_f32p)
+def _ptr(a):
+    if a is None:
+        return None
+    if hasattr(a, "ptr") and not isinstance(a, np.ndarray):      # DeviceArray
+        return a.ptr
+    return a.ctypes.data_as(_f32p)
+
+
+class DeviceArray:
+    """fp32 array that lives in GPU memory (library-owned; what sb_text_parse_device returns).  Accepted by
+    Trainer.load_dataset / eval_loss / predict in place of a numpy array."""
+
+    def __init__(self, ptr, shape, device: int = 0, owner: bool = True):
+        self.ptr, self.shape, self.device, self._own = ptr, tuple(shape), device, owner
+
+    @classmethod
+    def empty(cls, shape, device: int = 0) -> "DeviceArray":
+        p = _f32p()
+        n = int(np.prod(shape))
+        check(lib().sb_device_alloc_f32(C.byref(p), max(n, 1), device))
+        return cls(p, shape, device)
+
+    def __len__(self):
+        return self.shape[0]
+
+    @property
+    def size(self) -> int:
+        return int(np.prod(self.shape))
+
+    def numpy(self) -> np.ndarray:
+        out = np.empty(self.shape, np.float32)
+        if self.size:
+            check(lib().sb_device_read_f32(self.ptr, self.size, _ptr(out)))
+        return out
+
+    def patch(self, flat_index: int, value: float):
+        check(lib().sb_device_patch_f32(self.ptr, int(flat_index), float(value)))
+
+    def take_rows(self, rows) -> "DeviceArray":
+        """rows (host int64 indices) gathered on the device into a new DeviceArray"""
+        rows = np.ascontiguousarray(rows, dtype=np.int64)
+        n_cols = int(np.prod(self.shape[1:])) if len(self.shape) > 1 else 1
+        out = DeviceArray.empty((len(rows),) + self.shape[1:], self.device)
+        check(lib().sb_device_gather_rows(self.ptr, n_cols, rows.ctypes.data_as(_P(C.c_int64)), len(rows), out.ptr, self.device))
+        return out
+
+    def free(self):
+        if self._own and self.ptr:
+            lib().sb_device_free(C.cast(self.ptr, _vp))
+        self.ptr = None
+
+    __del__ = free
 
 
 class Trainer:
@@ -249,6 +306,11 @@ class Trainer:
 
     # ---- steps ----
     def _xyw(self, X, y, w):
+        if isinstance(X, DeviceArray):          # device-resident set: pointers pass through
+            rows = X.shape[0]
+            if len(X.shape) != 2 or X.shape[1] != self.n_features or y.size != rows or (w is not None and w.size != rows):
+                raise ValueError("device arrays must be X [rows, %d], y [rows], w [rows]" % self.n_features)
+            return X, y, w, rows
         X = _f32(X)
         rows = X.shape[0]
         if X.ndim != 2 or X.shape[1] != self.n_features:
@@ -533,6 +595,23 @@ def debug_gemm_bench(M: int, N: int, K: int, split_k: int = 1, a_mn: bool = Fals
     check(lib().sb_debug_gemm_bench(_ptr(A), _ptr(B), _ptr(D), M, N, K, split_k, int(a_mn), int(b_mn), cg, bn, device,
                                     iters, C.byref(ms)))
     return float(ms.value)
+
+
+def text_parse_device(text: bytes, col_map: Sequence[int], n_feat: int, delim: str = "|", device: int = 0, flag_cap: int = 65536):
+    """sb_text_parse_device: -> (X DeviceArray [rows, n_feat], y DeviceArray [rows], w DeviceArray [rows], flags, text, kernel_ms)"""
+    if not text.endswith(b"\n"):
+        text = text + b"\n"
+    cm = (C.c_int32 * len(col_map))(*[int(c) for c in col_map])
+    dX, dy, dw = _f32p(), _f32p(), _f32p()
+    flags = (CellFlag * flag_cap)()
+    n_rows, n_flags, kms = C.c_int64(0), C.c_int64(0), C.c_float(0)
+    check(lib().sb_text_parse_device(text, len(text), delim.encode()[:1], cm, len(col_map), n_feat, C.byref(dX), C.byref(dy), C.byref(dw),
+                                     C.byref(n_rows), flags, flag_cap, C.byref(n_flags), device, C.byref(kms)))
+    if n_flags.value > flag_cap:
+        raise ShifuB200Error(SB_ERR_FORMAT, "%d cells need the slow path, more than flag_cap=%d" % (n_flags.value, flag_cap))
+    fl = [(int(flags[i].row), int(flags[i].slot), int(flags[i].offset), int(flags[i].len)) for i in range(n_flags.value)]
+    n = n_rows.value
+    return DeviceArray(dX, (n, n_feat), device), DeviceArray(dy, (n,), device), DeviceArray(dw, (n,), device), fl, text, float(kms.value)
 
 
 def text_parse(text: bytes, col_map: Sequence[int], n_feat: int, delim: str = "|", device: int = 0, host_debug: bool = False,

@@ -398,6 +398,15 @@ static int finish_loss(sb_trainer* t, float* loss_out) {
   return SB_OK;
 }
 
+// X / y / w of load_dataset, eval_loss and predict may be HOST or DEVICE pointers (unified addressing: the copies use
+// cudaMemcpyDefault); the GPU text ingest hands over device arrays so that the parsed set never visits the host
+static bool is_device_ptr(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return at.type == cudaMemoryTypeDevice;
+}
+
 static int stage_host_batch(sb_trainer* t, const float* X, const float* y, const float* w, int rows) {
   Net& n = t->net;
   SB_CHECK(X && y, SB_ERR_INVALID, "X and y must not be null");
@@ -882,9 +891,9 @@ int sb_trainer_load_dataset(sb_trainer_t* t, const float* X, const float* y, con
   t->dsX = t->dsY = t->dsW = nullptr; t->dsXb = nullptr; t->dsP = nullptr; t->ds_rows = 0;
   SB_CUDA(cudaMalloc(&t->dsY, sizeof(float) * n_rows));
   SB_CUDA(cudaMalloc(&t->dsW, sizeof(float) * n_rows));
-  SB_CUDA(cudaMemcpyAsync(t->dsY, y, sizeof(float) * n_rows, cudaMemcpyHostToDevice, n.stream));
+  SB_CUDA(cudaMemcpyAsync(t->dsY, y, sizeof(float) * n_rows, cudaMemcpyDefault, n.stream));
   if (w) {
-    SB_CUDA(cudaMemcpyAsync(t->dsW, w, sizeof(float) * n_rows, cudaMemcpyHostToDevice, n.stream));
+    SB_CUDA(cudaMemcpyAsync(t->dsW, w, sizeof(float) * n_rows, cudaMemcpyDefault, n.stream));
   } else {
     fill_kernel<<<static_cast<unsigned>((n_rows + 255) / 256), 256, 0, n.stream>>>(t->dsW, 1.f, n_rows);
     SB_CUDA(cudaGetLastError());
@@ -902,7 +911,7 @@ int sb_trainer_load_dataset(sb_trainer_t* t, const float* X, const float* y, con
     SB_CUDA(cudaMalloc(&tmp, sizeof(float) * static_cast<size_t>(win < n_rows ? win : n_rows) * n.F));
     for (int64_t r0 = 0; r0 < n_rows; r0 += win) {
       const int64_t c = n_rows - r0 < win ? n_rows - r0 : win;
-      SB_CUDA(cudaMemcpyAsync(tmp, X + r0 * n.F, sizeof(float) * c * n.F, cudaMemcpyHostToDevice, n.stream));
+      SB_CUDA(cudaMemcpyAsync(tmp, X + r0 * n.F, sizeof(float) * c * n.F, cudaMemcpyDefault, n.stream));
       cast_bf16_kernel<<<static_cast<unsigned>((c * n.F + 255) / 256), 256, 0, n.stream>>>(tmp, static_cast<int>(c), n.F,
                                                                                            t->dsXb + r0 * n.ldF, n.ldF, n.nparts,
                                                                                            n.resident_ps);
@@ -912,7 +921,14 @@ int sb_trainer_load_dataset(sb_trainer_t* t, const float* X, const float* y, con
     cudaFree(tmp);
     std::vector<int> prefix(static_cast<size_t>(n_rows) + 1);
     prefix[0] = 0;
-    for (int64_t i = 0; i < n_rows; ++i) prefix[i + 1] = prefix[i] + ((w == nullptr || w[i] != 0.f) ? 1 : 0);
+    std::vector<float> w_host;
+    const float* wh = w;
+    if (is_device_ptr(w)) {      // 4 bytes per row: the only part of a device-resident set the host looks at
+      w_host.resize(static_cast<size_t>(n_rows));
+      SB_CUDA(cudaMemcpy(w_host.data(), w, sizeof(float) * n_rows, cudaMemcpyDeviceToHost));
+      wh = w_host.data();
+    }
+    for (int64_t i = 0; i < n_rows; ++i) prefix[i + 1] = prefix[i] + ((wh == nullptr || wh[i] != 0.f) ? 1 : 0);
     SB_CUDA(cudaMalloc(&t->dsP, sizeof(int) * (n_rows + 1)));
     SB_CUDA(cudaMemcpyAsync(t->dsP, prefix.data(), sizeof(int) * (n_rows + 1), cudaMemcpyHostToDevice, n.stream));
     SB_CUDA(cudaStreamSynchronize(n.stream));
@@ -920,7 +936,7 @@ int sb_trainer_load_dataset(sb_trainer_t* t, const float* X, const float* y, con
     n.resident_rows = n_rows;
   } else {
     SB_CUDA(cudaMalloc(&t->dsX, sizeof(float) * n_rows * n.F));
-    SB_CUDA(cudaMemcpyAsync(t->dsX, X, sizeof(float) * n_rows * n.F, cudaMemcpyHostToDevice, n.stream));
+    SB_CUDA(cudaMemcpyAsync(t->dsX, X, sizeof(float) * n_rows * n.F, cudaMemcpyDefault, n.stream));
   }
   SB_CUDA(cudaStreamSynchronize(n.stream));
   t->ds_rows = n_rows;
@@ -1201,16 +1217,16 @@ static int forward_chunks(Net& n, const float* X, const float* y, const float* w
   float h[SCAL_COUNT];
   for (int64_t r0 = 0; r0 < rows; r0 += n.max_batch) {
     const int c = static_cast<int>(rows - r0 < n.max_batch ? rows - r0 : n.max_batch);
-    SB_CUDA(cudaMemcpyAsync(n.stX, X + r0 * n.F, sizeof(float) * c * static_cast<size_t>(n.F), cudaMemcpyHostToDevice, n.stream));
+    SB_CUDA(cudaMemcpyAsync(n.stX, X + r0 * n.F, sizeof(float) * c * static_cast<size_t>(n.F), cudaMemcpyDefault, n.stream));
     if (do_loss) {
-      SB_CUDA(cudaMemcpyAsync(n.stY, y + r0, sizeof(float) * c, cudaMemcpyHostToDevice, n.stream));
-      if (w) SB_CUDA(cudaMemcpyAsync(n.stW, w + r0, sizeof(float) * c, cudaMemcpyHostToDevice, n.stream));
+      SB_CUDA(cudaMemcpyAsync(n.stY, y + r0, sizeof(float) * c, cudaMemcpyDefault, n.stream));
+      if (w) SB_CUDA(cudaMemcpyAsync(n.stW, w + r0, sizeof(float) * c, cudaMemcpyDefault, n.stream));
     }
     set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, n.stX, n.stY, (do_loss && w) ? n.stW : n.ones, 0.f, 1.f);
     SB_TRY(n.enqueue_load(c));
     SB_TRY(n.enqueue_hidden_forward(c));
     SB_TRY(n.enqueue_out(c, do_loss, false, n.yhat, nullptr));
-    if (out) SB_CUDA(cudaMemcpyAsync(out + r0, n.yhat, sizeof(float) * c, cudaMemcpyDeviceToHost, n.stream));
+    if (out) SB_CUDA(cudaMemcpyAsync(out + r0, n.yhat, sizeof(float) * c, cudaMemcpyDefault, n.stream));
     if (do_loss) SB_CUDA(cudaMemcpyAsync(h, n.scal, sizeof(h), cudaMemcpyDeviceToHost, n.stream));
     SB_CUDA(cudaStreamSynchronize(n.stream));
     if (do_loss) { *loss_sum += h[SCAL_LOSS_SUM]; *nnz += h[SCAL_NNZ]; }

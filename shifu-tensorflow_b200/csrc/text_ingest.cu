@@ -166,13 +166,29 @@ using namespace sb;
 
 static_assert(sizeof(sb_cell_flag) == sizeof(CellFlag), "flag layout");
 
-static int check_args(const char* text, int64_t n_bytes, const int32_t* col_map, int32_t n_map, int32_t n_feat, float* X, float* y,
-                      float* w, int64_t* n_rows_out, int64_t* n_flags_out) {
+// rows of a row-major fp32 matrix picked by index (train / valid split of the parsed set, on the device)
+static __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, int n_cols, const long long* __restrict__ rows,
+                                                                 long long n, float* __restrict__ dst) {
+  const long long total = n * n_cols;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += gridDim.x * 256ll) {
+    const long long r = i / n_cols;
+    dst[i] = __ldg(src + rows[r] * n_cols + (i - r * n_cols));
+  }
+}
+
+static int check_args(const char* text, int64_t n_bytes, const int32_t* col_map, int32_t n_map, int32_t n_feat, const void* X, const void* y,
+                      const void* w, int64_t* n_rows_out, int64_t* n_flags_out) {
   SB_CHECK(text && col_map && X && y && w && n_rows_out && n_flags_out, SB_ERR_INVALID, "null argument");
   SB_CHECK(n_bytes > 0 && n_map > 0 && n_feat > 0, SB_ERR_INVALID, "empty input");
   SB_CHECK(text[n_bytes - 1] == '\n', SB_ERR_INVALID, "text must end with a newline");
   return SB_OK;
 }
+
+// keep != nullptr: the parsed arrays stay on the device (keep[0..2] = X, y, w; caller frees with sb_device_free) and
+// nothing but the flags travels back; kernel_ms (nullable) = device time of the three parsing kernels
+static int text_parse_impl(const char* text, int64_t n_bytes, char delim, const int32_t* col_map, int32_t n_map, int32_t n_feat, float* X,
+                           float* y, float* w, int64_t max_rows, int64_t* n_rows_out, sb_cell_flag* flags, int64_t flag_cap,
+                           int64_t* n_flags_out, int device, float** keep, float* kernel_ms);
 
 extern "C" {
 
@@ -180,6 +196,71 @@ int sb_text_parse(const char* text, int64_t n_bytes, char delim, const int32_t* 
                   float* y, float* w, int64_t max_rows, int64_t* n_rows_out, sb_cell_flag* flags, int64_t flag_cap,
                   int64_t* n_flags_out, int device) {
   SB_TRY(check_args(text, n_bytes, col_map, n_map, n_feat, X, y, w, n_rows_out, n_flags_out));
+  return text_parse_impl(text, n_bytes, delim, col_map, n_map, n_feat, X, y, w, max_rows, n_rows_out, flags, flag_cap, n_flags_out, device,
+                         nullptr, nullptr);
+}
+
+int sb_text_parse_device(const char* text, int64_t n_bytes, char delim, const int32_t* col_map, int32_t n_map, int32_t n_feat,
+                         float** dX, float** dy, float** dw, int64_t* n_rows_out, sb_cell_flag* flags, int64_t flag_cap,
+                         int64_t* n_flags_out, int device, float* kernel_ms_out) {
+  SB_TRY(check_args(text, n_bytes, col_map, n_map, n_feat, dX, dy, dw, n_rows_out, n_flags_out));
+  float* keep[3] = {nullptr, nullptr, nullptr};
+  SB_TRY(text_parse_impl(text, n_bytes, delim, col_map, n_map, n_feat, nullptr, nullptr, nullptr, INT64_MAX, n_rows_out, flags, flag_cap,
+                         n_flags_out, device, keep, kernel_ms_out));
+  *dX = keep[0]; *dy = keep[1]; *dw = keep[2];
+  return SB_OK;
+}
+
+int sb_device_free(void* p) {
+  if (p) SB_CUDA(cudaFree(p));
+  return SB_OK;
+}
+
+int sb_device_alloc_f32(float** out, int64_t n, int device) {
+  SB_CHECK(out && n > 0, SB_ERR_INVALID, "bad argument");
+  SB_CUDA(cudaSetDevice(device));
+  void* q = nullptr;
+  SB_CUDA(cudaMalloc(&q, sizeof(float) * static_cast<size_t>(n)));
+  *out = static_cast<float*>(q);
+  return SB_OK;
+}
+
+int sb_device_patch_f32(float* d_base, int64_t index, float value) {
+  SB_CHECK(d_base && index >= 0, SB_ERR_INVALID, "bad argument");
+  SB_CUDA(cudaMemcpy(d_base + index, &value, sizeof(float), cudaMemcpyHostToDevice));
+  return SB_OK;
+}
+
+int sb_device_read_f32(const float* d_src, int64_t n, float* host_out) {
+  SB_CHECK(d_src && host_out && n >= 0, SB_ERR_INVALID, "bad argument");
+  SB_CUDA(cudaMemcpy(host_out, d_src, sizeof(float) * static_cast<size_t>(n), cudaMemcpyDeviceToHost));
+  return SB_OK;
+}
+
+int sb_device_gather_rows(const float* d_src, int32_t n_cols, const int64_t* rows_host, int64_t n, float* d_dst, int device) {
+  SB_CHECK(d_src && rows_host && d_dst && n_cols > 0 && n >= 0, SB_ERR_INVALID, "bad argument");
+  if (n == 0) return SB_OK;
+  SB_CUDA(cudaSetDevice(device));
+  long long* d_rows = nullptr;
+  SB_CUDA(cudaMalloc(&d_rows, sizeof(long long) * static_cast<size_t>(n)));
+  cudaError_t e = cudaMemcpy(d_rows, rows_host, sizeof(long long) * static_cast<size_t>(n), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    long long blocks = (n * n_cols + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    gather_rows_kernel<<<static_cast<unsigned>(blocks), 256>>>(d_src, n_cols, d_rows, n, d_dst);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  }
+  cudaFree(d_rows);
+  SB_CHECK(e == cudaSuccess, SB_ERR_CUDA, "gather_rows failed: %s", cudaGetErrorString(e));
+  return SB_OK;
+}
+
+}  // extern "C"
+
+static int text_parse_impl(const char* text, int64_t n_bytes, char delim, const int32_t* col_map, int32_t n_map, int32_t n_feat, float* X,
+                           float* y, float* w, int64_t max_rows, int64_t* n_rows_out, sb_cell_flag* flags, int64_t flag_cap,
+                           int64_t* n_flags_out, int device, float** keep, float* kernel_ms) {
   int n_dev = 0;
   SB_CHECK(cudaGetDeviceCount(&n_dev) == cudaSuccess && n_dev > 0, SB_ERR_CUDA,
            "no CUDA device available; this library has no CPU fallback");
@@ -194,16 +275,24 @@ int sb_text_parse(const char* text, int64_t n_bytes, char delim, const int32_t* 
   CellFlag* d_flags = nullptr;
   unsigned long long* d_nflags = nullptr;
   int s = SB_OK;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  float k_ms = 0.f;
   auto cleanup = [&]() {
     cudaFree(d_text); cudaFree(d_counts); cudaFree(d_base); cudaFree(d_lines); cudaFree(d_map);
     cudaFree(dX); cudaFree(dy); cudaFree(dw); cudaFree(d_flags); cudaFree(d_nflags);
+    if (ev[0]) cudaEventDestroy(ev[0]);
+    if (ev[1]) cudaEventDestroy(ev[1]);
   };
+  auto tick = [&](int i) { if (kernel_ms) { if (!ev[i]) cudaEventCreate(&ev[i]); cudaEventRecord(ev[i], 0); } };
+  auto tock = [&]() { if (kernel_ms) { float m = 0.f; cudaEventSynchronize(ev[1]); cudaEventElapsedTime(&m, ev[0], ev[1]); k_ms += m; } };
 #define SB_G(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return set_error(SB_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); } } while (0)
   SB_G(cudaMalloc(&d_text, padded));
   SB_G(cudaMemset(d_text + n_bytes, 0, padded - n_bytes));
   SB_G(cudaMemcpy(d_text, text, n_bytes, cudaMemcpyHostToDevice));
   SB_G(cudaMalloc(&d_counts, sizeof(int) * n_chunks));
+  tick(0);
   count_newlines_kernel<<<static_cast<unsigned>(n_chunks), 256>>>(d_text, n_bytes, d_counts);
+  tick(1); tock();
   std::vector<int> counts(static_cast<size_t>(n_chunks));
   SB_G(cudaMemcpy(counts.data(), d_counts, sizeof(int) * n_chunks, cudaMemcpyDeviceToHost));
   std::vector<long long> base(static_cast<size_t>(n_chunks));
@@ -214,7 +303,9 @@ int sb_text_parse(const char* text, int64_t n_bytes, char delim, const int32_t* 
   SB_G(cudaMemcpy(d_base, base.data(), sizeof(long long) * n_chunks, cudaMemcpyHostToDevice));
   SB_G(cudaMalloc(&d_lines, sizeof(long long) * (n_lines + 1)));
   SB_G(cudaMemset(d_lines, 0, sizeof(long long)));
+  tick(0);
   line_offsets_kernel<<<static_cast<unsigned>(n_chunks), 256>>>(d_text, n_bytes, d_base, d_lines);
+  tick(1); tock();
   SB_G(cudaMalloc(&d_map, sizeof(int) * n_map));
   SB_G(cudaMemcpy(d_map, col_map, sizeof(int) * n_map, cudaMemcpyHostToDevice));
   SB_G(cudaMalloc(&dX, sizeof(float) * n_lines * n_feat));
@@ -228,11 +319,18 @@ int sb_text_parse(const char* text, int64_t n_bytes, char delim, const int32_t* 
   SB_G(cudaMemset(d_nflags, 0, sizeof(unsigned long long)));
   ParseArgs a = {d_text, d_lines, n_lines, d_map, n_map, n_feat, static_cast<unsigned char>(delim), dX, dy, dw, d_flags,
                  flags ? flag_cap : 0, d_nflags};
+  tick(0);
   if (n_lines > 0) parse_lines_kernel<<<static_cast<unsigned>((n_lines + 127) / 128), 128>>>(a);
+  tick(1);
   SB_G(cudaGetLastError());
-  SB_G(cudaMemcpy(X, dX, sizeof(float) * n_lines * n_feat, cudaMemcpyDeviceToHost));
-  SB_G(cudaMemcpy(y, dy, sizeof(float) * n_lines, cudaMemcpyDeviceToHost));
-  SB_G(cudaMemcpy(w, dw, sizeof(float) * n_lines, cudaMemcpyDeviceToHost));
+  SB_G(cudaDeviceSynchronize());
+  tock();
+  if (kernel_ms) *kernel_ms = k_ms;
+  if (keep == nullptr) {
+    SB_G(cudaMemcpy(X, dX, sizeof(float) * n_lines * n_feat, cudaMemcpyDeviceToHost));
+    SB_G(cudaMemcpy(y, dy, sizeof(float) * n_lines, cudaMemcpyDeviceToHost));
+    SB_G(cudaMemcpy(w, dw, sizeof(float) * n_lines, cudaMemcpyDeviceToHost));
+  }
   unsigned long long nf = 0;
   SB_G(cudaMemcpy(&nf, d_nflags, sizeof(nf), cudaMemcpyDeviceToHost));
   if (flags && nf > 0) {
@@ -240,11 +338,14 @@ int sb_text_parse(const char* text, int64_t n_bytes, char delim, const int32_t* 
     SB_G(cudaMemcpy(flags, d_flags, sizeof(CellFlag) * m, cudaMemcpyDeviceToHost));
   }
 #undef SB_G
+  if (keep != nullptr) { keep[0] = dX; keep[1] = dy; keep[2] = dw; dX = dy = dw = nullptr; }   // ownership moves to the caller
   cleanup();
   *n_rows_out = n_lines;
   *n_flags_out = static_cast<int64_t>(nf);
   return s;
 }
+
+extern "C" {
 
 // TEST HOOK: the identical state machine (text_parse.cuh / parse_line) executed on the host, so that the number
 // parsing can be checked against Python's float() in the CPU test-suite.  Not a product path.

@@ -214,7 +214,8 @@ def load_data_gpu(data_file: str, feature_column_nums: Optional[List[int]], targ
     """load_data with the per-cell float() loop moved to the GPU (sb_text_parse): the host only gunzips and draws the
     train/valid coin per line (same `rng.random() >= ratio -> train` stream, ssgd_monitor.py:396); cells the exact
     fast path declines come back as a list and are resolved with float() here, exactly like the reference would.
-    Returns numpy arrays under the same keys as load_data."""
+    Returns capi.DeviceArray objects under the same keys as load_data: the parsed set never visits the host (the trainer's
+    load_dataset / eval_loss take device pointers)."""
     chunks = []
     for current_file in data_file.split(","):
         data = gzip.GzipFile(fileobj=io.BytesIO(_Fs.read_bytes(current_file))).read()
@@ -233,22 +234,31 @@ def load_data_gpu(data_file: str, feature_column_nums: Optional[List[int]], targ
     col_map[target_column_num] = capi.COL_TARGET
     if sample_weight_column_num >= 0:
         col_map[sample_weight_column_num] = capi.COL_WEIGHT
-    X, y, w, flags, text = capi.text_parse(text, col_map, len(feature_column_nums), DELIMITER, device=device)
+    n_feat = len(feature_column_nums)
+    X, y, w, flags, text, _kernel_ms = capi.text_parse_device(text, col_map, n_feat, DELIMITER, device=device)
     for row, slot, off, ln in flags:
         if slot == -100:
             raise ValueError("line %d does not have the selected columns" % row)
         cell = text[off:off + ln].decode('utf-8')
         v = float(cell.strip('\n'))        # ValueError here = the cell the reference would log and skip
         if slot >= 0:
-            X[row, slot] = v
+            X.patch(row * n_feat + slot, v)
         elif slot == capi.COL_TARGET:
-            y[row] = v
+            y.patch(row, v)
         else:
-            w[row] = 1.0 if v < 0.0 else v
+            w.patch(row, 1.0 if v < 0.0 else v)
+    # the Bernoulli coins come from the caller's RNG (one draw per line, in line order, like the reference); only the row
+    # indices of the two sides travel to the device, the parsed set itself stays there
     coins = np.fromiter((rng.random() >= valid_ratio for _ in range(len(y))), dtype=bool, count=len(y))
-    return {"train_data": X[coins], "train_target": y[coins].reshape(-1, 1), "train_data_sample_weight": w[coins].reshape(-1, 1),
-            "valid_data": X[~coins], "valid_target": y[~coins].reshape(-1, 1), "valid_data_sample_weight": w[~coins].reshape(-1, 1),
-            "feature_count": len(feature_column_nums)}
+    tr_rows, va_rows = np.flatnonzero(coins), np.flatnonzero(~coins)
+    out = {"feature_count": n_feat}
+    for pre, rows in (("train", tr_rows), ("valid", va_rows)):
+        out[pre + "_data"] = X.take_rows(rows)
+        out[pre + "_target"] = y.take_rows(rows)
+        out[pre + "_data_sample_weight"] = w.take_rows(rows)
+    for a in (X, y, w):
+        a.free()
+    return out
 
 
 def simple_save(trainer: capi.Trainer, export_dir: str) -> None:
@@ -533,19 +543,34 @@ def main(_=None, env=None, rng=random) -> int:
     else:
         context = load_data_gpu(training_data_path, feature_column_nums, target_column_num, sample_weight_column_num,
                                 valid_ratio, rng=rng, device=device)
-    train_x = np.asarray(context["train_data"], dtype=np.float32)
-    if train_x.ndim != 2 or train_x.shape[1] != feature_count:
-        raise ValueError("training rows do not all have %d parsable features" % feature_count)
-    train_y = np.asarray(context["train_target"], dtype=np.float32).reshape(-1)
-    train_w = np.asarray(context["train_data_sample_weight"], dtype=np.float32).reshape(-1)
-    valid_x = np.asarray(context["valid_data"], dtype=np.float32).reshape(-1, feature_count)
-    valid_y = np.asarray(context["valid_target"], dtype=np.float32).reshape(-1)
-    valid_w = np.asarray(context["valid_data_sample_weight"], dtype=np.float32).reshape(-1)
-    if env.get("SB_ROW_SHARD"):
-        # launcher.py: every local rank of a container reads the container's files and keeps rows g::G, cut to the
-        # same length on every rank so that all ranks run the same number of exchanges
-        train_x, train_y, train_w = row_shard(env["SB_ROW_SHARD"], train_x, train_y, train_w)
-        valid_x, valid_y, valid_w = row_shard(env["SB_ROW_SHARD"], valid_x, valid_y, valid_w)
+    on_device = isinstance(context["train_data"], capi.DeviceArray)
+    if on_device:
+        train_x, train_y, train_w = context["train_data"], context["train_target"], context["train_data_sample_weight"]
+        valid_x, valid_y, valid_w = context["valid_data"], context["valid_target"], context["valid_data_sample_weight"]
+        if len(train_x.shape) != 2 or train_x.shape[1] != feature_count:
+            raise ValueError("training rows do not all have %d parsable features" % feature_count)
+        if env.get("SB_ROW_SHARD"):
+            g, G = (int(v) for v in env["SB_ROW_SHARD"].split("/"))
+            if not (0 <= g < G):
+                raise ValueError("SB_ROW_SHARD must be g/G with 0 <= g < G, got %r" % env["SB_ROW_SHARD"])
+            def shard(a):
+                return a.take_rows(np.arange(g, len(a), G)[:len(a) // G])
+            train_x, train_y, train_w = shard(train_x), shard(train_y), shard(train_w)
+            valid_x, valid_y, valid_w = shard(valid_x), shard(valid_y), shard(valid_w)
+    else:
+        train_x = np.asarray(context["train_data"], dtype=np.float32)
+        if train_x.ndim != 2 or train_x.shape[1] != feature_count:
+            raise ValueError("training rows do not all have %d parsable features" % feature_count)
+        train_y = np.asarray(context["train_target"], dtype=np.float32).reshape(-1)
+        train_w = np.asarray(context["train_data_sample_weight"], dtype=np.float32).reshape(-1)
+        valid_x = np.asarray(context["valid_data"], dtype=np.float32).reshape(-1, feature_count)
+        valid_y = np.asarray(context["valid_target"], dtype=np.float32).reshape(-1)
+        valid_w = np.asarray(context["valid_data_sample_weight"], dtype=np.float32).reshape(-1)
+        if env.get("SB_ROW_SHARD"):
+            # launcher.py: every local rank of a container reads the container's files and keeps rows g::G, cut to the
+            # same length on every rank so that all ranks run the same number of exchanges
+            train_x, train_y, train_w = row_shard(env["SB_ROW_SHARD"], train_x, train_y, train_w)
+            valid_x, valid_y, valid_w = row_shard(env["SB_ROW_SHARD"], valid_x, valid_y, valid_w)
     logging.info("Testing set size: %d" % len(valid_x))
     logging.info("Training set size: %d" % len(train_x))
 

@@ -127,5 +127,32 @@ def test_load_data_gpu_equals_load_data(sb, tmp_path):
     a = tr.load_data(",".join(files), list(range(1, F + 1)), 0, F + 2, 0.25, rng=random.Random(9))
     b = tr.load_data_gpu(",".join(files), list(range(1, F + 1)), 0, F + 2, 0.25, rng=random.Random(9))
     for k in ("train_data", "valid_data", "train_target", "valid_target", "train_data_sample_weight", "valid_data_sample_weight"):
-        np.testing.assert_array_equal(np.asarray(a[k], np.float32), np.asarray(b[k], np.float32), err_msg=k)
+        assert isinstance(b[k], sb.capi.DeviceArray)                  # the parsed set stays on the device ...
+        got = b[k].numpy()
+        np.testing.assert_array_equal(np.asarray(a[k], np.float32).reshape(got.shape), got, err_msg=k)   # ... with the same bits
     assert a["feature_count"] == b["feature_count"] == F
+
+
+@pytest.mark.gpu
+def test_device_resident_set_feeds_the_trainer_without_a_host_copy(sb):
+    """sb_text_parse_device -> device gather (split) -> sb_trainer_load_dataset / eval_loss on DEVICE pointers: same losses as
+    the host-array path"""
+    from oracle import shifu_oracle as so
+    F = 12
+    text = _make_text(600, F, 3, True)
+    col_map = [sb.capi.COL_TARGET] + list(range(F)) + [sb.capi.COL_SKIP, sb.capi.COL_WEIGHT]
+    Xh, yh, wh, fl_h, _ = sb.capi.text_parse(text, col_map, F)
+    Xd, yd, wd, fl_d, _, kms = sb.capi.text_parse_device(text, col_map, F)
+    assert fl_h == fl_d and kms > 0
+    np.testing.assert_array_equal(Xd.numpy(), Xh); np.testing.assert_array_equal(yd.numpy(), yh); np.testing.assert_array_equal(wd.numpy(), wh)
+    rows = np.arange(0, 600, 3)
+    np.testing.assert_array_equal(Xd.take_rows(rows).numpy(), Xh[rows])
+    desc = sb.make_desc(F, [16, 8], [so.ACT_RELU, so.ACT_TANH], optimizer=so.OPT_SGD, learning_rate=0.1, max_batch=128, precision=sb.PREC_BF16)
+    with sb.Trainer(desc) as a, sb.Trainer(desc) as b:
+        for t in (a, b):
+            t.init_xavier(5)
+        a.load_dataset(Xh, yh, wh)
+        b.load_dataset(Xd, yd, wd)
+        for k in range(4):
+            assert a.step_resident(k * 128, 128) == b.step_resident(k * 128, 128)
+        assert a.eval_loss(Xh, yh, wh) == b.eval_loss(Xd, yd, wd)
