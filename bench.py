@@ -269,6 +269,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eval", action="store_true", help="skip the batch-scoring leg (BASELINE config 5)")
     ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-ingest", action="store_true", help="skip the text-ingest leg (load_data on the GPU)")
     ap.add_argument("--sustained-seconds", type=float, default=3.0)
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-buffer leg (default: min(steps, 50))")
     ap.add_argument("--also", default="cfg1", help="second config measured on the resident leg only and reported under 'also' ('' = none)")
@@ -480,6 +481,11 @@ def main():
         if not args.no_eval and prec == sb.PREC_BF16:
             res["eval"] = eval_leg(sb, torch, c, trained, X, world, rank, local_rank, barrier, max_over_ranks, peak_tf)
 
+        # ---------------- ingest leg: load_data's per-cell float() loop on the GPU ----------------
+        res["ingest"] = None
+        if rank == 0 and world == 1 and not args.no_ingest:
+            res["ingest"] = ingest_leg(sb, local_rank, float(peaks.get("hbm_gbs", 6650.0)))
+
         # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
         res["cpu_baseline"] = None
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -503,7 +509,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == sb.PREC_BF16 else "f32", "data": "synthetic",
             "config": main_res["config"], "clocks": main_res["clocks"], "e2e": main_res["e2e"],
             "gpu_launches": main_res["gpu_launches"], "roofline": main_res["roofline"], "cpu_baseline": main_res["cpu_baseline"],
-            "sustained": main_res.get("sustained"), "eval": main_res.get("eval"),
+            "sustained": main_res.get("sustained"), "eval": main_res.get("eval"), "ingest": main_res.get("ingest"),
             "last_loss": main_res["last_loss"], "gradient_exchange": main_res["gradient_exchange"],
         }
         if second is not None:
@@ -512,6 +518,47 @@ def main():
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def ingest_leg(sb, device, hbm_gbs):
+    """load_data (ssgd_monitor.py:348-454) on the GPU: '|'-delimited normalised text -> fp32 columns, result left on the device
+    (sb_text_parse_device).  cfg0-shaped rows (target + 200 features), 40 000 lines.  HBM roofline: the three kernels read the
+    text three times (newline count, line offsets, cells) and write X once."""
+    rows, F = 40000, 200
+    rng = np.random.default_rng(SEED)
+    vals = np.clip(rng.standard_normal((rows, F)), -4, 4)
+    ys = (rng.random(rows) < 0.2).astype(int)
+    text = "\n".join("%d|" % ys[i] + "|".join("%.6f" % v for v in vals[i]) for i in range(rows)).encode() + b"\n"
+    col_map = [sb.capi.COL_TARGET] + list(range(F))
+    sb.capi.text_parse_device(text[:200000 + text[200000:].index(b"\n") + 1], col_map, F, device=device)     # warm-up
+    best_k, best_w = None, None
+    for _ in range(3):
+        t0 = time.perf_counter()
+        X, y, w, flags, _, kms = sb.capi.text_parse_device(text, col_map, F, device=device)
+        wall = time.perf_counter() - t0
+        for a in (X, y, w):
+            a.free()
+        if best_k is None or kms < best_k:
+            best_k = kms
+        if best_w is None or wall < best_w:
+            best_w = wall
+    alg = 3 * len(text) + 4 * rows * (F + 2)
+    ach = alg / (best_k * 1e-3) / 1e9
+    # the reference's own loop on the same bytes: per-cell float() in Python (bounded sample: 2 000 lines)
+    sample = text.split(b"\n", 2000)[:2000]
+    t0 = time.perf_counter()
+    for line in sample:
+        cols = line.decode().split("|")
+        float(cols[0]); [float(c) for c in cols[1:]]
+    py_s = time.perf_counter() - t0
+    py_bytes = sum(len(l) + 1 for l in sample)
+    return {"metric": "text ingest (load_data)", "rows": rows, "cols": F + 1, "text_bytes": len(text), "flagged_cells": len(flags),
+            "kernel_ms": best_k, "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_gbs, "unit": "GB/s", "frac": ach / hbm_gbs,
+                                              "algorithmic_bytes": alg, "note": "3 x text read + X/y/w written once, device time of the three kernels"},
+            "e2e": {"value": len(text) / best_w / 1e9, "unit": "GB/s of text", "seconds": best_w,
+                    "note": "sb_text_parse_device wall time incl. cudaMalloc, H2D of the text and the host-side line-count prefix"},
+            "cpu_baseline": {"value": py_bytes / py_s / 1e9, "unit": "GB/s of text", "kind": "reference loop (split + float() per cell, "
+                             "ssgd_monitor.py:387-410), 2 000 lines, 1 thread"}}
 
 
 def eval_leg(sb, torch, c, trained_params, X_host, world, rank, local_rank, barrier, max_over_ranks, peak_tf):
