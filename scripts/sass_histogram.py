@@ -27,7 +27,7 @@ def main():
             name = re.sub(r"\(.*", "", name)
             cur = fam.setdefault(name, collections.Counter())
             continue
-        m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Za-z0-9_.]+)", line)
+        m = re.match(r"\s+/\*[0-9a-f]{4,6}\*/\s+(?:@!?U?P\d+\s+)?([A-Za-z0-9_.]+)", line)
         if m and cur is not None:
             cur[m.group(1)] += 1
             cur["#instructions"] += 1

@@ -134,7 +134,10 @@ __device__ __forceinline__ void epi_da_chunk(float (&v)[32], const __nv_bfloat16
 // SB_ACT_AT_RUNTIME = read p.act.
 constexpr int SB_ACT_AT_RUNTIME = -100;
 
-template <int BN, int EPI, bool A_MN, bool B_MN, int CG, int ACT_T = SB_ACT_AT_RUNTIME>
+// GENERIC = false: the plain-bf16 epilogues (performance mode; their instruction footprint decides the epilogue speed - a
+// 7.4 k-instruction epilogue spent 38 % of its issue slots waiting for instruction fetch).  GENERIC = true adds the cold
+// features at compile time: split-precision part stores / loads (np > 1) and the fp32 addend of the wide+deep first layer.
+template <int BN, int EPI, bool A_MN, bool B_MN, int CG, int ACT_T = SB_ACT_AT_RUNTIME, bool GENERIC = false>
 __global__ void __launch_bounds__(GemmTcCfg<BN, CG>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
   using Cfg = GemmTcCfg<BN, CG>;
@@ -412,9 +415,13 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
       // split-precision output: part 0 = bf16(v), part k = bf16(v - sum of the previous parts); np = 1 is the plain store.
       // x is left untouched (the residual of part k is re-derived from x: at most two extra cvt + sub per element).
       auto store_parts = [&](const float (&x)[32], __nv_bfloat16* base, long long ps, int ld, int col0_, bool all_cols) {
-        for (int part = 0; part < p.np; ++part) {
+        const int np_ = GENERIC ? p.np : 1;
+#pragma unroll 1
+        for (int part = 0; part < np_; ++part) {
           auto res = [&](float r) {
-            for (int i = 0; i < part; ++i) r -= __bfloat162float(__float2bfloat16_rn(r));
+            if constexpr (GENERIC) {
+              for (int i = 0; i < part; ++i) r -= __bfloat162float(__float2bfloat16_rn(r));
+            }
             return r;
           };
           uint4 o[4];
@@ -581,7 +588,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
         const bool full = col0 + 32 <= p.N;  // warp-uniform fast path
 
         if constexpr (EPI == EPI_FWD) {
-          if (p.addend != nullptr && row_ok) {
+          if (GENERIC && p.addend != nullptr && row_ok) {
             const float* ad = p.addend + static_cast<size_t>(row) * p.ld_add + col0;
             if (full && (p.ld_add & 3) == 0) {
 #pragma unroll
@@ -618,7 +625,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
             for (int k = 0; k < 4; ++k) aux_q[i][k] = aux_q[i + 1][k];
           }
           __nv_bfloat16* ah = reinterpret_cast<__nv_bfloat16*>(a4);
-          if (p.np > 1 && (act_sel == SB_ACT_SIGMOID || act_sel == SB_ACT_TANH)) {
+          if (GENERIC && p.np > 1 && (act_sel == SB_ACT_SIGMOID || act_sel == SB_ACT_TANH)) {
             // act' needs the VALUE of A_{l-1}: add the lower parts (fetched here, not prefetched: the split modes are the
             // parity modes).  relu / leaky relu only look at the sign, which part 0 carries.
             float af[32];

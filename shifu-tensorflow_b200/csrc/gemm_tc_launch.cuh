@@ -4,7 +4,7 @@
 
 namespace sb {
 
-template <int BN, int EPI, bool A_MN, bool B_MN, int CG, int ACT_T = SB_ACT_AT_RUNTIME>
+template <int BN, int EPI, bool A_MN, bool B_MN, int CG, int ACT_T = SB_ACT_AT_RUNTIME, bool GENERIC = false>
 static int launch_gemm_tc_one(const GemmPlan& pl, const TmapSet& tms, const GemmTcParams& p, cudaStream_t st,
                               bool pdl) {
   using Cfg = GemmTcCfg<BN, CG>;
@@ -27,7 +27,7 @@ static int launch_gemm_tc_one(const GemmPlan& pl, const TmapSet& tms, const Gemm
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  SB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, A_MN, B_MN, CG, ACT_T>, tms, p));
+  SB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, A_MN, B_MN, CG, ACT_T, GENERIC>, tms, p));
   return SB_OK;
 }
 
@@ -48,6 +48,24 @@ template <int EPI, bool A_MN, bool B_MN>
 int launch_gemm_tc(const GemmPlan& pl, const TmapSet& tms, GemmTcParams p, cudaStream_t st, bool pdl = false) {
   if (p.np < 1) p.np = 1;
   if (p.n_pairs < 1) p.n_pairs = 1;
+  // split-precision parts or an fp32 addend: the GENERIC instantiations (the fused output layer reads its activation at run
+  // time there - three kernels instead of fifteen)
+  if constexpr (EPI == EPI_FWD || EPI == EPI_DA || EPI == EPI_FWD_OUT) {
+    if (p.np > 1 || p.addend != nullptr) {
+      constexpr int ACT_G = SB_ACT_AT_RUNTIME;
+      if constexpr (EPI == EPI_FWD_OUT) {
+        if (pl.cg == 1 && pl.bn == 64) return launch_gemm_tc_one<64, EPI, A_MN, B_MN, 1, ACT_G, true>(pl, tms, p, st, pdl);
+        if (pl.cg == 1 && pl.bn == 128) return launch_gemm_tc_one<128, EPI, A_MN, B_MN, 1, ACT_G, true>(pl, tms, p, st, pdl);
+        if (pl.cg == 1 && pl.bn == 256) return launch_gemm_tc_one<256, EPI, A_MN, B_MN, 1, ACT_G, true>(pl, tms, p, st, pdl);
+      } else {
+        if (pl.cg == 1 && pl.bn == 64) return launch_gemm_tc_one<64, EPI, A_MN, B_MN, 1, ACT_G, true>(pl, tms, p, st, pdl);
+        if (pl.cg == 1 && pl.bn == 128) return launch_gemm_tc_one<128, EPI, A_MN, B_MN, 1, ACT_G, true>(pl, tms, p, st, pdl);
+        if (pl.cg == 2 && pl.bn == 128) return launch_gemm_tc_one<128, EPI, A_MN, B_MN, 2, ACT_G, true>(pl, tms, p, st, pdl);
+        if (pl.cg == 2 && pl.bn == 256) return launch_gemm_tc_one<256, EPI, A_MN, B_MN, 2, ACT_G, true>(pl, tms, p, st, pdl);
+      }
+      return set_error(SB_ERR_INVALID, "no generic gemm_tc instantiation for cg=%d bn=%d", pl.cg, pl.bn);
+    }
+  }
   p.split_k = pl.split_k;
   p.kb_per_split = pl.kb_per_split;
   if constexpr (EPI == EPI_FWD_OUT) {
@@ -76,6 +94,11 @@ int set_gemm_tc_attrs() {
     SB_ATTR_ALL(64); SB_ATTR_ALL(128); SB_ATTR_ALL(256);
 #undef SB_ATTR_ALL
 #undef SB_ATTR_ACT
+#define SB_ATTR_G(BN)                                                                                                \
+  SB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI_FWD_OUT, A_MN, B_MN, 1, SB_ACT_AT_RUNTIME, true>,              \
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, GemmTcCfg<BN, 1>::SMEM_BYTES))
+    SB_ATTR_G(64); SB_ATTR_G(128); SB_ATTR_G(256);
+#undef SB_ATTR_G
     return SB_OK;
   } else {
 #define SB_ATTR(BN, CG)                                                                                            \
@@ -83,6 +106,13 @@ int set_gemm_tc_attrs() {
                                GemmTcCfg<BN, CG>::SMEM_BYTES))
   SB_ATTR(64, 1); SB_ATTR(128, 1); SB_ATTR(128, 2); SB_ATTR(256, 2);
 #undef SB_ATTR
+  if constexpr (EPI == EPI_FWD || EPI == EPI_DA) {
+#define SB_ATTR_G(BN, CG)                                                                                            \
+  SB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, A_MN, B_MN, CG, SB_ACT_AT_RUNTIME, true>,                      \
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, GemmTcCfg<BN, CG>::SMEM_BYTES))
+    SB_ATTR_G(64, 1); SB_ATTR_G(128, 1); SB_ATTR_G(128, 2); SB_ATTR_G(256, 2);
+#undef SB_ATTR_G
+  }
   return SB_OK;
   }
 }
