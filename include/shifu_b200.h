@@ -141,6 +141,8 @@ int sb_trainer_set_sparse(sb_trainer_t* t, int32_t n_dense, int32_t n_onehot, in
 int sb_trainer_step_sparse(sb_trainer_t* t, const float* Xd, const int32_t* idx, const float* y, const float* w,
                            int32_t rows, float* loss_out);
 int sb_trainer_predict_sparse(sb_trainer_t* t, const float* Xd, const int32_t* idx, int64_t rows, float* out);
+int sb_trainer_eval_loss_sparse(sb_trainer_t* t, const float* Xd, const int32_t* idx, const float* y, const float* w,
+                                int64_t rows, float* loss_out);
 
 /* Same step, pipelined: returns as soon as the work is queued.  The H2D copy of this batch goes through a second
  * staging slot on a copy stream and overlaps the previous step's compute; the loss of the most recent step is read

@@ -94,6 +94,7 @@ PROTOTYPES = {
     "sb_trainer_set_sparse": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32]),
     "sb_trainer_step_sparse": (C.c_int, [_vp, _f32p, _P(C.c_int32), _f32p, _f32p, C.c_int32, _f32p]),
     "sb_trainer_predict_sparse": (C.c_int, [_vp, _f32p, _P(C.c_int32), C.c_int64, _f32p]),
+    "sb_trainer_eval_loss_sparse": (C.c_int, [_vp, _f32p, _P(C.c_int32), _f32p, _f32p, C.c_int64, _f32p]),
     "sb_trainer_step_async": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_int32]),
     "sb_trainer_accumulate": (C.c_int, [_vp, _f32p, _f32p, _f32p, C.c_int32, _f32p]),
     "sb_trainer_apply_accumulated": (C.c_int, [_vp]),
@@ -354,6 +355,15 @@ class Trainer:
         out = np.empty(Xd.shape[0], np.float32)
         check(lib().sb_trainer_predict_sparse(self._h, _ptr(Xd), idx.ctypes.data_as(_P(C.c_int32)), Xd.shape[0], _ptr(out)))
         return out
+
+    def eval_loss_sparse(self, Xd, idx, y, w=None) -> float:
+        Xd, idx = self._xd_idx(Xd, idx)
+        y = _f32(y).reshape(-1)
+        w = None if w is None else _f32(w).reshape(-1)
+        loss = C.c_float()
+        check(lib().sb_trainer_eval_loss_sparse(self._h, _ptr(Xd), idx.ctypes.data_as(_P(C.c_int32)), _ptr(y), _ptr(w), Xd.shape[0],
+                                                C.byref(loss)))
+        return float(loss.value)
 
     def step_async(self, X, y, w=None) -> None:
         """queue one step on HOST buffers without waiting (X/y/w should be pinned and not reused for two more steps)"""

@@ -774,22 +774,40 @@ int sb_trainer_step_sparse(sb_trainer_t* t, const float* Xd, const int32_t* idx,
   return finish_loss(t, loss_out);
 }
 
-int sb_trainer_predict_sparse(sb_trainer_t* t, const float* Xd, const int32_t* idx, int64_t rows, float* out) {
-  SB_CHECK(t && out, SB_ERR_INVALID, "null argument");
-  Net& n = t->net;
+// forward (+ loss) over any number of sparse rows in max_batch chunks; out / loss accumulators nullable
+static int forward_chunks_sparse(Net& n, const float* Xd, const int32_t* idx, const float* y, const float* w, int64_t rows, float* out,
+                                 double* loss_sum, double* nnz) {
   struct Scope { Net& n; ~Scope() { n.sparse_step = false; } } scope{n};
+  const bool do_loss = loss_sum != nullptr;
+  float h[SCAL_COUNT];
   for (int64_t r0 = 0; r0 < rows; r0 += n.max_batch) {
     const int c = static_cast<int>(rows - r0 < n.max_batch ? rows - r0 : n.max_batch);
-    SB_TRY(stage_sparse_batch(n, Xd + r0 * n.n_dense, idx + r0 * n.n_cat, nullptr, nullptr, c));
-    set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, n.stX, n.stY, n.ones, 0.f, 1.f);
+    SB_TRY(stage_sparse_batch(n, Xd + r0 * n.n_dense, idx + r0 * n.n_cat, do_loss ? y + r0 : nullptr, (do_loss && w) ? w + r0 : nullptr, c));
+    set_batch_kernel<<<1, 1, 0, n.stream>>>(n.desc, n.stX, n.stY, (do_loss && w) ? n.stW : n.ones, 0.f, 1.f);
     n.sparse_step = true;
     SB_TRY(n.enqueue_load(c));
     SB_TRY(n.enqueue_hidden_forward(c));
     n.sparse_step = false;
-    SB_TRY(n.enqueue_out(c, false, false, n.yhat, nullptr));
-    SB_CUDA(cudaMemcpyAsync(out + r0, n.yhat, sizeof(float) * c, cudaMemcpyDeviceToHost, n.stream));
+    SB_TRY(n.enqueue_out(c, do_loss, false, n.yhat, nullptr));
+    if (out) SB_CUDA(cudaMemcpyAsync(out + r0, n.yhat, sizeof(float) * c, cudaMemcpyDeviceToHost, n.stream));
+    if (do_loss) SB_CUDA(cudaMemcpyAsync(h, n.scal, sizeof(h), cudaMemcpyDeviceToHost, n.stream));
     SB_CUDA(cudaStreamSynchronize(n.stream));
+    if (do_loss) { *loss_sum += h[SCAL_LOSS_SUM]; *nnz += h[SCAL_NNZ]; }
   }
+  return SB_OK;
+}
+
+int sb_trainer_predict_sparse(sb_trainer_t* t, const float* Xd, const int32_t* idx, int64_t rows, float* out) {
+  SB_CHECK(t && out, SB_ERR_INVALID, "null argument");
+  return forward_chunks_sparse(t->net, Xd, idx, nullptr, nullptr, rows, out, nullptr, nullptr);
+}
+
+int sb_trainer_eval_loss_sparse(sb_trainer_t* t, const float* Xd, const int32_t* idx, const float* y, const float* w, int64_t rows,
+                                float* loss_out) {
+  SB_CHECK(t && y && loss_out && rows > 0, SB_ERR_INVALID, "bad argument");
+  double ls = 0, nz = 0;
+  SB_TRY(forward_chunks_sparse(t->net, Xd, idx, y, w, rows, nullptr, &ls, &nz));
+  *loss_out = nz > 0 ? static_cast<float>(ls / nz) : 0.f;
   return SB_OK;
 }
 

@@ -501,7 +501,19 @@ def main(_=None, env=None, rng=random) -> int:
     task_index = int(env["TASK_ID"])
     socket_server_port = int(env["SOCKET_SERVER_PORT"])
     total_training_data_number = int(env["TOTAL_TRAINING_DATA_NUMBER"])
-    feature_column_nums = [int(s) for s in str(env["SELECTED_COLUMN_NUMS"]).split(' ')]
+    # Column lists: SELECTED_COLUMN_NUMS, or - when the job configuration leaves it blank - the numeric / categorical pair the
+    # executor exports instead (TensorflowTaskExecutor.java:213-223).  The reference script only ever reads the first and dies
+    # with a KeyError on the second form; here the pair selects the wide+deep model (BASELINE config 4, oracle/wide_deep.py):
+    # numeric columns -> dense block, categorical columns -> integer codes 0 .. V_c-1 (anything else = missing) whose one-hot
+    # expansion is evaluated as an embedding gather.
+    numeric_cols = [int(v) for v in str(env.get("SELECTED_NUMERIC_COLUMN_NUMS", "")).split() if int(v) >= 0]
+    category_cols = [int(v) for v in str(env.get("SELECTED_CATEGORY_COLUMN_NUMS", "")).split() if int(v) >= 0]
+    sel = str(env.get("SELECTED_COLUMN_NUMS", "")).strip()
+    wide_deep = (sel in ("", "-1")) and bool(numeric_cols) and bool(category_cols)
+    if wide_deep:
+        feature_column_nums = numeric_cols + category_cols
+    else:
+        feature_column_nums = [int(s) for s in str(env["SELECTED_COLUMN_NUMS"]).split(' ')]
     feature_count = len(feature_column_nums)
     sample_weight_column_num = int(env["WEIGHT_COLUMN_NUM"])
     target_column_num = int(env["TARGET_COLUMN_NUM"])
@@ -571,6 +583,33 @@ def main(_=None, env=None, rng=random) -> int:
             # same length on every rank so that all ranks run the same number of exchanges
             train_x, train_y, train_w = row_shard(env["SB_ROW_SHARD"], train_x, train_y, train_w)
             valid_x, valid_y, valid_w = row_shard(env["SB_ROW_SHARD"], valid_x, valid_y, valid_w)
+    vocab = offsets = None
+    if wide_deep:
+        # category codes -> global one-hot column indices.  V_c = SB_CATEGORY_VOCAB (space separated) or max code + 1 over the
+        # data this rank sees (several ranks: set SB_CATEGORY_VOCAB so that every rank builds the same model)
+        to_np = lambda a: a.numpy() if isinstance(a, capi.DeviceArray) else np.asarray(a, np.float32)
+        train_x, train_y, train_w = to_np(train_x), to_np(train_y).reshape(-1), to_np(train_w).reshape(-1)
+        valid_x, valid_y, valid_w = to_np(valid_x).reshape(-1, feature_count), to_np(valid_y).reshape(-1), to_np(valid_w).reshape(-1)
+        n_dense, n_cat = len(numeric_cols), len(category_cols)
+        codes = lambda X: np.where((X[:, n_dense:] >= 0) & (X[:, n_dense:] == np.floor(X[:, n_dense:])), X[:, n_dense:], -1).astype(np.int64)
+        tr_codes, va_codes = codes(train_x), codes(valid_x)
+        if env.get("SB_CATEGORY_VOCAB"):
+            vocab = [int(v) for v in env["SB_CATEGORY_VOCAB"].split()]
+            if len(vocab) != n_cat:
+                raise ValueError("SB_CATEGORY_VOCAB must list %d sizes" % n_cat)
+        else:
+            if n_workers > 1:
+                raise ValueError("wide+deep with several workers needs SB_CATEGORY_VOCAB (every rank must build the same model)")
+            vocab = [int(max(1, tr_codes[:, c].max(initial=-1) + 1, va_codes[:, c].max(initial=-1) + 1)) for c in range(n_cat)]
+        offsets = np.concatenate([[0], np.cumsum(vocab)[:-1]]).astype(np.int64)
+
+        def to_idx(cd):
+            ok = (cd >= 0) & (cd < np.asarray(vocab)[None, :])
+            return np.where(ok, cd + offsets[None, :], -1).astype(np.int32)
+        train_idx, valid_idx = to_idx(tr_codes), to_idx(va_codes)
+        train_x, valid_x = np.ascontiguousarray(train_x[:, :n_dense]), np.ascontiguousarray(valid_x[:, :n_dense])
+        feature_count = n_dense + int(sum(vocab))
+        logging.info("wide+deep: %d dense + %d one-hot columns (%d categorical, vocabularies %s)" % (n_dense, sum(vocab), n_cat, vocab))
     logging.info("Testing set size: %d" % len(valid_x))
     logging.info("Training set size: %d" % len(train_x))
 
@@ -603,7 +642,13 @@ def main(_=None, env=None, rng=random) -> int:
     if n_workers > 1:
         trainer.broadcast_state(0)
     rdv.close()
-    trainer.load_dataset(train_x, train_y, train_w)
+    if wide_deep:
+        trainer.set_sparse(len(numeric_cols), int(sum(vocab)), len(category_cols))
+        if not per_batch_update:
+            logging.info("wide+deep trains with one update per mini-batch (Schedule=batch); the sync-replicas accumulator is not wired for sparse steps")
+            per_batch_update = True
+    else:
+        trainer.load_dataset(train_x, train_y, train_w)
 
     # replicas_to_aggregate (ssgd_monitor.py:139): accepted pushes per global update, over all workers
     R = max(1, int(total_training_data_number * (1 - valid_ratio) / batch_size * REPLICAS_TO_AGGREGATE_RATIO))
@@ -616,7 +661,13 @@ def main(_=None, env=None, rng=random) -> int:
     while trainer.global_step < epochs:           # StopAtStepHook(num_steps=EPOCH) (ssgd_monitor.py:235)
         start = time.time()
         l = 0.0
-        if per_batch_update:
+        if wide_deep:
+            for i in range(total_batch):
+                a, b = int(bounds[i]), int(bounds[i + 1])
+                l = trainer.step_sparse(train_x[a:b], train_idx[a:b], train_y[a:b], train_w[a:b])
+                if trainer.global_step >= epochs:
+                    break
+        elif per_batch_update:
             # the whole `for i in range(total_batch): sess.run(train_step)` loop (ssgd_monitor.py:272-276) as one
             # asynchronous call per run of equally sized batches (np.array_split sizes differ by at most one row)
             for first, count, rows in equal_size_runs(bounds):
@@ -641,7 +692,10 @@ def main(_=None, env=None, rng=random) -> int:
                 if trainer.global_step >= epochs:
                     break
         training_time = time.time() - start
-        valid_loss = trainer.eval_loss(valid_x, valid_y, valid_w) if len(valid_x) else 0.0
+        if wide_deep:
+            valid_loss = trainer.eval_loss_sparse(valid_x, valid_idx, valid_y, valid_w) if len(valid_x) else 0.0
+        else:
+            valid_loss = trainer.eval_loss(valid_x, valid_y, valid_w) if len(valid_x) else 0.0
         gs = trainer.global_step
         logging.info('Step: ' + str(gs) + ' worker: ' + str(task_index) + " training loss:" + str(l) +
                      " valid loss:" + str(valid_loss))

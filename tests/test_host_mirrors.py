@@ -511,3 +511,56 @@ def test_worker_reads_and_writes_scheme_paths_through_the_hdfs_cli(sb, tmp_path,
     monkeypatch.setattr(tr._Fs, "CLI", str(tmp_path / "no_such_hdfs"))
     with pytest.raises(RuntimeError, match="needs the"):
         tr._Fs.read_bytes("hdfs://nn/data/part-00000.gz")
+
+
+@pytest.mark.gpu
+def test_worker_wide_deep_from_the_numeric_and_category_column_lists(sb, tmp_path):
+    """SELECTED_COLUMN_NUMS blank + SELECTED_NUMERIC_/CATEGORY_COLUMN_NUMS (TensorflowTaskExecutor.java:213-223): the worker
+    trains the wide+deep model through sparse steps and exports an ordinary SavedModel whose first layer has
+    n_dense + sum(vocab) inputs; its losses follow the dense oracle on the materialised one-hot matrix"""
+    from oracle import wide_deep as wd
+    from shifu_tensorflow_b200 import trainer as tr
+    n_dense, vocab, n_rows = 6, [4, 7, 3], 900
+    Xd, idx, y, w = wd.synth_wide_deep_batch(n_rows, n_dense, vocab, 3)
+    offs = np.concatenate([[0], np.cumsum(vocab)[:-1]])
+    codes = np.where(idx >= 0, idx - offs[None, :], -1)
+    data = str(tmp_path / "part-00000.gz")
+    with gzip.open(data, "wb") as f:
+        for i in range(n_rows):
+            cols = [str(int(y[i, 0]))] + [repr(float(v)) for v in Xd[i]] + [str(int(c)) for c in codes[i]]
+            f.write(("|".join(cols) + "\n").encode())
+    conf = {"train": {"params": {"NumHiddenLayers": 2, "NumHiddenNodes": [16, 8], "ActivationFunc": ["relu", "tanh"], "LearningRate": 0.1,
+                                 "Optimizer": "sgd", "Precision": "fp32", "MiniBatchs": 100}, "numTrainEpochs": 14, "validSetRate": 0.2}}
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    json.dump(conf, open("ModelConfig.json", "w"))
+    env = {"CLUSTER_SPEC": json.dumps({"ps": ["127.0.0.1:1"], "worker": ["127.0.0.1:2"]}), "WORKER_CNT": "1", "JOB_NAME": "worker",
+           "TASK_ID": "0", "SOCKET_SERVER_PORT": "1", "SB_REQUIRE_SOCKET": "0", "TOTAL_TRAINING_DATA_NUMBER": str(n_rows),
+           "SELECTED_COLUMN_NUMS": "", "SELECTED_NUMERIC_COLUMN_NUMS": " ".join(str(1 + i) for i in range(n_dense)),
+           "SELECTED_CATEGORY_COLUMN_NUMS": " ".join(str(1 + n_dense + i) for i in range(len(vocab))),
+           "SB_CATEGORY_VOCAB": " ".join(str(v) for v in vocab), "WEIGHT_COLUMN_NUM": "-1", "TARGET_COLUMN_NUM": "0",
+           "TMP_MODEL_PATH": str(tmp_path / "tmp_model"), "FINAL_MODEL_PATH": str(tmp_path / "final_model"),
+           "TRAINING_DATA_PATH": data, "SB_SEED": "11"}
+    try:
+        rc = tr.main(env=env, rng=_Seq(5))
+    finally:
+        os.chdir(cwd)
+    assert rc == 0
+    Fn, hidden, acts, out_act, flat = sb.capi.savedmodel_read(env["FINAL_MODEL_PATH"], "shifu_input_0", "shifu_output_0")
+    assert Fn == n_dense + sum(vocab) and hidden == [16, 8]
+    # replay with the dense oracle on the one-hot matrix: same split, same init, one SGD update per mini-batch
+    coins = np.array([_c >= 0.2 for _c in (lambda r: [r.random() for _ in range(n_rows)])(_Seq(5))])
+    Xfull = np.concatenate([Xd, wd.onehot_matrix(idx, sum(vocab))], axis=1).astype(np.float32)
+    tx, ty = Xfull[coins], y[coins]
+    net = so.NetDesc(Fn, [16, 8], [so.ACT_RELU, so.ACT_TANH])
+    with sb.Trainer(sb.make_desc(Fn, [16, 8], [so.ACT_RELU, so.ACT_TANH], max_batch=128)) as t0:
+        t0.init_xavier(11)
+        theta = t0.get_params()
+    ref = so.CleanTrainer(net, so.unflatten_params(net, theta), so.OptConfig(kind=so.OPT_SGD, lr=0.1))
+    steps = 0
+    while steps < 14:
+        for b in so.split_batches(len(tx), 100):
+            ref.step([(tx[b], ty[b], np.ones((len(b), 1), np.float32))]); steps += 1
+            if steps >= 14:
+                break
+    assert np.abs(flat - ref.theta).max() <= 1e-4

@@ -63,3 +63,67 @@ def test_two_gpu_data_parallel_matches_oracle(sb, tmp_path, precision, exchange)
             assert abs(want[0] - r[0]["losses"][s]) <= 1e-5 and abs(want[1] - r[1]["losses"][s]) <= 1e-5
     tol = 1e-5 if precision == 0 else 5e-3
     assert np.abs(r[0]["theta"] - ref.theta).max() <= tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("schedule", ["batch", "sync_replicas"])
+def test_launcher_with_two_real_ranks(sb, tmp_path, schedule):
+    """the per-node launcher (launcher.py) with REAL workers on 2 GPUs: env rewriting -> two `trainer.py` processes ->
+    rendezvous on the CLUSTER_SPEC address -> NCCL communicator + state broadcast from worker 0 -> CUDA-IPC peer exchange
+    -> training -> one aggregated metrics line per epoch upstream -> chief exports the SavedModel -> exit code 0.
+    No SB_SEED: every rank would draw its own initial weights without the broadcast."""
+    if sb.capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import gzip
+    import json
+    import sys
+    import threading
+    from shifu_tensorflow_b200 import launcher as la
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    F, n_rows = 24, 4000
+    X, y, w = so.synth_batch(n_rows, F, 2)
+    data = str(tmp_path / "part-00000.gz")
+    with gzip.open(data, "wb") as f:
+        for i in range(n_rows):
+            f.write(("|".join([str(int(y[i, 0]))] + [repr(float(v)) for v in X[i]]) + "\n").encode())
+    conf = {"train": {"params": {"NumHiddenLayers": 2, "NumHiddenNodes": [32, 16], "ActivationFunc": ["relu", "tanh"], "LearningRate": 0.05,
+                                 "Optimizer": "momentum", "Schedule": schedule, "MiniBatchs": 200, "Precision": "bf16"},
+                      "numTrainEpochs": 12 if schedule == "batch" else 3, "validSetRate": 0.2}}
+    work = tmp_path / "cwd"; work.mkdir()
+    json.dump(conf, open(work / "ModelConfig.json", "w"))
+    srv = socket.socket(); srv.bind(("127.0.0.1", 0)); srv.listen(1)
+    got = []
+
+    def serve():
+        c, _ = srv.accept()
+        buf = b""
+        while True:
+            d = c.recv(4096)
+            if not d:
+                break
+            buf += d
+        got.extend(buf.decode().splitlines())
+
+    th = threading.Thread(target=serve, daemon=True); th.start()
+    env = dict(os.environ)
+    env.update({"JOB_NAME": "worker", "TASK_ID": "0", "WORKER_CNT": "1",
+                "CLUSTER_SPEC": json.dumps({"ps": ["127.0.0.1:1"], "worker": ["127.0.0.1:%d" % _free_port()]}),
+                "SOCKET_SERVER_PORT": str(srv.getsockname()[1]), "TRAINING_DATA_PATH": data, "TOTAL_TRAINING_DATA_NUMBER": str(n_rows),
+                "SELECTED_COLUMN_NUMS": " ".join(str(i) for i in range(1, F + 1)), "WEIGHT_COLUMN_NUM": "-1", "TARGET_COLUMN_NUM": "0",
+                "TMP_MODEL_PATH": str(tmp_path / "tmp_model"), "FINAL_MODEL_PATH": str(tmp_path / "final_model"),
+                "SB_LOCAL_GPUS": "2", "PYTHONPATH": root + os.pathsep + env.get("PYTHONPATH", ""), "SB_XCHG_TIMEOUT_S": "60"})
+    cwd = os.getcwd()
+    os.chdir(work)
+    try:
+        rc = la.main(env=env, worker_cmd=[sys.executable, "-c", "import sys, shifu_tensorflow_b200.trainer as t; sys.exit(t.main())"])
+    finally:
+        os.chdir(cwd)
+    th.join(20); srv.close()
+    assert rc == 0
+    assert got and all(l.startswith("worker_index:0,") for l in got)
+    last = la.parse_metrics_line(got[-1])
+    assert int(last["current_epoch"]) == conf["train"]["numTrainEpochs"] and np.isfinite(last["valid_loss"]) and 0 < last["valid_loss"] < 1
+    final = str(tmp_path / "final_model")
+    assert sorted(os.listdir(final)) == ["GenericModelConfig.json", "saved_model.pb", "variables"]
+    Fn, hidden, acts, out_act, flat = sb.capi.savedmodel_read(final, "shifu_input_0", "shifu_output_0")
+    assert (Fn, hidden) == (F, [32, 16]) and np.isfinite(flat).all()
