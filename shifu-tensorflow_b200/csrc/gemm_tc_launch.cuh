@@ -48,6 +48,8 @@ template <int EPI, bool A_MN, bool B_MN>
 int launch_gemm_tc(const GemmPlan& pl, const TmapSet& tms, GemmTcParams p, cudaStream_t st, bool pdl = false) {
   if (p.np < 1) p.np = 1;
   if (p.n_pairs < 1) p.n_pairs = 1;
+  p.split_k = pl.split_k;
+  p.kb_per_split = pl.kb_per_split;
   // split-precision parts or an fp32 addend: the GENERIC instantiations (the fused output layer reads its activation at run
   // time there - three kernels instead of fifteen)
   if constexpr (EPI == EPI_FWD || EPI == EPI_DA || EPI == EPI_FWD_OUT) {
@@ -66,8 +68,6 @@ int launch_gemm_tc(const GemmPlan& pl, const TmapSet& tms, GemmTcParams p, cudaS
       return set_error(SB_ERR_INVALID, "no generic gemm_tc instantiation for cg=%d bn=%d", pl.cg, pl.bn);
     }
   }
-  p.split_k = pl.split_k;
-  p.kb_per_split = pl.kb_per_split;
   if constexpr (EPI == EPI_FWD_OUT) {
     if (pl.cg == 1 && pl.bn == 64) return launch_fwd_out_act<64, A_MN, B_MN>(pl, tms, p, st, pdl);
     if (pl.cg == 1 && pl.bn == 128) return launch_fwd_out_act<128, A_MN, B_MN>(pl, tms, p, st, pdl);
