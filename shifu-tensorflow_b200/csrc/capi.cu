@@ -1560,6 +1560,8 @@ static int debug_gemm_impl(const float* A, const float* B, float* D, int32_t M, 
       GemmTcParams q = p;
       q.bias = d_bias; q.act = SB_ACT_RELU; q.out = d_out; q.ld_out = ldn; q.aux = d_aux; q.ld_aux = ldn; q.colsum = d_colsum;
       q.acc_vec4 = (N % 4 == 0) ? 1 : 0;
+      if (s == SB_OK) s = make_tmap_bf16(&tms.o, d_out, M, N, ldn, 128);
+      if (s == SB_OK) s = make_tmap_bf16(&tms.x, d_aux, M, N, ldn, 128);
       const bool bench_pdl = getenv("SB_BENCH_PDL") != nullptr;
       auto real = [&]() -> int {
         if (!a_mn && !b_mn) return launch_gemm_tc<EPI_DA, false, false>(pl, tms, q, 0, bench_pdl);

@@ -94,9 +94,17 @@ struct GemmTcParams {
 struct TmapSet {
   CUtensorMap a[3];
   CUtensorMap b[3];
+  CUtensorMap o;   // TMA-staged epilogues: the bf16 output matrix [M, N] (box 64 columns x 128 rows, 128-byte swizzle)
+  CUtensorMap x;   // EPI_DA: A_{l-1} [M, N], same box
 };
 
-template <int BN, int CG>
+// bytes of TMA staging the epilogue of an instantiation needs: the plain-bf16 forward and dA epilogues move their global
+// data through 128 x 64 bf16 tiles (16 KB) with TMA - output tile double-buffered, dA additionally its A_{l-1} tile
+__host__ __device__ constexpr int epi_tma_bytes(int EPI, bool GENERIC) {
+  return GENERIC ? 0 : (EPI == 0 /*EPI_FWD*/ ? 2 * 16384 : (EPI == 1 /*EPI_DA*/ ? 4 * 16384 : 0));
+}
+
+template <int BN, int CG, int XB = 0>
 struct GemmTcCfg {
   static_assert(CG == 1 || CG == 2, "cta group");
   static_assert(BN == 64 || BN == 128 || BN == 256, "tile N");
@@ -108,11 +116,15 @@ struct GemmTcCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN_CTA * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  // shared memory besides the operand ring: align slack, barriers, epilogue scratch, bias (+ w_o), per-warp transpose tiles
+  // (only the epilogues without TMA staging use them), column-sum accumulators, TMA staging tiles (XB)
+  static constexpr int TR_BYTES = XB > 0 ? 0 : 8 * 2048;
+  static constexpr int FIXED_BYTES = 1024 + 256 + 2048 + 2048 + TR_BYTES + 4096 + XB;
+  static constexpr int RING_BUDGET = (XB > 0 ? 232448 - FIXED_BYTES : 200 * 1024);   // (the un-staged kernels keep their round-1 depth)
+  static constexpr int STAGES = RING_BUDGET / STAGE_BYTES > 8 ? 8 : RING_BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 2048 /*epilogue scratch*/ +
-                                    2048 /*bias (+ w_o) of the tile*/ + 8 * 2048 /*per-warp transpose tile*/ +
-                                    4096 /*column-sum accumulators of the tile (db, dw_o), double-buffered*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static constexpr int EPI_WARPS = 8;
   static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
@@ -140,13 +152,15 @@ constexpr int SB_ACT_AT_RUNTIME = -100;
 template <int BN, int EPI, bool A_MN, bool B_MN, int CG, int ACT_T = SB_ACT_AT_RUNTIME, bool GENERIC = false>
 __global__ void __launch_bounds__(GemmTcCfg<BN, CG>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
-  using Cfg = GemmTcCfg<BN, CG>;
+  using Cfg = GemmTcCfg<BN, CG, epi_tma_bytes(EPI, GENERIC)>;
+  constexpr bool TMA_EPI = epi_tma_bytes(EPI, GENERIC) > 0;
   const int act_sel = (ACT_T == SB_ACT_AT_RUNTIME) ? p.act : ACT_T;
   constexpr int BM = Cfg::BM, BK = Cfg::BK, STAGES = Cfg::STAGES, TILE_M = Cfg::TILE_M, BN_CTA = Cfg::BN_CTA;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B needs 1024 B alignment
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t xbuf_base = smem_base + STAGES * Cfg::STAGE_BYTES;            // TMA staging tiles (1024-byte aligned)
+  const uint32_t bar_base = xbuf_base + epi_tma_bytes(EPI, GENERIC);
   // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem base slot.
   // CG = 2: full[] and tmem_empty[] are only used in the leader CTA (rank 0); empty[] / tmem_full[] in both.
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -322,7 +336,23 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
     // one red per warp and chunk, the 8192 x 1024 dA GEMM of cfg2 sent 262 k reds to 32 cache lines and spent 3/4 of its time
     // waiting for the L2 atomic units (tensor pipe 25 % active, profiles/ncu_r01_cfg2_gemm_full.txt).
     // layout: [buffer (tile parity)][array 0: db | array 1: dw_o][BN] floats
-    const uint32_t sm_col = sm_vec + 2048u + 8u * 2048u;
+    const uint32_t sm_col = sm_vec + 2048u + static_cast<uint32_t>(Cfg::TR_BYTES);
+    // TMA-staged epilogue (plain-bf16 forward / dA): the 128 x BN tile leaves in 64-column blocks.  Block k: every thread
+    // writes the 32 bf16 of its row-chunk as four 16-byte pieces into the 128-byte-swizzled 128 x 64 tile xo[k & 1] (the layout
+    // the output tensor map expects; a quarter-warp covers all 32 banks), one thread issues cp.async.bulk.tensor (store) for
+    // the tile; dA additionally gets its A_{l-1} block by TMA load into xa[k & 1] (issued two blocks ahead) and reads it back
+    // with the same swizzle.  No ld.shared / st.global per element, no transposes, M / N tails clipped by the tensor map.
+    auto xo = [&](int b) { return xbuf_base + static_cast<uint32_t>(b) * 16384u; };
+    auto xa = [&](int b) { return xbuf_base + 32768u + static_cast<uint32_t>(b) * 16384u; };
+    auto aux_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4) + 16u + 8u * static_cast<uint32_t>(b); };   // (scratch of EPI_FWD_OUT, unused here)
+    const int rt = quarter * 32 + lane;                                   // row of this thread inside the CTA's 128 rows
+    auto piece = [&](int half_, int i) { return static_cast<uint32_t>(rt) * 128u + static_cast<uint32_t>(((half_ * 4 + i) ^ (rt & 7)) << 4); };
+    const bool xthread = (warp == 2 && lane == 0);                        // issues the epilogue's TMA loads / stores
+    unsigned xblk = 0;                                                    // 64-column blocks processed so far by this CTA
+    if constexpr (TMA_EPI && EPI == EPI_DA) {
+      if (xthread) { mbar_init(aux_bar(0), 1); mbar_init(aux_bar(1), 1); fence_barrier_init(); }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     auto col_slot = [&](int buf, int arr, int j) { return sm_col + static_cast<uint32_t>(((buf * 2 + arr) * BN + j) * 4); };
     auto red_shared = [](uint32_t a, float v) { asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); };
     if constexpr (EPI == EPI_DA || EPI == EPI_FWD_OUT) {
@@ -396,7 +426,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
       // dA epilogue: A_{l-1} of EVERY chunk this warp will handle is fetched before the accumulator wait (the loads do not
       // depend on it) and kept in registers as a shift queue, so that one L2 / HBM latency is paid per tile instead of one
       // per 32-column chunk (the chunk-ahead prefetch left this epilogue latency bound: 5 us per 256 x 256 tile at cfg2)
-      constexpr int AUXQ = (EPI == EPI_DA) ? (BN / 64 > 0 ? BN / 64 : 1) : 1;
+      constexpr int AUXQ = (EPI == EPI_DA && !TMA_EPI) ? (BN / 64 > 0 ? BN / 64 : 1) : 1;
       uint4 aux_q[AUXQ][4];
       const int row_base = tm * TILE_M + static_cast<int>(rank) * BM + quarter * 32;   // first row of this warp's 32
       // store a 32 x 64 B tile held one-row-per-thread (4 pieces each) to a row-major bf16 matrix, coalesced
@@ -452,9 +482,22 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
         pre_nnz = p.scal[SCAL_NNZ];
         pre_bo = __ldg(p.bo);
       }
-      if constexpr (EPI == EPI_DA) {
+      if constexpr (EPI == EPI_DA && !TMA_EPI) {
 #pragma unroll
         for (int i = 0; i < AUXQ; ++i) load_aux(half + 2 * i, aux_q[i]);
+      }
+      // blocks of 64 columns this tile really has (the same number for every warp: the block loop contains barriers)
+      const int tile_cols = (p.N - tn * BN) < BN ? (p.N - tn * BN) : BN;
+      const int nblk = (tile_cols + 63) / 64;
+      const int x_row0 = tm * TILE_M + static_cast<int>(rank) * BM;      // TMA row coordinate of this CTA's 128 rows
+      if constexpr (TMA_EPI && EPI == EPI_DA) {
+        if (xthread) {
+          for (int k = 0; k < 2 && k < nblk; ++k) {       // A_{l-1} of the first two blocks (buffers free: every warp has left the previous tile)
+            const int b = (xblk + k) & 1;
+            mbar_arrive_expect_tx(aux_bar(b), 16384u);
+            tma_load_2d(xa(b), &tms.x, aux_bar(b), tn * BN + k * 64, x_row0);
+          }
+        }
       }
       const uint32_t sm_bias = sm_vec + static_cast<uint32_t>(it & 1) * (BN * 4u);   // EPI_FWD: this tile's bias, double-buffered
       if constexpr (EPI == EPI_FWD) {
@@ -578,14 +621,25 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
 #pragma unroll 1
       for (int c = half; c < BN / 32; c += 2) {
         const int col0 = tn * BN + c * 32;
-        if (col0 >= p.N) break;  // whole chunk out of range (warp-uniform)
+        if constexpr (TMA_EPI) {
+          if ((c >> 1) >= nblk) break;          // same trip count for all eight warps
+        } else {
+          if (col0 >= p.N) break;  // whole chunk out of range (warp-uniform)
+        }
+        const bool chunk_ok = col0 < p.N;       // (TMA path: a warp whose 32 columns lie beyond N only joins the barriers)
         uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, raw);
-        tmem_ld_wait();
+        if (chunk_ok) {
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BN + c * 32, raw);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) raw[j] = 0u;
+        }
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
         const bool full = col0 + 32 <= p.N;  // warp-uniform fast path
+        const int xb = static_cast<int>(xblk & 1u);
 
         if constexpr (EPI == EPI_FWD) {
           if (GENERIC && p.addend != nullptr && row_ok) {
@@ -618,11 +672,17 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
         } else if constexpr (EPI == EPI_DA) {
           // multiply by act'(A_{l-1}[row, col]) read as bf16 (64 B per thread per chunk, fetched one chunk ahead)
           uint4 a4[4];
-          lanes_to_row(aux_q[0], a4);
+          if constexpr (TMA_EPI) {
+            mbar_wait(aux_bar(xb), (xblk >> 1) & 1u);        // this block's A_{l-1} tile has landed
 #pragma unroll
-          for (int i = 0; i + 1 < AUXQ; ++i) {
+            for (int i = 0; i < 4; ++i) a4[i] = lds4(xa(xb) + piece(half, i));
+          } else {
+            lanes_to_row(aux_q[0], a4);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) aux_q[i][k] = aux_q[i + 1][k];
+            for (int i = 0; i + 1 < AUXQ; ++i) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) aux_q[i][k] = aux_q[i + 1][k];
+            }
           }
           __nv_bfloat16* ah = reinterpret_cast<__nv_bfloat16*>(a4);
           if (GENERIC && p.np > 1 && (act_sel == SB_ACT_SIGMOID || act_sel == SB_ACT_TANH)) {
@@ -657,11 +717,38 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
         }
 
         if constexpr (EPI == EPI_FWD || EPI == EPI_DA) {
-          // row-major bf16 (ld_out is a multiple of 8, pad columns belong to the buffer); split modes: np part arrays
-          store_parts(v, p.out, p.out_ps, p.ld_out, col0, full);
+          if constexpr (TMA_EPI) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 o;
+              o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+              o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+              o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+              o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
+              sts4(xo(xb) + piece(half, q), o);
+            }
+            fence_proxy_async();                                   // generic-proxy writes -> visible to the TMA engine
+            asm volatile("bar.sync 1, 256;" ::: "memory");         // (A) the block's tile is complete; A_{l-1} tile consumed
+            if (xthread) {
+              tma_store_2d(&tms.o, xo(xb), tn * BN + (c >> 1) * 64, x_row0);
+              tma_store_commit();
+              if constexpr (EPI == EPI_DA) {
+                if ((c >> 1) + 2 < nblk) {                         // A_{l-1} two blocks ahead, into the tile just consumed
+                  mbar_arrive_expect_tx(aux_bar(xb), 16384u);
+                  tma_load_2d(xa(xb), &tms.x, aux_bar(xb), tn * BN + ((c >> 1) + 2) * 64, x_row0);
+                }
+              }
+              tma_store_wait_read<1>();                            // the OTHER output tile has been read: free for the next block
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");         // (B)
+            ++xblk;
+          } else {
+            // row-major bf16 (ld_out is a multiple of 8, pad columns belong to the buffer); split modes: np part arrays
+            store_parts(v, p.out, p.out_ps, p.ld_out, col0, full);
+          }
           if constexpr (EPI == EPI_DA) {
             if (p.colsum != nullptr) {
-              // bias gradient: per-column sum over this warp's 32 rows, one atomic per column per warp
+              // bias gradient: per-column sum over this warp's 32 rows, accumulated per CTA in shared memory
               const float s = warp_colsum_32x32(v, lane);
               red_shared(col_slot(it & 1, 0, c * 32 + lane), s);     // columns beyond N / rows beyond M were zeroed above
             }
@@ -721,6 +808,9 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
     }
   }
 
+  if constexpr (TMA_EPI) {
+    if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last tiles are in global memory
+  }
   tcgen05_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (threadIdx.x == 0) stamp(8);  // all roles finished

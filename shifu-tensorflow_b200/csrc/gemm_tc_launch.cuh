@@ -7,7 +7,7 @@ namespace sb {
 template <int BN, int EPI, bool A_MN, bool B_MN, int CG, int ACT_T = SB_ACT_AT_RUNTIME, bool GENERIC = false>
 static int launch_gemm_tc_one(const GemmPlan& pl, const TmapSet& tms, const GemmTcParams& p, cudaStream_t st,
                               bool pdl) {
-  using Cfg = GemmTcCfg<BN, CG>;
+  using Cfg = GemmTcCfg<BN, CG, epi_tma_bytes(EPI, GENERIC)>;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(static_cast<unsigned>(pl.grid));
   cfg.blockDim = dim3(Cfg::THREADS);
@@ -103,7 +103,7 @@ int set_gemm_tc_attrs() {
   } else {
 #define SB_ATTR(BN, CG)                                                                                            \
   SB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, A_MN, B_MN, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                               GemmTcCfg<BN, CG>::SMEM_BYTES))
+                               (GemmTcCfg<BN, CG, epi_tma_bytes(EPI, false)>::SMEM_BYTES)))
   SB_ATTR(64, 1); SB_ATTR(128, 1); SB_ATTR(128, 2); SB_ATTR(256, 2);
 #undef SB_ATTR
   if constexpr (EPI == EPI_FWD || EPI == EPI_DA) {

@@ -439,6 +439,8 @@ int Net::enqueue_hidden_forward(int rows, float* grad, bool* fused_out) {
         zero_buf = nullptr;
       }
       p.trace = next_trace("fwd");
+      if (nparts == 1 && p.addend == nullptr)      // plain bf16: the epilogue stores its tiles by TMA
+        SB_TRY(make_tmap_bf16(&tm.o, A[l], rows, ly.out, ly.ld_out, 128));
       SB_TRY((launch_gemm_tc<EPI_FWD, false, true>(pl, tm, p, stream, use_pdl)));
     } else {
       GemmF32Params p = {};
@@ -594,6 +596,10 @@ int Net::enqueue_backward(int rows, float* grad) {
         p.out = dZ[l - 1]; p.ld_out = pl.ld_out; p.out_ps = A_ps[l - 1];
         p.colsum = grad + pl.b_off;
         p.trace = next_trace("dA");
+        if (nparts == 1) {                           // plain bf16: A_{l-1} in and dZ_{l-1} out move as TMA tiles
+          SB_TRY(make_tmap_bf16(&tm.o, dZ[l - 1], rows, ly.in, pl.ld_out, 128));
+          SB_TRY(make_tmap_bf16(&tm.x, A[l - 1], rows, ly.in, pl.ld_out, 128));
+        }
         SB_TRY((launch_gemm_tc<EPI_DA, false, false>(gp, tm, p, stream, use_pdl)));
         mark("gemm_da");
         if (l == 1 && fork && defer_join) SB_CUDA(cudaEventRecord(ev_da_done, stream));
