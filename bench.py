@@ -605,7 +605,29 @@ def eval_leg(sb, torch, c, trained_params, X_host, world, rank, local_rank, barr
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - e0)
     m.close()
-    return {"metric": "rows/sec batch scoring (eval path)", "value": val, "unit": "rows/s", "rows": rows_done, "seconds": ms / 1e3,
+    # the two tensor-core parity modes on the same net (device-resident, a shorter run): fp32-class scores, 6 / 3 part products
+    parity = {}
+    for pname, pid in (("fp32_tc", sb.PREC_FP32_TC), ("bf16x2", sb.PREC_BF16X2)):
+        mp = sb.Model.create(sb.make_desc(F, hidden, [sb.ACT_RELU] * len(hidden), precision=pid), trained_params, device=local_rank)
+        sp = torch.cuda.ExternalStream(mp.stream, device=dev)
+        rows_p = 1 << 18
+        Xp = torch.empty((rows_p, F), dtype=torch.float32, device=dev).normal_(generator=g).clamp_(-4, 4)
+        op = torch.empty(rows_p, dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        mp.score_device(Xp.data_ptr(), rows_p, op.data_ptr()); mp.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 8
+        e0.record(sp)
+        for _ in range(reps):
+            mp.score_device(Xp.data_ptr(), rows_p, op.data_ptr())
+        e1.record(sp)
+        mp.sync()
+        msp = e0.elapsed_time(e1)
+        parity[pname] = {"value": reps * rows_p / (msp / 1e3), "unit": "rows/s", "rows": reps * rows_p,
+                         "mma_products_per_contraction": 6 if pname == "fp32_tc" else 3}
+        mp.close()
+        del Xp, op
+    return {"metric": "rows/sec batch scoring (eval path)", "value": val, "parity_modes": parity, "unit": "rows/s", "rows": rows_done, "seconds": ms / 1e3,
             "dtype": "bf16", "workload": "BASELINE config 5: %d M rows x %d cols through MLP %s, %d rank(s), device-resident fp32 rows "
                                          "(1 Mi-row chunks, larger than L2)" % (rows_done // 1_000_000, F, hidden, world),
             "roofline": {"bound": "tensor", "achieved": val / world * f_score / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
