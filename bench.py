@@ -407,6 +407,7 @@ def main():
             barrier()
             names, stamps = tt.debug_step_trace()
             tl = step_timeline(names, stamps, B, F, hidden)
+            barrier()
             tt.close()
             if tl:
                 gem = [k for k in tl["kernels"] if k["flops"]]
@@ -434,6 +435,7 @@ def main():
                         "kernel": "whole step (no in-graph trace in this precision mode)"}
         res["roofline"] = roofline
         if not full:
+            barrier()
             t.close()
             return res
 
@@ -473,7 +475,8 @@ def main():
                       "timer": "host wall clock around sb_trainer_step_async x steps + sb_trainer_last_loss (pinned host buffers, "
                                "H2D of every batch and D2H of every step's loss scalars inside), max over ranks; "
                                "synchronous_value = the same with sb_trainer_step (host waits for each loss)"}
-        trained = t.get_params()
+        trained = t.get_params()      # (sharded update: pulls every run's fp32 master from its owner rank)
+        barrier()                     # no rank may free its arena while a peer still reads it
         t.close()
 
         # ---------------- eval leg: BASELINE config 5 (batch scoring of the trained net) ----------------

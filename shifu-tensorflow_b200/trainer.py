@@ -714,6 +714,10 @@ def main(_=None, env=None, rng=random) -> int:
         logging.info("Exporting saved_model to: {}".format(final_model_path))
         simple_save(trainer, final_model_path)
         logging.info("Exported saved_model")
+    if n_workers > 1:
+        # the chief's export / last checkpoint pull every rank's share of the fp32 master over peer memory: nobody frees
+        # its arena before the chief is done (an all-reduce of nothing on the trainers' own communicator is the barrier)
+        trainer.broadcast_state(0)
     trainer.close()
     if socket_client is not None:
         socket_client.close()

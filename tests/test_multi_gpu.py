@@ -37,7 +37,9 @@ def _rank_main(rank, world, port, out_dir, precision, exchange="nccl"):
         X, y, w = so.synth_batch(256, 96, 20 + s, weights="mixed")
         idx = du.shard_rows(256, rank, world)
         losses.append(t.step(X[idx], y[idx], w[idx]))
-    np.savez(os.path.join(out_dir, "r%d.npz" % rank), theta=t.get_params(), grads=t.get_grads(), losses=np.array(losses))
+    theta, grads = t.get_params(), t.get_grads()      # (sharded exchange: gathered from the owner ranks)
+    dist.barrier()                                    # nobody frees its arena while a peer still reads it
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), theta=theta, grads=grads, losses=np.array(losses))
     t.close()
     dist.destroy_process_group()
 
