@@ -155,7 +155,7 @@ int sb_trainer_step_async(sb_trainer_t* t, const float* X, const float* y, const
  * mini-batch gradients (averaged over ranks as well) as ONE optimizer update. */
 int sb_trainer_accumulate(sb_trainer_t* t, const float* X, const float* y, const float* w, int32_t rows,
                           float* loss_out);
-int sb_trainer_apply_accumulated(sb_trainer_t* t);
+int sb_trainer_apply_accumulated(sb_trainer_t* t);     /* queued on the trainer's stream; sb_trainer_sync / get_params wait */
 /* Same, with the divisor given explicitly: the update uses (sum over ranks of the locally accumulated gradients) /
  * total_pushes.  This is ConditionalAccumulator.take_grad(R) when ranks accepted different numbers of pushes (stale pushes
  * are dropped per worker, ssgd_monitor.py:136-141; the host-side token bookkeeping lives in trainer.py). */

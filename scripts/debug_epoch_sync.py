@@ -27,12 +27,13 @@ for r, n_acc in ((0, 3), (1, 2)):
         got = ts[r].get_grads()
         print("rank", r, "batch", k, "per-step grad err", np.abs(got - g).max(), "elems", got[[0, 1, -1]], g[[0, 1, -1]])
         want[(r, k)] = g
-res = {}
-def run(r):
-    ts[r].apply_accumulated(5); res[r] = "ok"
-th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
-[x.start() for x in th]; [x.join(60) for x in th]
-print(res)
+import time
+t0 = time.time()
+for t in ts:
+    t.apply_accumulated(5)
+for t in ts:
+    t.sync()
+print("apply took %.2f s" % (time.time() - t0))
 tot = sum(want.values())
 for r in range(2):
     g = ts[r].get_grads()

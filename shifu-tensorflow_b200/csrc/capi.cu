@@ -886,7 +886,8 @@ static int apply_accumulated_impl(sb_trainer_t* t, int64_t total_pushes) {
   SB_CUDA(cudaGetLastError());
   t->grad_out_scale = 1.f;  // scale_kernel already applied 1/(world * n_acc)
   SB_CUDA(cudaMemsetAsync(t->acc, 0, sizeof(float) * np, n.stream));
-  SB_CUDA(cudaStreamSynchronize(n.stream));
+  // queued, not waited for (like a step): with a peer exchange inside, a host thread that drives several replicas must be able
+  // to queue the update on all of them before any can complete; everything that reads the result synchronises the stream
   t->n_acc = 0;
   return SB_OK;
 }

@@ -133,9 +133,10 @@ def test_epoch_sync_schedule_over_the_exchange(sb, monkeypatch):
         ts[0].accumulate_resident(k * B, B)
     for k in range(2):
         ts[1].accumulate_resident(k * B, B)
-    import threading
-    th = [threading.Thread(target=t.apply_accumulated, args=(5,)) for t in ts]     # apply waits for the device: one host thread per rank
-    [x.start() for x in th]; [x.join(120) for x in th]
+    for t in ts:
+        t.apply_accumulated(5)          # queued on every replica, then waited for
+    for t in ts:
+        t.sync()
     P = params
     gsum = np.zeros(so.flatten_params(params).size, np.float32)
     for r, n_acc in ((0, 3), (1, 2)):
