@@ -576,8 +576,26 @@ static void close_peer_mappings(sb_trainer* t) {
   t->peer_bases.clear();
 }
 
+// CUDA loads kernels lazily, at their first launch, and that load may synchronise the device: behind an exchange kernel that
+// is still spinning for a peer whose work the same host thread has not queued yet (replicas in one process), the load - and
+// with it the thread - would never return.  Everything a non-captured path launches around an exchange is loaded up front.
+static int preload_exchange_kernels() {
+  cudaFuncAttributes a;
+  SB_CUDA(cudaFuncGetAttributes(&a, xchg_update_kernel<2>));
+  SB_CUDA(cudaFuncGetAttributes(&a, xchg_update_kernel<4>));
+  SB_CUDA(cudaFuncGetAttributes(&a, xchg_update_kernel<8>));
+  SB_CUDA(cudaFuncGetAttributes(&a, xchg_update_kernel<16>));
+  SB_CUDA(cudaFuncGetAttributes(&a, gather_master_kernel));
+  SB_CUDA(cudaFuncGetAttributes(&a, set_batch_kernel));
+  SB_CUDA(cudaFuncGetAttributes(&a, scale_kernel));
+  SB_CUDA(cudaFuncGetAttributes(&a, zero_f32_kernel));
+  SB_CUDA(cudaFuncGetAttributes(&a, axpy_kernel));
+  return SB_OK;
+}
+
 // peers' exchange allocations -> device table; bases[rank] is ignored (own allocation)
 static int install_peer_table(sb_trainer* t, void* const* bases) {
+  SB_TRY(preload_exchange_kernels());
   P2PPeers hp;
   memset(&hp, 0, sizeof(hp));
   for (int q = 0; q < t->world; ++q) hp.base[q] = static_cast<char*>((q == t->rank) ? t->xch : bases[q]);
@@ -885,7 +903,8 @@ static int apply_accumulated_impl(sb_trainer_t* t, int64_t total_pushes) {
   scale_kernel<<<static_cast<unsigned>((np + 255) / 256), 256, 0, n.stream>>>(t->grad, n.desc, np);
   SB_CUDA(cudaGetLastError());
   t->grad_out_scale = 1.f;  // scale_kernel already applied 1/(world * n_acc)
-  SB_CUDA(cudaMemsetAsync(t->acc, 0, sizeof(float) * np, n.stream));
+  zero_f32_kernel<<<static_cast<unsigned>((np + 255) / 256), 256, 0, n.stream>>>(t->acc, np);   // (a preloaded kernel, see preload_exchange_kernels)
+  SB_CUDA(cudaGetLastError());
   // queued, not waited for (like a step): with a peer exchange inside, a host thread that drives several replicas must be able
   // to queue the update on all of them before any can complete; everything that reads the result synchronises the stream
   t->n_acc = 0;

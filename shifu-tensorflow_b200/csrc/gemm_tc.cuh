@@ -125,8 +125,12 @@ struct GemmTcCfg {
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-  static constexpr int EPI_WARPS = 8;
-  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  // Epilogue warps.  The epilogues are instruction-latency bound (a warp's chunk is a ~500-instruction chain; 8 warps = 2 per
+  // scheduler issued 0.18 instructions per cycle in the ncu capture of the cfg2 dA GEMM), so the TMA-staged epilogues - whose
+  // register need dropped to ~115 - run SIXTEEN warps in two groups of eight that work on alternate 64-column blocks.
+  static constexpr int EPI_WARPS = XB > 0 ? 16 : 8;
+  static constexpr int EPI_THREADS = 32 * EPI_WARPS;
+  static constexpr int THREADS = 64 + EPI_THREADS;
 };
 
 // ---- epilogue element functions, specialised per activation so the switch is hoisted out of the element loop
@@ -150,7 +154,7 @@ constexpr int SB_ACT_AT_RUNTIME = -100;
 // 7.4 k-instruction epilogue spent 38 % of its issue slots waiting for instruction fetch).  GENERIC = true adds the cold
 // features at compile time: split-precision part stores / loads (np > 1) and the fp32 addend of the wide+deep first layer.
 template <int BN, int EPI, bool A_MN, bool B_MN, int CG, int ACT_T = SB_ACT_AT_RUNTIME, bool GENERIC = false>
-__global__ void __launch_bounds__(GemmTcCfg<BN, CG>::THREADS, 1)
+__global__ void __launch_bounds__((GemmTcCfg<BN, CG, epi_tma_bytes(EPI, GENERIC)>::THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
   using Cfg = GemmTcCfg<BN, CG, epi_tma_bytes(EPI, GENERIC)>;
   constexpr bool TMA_EPI = epi_tma_bytes(EPI, GENERIC) > 0;
@@ -314,13 +318,17 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
   } else {
     // ================= epilogue warps (2..9), every CTA: its own 128 rows x BN columns =================
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;    // which of the two warps sharing the quarter
-    const int et = static_cast<int>(threadIdx.x) - 64;   // 0..255 inside the epilogue group
+    const int half = ((warp - 2) >> 2) & 1;    // which of the two warps (of a group) sharing the quarter
+    const int grp = (warp - 2) >> 3;           // TMA-staged epilogues: group 0 / 1 takes the even / odd 64-column blocks
+    const int et = static_cast<int>(threadIdx.x) - 64;   // 0 .. EPI_THREADS-1 over all epilogue warps
+    constexpr int ET = Cfg::EPI_THREADS;
+    auto bar_all = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_THREADS) : "memory"); };    // every epilogue warp
+    auto bar_grp = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(2 + grp) : "memory"); };              // the eight warps of a group
     if (p.zero_buf != nullptr) {
       // idle time before the first accumulator completes: clear the step's gradient buffer (read by nobody before the
       // next kernel boundary)
       const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (long long i = blockIdx.x * 256ll + et; i < p.zero_n4; i += gridDim.x * 256ll) p.zero_buf[i] = z4;
+      for (long long i = static_cast<long long>(blockIdx.x) * ET + et; i < p.zero_n4; i += static_cast<long long>(gridDim.x) * ET) p.zero_buf[i] = z4;
     }
     // EPI_FWD_OUT: bias and w_o of the (single) n-tile staged in shared memory once, before the accumulator wait, so the
     // two epilogue passes read them with broadcast ld.shared instead of dependent global loads
@@ -347,22 +355,22 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
     auto aux_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 4) + 16u + 8u * static_cast<uint32_t>(b); };   // (scratch of EPI_FWD_OUT, unused here)
     const int rt = quarter * 32 + lane;                                   // row of this thread inside the CTA's 128 rows
     auto piece = [&](int half_, int i) { return static_cast<uint32_t>(rt) * 128u + static_cast<uint32_t>(((half_ * 4 + i) ^ (rt & 7)) << 4); };
-    const bool xthread = (warp == 2 && lane == 0);                        // issues the epilogue's TMA loads / stores
-    unsigned xblk = 0;                                                    // 64-column blocks processed so far by this CTA
+    const bool xthread = (((warp - 2) & 7) == 0 && lane == 0);            // first lane of a group: issues its TMA loads / stores
+    unsigned xblk = 0;                                                    // 64-column blocks processed so far by this GROUP
     if constexpr (TMA_EPI && EPI == EPI_DA) {
-      if (xthread) { mbar_init(aux_bar(0), 1); mbar_init(aux_bar(1), 1); fence_barrier_init(); }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 2 && lane == 0) { mbar_init(aux_bar(0), 1); mbar_init(aux_bar(1), 1); fence_barrier_init(); }
+      bar_all();
     }
     auto col_slot = [&](int buf, int arr, int j) { return sm_col + static_cast<uint32_t>(((buf * 2 + arr) * BN + j) * 4); };
     auto red_shared = [](uint32_t a, float v) { asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); };
     if constexpr (EPI == EPI_DA || EPI == EPI_FWD_OUT) {
-      for (int j = et; j < 4 * BN; j += 256) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sm_col + static_cast<uint32_t>(j) * 4u), "f"(0.f) : "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int j = et; j < 4 * BN; j += ET) asm volatile("st.shared.f32 [%0], %1;" ::"r"(sm_col + static_cast<uint32_t>(j) * 4u), "f"(0.f) : "memory");
+      bar_all();
     }
     // after every epilogue warp has added its sums of tile `it`: one thread per column flushes and clears buffer it & 1
     auto flush_cols = [&](int it_, int tn_, float* dst0, float* dst1) {
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      for (int j = et; j < BN; j += 256) {
+      bar_all();
+      for (int j = et; j < BN; j += ET) {
         const int col = tn_ * BN + j;
 #pragma unroll
         for (int arr = 0; arr < 2; ++arr) {
@@ -403,13 +411,13 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
     };
     if constexpr (EPI == EPI_FWD_OUT) {
 #pragma unroll
-      for (int j = et; j < 2 * BN; j += 256) {
+      for (int j = et; j < 2 * BN; j += ET) {
         const int col = (j < BN) ? j : j - BN;
         const float* src = (j < BN) ? p.bias : p.wo;
         const float v = (col < p.N) ? __ldg(src + col) : 0.f;
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(sm_vec + static_cast<uint32_t>(j) * 4u), "f"(v) : "memory");
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      bar_all();
     }
     int it = 0;
     for (int w = w_first; w < n_work; w += w_step, ++it) {
@@ -491,24 +499,21 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
       const int nblk = (tile_cols + 63) / 64;
       const int x_row0 = tm * TILE_M + static_cast<int>(rank) * BM;      // TMA row coordinate of this CTA's 128 rows
       if constexpr (TMA_EPI && EPI == EPI_DA) {
-        if (xthread) {
-          for (int k = 0; k < 2 && k < nblk; ++k) {       // A_{l-1} of the first two blocks (buffers free: every warp has left the previous tile)
-            const int b = (xblk + k) & 1;
-            mbar_arrive_expect_tx(aux_bar(b), 16384u);
-            tma_load_2d(xa(b), &tms.x, aux_bar(b), tn * BN + k * 64, x_row0);
-          }
+        if (xthread && grp < nblk) {       // A_{l-1} of this group's first block (its buffer is free: the group has left the previous tile)
+          mbar_arrive_expect_tx(aux_bar(grp), 16384u);
+          tma_load_2d(xa(grp), &tms.x, aux_bar(grp), tn * BN + grp * 64, x_row0);
         }
       }
       const uint32_t sm_bias = sm_vec + static_cast<uint32_t>(it & 1) * (BN * 4u);   // EPI_FWD: this tile's bias, double-buffered
       if constexpr (EPI == EPI_FWD) {
         // (a warp reaches this barrier only after finishing the previous tile, so buffer it & 1 is no longer read)
 #pragma unroll
-        for (int j = et; j < BN; j += 256) {
+        for (int j = et; j < BN; j += ET) {
           const int col = tn * BN + j;
           const float bv = (col < p.N) ? __ldg(p.bias + col) : 0.f;
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(sm_bias + static_cast<uint32_t>(j) * 4u), "f"(bv) : "memory");
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        bar_all();
       }
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
@@ -619,10 +624,10 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
         continue;
       }
 #pragma unroll 1
-      for (int c = half; c < BN / 32; c += 2) {
+      for (int c = TMA_EPI ? 2 * grp + half : half; c < BN / 32; c += (TMA_EPI ? 4 : 2)) {
         const int col0 = tn * BN + c * 32;
         if constexpr (TMA_EPI) {
-          if ((c >> 1) >= nblk) break;          // same trip count for all eight warps
+          if ((c >> 1) >= nblk) break;          // same trip count for the eight warps of a group
         } else {
           if (col0 >= p.N) break;  // whole chunk out of range (warp-uniform)
         }
@@ -639,7 +644,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
         const bool full = col0 + 32 <= p.N;  // warp-uniform fast path
-        const int xb = static_cast<int>(xblk & 1u);
+        const int xb = grp;                     // TMA-staged epilogues: each group owns one output tile and one A_{l-1} tile
 
         if constexpr (EPI == EPI_FWD) {
           if (GENERIC && p.addend != nullptr && row_ok) {
@@ -673,7 +678,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
           // multiply by act'(A_{l-1}[row, col]) read as bf16 (64 B per thread per chunk, fetched one chunk ahead)
           uint4 a4[4];
           if constexpr (TMA_EPI) {
-            mbar_wait(aux_bar(xb), (xblk >> 1) & 1u);        // this block's A_{l-1} tile has landed
+            mbar_wait(aux_bar(xb), xblk & 1u);               // this block's A_{l-1} tile has landed
 #pragma unroll
             for (int i = 0; i < 4; ++i) a4[i] = lds4(xa(xb) + piece(half, i));
           } else {
@@ -718,29 +723,30 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
 
         if constexpr (EPI == EPI_FWD || EPI == EPI_DA) {
           if constexpr (TMA_EPI) {
+            uint4 o[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              uint4 o;
-              o.x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
-              o.y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
-              o.z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
-              o.w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
-              sts4(xo(xb) + piece(half, q), o);
+              o[q].x = pack_bf16x2(v[q * 8 + 0], v[q * 8 + 1]);
+              o[q].y = pack_bf16x2(v[q * 8 + 2], v[q * 8 + 3]);
+              o[q].z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
+              o[q].w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
             }
+            if (xthread) tma_store_wait_read<0>();                 // the group's previous store has finished reading its tile ...
+            bar_grp();                                             // (B) ... which every warp of the group may now overwrite
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sts4(xo(xb) + piece(half, q), o[q]);
             fence_proxy_async();                                   // generic-proxy writes -> visible to the TMA engine
-            asm volatile("bar.sync 1, 256;" ::: "memory");         // (A) the block's tile is complete; A_{l-1} tile consumed
+            bar_grp();                                             // (A) the block's tile is complete; A_{l-1} tile consumed
             if (xthread) {
               tma_store_2d(&tms.o, xo(xb), tn * BN + (c >> 1) * 64, x_row0);
               tma_store_commit();
               if constexpr (EPI == EPI_DA) {
-                if ((c >> 1) + 2 < nblk) {                         // A_{l-1} two blocks ahead, into the tile just consumed
+                if ((c >> 1) + 2 < nblk) {                         // A_{l-1} of the group's next block, into the tile just consumed
                   mbar_arrive_expect_tx(aux_bar(xb), 16384u);
                   tma_load_2d(xa(xb), &tms.x, aux_bar(xb), tn * BN + ((c >> 1) + 2) * 64, x_row0);
                 }
               }
-              tma_store_wait_read<1>();                            // the OTHER output tile has been read: free for the next block
             }
-            asm volatile("bar.sync 1, 256;" ::: "memory");         // (B)
             ++xblk;
           } else {
             // row-major bf16 (ld_out is a multiple of 8, pad columns belong to the buffer); split modes: np part arrays
@@ -809,7 +815,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
   }
 
   if constexpr (TMA_EPI) {
-    if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last tiles are in global memory
+    if (warp >= 2 && ((warp - 2) & 7) == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the last tiles are in global memory
   }
   tcgen05_fence_before();
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();

@@ -155,4 +155,5 @@ def test_device_resident_set_feeds_the_trainer_without_a_host_copy(sb):
         b.load_dataset(Xd, yd, wd)
         for k in range(4):
             assert a.step_resident(k * 128, 128) == b.step_resident(k * 128, 128)
-        assert a.eval_loss(Xh, yh, wh) == b.eval_loss(Xd, yd, wd)
+        # (the evaluation loss is summed with fp32 atomics across CTAs: equal up to the summation order)
+        assert abs(a.eval_loss(Xh, yh, wh) - b.eval_loss(Xd, yd, wd)) <= 1e-6
