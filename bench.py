@@ -201,23 +201,10 @@ def run_reference(args, cfg, rank, world):
     print(json.dumps(out), flush=True)
 
 
-def gemm_shapes(B, F, hidden):
-    """launch order of the traced kernels of one step -> (role, M, N, K) of each GEMM-class launch"""
-    dims = [F] + list(hidden)
-    L = len(hidden)
-    fwd = [("fwd%d" % l, B, dims[l + 1], dims[l]) for l in range(L)]
-    bwd = []
-    for l in range(L - 1, -1, -1):
-        bwd.append(("dW%d" % l, dims[l], dims[l + 1], B))
-        if l > 0:
-            bwd.append(("dA%d" % l, B, dims[l], dims[l + 1]))
-    return fwd, bwd
-
-
 def step_timeline(names, stamps, B, F, hidden):
-    """stamps [k,16] ns of the last captured step: slot 0 entry (CTA 0), 2 dependencies resolved, 10 last CTA exit"""
-    fwd, bwd = gemm_shapes(B, F, hidden)
-    fi, bi = iter(fwd), iter(bwd)
+    """stamps [k,16] ns of the traced step: slot 0 entry (CTA 0), 2 dependencies resolved, 10 last CTA exit.  Names come from
+    the library as role[layer][.chunk][@MxNxK] (Net::next_trace)."""
+    L = len(hidden)
     rows = []
     for nm, st in zip(names, stamps):
         begin = int(st[2]) if st[2] else int(st[0])
@@ -225,16 +212,20 @@ def step_timeline(names, stamps, B, F, hidden):
         if not begin or not end:
             continue
         role, flops = nm, 0
-        if nm in ("fwd", "fwd_out"):
-            role, M, N, K = next(fi); flops = 2 * M * N * K
-            if nm == "fwd_out":
-                role += "+out"
-        elif nm in ("dW", "dA"):
-            role, M, N, K = next(bi); flops = 2 * M * N * K
+        if "@" in nm:
+            role, dims = nm.split("@")
+            M, N, K = (int(v) for v in dims.split("x"))
+            flops = 2 * M * N * K
+            if role.startswith("fwd_out"):
+                role = "fwd%s+out" % role[len("fwd_out"):]
         cta0 = None
         if flops and st[3] and st[6]:      # CTA 0's pipeline milestones (us after its dependencies resolved)
             cta0 = {"first_tma": (int(st[3]) - begin) / 1e3, "first_acc": (int(st[6]) - begin) / 1e3,
                     "first_epilogue": (int(st[7]) - begin) / 1e3 if st[7] else None, "exit": (int(st[8]) - begin) / 1e3 if st[8] else None}
+        elif role.startswith("xchg") and st[3]:
+            # exchange kernel: every peer arrived (block 0) / last block's runs done / its stores fenced / every peer done
+            cta0 = {"peers_arrived": (int(st[3]) - begin) / 1e3, "runs_done": (int(st[4]) - begin) / 1e3 if st[4] else None,
+                    "fenced": (int(st[5]) - begin) / 1e3 if st[5] else None, "peers_done": (int(st[6]) - begin) / 1e3 if st[6] else None}
         rows.append({"kernel": role, "entry": int(st[0]), "begin": begin, "end": end, "flops": flops, "cta0": cta0})
     if not rows:
         return None

@@ -462,9 +462,9 @@ class Trainer:
     def debug_step_trace(self):
         """-> (names, stamps[k,16] uint64 ns) of the last step's GEMM launches (needs SB_STEP_TRACE=1 at creation)"""
         buf = np.zeros((32, 16), np.uint64)
-        names = C.create_string_buffer(1024)
+        names = C.create_string_buffer(4096)
         k = C.c_int32()
-        check(lib().sb_debug_step_trace(self._h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), 32, names, 1024, C.byref(k)))
+        check(lib().sb_debug_step_trace(self._h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), 32, names, 4096, C.byref(k)))
         return names.value.decode().split(","), buf[:k.value].copy()
 
     @property

@@ -58,7 +58,15 @@ struct sb_trainer {
   unsigned int* h_err = nullptr;   // pinned + mapped: a peer that never arrived (xchg_p2p.cuh), 0 = none
   unsigned int* d_herr = nullptr;
   unsigned long long xchg_timeout_ns = 300ull * 1000000000ull;
-  int xchg_blocks = 0;             // grid of the exchange kernels (0 = one block per SM)
+  int xchg_blocks = 0;             // grid cap of the exchange kernels (0 = one block per SM)
+  // slot table of the exchange (fixed for the trainer's life: it defines who owns which run): slot 0 = every layer but
+  // hidden layer 0, slots 1..x_chunks = row chunks of hidden layer 0 (the last one also carries b_0)
+  int x_chunks = 1, x_slots = 2;
+  int x_begin[SB_XCHG_SLOTS] = {}, x_end[SB_XCHG_SLOTS] = {};
+  cudaEvent_t ev_x[SB_XCHG_SLOTS] = {};   // exchange of slot s complete (recorded on its comm stream)
+  cudaEvent_t ev_c[SB_XCHG_SLOTS] = {};   // dW_0 chunk c complete on the main stream / tail of the main stream
+  int x_sent = 0;                  // (while enqueueing a step) slots whose exchange the dW_0 chunk hook has launched
+  bool pending_xA = false;         // (while capturing) slot 0's exchange of the previous step has not been joined yet
   // pipelined host-buffer steps (sb_trainer_step_async): second staging slot + copy stream, so the H2D of batch i+1
   // overlaps the compute of batch i
   cudaStream_t copy_stream = nullptr;
@@ -118,8 +126,9 @@ static int enqueue_optimizer(sb_trainer* t, const float* g, int w0 = 0, int w1 =
   return SB_OK;
 }
 
-// segments of the sharded exchange: bit 0 = A (every layer but hidden layer 0), bit 1 = B (hidden layer 0)
-enum { XSEG_A = 1, XSEG_B = 2, XSEG_ALL = 3 };
+// slots of the sharded exchange: bit 0 = A (every layer but hidden layer 0), bits 1.. = the row chunks of hidden layer 0
+enum { XSEG_A = 1 };
+static int xseg_all(const sb_trainer* t) { return (1 << t->x_slots) - 1; }
 
 static XchgParams xchg_params(sb_trainer* t) {
   Net& n = t->net;
@@ -130,8 +139,8 @@ static XchgParams xchg_params(sb_trainer* t) {
   p.s1_off = static_cast<long long>(n.s1_off); p.s2_off = static_cast<long long>(n.s2_off);
   p.grad_off = t->grad_off; p.flags_off = t->flags_off;
   p.work = n.work;
-  p.seg_begin[0] = n.work_end[0]; p.seg_end[0] = n.n_work;     // A: layers 1 .. L (output layer)
-  p.seg_begin[1] = 0; p.seg_end[1] = n.work_end[0];            // B: hidden layer 0
+  p.n_slots = t->x_slots;
+  for (int sl = 0; sl < t->x_slots; ++sl) { p.slot_begin[sl] = t->x_begin[sl]; p.slot_end[sl] = t->x_end[sl]; }
   p.desc = n.desc;
   p.hyper = t->hyper;
   p.host_err = t->d_herr;
@@ -141,21 +150,25 @@ static XchgParams xchg_params(sb_trainer* t) {
 }
 
 // reduce-scatter -> owner update -> all-gather of the operands for the given segments (xchg_p2p.cuh); `g` must be t->grad
-static int enqueue_xchg(sb_trainer* t, int seg_mask, cudaStream_t st, bool publish_scalars, bool pdl) {
+static int enqueue_xchg(sb_trainer* t, int slot_mask, cudaStream_t st, bool publish_scalars, bool pdl) {
   Net& n = t->net;
   XchgParams p = xchg_params(t);
-  p.seg_mask = seg_mask;
+  p.slot_mask = slot_mask;
   p.scal = publish_scalars ? n.scal : nullptr;
   p.host_scal = publish_scalars ? t->d_hscal : nullptr;
-  p.trace = n.next_trace(seg_mask == XSEG_A ? "xchg_A" : (seg_mask == XSEG_B ? "xchg_B" : "xchg"));
-  int runs = 0;
-  for (int sgi = 0; sgi < 2; ++sgi)
-    if ((seg_mask >> sgi) & 1) {
-      const int r = (p.seg_end[sgi] - p.seg_begin[sgi] + t->world - 1) / t->world;
-      if (r > runs) runs = r;
-    }
+  char nm[24];
+  if (slot_mask == XSEG_A) snprintf(nm, sizeof(nm), "xchg_A");
+  else if ((slot_mask & (slot_mask - 1)) == 0) snprintf(nm, sizeof(nm), "xchg_B%d", __builtin_ctz(slot_mask) - 1);
+  else snprintf(nm, sizeof(nm), "xchg");
+  p.trace = n.next_trace(nm);
+  int runs = 0;      // owned runs of the launch (the largest share)
+  for (int sl = 0; sl < t->x_slots; ++sl)
+    if ((slot_mask >> sl) & 1) runs += (p.slot_end[sl] - p.slot_begin[sl] + t->world - 1) / t->world;
+  const int U = t->world <= 2 ? 4 : (t->world <= 4 ? 2 : 1);      // runs per block iteration (xchg_update_kernel)
+  // at most one block per SM and launch: a block must fit beside whatever persistent GEMM CTA shares its SM (xchg_p2p.cuh)
   int grid = t->xchg_blocks > 0 ? t->xchg_blocks : n.num_sms;
-  if (grid > runs) grid = runs;
+  if (t->peers_share_device && grid > 32) grid = 32;    // replicas on ONE device: leave registers to the replica being waited for
+  if (grid > (runs + U - 1) / U) grid = (runs + U - 1) / U;
   if (grid < 1) grid = 1;
   const dim3 g(static_cast<unsigned>(grid)), b(256);
   if (t->world <= 2) SB_TRY(n.launch(xchg_update_kernel<2>, g, b, 0, st, pdl, p));
@@ -191,12 +204,47 @@ static bool step_is_pipelined(const sb_trainer* t, int kind) {
 }
 
 // the body of one step as a sequence of stream operations (captured into a CUDA graph)
-static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = false, bool sparse = false) {
+static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = false, bool sparse = false, bool last_in_graph = true) {
   Net& n = t->net;
-  struct Scope { Net& n; ~Scope() { n.from_resident = false; n.zero_buf = nullptr; n.dw0_on_main = n.defer_join = false; n.sparse_step = false; } } scope{n};
+  struct Scope {
+    Net& n;
+    ~Scope() {
+      n.from_resident = false; n.zero_buf = nullptr; n.dw0_on_main = n.defer_join = false; n.sparse_step = false;
+      n.dw0_chunks = 1; n.dw1_last = false; n.on_dw0_chunk = nullptr; n.before_layer1 = nullptr; n.zero_layer = 0;
+    }
+  } scope{n};
   n.from_resident = resident;
   n.sparse_step = sparse;
   n.trace_k = 0;
+  // ---- schedule of the step's tail (decided first: the peer-exchange schedule also changes the forward pass) ----
+  const bool pipelined = step_is_pipelined(t, kind);
+  // Single GPU, one update per mini-batch: no exchange, so nothing needs ALL gradients at once.  dW_0 runs on the main
+  // stream behind the last dA GEMM and is followed (PDL) by the optimizer of layer 0 alone; the side stream updates the
+  // other layers right after their dW GEMMs; the two streams only join at the end of the graph.
+  static const bool old_sched = getenv("SB_OLD_SCHED") != nullptr;
+  static const bool one_xchg = getenv("SB_XCHG_ONE") != nullptr;    // experiment: one exchange launch for everything after a join
+  const bool split_tail = !old_sched && kind == G_STEP && (t->world == 1 || (t->p2p_ready && !one_xchg)) && !pipelined &&
+                          n.concurrent_bwd && !n.profiling && n.side != nullptr && n.tc() && n.L > 1;
+  // Peer exchange (world > 1): the chain  arrive -> P2P loads -> update -> P2P stores + fence -> done  costs ~17 us through
+  // NVSwitch however little data it moves (xchg_p2p.cuh), so every exchange launch gets a GEMM to hide behind:
+  //   main:  ... dA_1 -> dW_0 chunk 0 -> dW_0 chunk 1 -> dW_1        | next step: layer-0 forward -> layer-1 forward ...
+  //   comm:              xchg B0 ---------> xchg B1 ------> xchg A ---------------------------->|
+  // B0 runs beside dW_0's second chunk, B1 beside dW_1, A (every other layer) beside the NEXT step's layer-0 forward GEMM,
+  // which reads nothing slot A writes: layer 1's forward waits for A, and - because peers still read this rank's gradient
+  // buffer until then - the buffer is cleared by layer 1's forward GEMM instead of layer 0's.
+  const bool xsched = split_tail && t->world > 1;
+  static const bool no_defer = getenv("SB_XCHG_NO_DEFER") != nullptr;
+  const bool defer_A = xsched && resident && n.L >= 3 && !no_defer;
+  if (xsched) {
+    n.zero_layer = defer_A ? 1 : 0;
+    if (t->pending_xA) {
+      n.before_layer1 = [t]() -> int {
+        SB_CUDA(cudaStreamWaitEvent(t->net.stream, t->ev_x[0], 0));
+        t->pending_xA = false;
+        return SB_OK;
+      };
+    }
+  }
   if (resident) {
     // no load kernel: the batch is read by TMA from the bf16 resident set; set_batch_kernel already published n_nz.
     // The gradient buffer is first written by the last forward layer's epilogue, so with more than one hidden layer the
@@ -221,7 +269,6 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   // Measured on 2x B200 (profiles/scaling_r01.md): with NCCL as the exchange, ONE all-reduce of the whole flat gradient
   // after the backward pass beats per-layer / per-chunk calls (each NCCL launch costs ~20-50 us and its CTAs evict
   // persistent GEMM CTAs), so the pipelined variant is opt-in (SB_PIPELINE_AR=1).
-  const bool pipelined = step_is_pipelined(t, kind);
   if (pipelined) {
     n.on_layer_grads = [t](int l, cudaStream_t cs, int phase, long long e0, long long e1) -> int {
       Net& nn = t->net;
@@ -241,30 +288,55 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   } else {
     n.on_layer_grads = nullptr;
   }
-  // Single GPU, one update per mini-batch: no exchange, so nothing needs ALL gradients at once.  dW_0 runs on the main
-  // stream behind the last dA GEMM and is followed (PDL) by the optimizer of layer 0 alone; the side stream updates the
-  // other layers right after their dW GEMMs; the two streams only join at the end of the graph.
-  static const bool old_sched = getenv("SB_OLD_SCHED") != nullptr;
-  // With the peer-memory exchange (world > 1) the tail has the SAME shape: the two optimizer launches become the two
-  // segment launches of xchg_update_kernel (segment A on the side stream overlaps dW_0, segment B follows dW_0).
-  static const bool one_xchg = getenv("SB_XCHG_ONE") != nullptr;    // experiment: one launch for both segments after a join
-  const bool split_tail = !old_sched && kind == G_STEP && (t->world == 1 || (t->p2p_ready && !one_xchg)) && !pipelined &&
-                          n.concurrent_bwd && !n.profiling && n.side != nullptr && n.tc() && n.L > 1;
   // (dW_0 on the main stream also when an exchange or the accumulate kernel follows: it is then joined with the side
   // stream as before)
   n.dw0_on_main = !old_sched && !pipelined && n.concurrent_bwd && !n.profiling && n.side != nullptr &&
                   n.tc() && n.L > 1;
   n.defer_join = split_tail;
+  cudaStream_t comms[2] = {n.comm2, n.comm};
+  if (xsched) {
+    static const bool dw1_beside = getenv("SB_XCHG_DW1_BESIDE") != nullptr;   // experiment: keep dW_1 beside dW_0 (side stream)
+    n.dw0_chunks = t->x_chunks;
+    n.dw1_last = !dw1_beside;
+    t->x_sent = 0;
+    n.on_dw0_chunk = [t, comms](int c) -> int {
+      Net& nn = t->net;
+      cudaStream_t cs = comms[c & 1];
+      SB_CUDA(cudaEventRecord(t->ev_c[1 + c], nn.stream));
+      SB_CUDA(cudaStreamWaitEvent(cs, t->ev_c[1 + c], 0));
+      SB_TRY(enqueue_xchg(t, 1 << (1 + c), cs, c == t->x_chunks - 1, false));   // (the last chunk publishes the step scalars)
+      SB_CUDA(cudaEventRecord(t->ev_x[1 + c], cs));
+      t->x_sent |= 1 << (1 + c);
+      return SB_OK;
+    };
+  }
   int bs = n.enqueue_backward(rows, t->grad);
   n.on_layer_grads = nullptr;
   SB_TRY(bs);
+  if (xsched) {
+    // slot A: every gradient but hidden layer 0's - complete behind dW_1 (main stream) and the other dW GEMMs (side stream)
+    cudaStream_t ca = comms[t->x_chunks & 1];
+    SB_CUDA(cudaEventRecord(t->ev_c[0], n.stream));
+    SB_CUDA(cudaStreamWaitEvent(ca, t->ev_c[0], 0));
+    SB_CUDA(cudaEventRecord(n.ev_join, n.side));
+    SB_CUDA(cudaStreamWaitEvent(ca, n.ev_join, 0));
+    SB_TRY(enqueue_xchg(t, XSEG_A, ca, false, false));
+    SB_CUDA(cudaEventRecord(t->ev_x[0], ca));
+    // whatever follows on the main stream (the next step's layer-0 forward, or the end of the graph) needs hidden layer 0
+    for (int c = 0; c < t->x_chunks; ++c)
+      if ((t->x_sent >> (1 + c)) & 1) SB_CUDA(cudaStreamWaitEvent(n.stream, t->ev_x[1 + c], 0));
+    // (a layer-0 dW that was not cut into the trainer's chunks - wide+deep steps - is exchanged here, behind everything)
+    const int missing = (xseg_all(t) & ~XSEG_A) & ~t->x_sent;
+    if (missing) SB_TRY(enqueue_xchg(t, missing, n.stream, true, false));
+    if (defer_A && !last_in_graph) t->pending_xA = true;
+    else SB_CUDA(cudaStreamWaitEvent(n.stream, t->ev_x[0], 0));
+    return SB_OK;
+  }
   if (split_tail) {
-    if (t->world > 1) SB_TRY(enqueue_xchg(t, XSEG_B, n.stream, true, n.use_pdl));
-    else SB_TRY(enqueue_optimizer(t, t->grad, n.work_begin[0], n.work_end[0], n.stream, true, n.use_pdl));
+    SB_TRY(enqueue_optimizer(t, t->grad, n.work_begin[0], n.work_end[0], n.stream, true, n.use_pdl));
     // the other layers' shadows are read by the dA GEMMs on the main stream: update them only after the last one
     SB_CUDA(cudaStreamWaitEvent(n.side, n.ev_da_done, 0));
-    if (t->world > 1) SB_TRY(enqueue_xchg(t, XSEG_A, n.side, false, false));
-    else SB_TRY(enqueue_optimizer(t, t->grad, n.work_end[0], n.n_work, n.side));
+    SB_TRY(enqueue_optimizer(t, t->grad, n.work_end[0], n.n_work, n.side));
     SB_CUDA(cudaEventRecord(n.ev_join, n.side));
     SB_CUDA(cudaStreamWaitEvent(n.stream, n.ev_join, 0));
     return SB_OK;
@@ -273,7 +345,7 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
     if (pipelined) return SB_OK;
     if (t->world > 1 && t->p2p_ready) {
       // (fp32 mode, one hidden layer, profiling, SB_XCHG_ONE: no split tail) one launch handles both segments
-      SB_TRY(enqueue_xchg(t, XSEG_ALL, n.stream, true, false));
+      SB_TRY(enqueue_xchg(t, xseg_all(t), n.stream, true, false));
     } else {
       SB_TRY(enqueue_allreduce(t, t->grad));
       if (t->world > 1 && n.profiling) { n.mark("allreduce"); --n.launches; }
@@ -382,8 +454,8 @@ static int poll_xchg(sb_trainer* t) {
   if (!t->h_err) return SB_OK;
   const unsigned int e = *reinterpret_cast<volatile unsigned int*>(t->h_err);
   if (e == 0) return SB_OK;
-  return set_error(SB_ERR_NCCL, "gradient exchange timed out on rank %d: rank %u did not reach segment %c of the exchange within %.0f s "
-                   "(peer process dead or stuck); this trainer is no longer usable", t->rank, (e - 1) & 15u, ((e - 1) >> 4) ? 'B' : 'A',
+  return set_error(SB_ERR_NCCL, "gradient exchange timed out on rank %d: rank %u did not reach slot %u of the exchange within %.0f s "
+                   "(peer process dead or stuck); this trainer is no longer usable", t->rank, (e - 1) & 15u, (e - 1) >> 4,
                    t->xchg_timeout_ns * 1e-9);
 }
 
@@ -499,6 +571,34 @@ int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, 
   memset(t->h_err, 0, sizeof(unsigned int) * 4);
   if (const char* e = getenv("SB_XCHG_TIMEOUT_S")) t->xchg_timeout_ns = static_cast<unsigned long long>(atof(e) * 1e9);
   if (const char* e = getenv("SB_XCHG_BLOCKS")) t->xchg_blocks = atoi(e);
+  {
+    // exchange slots: hidden layer 0 in row chunks of W_0 (128-row multiples; runs are 1024 parameters, so chunk borders fall
+    // on run borders when out % 8 == 0), the last chunk also carries b_0; everything else is slot 0
+    int chunks = 2;
+    if (const char* e = getenv("SB_XCHG_CHUNKS")) chunks = atoi(e);
+    if (chunks > SB_XCHG_SLOTS - 1) chunks = SB_XCHG_SLOTS - 1;
+    const Layer& l0 = n.layers[0];
+    if (chunks < 1 || !n.tc() || (l0.out % 8) != 0 || l0.in < 256 * chunks) chunks = 1;
+    n.dw0_chunks = chunks;
+    const int cr = n.dw0_chunk_rows();
+    chunks = (l0.in + cr - 1) / cr;           // (rounding to 128 rows may need fewer chunks)
+    n.dw0_chunks = 1;                          // the GEMM is only cut while a step with the peer exchange is enqueued
+    t->x_chunks = chunks;
+    t->x_slots = 1 + chunks;
+    t->x_begin[0] = n.work_end[0]; t->x_end[0] = n.n_work;
+    for (int c = 0; c < chunks; ++c) {
+      const long long e0 = static_cast<long long>(c) * cr * l0.out, e1 = static_cast<long long>(c + 1) * cr * l0.out;
+      t->x_begin[1 + c] = n.work_begin[0] + static_cast<int>(e0 / 1024);
+      t->x_end[1 + c] = (c == chunks - 1) ? n.work_end[0] : n.work_begin[0] + static_cast<int>(e1 / 1024);
+    }
+    for (int i = 0; i < SB_XCHG_SLOTS; ++i) {
+      if (cudaEventCreateWithFlags(&t->ev_x[i], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&t->ev_c[i], cudaEventDisableTiming) != cudaSuccess) {
+        n.destroy();
+        return set_error(SB_ERR_CUDA, "cudaEventCreate failed");
+      }
+    }
+  }
   if (cudaHostAlloc(reinterpret_cast<void**>(&t->h_scal), sizeof(float) * SCAL_COUNT, cudaHostAllocMapped) != cudaSuccess) {
     n.destroy();
     return set_error(SB_ERR_CUDA, "cudaHostAlloc failed");
@@ -894,7 +994,7 @@ static int apply_accumulated_impl(sb_trainer_t* t, int64_t total_pushes) {
   // exchange + apply through the (IPC-exported) gradient buffer; it then holds the applied mean for sb_trainer_get_grads
   SB_CUDA(cudaMemcpyAsync(t->grad, t->acc, sizeof(float) * n.n_params, cudaMemcpyDeviceToDevice, n.stream));
   if (t->world > 1 && t->p2p_ready) {
-    SB_TRY(enqueue_xchg(t, XSEG_ALL, n.stream, false, false));
+    SB_TRY(enqueue_xchg(t, xseg_all(t), n.stream, false, false));
   } else {
     SB_TRY(enqueue_allreduce(t, t->grad));
     SB_TRY(enqueue_optimizer(t, t->grad));
@@ -1001,11 +1101,17 @@ static int get_run_graph(sb_trainer* t, int rows, int set, cudaGraphExec_t* out)
   cudaGraph_t g = nullptr;
   SB_CUDA(cudaStreamBeginCapture(n.stream, cudaStreamCaptureModeThreadLocal));
   int s = SB_OK;
+  t->pending_xA = false;
   for (int k = 0; k < sb_trainer::RUN_S && s == SB_OK; ++k) {
     n.desc = t->run_descs[set][k];
     n.scal = t->run_scals[set][k];
-    s = enqueue_step_body(t, rows, G_STEP, true);
+    // (SB_STEP_TRACE: an interior step is the one traced - with the peer exchange, the last step of a graph joins the
+    // exchange of slot A at its end instead of hiding it behind the next step's layer-0 forward)
+    n.trace_on = (k == 1);
+    s = enqueue_step_body(t, rows, G_STEP, true, false, k == sb_trainer::RUN_S - 1);
   }
+  n.trace_on = true;
+  t->pending_xA = false;
   n.desc = d0; n.scal = s0;
   cudaError_t e = cudaStreamEndCapture(n.stream, &g);
   if (s != SB_OK) { if (g) cudaGraphDestroy(g); return s; }
@@ -1216,7 +1322,7 @@ int sb_trainer_profile_step(sb_trainer_t* t, int64_t row_offset, int32_t rows, c
     if (s == SB_OK && !fused_out) s = n.enqueue_out(rows, true, true, nullptr, t->grad);
     if (s == SB_OK) s = n.enqueue_backward(rows, t->grad);
     if (t->world > 1 && t->p2p_ready) {
-      if (s == SB_OK) s = enqueue_xchg(t, XSEG_ALL, n.stream, false, false);
+      if (s == SB_OK) s = enqueue_xchg(t, xseg_all(t), n.stream, false, false);
     } else {
       if (s == SB_OK) s = enqueue_allreduce(t, t->grad);
       if (s == SB_OK && t->world > 1) { n.mark("allreduce"); --n.launches; }
@@ -1479,7 +1585,7 @@ int sb_debug_step_trace(sb_trainer_t* t, uint64_t* stamps, int32_t cap_kernels, 
   SB_CHECK(n.step_trace != nullptr, SB_ERR_STATE, "create the trainer with SB_STEP_TRACE=1 in the environment");
   SB_CUDA(cudaSetDevice(n.device));
   SB_CUDA(cudaStreamSynchronize(n.stream));
-  const int k = n.trace_k < cap_kernels ? n.trace_k : cap_kernels;
+  const int k = n.trace_n < cap_kernels ? n.trace_n : cap_kernels;
   SB_CUDA(cudaMemcpy(stamps, n.step_trace, sizeof(uint64_t) * 16 * k, cudaMemcpyDeviceToHost));
   *n_kernels = k;
   if (names && names_cap > 0) {

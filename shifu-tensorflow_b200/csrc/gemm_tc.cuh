@@ -125,10 +125,12 @@ struct GemmTcCfg {
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
-  // Epilogue warps.  The epilogues are instruction-latency bound (a warp's chunk is a ~500-instruction chain; 8 warps = 2 per
-  // scheduler issued 0.18 instructions per cycle in the ncu capture of the cfg2 dA GEMM), so the TMA-staged epilogues - whose
-  // register need dropped to ~115 - run SIXTEEN warps in two groups of eight that work on alternate 64-column blocks.
-  static constexpr int EPI_WARPS = XB > 0 ? 16 : 8;
+  // Epilogue warps.  The dA epilogue (the longest: A_{l-1} tile in, act', column sums, dZ tile out) runs SIXTEEN warps in two
+  // groups of eight that work on alternate 64-column blocks (cfg2 dA_1 19.7 -> 18.8 us, dA_2 7.9 -> 6.8 us; the forward
+  // epilogue gained nothing and keeps eight: 320 threads x <= 115 registers leave room for an exchange block on the same SM,
+  // see xchg_p2p.cuh).
+  static constexpr int EPI_WARPS = XB >= 4 * 16384 ? 16 : 8;
+  static constexpr int EPI_GROUPS = EPI_WARPS / 8;
   static constexpr int EPI_THREADS = 32 * EPI_WARPS;
   static constexpr int THREADS = 64 + EPI_THREADS;
 };
@@ -322,6 +324,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
     const int grp = (warp - 2) >> 3;           // TMA-staged epilogues: group 0 / 1 takes the even / odd 64-column blocks
     const int et = static_cast<int>(threadIdx.x) - 64;   // 0 .. EPI_THREADS-1 over all epilogue warps
     constexpr int ET = Cfg::EPI_THREADS;
+    constexpr int NGRP = Cfg::EPI_GROUPS;
     auto bar_all = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_THREADS) : "memory"); };    // every epilogue warp
     auto bar_grp = [&]() { asm volatile("bar.sync %0, 256;" ::"r"(2 + grp) : "memory"); };              // the eight warps of a group
     if (p.zero_buf != nullptr) {
@@ -499,9 +502,19 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
       const int nblk = (tile_cols + 63) / 64;
       const int x_row0 = tm * TILE_M + static_cast<int>(rank) * BM;      // TMA row coordinate of this CTA's 128 rows
       if constexpr (TMA_EPI && EPI == EPI_DA) {
-        if (xthread && grp < nblk) {       // A_{l-1} of this group's first block (its buffer is free: the group has left the previous tile)
-          mbar_arrive_expect_tx(aux_bar(grp), 16384u);
-          tma_load_2d(xa(grp), &tms.x, aux_bar(grp), tn * BN + grp * 64, x_row0);
+        if constexpr (NGRP == 2) {
+          if (xthread && grp < nblk) {       // A_{l-1} of this group's first block (its buffer is free: the group has left the previous tile)
+            mbar_arrive_expect_tx(aux_bar(grp), 16384u);
+            tma_load_2d(xa(grp), &tms.x, aux_bar(grp), tn * BN + grp * 64, x_row0);
+          }
+        } else {
+          if (xthread) {
+            for (int k = 0; k < 2 && k < nblk; ++k) {       // A_{l-1} of the first two blocks (buffers free: every warp has left the previous tile)
+              const int b = (xblk + k) & 1;
+              mbar_arrive_expect_tx(aux_bar(b), 16384u);
+              tma_load_2d(xa(b), &tms.x, aux_bar(b), tn * BN + k * 64, x_row0);
+            }
+          }
         }
       }
       const uint32_t sm_bias = sm_vec + static_cast<uint32_t>(it & 1) * (BN * 4u);   // EPI_FWD: this tile's bias, double-buffered
@@ -624,7 +637,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
         continue;
       }
 #pragma unroll 1
-      for (int c = TMA_EPI ? 2 * grp + half : half; c < BN / 32; c += (TMA_EPI ? 4 : 2)) {
+      for (int c = TMA_EPI ? 2 * grp + half : half; c < BN / 32; c += (TMA_EPI ? 2 * NGRP : 2)) {
         const int col0 = tn * BN + c * 32;
         if constexpr (TMA_EPI) {
           if ((c >> 1) >= nblk) break;          // same trip count for the eight warps of a group
@@ -644,7 +657,8 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
         const bool full = col0 + 32 <= p.N;  // warp-uniform fast path
-        const int xb = grp;                     // TMA-staged epilogues: each group owns one output tile and one A_{l-1} tile
+        // staging tiles: two groups -> each owns one output and one A_{l-1} tile; one group -> it alternates between two
+        const int xb = NGRP == 2 ? grp : static_cast<int>(xblk & 1u);
 
         if constexpr (EPI == EPI_FWD) {
           if (GENERIC && p.addend != nullptr && row_ok) {
@@ -678,7 +692,7 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
           // multiply by act'(A_{l-1}[row, col]) read as bf16 (64 B per thread per chunk, fetched one chunk ahead)
           uint4 a4[4];
           if constexpr (TMA_EPI) {
-            mbar_wait(aux_bar(xb), xblk & 1u);               // this block's A_{l-1} tile has landed
+            mbar_wait(aux_bar(xb), (NGRP == 2 ? xblk : (xblk >> 1)) & 1u);   // this block's A_{l-1} tile has landed
 #pragma unroll
             for (int i = 0; i < 4; ++i) a4[i] = lds4(xa(xb) + piece(half, i));
           } else {
@@ -731,7 +745,9 @@ gemm_tc_kernel(const __grid_constant__ TmapSet tms, const GemmTcParams p) {
               o[q].z = pack_bf16x2(v[q * 8 + 4], v[q * 8 + 5]);
               o[q].w = pack_bf16x2(v[q * 8 + 6], v[q * 8 + 7]);
             }
-            if (xthread) tma_store_wait_read<0>();                 // the group's previous store has finished reading its tile ...
+            if (xthread) {                                         // the last store out of this tile has finished reading it ...
+              if constexpr (NGRP == 2) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+            }
             bar_grp();                                             // (B) ... which every warp of the group may now overwrite
 #pragma unroll
             for (int q = 0; q < 4; ++q) sts4(xo(xb) + piece(half, q), o[q]);

@@ -166,6 +166,7 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
     SB_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     SB_CUDA(cudaEventCreateWithFlags(&ev_da_done, cudaEventDisableTiming));
     SB_CUDA(cudaStreamCreateWithFlags(&comm, cudaStreamNonBlocking));
+    SB_CUDA(cudaStreamCreateWithFlags(&comm2, cudaStreamNonBlocking));
     ev_dw.resize(d->n_hidden);
     for (auto& e : ev_dw) SB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     ev_da.resize(d->n_hidden);
@@ -318,6 +319,8 @@ void Net::destroy() {
   ev_comm = nullptr;
   if (comm) cudaStreamDestroy(comm);
   comm = nullptr;
+  if (comm2) cudaStreamDestroy(comm2);
+  comm2 = nullptr;
   if (side) cudaStreamDestroy(side);
   side = nullptr;
   if (stream) cudaStreamDestroy(stream);
@@ -392,6 +395,7 @@ int Net::enqueue_hidden_forward(int rows, float* grad, bool* fused_out) {
   if (fused_out) *fused_out = false;
   for (int l = 0; l < L; ++l) {
     Layer& ly = layers[l];
+    if (l == 1 && before_layer1) SB_TRY(before_layer1());
     const bool sp0 = (l == 0) && sparse_step;       // wide+deep: contract the dense columns only, add the embedding sums
     const int k_in = sp0 ? n_dense : ly.in;
     const int ld_k = sp0 ? ldD : ly.ld_in;
@@ -428,17 +432,17 @@ int Net::enqueue_hidden_forward(int rows, float* grad, bool* fused_out) {
         p.wo = theta + ol.w_off; p.bo = theta + ol.b_off;
         p.desc = desc; p.scal = scal; p.loss = loss;
         p.g_wo = grad + ol.w_off; p.g_bo = grad + ol.b_off; p.g_bL = grad + ly.b_off;
-        p.trace = next_trace("fwd_out");
+        p.trace = next_trace("fwd_out", l, rows, ly.out, k_in);
         SB_TRY((launch_gemm_tc<EPI_FWD_OUT, false, true>(fp, tm, p, stream, use_pdl)));
         if (fused_out) *fused_out = true;
         mark("gemm_fwd_out");
         continue;
       }
-      if (l == 0 && zero_buf != nullptr) {
+      if (l == zero_layer && zero_buf != nullptr) {
         p.zero_buf = zero_buf; p.zero_n4 = zero_n4;
         zero_buf = nullptr;
       }
-      p.trace = next_trace("fwd");
+      p.trace = next_trace("fwd", l, rows, ly.out, k_in);
       if (nparts == 1 && p.addend == nullptr)      // plain bf16: the epilogue stores its tiles by TMA
         SB_TRY(make_tmap_bf16(&tm.o, A[l], rows, ly.out, ly.ld_out, 128));
       SB_TRY((launch_gemm_tc<EPI_FWD, false, true>(pl, tm, p, stream, use_pdl)));
@@ -508,7 +512,7 @@ int Net::enqueue_backward(int rows, float* grad) {
   // finishing after dW_0" against "dW_1 on a third of the SMs, dW_0 on the rest" and take the shorter.
   int dw_sms[2] = {gemm_sms, gemm_sms};
   static const bool no_budget = getenv("SB_NO_DW_BUDGET") != nullptr;
-  if (fork && dw0_on_main && L > 1 && !on_layer_grads && !no_budget) {
+  if (fork && dw0_on_main && L > 1 && !on_layer_grads && !no_budget && !dw1_last) {
     const int kx = round_up(rows, 64) * pairs_of(nparts);
     const GemmPlan n0 = plan_gemm(layers[0].in, layers[0].out, kx, gemm_sms, true);
     const GemmPlan n1 = plan_gemm(layers[1].in, layers[1].out, kx, gemm_sms, true);
@@ -526,23 +530,20 @@ int Net::enqueue_backward(int rows, float* grad) {
       if ((t0 > t1 ? t0 : t1) < t_nat) { dw_sms[1] = gemm_sms / 3; dw_sms[0] = gemm_sms - b1.grid; }
     }
   }
-  for (int l = L - 1; l >= 0; --l) {
-    Layer& ly = layers[l];
-    if (tc()) {
-      // dW_l[in,out] += sum_rows A_{l-1}[rows,in] (MN-major A) * dZ_l[rows,out] (MN-major B), split-K over rows.
-      // With a gradient exchange behind it, a big layer is cut into row chunks of W_l (each a contiguous slice of the
-      // flat gradient) so that the all-reduce of chunk c overlaps the GEMM of chunk c+1.
-      {
+  auto emit_dw_tc = [&](int l, bool force_main) -> int {
+        Layer& ly = layers[l];
         const long long wl_elems = static_cast<long long>(ly.in) * ly.out;
         int n_chunks = 1;
         if (fork && on_layer_grads && dw_chunk_bytes > 0 && (ly.out % 8) == 0 && wl_elems * 4 > 2 * dw_chunk_bytes) {
           n_chunks = static_cast<int>((wl_elems * 4 + dw_chunk_bytes - 1) / dw_chunk_bytes);
           if (n_chunks > 8) n_chunks = 8;
         }
-        int chunk_rows = round_up((ly.in + n_chunks - 1) / n_chunks, 128);
+        const bool xchg_chunks = l == 0 && dw0_chunks >= 1 && on_dw0_chunk && (ly.out % 8 == 0 || dw0_chunks == 1) && !sparse_step;
+        if (xchg_chunks) n_chunks = dw0_chunks;
+        int chunk_rows = xchg_chunks ? dw0_chunk_rows() : round_up((ly.in + n_chunks - 1) / n_chunks, 128);
         // dW_0 has nothing to overlap with (no dA_0): PDL-chained on the main stream right behind the last dA GEMM it
         // starts ~6 us earlier than as a cross-stream launch (measured, scripts/step_timeline.py)
-        const bool on_main = !fork || (l == 0 && dw0_on_main && L > 1);
+        const bool on_main = !fork || (l == 0 && dw0_on_main && L > 1) || force_main;
         if (!on_main) {
           SB_CUDA(cudaEventRecord(ev_dz[l], stream));
           SB_CUDA(cudaStreamWaitEvent(side, ev_dz[l], 0));
@@ -569,9 +570,10 @@ int Net::enqueue_backward(int rows, float* grad) {
           p.a_rows = res0 ? desc : nullptr;
           p.accum = grad + ly.w_off + static_cast<long long>(r0) * ly.out; p.ld_acc = ly.out;
           p.acc_vec4 = (ly.out % 4 == 0 && ly.w_off % 4 == 0) ? 1 : 0;
-          p.trace = next_trace("dW");
+          p.trace = next_trace("dW", l, r1 - r0, ly.out, rows, n_chunks > 1 ? r0 / chunk_rows : -1);
           SB_TRY((launch_gemm_tc<EPI_DW, true, true>(pl, tm, p, on_main ? stream : side, use_pdl && on_main)));
           mark("gemm_dw");
+          if (xchg_chunks) SB_TRY(on_dw0_chunk(r0 / chunk_rows));
           if (fork && on_layer_grads) {
             const long long e0 = static_cast<long long>(r0) * ly.out, e1 = static_cast<long long>(r1) * ly.out;
             SB_CUDA(cudaEventRecord(ev_dw[l], side));
@@ -580,7 +582,16 @@ int Net::enqueue_backward(int rows, float* grad) {
             if (l == 0) SB_TRY(on_layer_grads(l, comm, 1, e0, e1));  // no dA_0: W_0 is free to be updated
           }
         }
-      }
+        return SB_OK;
+  };
+  for (int l = L - 1; l >= 0; --l) {
+    Layer& ly = layers[l];
+    if (tc()) {
+      // dW_l[in,out] += sum_rows A_{l-1}[rows,in] (MN-major A) * dZ_l[rows,out] (MN-major B), split-K over rows.
+      // With a gradient exchange behind it, a big layer is cut into row chunks of W_l (each a contiguous slice of the
+      // flat gradient) so that the all-reduce of chunk c overlaps the GEMM of chunk c+1.
+      if (!(dw1_last && l == 1 && L > 1)) SB_TRY(emit_dw_tc(l, false));
+      if (dw1_last && l == 0 && L > 1) SB_TRY(emit_dw_tc(1, true));   // behind dW_0 on the main stream (covers its last exchange)
       if (l > 0) {
         // dZ_{l-1}[rows,in] = (dZ_l[rows,out] (K-major) x W_l[in,out] (K-major B: k = out contiguous)) .* act'(A_{l-1})
         Layer& pl = layers[l - 1];
@@ -595,7 +606,7 @@ int Net::enqueue_backward(int rows, float* grad) {
         p.aux = A[l - 1]; p.ld_aux = pl.ld_out; p.aux_ps = A_ps[l - 1];
         p.out = dZ[l - 1]; p.ld_out = pl.ld_out; p.out_ps = A_ps[l - 1];
         p.colsum = grad + pl.b_off;
-        p.trace = next_trace("dA");
+        p.trace = next_trace("dA", l, rows, ly.in, ly.out);
         if (nparts == 1) {                           // plain bf16: A_{l-1} in and dZ_{l-1} out move as TMA tiles
           SB_TRY(make_tmap_bf16(&tm.o, dZ[l - 1], rows, ly.in, pl.ld_out, 128));
           SB_TRY(make_tmap_bf16(&tm.x, A[l - 1], rows, ly.in, pl.ld_out, 128));

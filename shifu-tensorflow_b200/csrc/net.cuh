@@ -27,6 +27,23 @@ struct Net {
   std::vector<cudaEvent_t> ev_dz;            // ev_dz[l]: dZ_l is complete on `stream`
   cudaEvent_t ev_join = nullptr;
   cudaStream_t comm = nullptr;               // per-layer gradient all-reduce + optimizer, pipelined behind the dW GEMMs
+  cudaStream_t comm2 = nullptr;              // second exchange stream (the chunk exchanges of hidden layer 0 alternate)
+  // Peer-exchange schedule (world > 1, set by the trainer around enqueue_backward / enqueue_hidden_forward):
+  //   dW_0 runs on the main stream in `dw0_chunks` row chunks of W_0, on_dw0_chunk(c) is called behind each (its exchange
+  //   goes to a comm stream and overlaps the GEMMs that follow); dW_1 follows dW_0 on the main stream instead of running
+  //   beside it, so that the LAST chunk's exchange is covered too; before_layer1 is called in front of layer 1's forward
+  //   GEMM (the previous step's exchange of the other layers may still run beside the layer-0 forward GEMM);
+  //   zero_layer = the forward GEMM whose idle epilogue warps clear zero_buf (1: peers may still read the gradient
+  //   buffer while layer 0 runs).
+  int dw0_chunks = 1;
+  bool dw1_last = false;
+  std::function<int(int /*chunk*/)> on_dw0_chunk;
+  std::function<int()> before_layer1;
+  int zero_layer = 0;
+  int dw0_chunk_rows() const {
+    const int c = dw0_chunks > 1 ? dw0_chunks : 1;
+    return ((layers[0].in + c - 1) / c + 127) / 128 * 128;
+  }
   // resident steps: the layer-0 forward GEMM's epilogue warps clear this buffer (the step's gradient) while they wait for
   // their first accumulator; consumed (and reset) by enqueue_hidden_forward
   float4* zero_buf = nullptr;
@@ -87,10 +104,18 @@ struct Net {
   unsigned long long* step_trace = nullptr;
   int trace_k = 0;
   std::vector<std::string> trace_names;
-  unsigned long long* next_trace(const char* name) {
-    if (!step_trace || trace_k >= 32) return nullptr;
+  bool trace_on = true;
+  int trace_n = 0;                 // kernels of the last traced step
+  // name = role (+ layer, + ".chunk"); GEMMs append "@MxNxK" so that a reader needs no knowledge of the launch order
+  unsigned long long* next_trace(const char* name, int layer = -1, int M = 0, int N = 0, int K = 0, int chunk = -1) {
+    if (!step_trace || !trace_on || trace_k >= 32) return nullptr;
     if (static_cast<int>(trace_names.size()) <= trace_k) trace_names.resize(trace_k + 1);
-    trace_names[trace_k] = name;
+    std::string nm = name;
+    if (layer >= 0) nm += std::to_string(layer);
+    if (chunk >= 0) nm += "." + std::to_string(chunk);
+    if (M > 0) nm += "@" + std::to_string(M) + "x" + std::to_string(N) + "x" + std::to_string(K);
+    trace_names[trace_k] = nm;
+    trace_n = trace_k + 1;
     return step_trace + 16 * (trace_k++);
   }
   // optional per-launch CUDA-event timing (sb_trainer_profile_step): one event after every launch

@@ -1,4 +1,4 @@
-// Sharded gradient exchange + optimizer over NVLink peer memory (CUDA IPC / in-process peers), ONE kernel per segment:
+// Sharded gradient exchange + optimizer over NVLink peer memory (CUDA IPC / in-process peers), ONE kernel per launch:
 //
 //     reduce-scatter (P2P loads)  ->  optimizer on the owned slice only  ->  all-gather of the GEMM operands (P2P stores)
 //
@@ -8,29 +8,31 @@
 // parameters is the rank that owns it:
 //
 //   every rank exports ONE allocation (the parameter arena, net.cuh):  [theta | s1 | s2 | bf16 shadows | gradient | flags]
-//   the flat vector is cut into the optimizer's work runs (<= 1024 parameters each); the runs of a SEGMENT are dealt out
-//   to the ranks in equal contiguous shares.  Two segments: B = hidden layer 0 (its gradient is complete last, after the
-//   dW_0 GEMM), A = every other layer (complete when the side stream's dW GEMMs and the last dA GEMM are done, i.e.
-//   while dW_0 still runs) - one launch per segment, so the exchange of segment A overlaps the dW_0 GEMM.
+//   the flat vector is cut into the optimizer's work runs (<= 1024 parameters each); the runs of a SLOT are dealt out to the
+//   ranks in equal contiguous shares.  Slot 0 = every layer but hidden layer 0; slots 1..C = row chunks of hidden layer 0
+//   (the big one, whose gradient is complete last).  The slot table is fixed for a trainer's life - it defines who owns
+//   which run - while a launch may handle any set of slots (the flags of the lowest one synchronise it).
 //
-//   per launch (flag slot = segment, value = the step's exchange epoch):
-//     arrive   "my gradient of this segment is complete": store epoch into arrive[seg][me] of every peer
-//              (st.release.sys), every block waits until all peers' slots in MY flag block carry it (ld.acquire.sys)
+//   per launch (flag value = the step's exchange epoch):
+//     arrive   "my gradient of these slots is complete": store epoch into arrive[slot][me] of every peer
+//              (st.release.sys), every block waits until all peers' words in MY flag block carry it (ld.acquire.sys)
 //     owned runs, 256 threads x 4 parameters each:
 //              g = sum over ranks (fixed order 0..W-1 -> the same bits wherever it is computed) of the peers' gradients,
 //              all W x U 16-byte P2P loads of a thread in flight before the first add;
 //              fp32 master + optimizer state of the run are LOCAL (only the owner ever updates them);
 //              the result is stored to EVERY rank: bf16 into the weight shadow the GEMMs read (8 B per thread - half the
 //              bytes of an fp32 all-gather) or, for runs without a shadow (biases, output layer, fp32 mode), fp32 theta.
-//     done     last block publishes done[seg][me] = epoch to every peer and waits for every peer's: on exit all slices
+//     done     last block publishes done[slot][me] = epoch to every peer and waits for every peer's: on exit all slices
 //              of my shadows are final and nobody reads my gradient any more.
+//
+//   The schedule that hides the launches behind GEMMs lives in capi.cu (enqueue_step_body).
 //
 // A rank only reads other ranks' gradients of ITS runs and only writes ITS runs of other ranks' operands; the writes
 // happen after every rank has arrived, i.e. after every rank's last reader of those operands in this step (the launch is
 // stream-ordered behind them).  Non-owners keep a stale fp32 master / state for shadow-backed runs: gather_master_kernel
 // refreshes them before anything reads theta on the host side (get_params, checkpoint, export).
 //
-// A lost peer is reported, not trapped: after `timeout_ns` a waiting block records (segment, missing rank) in mapped host
+// A lost peer is reported, not trapped: after `timeout_ns` a waiting block records (slot, missing rank) in mapped host
 // memory and every block leaves the kernel; the host turns that into SB_ERR_NCCL at its next wait.
 #pragma once
 #include "common.cuh"
@@ -39,12 +41,13 @@
 namespace sb {
 
 #define SB_MAX_RANKS 16
+#define SB_XCHG_SLOTS 8                   // slot 0: every layer but hidden layer 0; slots 1..C: row chunks of hidden layer 0
 
-struct P2PFlags {                         // at arena + flags_off on every rank
-  unsigned int arrive[2][SB_MAX_RANKS];   // arrive[seg][q] written by rank q
-  unsigned int done[2][SB_MAX_RANKS];     // done[seg][q]   written by rank q
-  unsigned int blocks_done[2];            // local: grid-wide completion counter per segment
-  unsigned int pad[30];
+struct P2PFlags {                                     // at arena + flags_off on every rank
+  unsigned int arrive[SB_XCHG_SLOTS][SB_MAX_RANKS];   // arrive[slot][q] written by rank q
+  unsigned int done[SB_XCHG_SLOTS][SB_MAX_RANKS];     // done[slot][q]   written by rank q
+  unsigned int blocks_done[SB_XCHG_SLOTS];            // local: grid-wide completion counter per slot
+  unsigned int pad[24];
 };
 
 struct P2PPeers {                         // device-resident table, same order on every rank
@@ -56,19 +59,22 @@ struct XchgParams {
   int rank, world;
   long long s1_off, s2_off, grad_off, flags_off;   // byte offsets inside every arena (theta at 0)
   const OptWork* work;
-  int seg_begin[2], seg_end[2];           // work-table range of segment 0 (A: layers >= 1) and 1 (B: layer 0)
-  int seg_mask;                           // bit s set: this launch handles segment s
+  int n_slots;
+  int slot_begin[SB_XCHG_SLOTS], slot_end[SB_XCHG_SLOTS];   // work-table range of every slot (the same table on every rank:
+                                                            // it defines who owns which run, whatever the launch pattern)
+  int slot_mask;                          // bit s set: this launch handles slot s (flags of the LOWEST set slot synchronise it)
   const BatchDesc* desc;
   OptHyper hyper;
   const float* scal;                      // step scalars to publish (nullable)
   float* host_scal;
-  unsigned int* host_err;                 // mapped pinned: [0] = 0 ok | 1 + 16 * seg + missing rank
+  unsigned int* host_err;                 // mapped pinned: [0] = 0 ok | 1 + 16 * slot + missing rank
   unsigned long long timeout_ns;          // 0 = wait forever
   int early_dependents;                   // 1: let the next kernel of the stream (PDL) become resident while this one still
                                           // waits for its peers.  0 when the peers share this device (in-process replicas):
                                           // the next step's persistent GEMM CTAs would take every SM's shared memory while
                                           // they wait for this kernel, and the replica this kernel waits for could never run
-  unsigned long long* trace;
+  unsigned long long* trace;              // slots: 0 entry, 2 dependencies resolved, 3 every peer arrived (block 0), 4 last block's
+                                          // runs done, 5 last block's stores fenced, 6 every peer done, 10 exit
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -125,18 +131,22 @@ __device__ __forceinline__ bool xchg_wait(const unsigned int* slots, int world, 
   return *reinterpret_cast<volatile unsigned int*>(sh_fail) == 0u;
 }
 
-// W = compile-time upper bound of `world`; U runs per block iteration, W * U (<= 16) float4 per thread in flight.
-// <= 128 registers per thread (two blocks per SM by register count), so that a block fits beside a persistent GEMM CTA
-// (320 threads x <= 128 registers) - segment A runs while the dW_0 GEMM still occupies every SM.
+// W = compile-time upper bound of `world`; a block iteration handles U consecutive runs, W * U = 8 sixteen-byte P2P loads per
+// thread in flight before the first add.  <= 85 registers per thread: one block (21 k registers) fits beside ANY of the
+// persistent GEMM CTAs that may be resident while an exchange runs - the dW GEMMs of the same step (320 threads x 64) and
+// the next step's layer-0 forward (320 x <= 115) - so the exchange really overlaps them.
+// Measured on 2 x B200 through NVSwitch (scripts/p2p_probe.cu, profiles/p2p_probe_r02.txt): a flag takes 2.7 us one way, a
+// P2P load round trip ~5 us, bandwidth 750 GB/s only beyond ~16 MB in flight (4 MB: 14 us).  The chain arrive -> loads ->
+// stores + fence -> done therefore costs ~17 us however little data moves: the schedule (capi.cu) hides it behind GEMMs.
 template <int W>
-static __global__ void __launch_bounds__(256, 2)
+static __global__ void __launch_bounds__(256, W <= 8 ? 3 : 2)
 xchg_update_kernel(const XchgParams p) {
-  constexpr int U = (W <= 4) ? 4 : 16 / W;
+  constexpr int U = W >= 8 ? 1 : 8 / W;
   __shared__ unsigned int sh_fail;
   __shared__ unsigned int sh_last;
   if (threadIdx.x == 0) sh_fail = 0u;
   trace_begin(p.trace, true);
-  pdl_wait();                 // the gradient of this segment is complete (programmatic dependent of the last GEMM)
+  pdl_wait();                 // the gradient of these slots is complete (stream order / programmatic dependency)
   if (p.early_dependents) pdl_launch_dependents();
   trace_begin(p.trace, false);
   __syncthreads();
@@ -157,44 +167,54 @@ xchg_update_kernel(const XchgParams p) {
   const bool use_s2 = p.hyper.kind == SB_OPT_ADAM || p.hyper.kind == SB_OPT_ADADELTA;
   float* const s1 = reinterpret_cast<float*>(my_base + p.s1_off);
   float* const s2 = reinterpret_cast<float*>(my_base + p.s2_off);
-  bool alive = true;
+  float* const my_grad = reinterpret_cast<float*>(my_base + p.grad_off);
+  const int sync = __ffs(p.slot_mask) - 1;          // the slot whose flags carry this launch
+  auto stamp_max = [&](int slot) { if (p.trace != nullptr && threadIdx.x == 0) atomicMax(p.trace + slot, static_cast<unsigned long long>(globaltimer_ns())); };
+  // ---- arrive ----
+  if (blockIdx.x == 0 && threadIdx.x < p.world)
+    st_release_sys(&reinterpret_cast<P2PFlags*>(p.peers->base[threadIdx.x] + p.flags_off)->arrive[sync][p.rank], epoch);
+  bool alive = xchg_wait(mine->arrive[sync], p.world, epoch, p, sync, &sh_fail);
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[3] = globaltimer_ns();
+  // ---- owned runs of every slot of the launch ----
+  if (alive) {
 #pragma unroll 1
-  for (int seg = 0; seg < 2; ++seg) {
-    if (!((p.seg_mask >> seg) & 1)) continue;
-    // ---- arrive ----
-    if (blockIdx.x == 0 && threadIdx.x < p.world)
-      st_release_sys(&reinterpret_cast<P2PFlags*>(p.peers->base[threadIdx.x] + p.flags_off)->arrive[seg][p.rank], epoch);
-    if (alive) alive = xchg_wait(mine->arrive[seg], p.world, epoch, p, seg, &sh_fail);
-    // ---- owned runs ----
-    const int w0 = xchg_share(p.seg_begin[seg], p.seg_end[seg], p.rank, p.world);
-    const int w1 = xchg_share(p.seg_begin[seg], p.seg_end[seg], p.rank + 1, p.world);
-    if (alive) {
+    for (int slot = 0; slot < p.n_slots; ++slot) {
+      if (!((p.slot_mask >> slot) & 1)) continue;
+      const int w0 = xchg_share(p.slot_begin[slot], p.slot_end[slot], p.rank, p.world);
+      const int w1 = xchg_share(p.slot_begin[slot], p.slot_end[slot], p.rank + 1, p.world);
+#pragma unroll 1
       for (int wb = w0 + static_cast<int>(blockIdx.x) * U; wb < w1; wb += static_cast<int>(gridDim.x) * U) {
-        OptWork wk[U];
-        bool vec[U];
         float4 g[U][W];
+        bool vec[U];
+        const int e = threadIdx.x * 4;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int w = wb + u;
-          if (w < w1) wk[u] = p.work[w]; else { wk[u].count = 0; wk[u].off = 0; wk[u].Wn = nullptr; wk[u].out_dim = 0; wk[u].mat_off = 0; wk[u].ld_out = 0; wk[u].np = 1; wk[u].part_stride = 0; }
-          vec[u] = (wk[u].off & 3) == 0 && (wk[u].count & 3) == 0 &&
-                   (wk[u].Wn == nullptr || ((wk[u].out_dim & 3) == 0 && ((wk[u].off - wk[u].mat_off) & 3) == 0 && (wk[u].ld_out & 3) == 0));
-          const int e = threadIdx.x * 4;
+          vec[u] = false;
+          if (wb + u < w1) {
+            const OptWork& wk = p.work[wb + u];
+            const long long off = wk.off;
+            const int cnt = wk.count;
+            vec[u] = (off & 3) == 0 && (cnt & 3) == 0 &&
+                     (wk.Wn == nullptr || ((wk.out_dim & 3) == 0 && ((off - wk.mat_off) & 3) == 0 && (wk.ld_out & 3) == 0));
+            if (vec[u] && e < cnt) {
 #pragma unroll
-          for (int q = 0; q < W; ++q)
-            g[u][q] = (vec[u] && q < p.world && e < wk[u].count) ? ld_peer_f4(reinterpret_cast<const float*>(pb[q] + p.grad_off) + wk[u].off + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int q = 0; q < W; ++q)
+                if (q < p.world) g[u][q] = ld_peer_f4(reinterpret_cast<const float*>(pb[q] + p.grad_off) + off + e);
+            }
+          }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (wk[u].count == 0) continue;
-          const long long shadow_rel = wk[u].Wn != nullptr ? reinterpret_cast<char*>(wk[u].Wn) - my_base : 0;
+          if (wb + u >= w1) continue;
+          const OptWork wk = p.work[wb + u];
+          const long long shadow_rel = wk.Wn != nullptr ? reinterpret_cast<char*>(wk.Wn) - my_base : 0;
           if (vec[u]) {
-            const int e = threadIdx.x * 4;
-            if (e < wk[u].count) {
-              float4 acc = g[u][0];               // fixed rank order
+            if (e < wk.count) {
+              float4 acc = g[u][0];               // fixed rank order -> the same bits wherever a sum is computed
 #pragma unroll
-              for (int q = 1; q < W; ++q) { acc.x += g[u][q].x; acc.y += g[u][q].y; acc.z += g[u][q].z; acc.w += g[u][q].w; }
-              const long long idx = wk[u].off + e;
+              for (int q = 1; q < W; ++q)
+                if (q < p.world) { acc.x += g[u][q].x; acc.y += g[u][q].y; acc.z += g[u][q].z; acc.w += g[u][q].w; }
+              const long long idx = wk.off + e;
               const float4 th = *reinterpret_cast<const float4*>(theta + idx);
               float4 a = use_s1 ? *reinterpret_cast<const float4*>(s1 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
               float4 b = use_s2 ? *reinterpret_cast<const float4*>(s2 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -205,18 +225,18 @@ xchg_update_kernel(const XchgParams p) {
               t.w = opt_update(p.hyper, lr_t, th.w, acc.w * gs, a.w, b.w);
               *reinterpret_cast<float4*>(theta + idx) = t;
               // the owner keeps the reduced gradient of its runs (nobody else reads this part of my buffer): parity hook
-              *reinterpret_cast<float4*>(reinterpret_cast<float*>(my_base + p.grad_off) + idx) = acc;
+              *reinterpret_cast<float4*>(my_grad + idx) = acc;
               if (use_s1) *reinterpret_cast<float4*>(s1 + idx) = a;
               if (use_s2) *reinterpret_cast<float4*>(s2 + idx) = b;
-              if (wk[u].Wn != nullptr) {
-                const long long m = idx - wk[u].mat_off;
-                const long long r = m / wk[u].out_dim;     // 4 consecutive elements never straddle a row
-                const long long rel = shadow_rel + (r * wk[u].ld_out + (m - r * wk[u].out_dim)) * 2;
-                for (int part = 0; part < wk[u].np; ++part) {      // split-precision modes: every part of the shadow
+              if (wk.Wn != nullptr) {
+                const long long m = idx - wk.mat_off;
+                const long long r = m / wk.out_dim;     // 4 consecutive elements never straddle a row
+                const long long rel = shadow_rel + (r * wk.ld_out + (m - r * wk.out_dim)) * 2;
+                for (int part = 0; part < wk.np; ++part) {      // split-precision modes: every part of the shadow
                   uint2 o;
                   o.x = pack_bf16x2(bf16_residual(t.x, part), bf16_residual(t.y, part));
                   o.y = pack_bf16x2(bf16_residual(t.z, part), bf16_residual(t.w, part));
-                  const long long prel = rel + part * wk[u].part_stride * 2;
+                  const long long prel = rel + part * wk.part_stride * 2;
 #pragma unroll
                   for (int q = 0; q < W; ++q)
                     if (q < p.world) *reinterpret_cast<uint2*>(pb[q] + prel) = o;
@@ -229,27 +249,27 @@ xchg_update_kernel(const XchgParams p) {
             }
           } else {
             // unaligned run (odd widths): scalar path, 4 elements per thread strided by 256
-#pragma unroll
+#pragma unroll 1
             for (int i = 0; i < 4; ++i) {
-              const int e = threadIdx.x + 256 * i;
-              if (e < wk[u].count) {
-                const long long idx = wk[u].off + e;
+              const int es = threadIdx.x + 256 * i;
+              if (es < wk.count) {
+                const long long idx = wk.off + es;
                 float acc = 0.f;
                 for (int q = 0; q < p.world; ++q) acc += ld_peer_f1(reinterpret_cast<const float*>(p.peers->base[q] + p.grad_off) + idx);
                 float a = use_s1 ? s1[idx] : 0.f, b = use_s2 ? s2[idx] : 0.f;
                 const float t = opt_update(p.hyper, lr_t, theta[idx], acc * gs, a, b);
                 theta[idx] = t;
-                reinterpret_cast<float*>(my_base + p.grad_off)[idx] = acc;
+                my_grad[idx] = acc;
                 if (use_s1) s1[idx] = a;
                 if (use_s2) s2[idx] = b;
-                if (wk[u].Wn != nullptr) {
-                  const long long m = idx - wk[u].mat_off;
-                  const long long r = m / wk[u].out_dim;
-                  const long long rel = shadow_rel + (r * wk[u].ld_out + (m - r * wk[u].out_dim)) * 2;
-                  for (int part = 0; part < wk[u].np; ++part) {
+                if (wk.Wn != nullptr) {
+                  const long long m = idx - wk.mat_off;
+                  const long long r = m / wk.out_dim;
+                  const long long rel = shadow_rel + (r * wk.ld_out + (m - r * wk.out_dim)) * 2;
+                  for (int part = 0; part < wk.np; ++part) {
                     const __nv_bfloat16 hv = __float2bfloat16_rn(bf16_residual(t, part));
                     for (int q = 0; q < p.world; ++q)
-                      *reinterpret_cast<__nv_bfloat16*>(p.peers->base[q] + rel + part * wk[u].part_stride * 2) = hv;
+                      *reinterpret_cast<__nv_bfloat16*>(p.peers->base[q] + rel + part * wk.part_stride * 2) = hv;
                   }
                 } else {
                   for (int q = 0; q < p.world; ++q)
@@ -261,20 +281,23 @@ xchg_update_kernel(const XchgParams p) {
         }
       }
     }
-    // ---- done ----
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) sh_last = (atomicAdd(&mine->blocks_done[seg], 1u) == gridDim.x - 1) ? 1u : 0u;
-    __syncthreads();
-    if (sh_last) {
-      if (threadIdx.x == 0) mine->blocks_done[seg] = 0;
-      __threadfence_system();
-      if (threadIdx.x < p.world)
-        st_release_sys(&reinterpret_cast<P2PFlags*>(p.peers->base[threadIdx.x] + p.flags_off)->done[seg][p.rank], epoch);
-      if (alive) alive = xchg_wait(mine->done[seg], p.world, epoch, p, seg, &sh_fail);
-    }
-    __syncthreads();
   }
+  stamp_max(4);
+  // ---- done ----
+  __threadfence_system();
+  stamp_max(5);
+  __syncthreads();
+  if (threadIdx.x == 0) sh_last = (atomicAdd(&mine->blocks_done[sync], 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (sh_last) {
+    if (threadIdx.x == 0) mine->blocks_done[sync] = 0;
+    __threadfence_system();
+    if (threadIdx.x < p.world)
+      st_release_sys(&reinterpret_cast<P2PFlags*>(p.peers->base[threadIdx.x] + p.flags_off)->done[sync][p.rank], epoch);
+    if (alive) alive = xchg_wait(mine->done[sync], p.world, epoch, p, sync, &sh_fail);
+    if (p.trace != nullptr && threadIdx.x == 0) p.trace[6] = globaltimer_ns();
+  }
+  __syncthreads();
   trace_end(p.trace);
 }
 
@@ -286,10 +309,10 @@ gather_master_kernel(const XchgParams p, int what) {
   const int w = blockIdx.x;
   float* const theta = reinterpret_cast<float*>(p.peers->base[p.rank]);
   int owner = -1;
-  for (int seg = 0; seg < 2; ++seg) {
-    if (w >= p.seg_begin[seg] && w < p.seg_end[seg]) {
+  for (int slot = 0; slot < p.n_slots; ++slot) {
+    if (w >= p.slot_begin[slot] && w < p.slot_end[slot]) {
       for (int r = 0; r < p.world; ++r)
-        if (w >= xchg_share(p.seg_begin[seg], p.seg_end[seg], r, p.world) && w < xchg_share(p.seg_begin[seg], p.seg_end[seg], r + 1, p.world)) owner = r;
+        if (w >= xchg_share(p.slot_begin[slot], p.slot_end[slot], r, p.world) && w < xchg_share(p.slot_begin[slot], p.slot_end[slot], r + 1, p.world)) owner = r;
     }
   }
   if (owner < 0 || owner == p.rank) return;
