@@ -11,6 +11,11 @@ from typing import Optional, Sequence
 
 import numpy as np
 
+# A step runs on up to five streams (main, side, two exchange streams, descriptor prefetch); with the default of 8 hardware
+# queues CUDA maps several of them onto one queue and their kernels falsely serialise (an exchange kernel that waits for
+# its peers then holds back an unrelated GEMM).  Read by the driver when the context is created, i.e. at the first CUDA call.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libshifu_b200.so")
 

@@ -227,11 +227,13 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
                           n.concurrent_bwd && !n.profiling && n.side != nullptr && n.tc() && n.L > 1;
   // Peer exchange (world > 1): the chain  arrive -> P2P loads -> update -> P2P stores + fence -> done  costs ~17 us through
   // NVSwitch however little data it moves (xchg_p2p.cuh), so every exchange launch gets a GEMM to hide behind:
-  //   main:  ... dA_1 -> dW_0 chunk 0 -> dW_0 chunk 1 -> dW_1        | next step: layer-0 forward -> layer-1 forward ...
-  //   comm:              xchg B0 ---------> xchg B1 ------> xchg A ---------------------------->|
-  // B0 runs beside dW_0's second chunk, B1 beside dW_1, A (every other layer) beside the NEXT step's layer-0 forward GEMM,
-  // which reads nothing slot A writes: layer 1's forward waits for A, and - because peers still read this rank's gradient
-  // buffer until then - the buffer is cleared by layer 1's forward GEMM instead of layer 0's.
+  //   main:  ... dA_1 -> dW_0 chunk 0 -> dW_0 chunk 1 |          next step: layer-0 forward -> layer-1 forward ...
+  //   side:  ... dW_2 ... dW_1 (beside dW_0)          |
+  //   comm:               xchg A, xchg B0 ------------> xchg B1 ->|
+  // A (every other layer) and B0 run beside dW_0's chunks; only B1 - half of layer 0 - is exposed.  The main stream does
+  // not wait for A at the end of the step: the NEXT step's layer-0 forward GEMM reads nothing slot A writes, layer 1's
+  // forward waits for it, and - because peers may read this rank's gradient buffer until then - the buffer is cleared by
+  // layer 1's forward GEMM instead of layer 0's.
   const bool xsched = split_tail && t->world > 1;
   static const bool no_defer = getenv("SB_XCHG_NO_DEFER") != nullptr;
   const bool defer_A = xsched && resident && n.L >= 3 && !no_defer;
@@ -295,9 +297,11 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   n.defer_join = split_tail;
   cudaStream_t comms[2] = {n.comm2, n.comm};
   if (xsched) {
-    static const bool dw1_beside = getenv("SB_XCHG_DW1_BESIDE") != nullptr;   // experiment: keep dW_1 beside dW_0 (side stream)
+    // SB_XCHG_SERIAL=1: dW_1 behind dW_0 on the main stream (cover for the last chunk's exchange, but the dW GEMMs lose the
+    // concurrency the single-GPU schedule has: measured 59 us for dW_0 + dW_1 + dW_2 in a row against 41 us side by side)
+    static const bool serial = getenv("SB_XCHG_SERIAL") != nullptr;
     n.dw0_chunks = t->x_chunks;
-    n.dw1_last = !dw1_beside;
+    n.dw1_last = serial;
     t->x_sent = 0;
     n.on_dw0_chunk = [t, comms](int c) -> int {
       Net& nn = t->net;
@@ -316,8 +320,12 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   if (xsched) {
     // slot A: every gradient but hidden layer 0's - complete behind dW_1 (main stream) and the other dW GEMMs (side stream)
     cudaStream_t ca = comms[t->x_chunks & 1];
-    SB_CUDA(cudaEventRecord(t->ev_c[0], n.stream));
-    SB_CUDA(cudaStreamWaitEvent(ca, t->ev_c[0], 0));
+    if (n.dw1_last) {
+      SB_CUDA(cudaEventRecord(t->ev_c[0], n.stream));
+      SB_CUDA(cudaStreamWaitEvent(ca, t->ev_c[0], 0));
+    } else {
+      SB_CUDA(cudaStreamWaitEvent(ca, n.ev_da_done, 0));     // the last reader of the other layers' weight shadows
+    }
     SB_CUDA(cudaEventRecord(n.ev_join, n.side));
     SB_CUDA(cudaStreamWaitEvent(ca, n.ev_join, 0));
     SB_TRY(enqueue_xchg(t, XSEG_A, ca, false, false));

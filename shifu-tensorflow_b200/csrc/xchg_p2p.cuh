@@ -20,10 +20,12 @@
 //              g = sum over ranks (fixed order 0..W-1 -> the same bits wherever it is computed) of the peers' gradients,
 //              all W x U 16-byte P2P loads of a thread in flight before the first add;
 //              fp32 master + optimizer state of the run are LOCAL (only the owner ever updates them);
-//              the result is stored to EVERY rank: bf16 into the weight shadow the GEMMs read (8 B per thread - half the
-//              bytes of an fp32 all-gather) or, for runs without a shadow (biases, output layer, fp32 mode), fp32 theta.
-//     done     last block publishes done[slot][me] = epoch to every peer and waits for every peer's: on exit all slices
-//              of my shadows are final and nobody reads my gradient any more.
+//              the result is written LOCALLY: fp32 master, state, and the bf16 weight shadow the GEMMs read.
+//     updated  the last block to finish publishes done[slot][me] = epoch to every peer (local stores only: no fabric fence)
+//     gather   every block waits for every peer's `updated`, then the runs other ranks own are pulled from their owners by
+//              P2P loads: the bf16 shadow (8 B per thread - half the bytes of an fp32 all-gather) or, for runs without a
+//              shadow (biases, output layer, fp32 mode), fp32 theta.  A peer's `updated` also says it no longer reads my
+//              gradient: on exit all my operands are final and my gradient buffer is free.
 //
 //   The schedule that hides the launches behind GEMMs lives in capi.cu (enqueue_step_body).
 //
@@ -74,7 +76,7 @@ struct XchgParams {
                                           // the next step's persistent GEMM CTAs would take every SM's shared memory while
                                           // they wait for this kernel, and the replica this kernel waits for could never run
   unsigned long long* trace;              // slots: 0 entry, 2 dependencies resolved, 3 every peer arrived (block 0), 4 last block's
-                                          // runs done, 5 last block's stores fenced, 6 every peer done, 10 exit
+                                          // runs done, 5 `updated` published, 6 every peer updated (block 0), 10 exit (gathered)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
@@ -236,15 +238,8 @@ xchg_update_kernel(const XchgParams p) {
                   uint2 o;
                   o.x = pack_bf16x2(bf16_residual(t.x, part), bf16_residual(t.y, part));
                   o.y = pack_bf16x2(bf16_residual(t.z, part), bf16_residual(t.w, part));
-                  const long long prel = rel + part * wk.part_stride * 2;
-#pragma unroll
-                  for (int q = 0; q < W; ++q)
-                    if (q < p.world) *reinterpret_cast<uint2*>(pb[q] + prel) = o;
+                  *reinterpret_cast<uint2*>(my_base + rel + part * wk.part_stride * 2) = o;     // peers pull it in phase 2
                 }
-              } else {
-#pragma unroll
-                for (int q = 0; q < W; ++q)
-                  if (q < p.world && q != p.rank) *reinterpret_cast<float4*>(pb[q] + idx * 4) = t;
               }
             }
           } else {
@@ -268,12 +263,8 @@ xchg_update_kernel(const XchgParams p) {
                   const long long rel = shadow_rel + (r * wk.ld_out + (m - r * wk.out_dim)) * 2;
                   for (int part = 0; part < wk.np; ++part) {
                     const __nv_bfloat16 hv = __float2bfloat16_rn(bf16_residual(t, part));
-                    for (int q = 0; q < p.world; ++q)
-                      *reinterpret_cast<__nv_bfloat16*>(p.peers->base[q] + rel + part * wk.part_stride * 2) = hv;
+                    *reinterpret_cast<__nv_bfloat16*>(my_base + rel + part * wk.part_stride * 2) = hv;
                   }
-                } else {
-                  for (int q = 0; q < p.world; ++q)
-                    if (q != p.rank) reinterpret_cast<float*>(p.peers->base[q])[idx] = t;
                 }
               }
             }
@@ -283,9 +274,8 @@ xchg_update_kernel(const XchgParams p) {
     }
   }
   stamp_max(4);
-  // ---- done ----
+  // ---- updated: my owned runs carry the new values (local stores only, so this fence does not wait for the fabric) ----
   __threadfence_system();
-  stamp_max(5);
   __syncthreads();
   if (threadIdx.x == 0) sh_last = (atomicAdd(&mine->blocks_done[sync], 1u) == gridDim.x - 1) ? 1u : 0u;
   __syncthreads();
@@ -294,8 +284,85 @@ xchg_update_kernel(const XchgParams p) {
     __threadfence_system();
     if (threadIdx.x < p.world)
       st_release_sys(&reinterpret_cast<P2PFlags*>(p.peers->base[threadIdx.x] + p.flags_off)->done[sync][p.rank], epoch);
-    if (alive) alive = xchg_wait(mine->done[sync], p.world, epoch, p, sync, &sh_fail);
-    if (p.trace != nullptr && threadIdx.x == 0) p.trace[6] = globaltimer_ns();
+  }
+  stamp_max(5);
+  // ---- all-gather by P2P LOADS: every run somebody else owns is pulled from its owner once that owner has updated ----
+  // (a pushed all-gather has to fence its remote stores before it may raise a flag: 12 us per launch on 2 x B200 while the
+  // peer's GEMMs kept its L2 busy; a pull needs no fence, and a peer's "updated" flag also tells that it has finished
+  // reading MY gradient - on exit my operands are final and my gradient buffer is free)
+  if (alive) alive = xchg_wait(mine->done[sync], p.world, epoch, p, sync, &sh_fail);
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[6] = globaltimer_ns();
+  if (alive) {
+    constexpr int U2 = 4;
+#pragma unroll 1
+    for (int slot = 0; slot < p.n_slots; ++slot) {
+      if (!((p.slot_mask >> slot) & 1)) continue;
+      const int sb = p.slot_begin[slot], se = p.slot_end[slot];
+      const int w0 = xchg_share(sb, se, p.rank, p.world);
+      const int w1 = xchg_share(sb, se, p.rank + 1, p.world);
+      const int n_other = (se - sb) - (w1 - w0);
+      const int e = threadIdx.x * 4;
+#pragma unroll 1
+      for (int i0 = static_cast<int>(blockIdx.x) * U2; i0 < n_other; i0 += static_cast<int>(gridDim.x) * U2) {
+        uint2 sh[U2];
+        float4 th[U2];
+        long long dst[U2];          // byte offset inside the arenas (the same on every rank); -1 = nothing to do
+        bool is_sh[U2];
+#pragma unroll
+        for (int u = 0; u < U2; ++u) {
+          dst[u] = -1; is_sh[u] = false;
+          const int j = i0 + u;
+          if (j >= n_other) continue;
+          const int w = sb + j + ((sb + j >= w0) ? (w1 - w0) : 0);
+          int q = 0;
+          while (q + 1 < p.world && w >= xchg_share(sb, se, q + 1, p.world)) ++q;     // owner of run w
+          const OptWork& wk = p.work[w];
+          const bool vec = (wk.off & 3) == 0 && (wk.count & 3) == 0 &&
+                           (wk.Wn == nullptr || ((wk.out_dim & 3) == 0 && ((wk.off - wk.mat_off) & 3) == 0 && (wk.ld_out & 3) == 0));
+          const char* ob = p.peers->base[q];
+          if (vec && wk.np == 1) {
+            if (e < wk.count) {
+              const long long idx = wk.off + e;
+              if (wk.Wn != nullptr) {
+                const long long m = idx - wk.mat_off;
+                const long long r = m / wk.out_dim;
+                dst[u] = (reinterpret_cast<char*>(wk.Wn) - my_base) + (r * wk.ld_out + (m - r * wk.out_dim)) * 2;
+                is_sh[u] = true;
+                asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(sh[u].x), "=r"(sh[u].y) : "l"(ob + dst[u]) : "memory");
+              } else {
+                dst[u] = idx * 4;
+                th[u] = ld_peer_f4(reinterpret_cast<const float*>(ob) + idx);
+              }
+            }
+          } else {
+            // odd widths / split-precision parts: element by element (parity modes, small layers)
+            for (int i = 0; i < 4; ++i) {
+              const int es = threadIdx.x + 256 * i;
+              if (es >= wk.count) continue;
+              const long long idx = wk.off + es;
+              if (wk.Wn != nullptr) {
+                const long long m = idx - wk.mat_off;
+                const long long r = m / wk.out_dim;
+                const long long rel = (reinterpret_cast<char*>(wk.Wn) - my_base) + (r * wk.ld_out + (m - r * wk.out_dim)) * 2;
+                for (int part = 0; part < wk.np; ++part) {
+                  unsigned short hv;
+                  asm volatile("ld.relaxed.sys.global.u16 %0, [%1];" : "=h"(hv) : "l"(ob + rel + part * wk.part_stride * 2) : "memory");
+                  *reinterpret_cast<unsigned short*>(my_base + rel + part * wk.part_stride * 2) = hv;
+                }
+              } else {
+                theta[idx] = ld_peer_f1(reinterpret_cast<const float*>(ob) + idx);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U2; ++u) {
+          if (dst[u] < 0) continue;
+          if (is_sh[u]) *reinterpret_cast<uint2*>(my_base + dst[u]) = sh[u];
+          else *reinterpret_cast<float4*>(my_base + dst[u]) = th[u];
+        }
+      }
+    }
   }
   __syncthreads();
   trace_end(p.trace);
