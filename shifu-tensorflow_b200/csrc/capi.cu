@@ -326,8 +326,10 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
     } else {
       SB_CUDA(cudaStreamWaitEvent(ca, n.ev_da_done, 0));     // the last reader of the other layers' weight shadows
     }
-    SB_CUDA(cudaEventRecord(n.ev_join, n.side));
-    SB_CUDA(cudaStreamWaitEvent(ca, n.ev_join, 0));
+    if (!n.dw1_last || n.L > 2) {                           // (the side stream carries the dW GEMMs of the layers >= 1 / >= 2)
+      SB_CUDA(cudaEventRecord(n.ev_join, n.side));
+      SB_CUDA(cudaStreamWaitEvent(ca, n.ev_join, 0));
+    }
     SB_TRY(enqueue_xchg(t, XSEG_A, ca, false, false));
     SB_CUDA(cudaEventRecord(t->ev_x[0], ca));
     // whatever follows on the main stream (the next step's layer-0 forward, or the end of the graph) needs hidden layer 0
