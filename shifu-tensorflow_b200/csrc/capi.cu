@@ -164,7 +164,7 @@ static int enqueue_xchg(sb_trainer* t, int slot_mask, cudaStream_t st, bool publ
   int runs = 0;      // owned runs of the launch (the largest share)
   for (int sl = 0; sl < t->x_slots; ++sl)
     if ((slot_mask >> sl) & 1) runs += (p.slot_end[sl] - p.slot_begin[sl] + t->world - 1) / t->world;
-  const int U = t->world <= 2 ? 4 : (t->world <= 4 ? 2 : 1);      // runs per block iteration (xchg_update_kernel)
+  const int U = t->world <= 2 ? 2 : 1;      // runs per block iteration (xchg_update_kernel)
   // at most one block per SM and launch: a block must fit beside whatever persistent GEMM CTA shares its SM (xchg_p2p.cuh)
   int grid = t->xchg_blocks > 0 ? t->xchg_blocks : n.num_sms;
   if (t->peers_share_device && grid > 32) grid = 32;    // replicas on ONE device: leave registers to the replica being waited for
@@ -227,13 +227,12 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
                           n.concurrent_bwd && !n.profiling && n.side != nullptr && n.tc() && n.L > 1;
   // Peer exchange (world > 1): the chain  arrive -> P2P loads -> update -> P2P stores + fence -> done  costs ~17 us through
   // NVSwitch however little data it moves (xchg_p2p.cuh), so every exchange launch gets a GEMM to hide behind:
-  //   main:  ... dA_1 -> dW_0 chunk 0 -> dW_0 chunk 1 |          next step: layer-0 forward -> layer-1 forward ...
-  //   side:  ... dW_2 ... dW_1 (beside dW_0)          |
-  //   comm:               xchg A, xchg B0 ------------> xchg B1 ->|
-  // A (every other layer) and B0 run beside dW_0's chunks; only B1 - half of layer 0 - is exposed.  The main stream does
-  // not wait for A at the end of the step: the NEXT step's layer-0 forward GEMM reads nothing slot A writes, layer 1's
-  // forward waits for it, and - because peers may read this rank's gradient buffer until then - the buffer is cleared by
-  // layer 1's forward GEMM instead of layer 0's.
+  //   main:  ... dA_1 -> dW_0 chunk 0 -> dW_0 chunk 1 -> dW_1        | next step: layer-0 forward -> layer-1 forward ...
+  //   comm:              xchg B0 ---------> xchg B1 ------>           |
+  //   side:  ... dW_2 ...                                   xchg A ---------------------------->|
+  // B0 runs beside dW_0's second chunk, B1 beside dW_1, A (every other layer) beside the NEXT step's layer-0 forward GEMM,
+  // which reads nothing slot A writes: layer 1's forward waits for A, and - because peers may read this rank's gradient
+  // buffer until then - the buffer is cleared by layer 1's forward GEMM instead of layer 0's.
   const bool xsched = split_tail && t->world > 1;
   static const bool no_defer = getenv("SB_XCHG_NO_DEFER") != nullptr;
   const bool defer_A = xsched && resident && n.L >= 3 && !no_defer;
@@ -297,11 +296,12 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   n.defer_join = split_tail;
   cudaStream_t comms[2] = {n.comm2, n.comm};
   if (xsched) {
-    // SB_XCHG_SERIAL=1: dW_1 behind dW_0 on the main stream (cover for the last chunk's exchange, but the dW GEMMs lose the
-    // concurrency the single-GPU schedule has: measured 59 us for dW_0 + dW_1 + dW_2 in a row against 41 us side by side)
-    static const bool serial = getenv("SB_XCHG_SERIAL") != nullptr;
+    // dW_1 runs BEHIND dW_0 on the main stream: it is the cover of the last chunk's exchange.  (SB_XCHG_BESIDE=1 keeps it
+    // beside dW_0 on the side stream like the single-GPU schedule; measured on 2 x B200: the chunks of dW_0 then share the
+    // SMs with dW_1 - 31 + 19 us instead of 18 + 19 - and the last exchange has nothing to hide behind.)
+    static const bool beside = getenv("SB_XCHG_BESIDE") != nullptr;
     n.dw0_chunks = t->x_chunks;
-    n.dw1_last = serial;
+    n.dw1_last = !beside;
     t->x_sent = 0;
     n.on_dw0_chunk = [t, comms](int c) -> int {
       Net& nn = t->net;
@@ -318,20 +318,18 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   n.on_layer_grads = nullptr;
   SB_TRY(bs);
   if (xsched) {
-    // slot A: every gradient but hidden layer 0's - complete behind dW_1 (main stream) and the other dW GEMMs (side stream)
-    cudaStream_t ca = comms[t->x_chunks & 1];
+    // slot A: every gradient but hidden layer 0's - complete behind the other layers' dW GEMMs (dW_1: main stream, or side
+    // stream with SB_XCHG_BESIDE; the rest: side stream) and the last dA GEMM (the last reader of their weight shadows).
+    // It is launched ON the side stream: as a node whose parents sit on several branches, the graph executor queued it
+    // behind the main chain's next kernels and it started 100 us late (measured).
     if (n.dw1_last) {
       SB_CUDA(cudaEventRecord(t->ev_c[0], n.stream));
-      SB_CUDA(cudaStreamWaitEvent(ca, t->ev_c[0], 0));
+      SB_CUDA(cudaStreamWaitEvent(n.side, t->ev_c[0], 0));
     } else {
-      SB_CUDA(cudaStreamWaitEvent(ca, n.ev_da_done, 0));     // the last reader of the other layers' weight shadows
+      SB_CUDA(cudaStreamWaitEvent(n.side, n.ev_da_done, 0));
     }
-    if (!n.dw1_last || n.L > 2) {                           // (the side stream carries the dW GEMMs of the layers >= 1 / >= 2)
-      SB_CUDA(cudaEventRecord(n.ev_join, n.side));
-      SB_CUDA(cudaStreamWaitEvent(ca, n.ev_join, 0));
-    }
-    SB_TRY(enqueue_xchg(t, XSEG_A, ca, false, false));
-    SB_CUDA(cudaEventRecord(t->ev_x[0], ca));
+    SB_TRY(enqueue_xchg(t, XSEG_A, n.side, false, false));
+    SB_CUDA(cudaEventRecord(t->ev_x[0], n.side));
     // whatever follows on the main stream (the next step's layer-0 forward, or the end of the graph) needs hidden layer 0
     for (int c = 0; c < t->x_chunks; ++c)
       if ((t->x_sent >> (1 + c)) & 1) SB_CUDA(cudaStreamWaitEvent(n.stream, t->ev_x[1 + c], 0));

@@ -133,8 +133,8 @@ __device__ __forceinline__ bool xchg_wait(const unsigned int* slots, int world, 
   return *reinterpret_cast<volatile unsigned int*>(sh_fail) == 0u;
 }
 
-// W = compile-time upper bound of `world`; a block iteration handles U consecutive runs, W * U = 8 sixteen-byte P2P loads per
-// thread in flight before the first add.  <= 85 registers per thread: one block (21 k registers) fits beside ANY of the
+// W = compile-time upper bound of `world`; a block iteration handles U consecutive runs with every load of the iteration in
+// flight before the first add.  <= 85 registers per thread: one block (21 k registers) fits beside ANY of the
 // persistent GEMM CTAs that may be resident while an exchange runs - the dW GEMMs of the same step (320 threads x 64) and
 // the next step's layer-0 forward (320 x <= 115) - so the exchange really overlaps them.
 // Measured on 2 x B200 through NVSwitch (scripts/p2p_probe.cu, profiles/p2p_probe_r02.txt): a flag takes 2.7 us one way, a
@@ -143,7 +143,7 @@ __device__ __forceinline__ bool xchg_wait(const unsigned int* slots, int world, 
 template <int W>
 static __global__ void __launch_bounds__(256, W <= 8 ? 3 : 2)
 xchg_update_kernel(const XchgParams p) {
-  constexpr int U = W >= 8 ? 1 : 8 / W;
+  constexpr int U = W <= 2 ? 2 : 1;       // runs per block iteration: U x (W + 3) sixteen-byte loads per thread in flight
   __shared__ unsigned int sh_fail;
   __shared__ unsigned int sh_last;
   if (threadIdx.x == 0) sh_fail = 0u;
@@ -178,6 +178,9 @@ xchg_update_kernel(const XchgParams p) {
   bool alive = xchg_wait(mine->arrive[sync], p.world, epoch, p, sync, &sh_fail);
   if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[3] = globaltimer_ns();
   // ---- owned runs of every slot of the launch ----
+  // (every load of an iteration - the peers' gradients, the local master and state - is issued before the first store, so a
+  // thread pays the fabric round trip once per iteration; the first version interleaved them run by run and took 20 us for
+  // 512 runs beside a GEMM)
   if (alive) {
 #pragma unroll 1
     for (int slot = 0; slot < p.n_slots; ++slot) {
@@ -186,22 +189,27 @@ xchg_update_kernel(const XchgParams p) {
       const int w1 = xchg_share(p.slot_begin[slot], p.slot_end[slot], p.rank + 1, p.world);
 #pragma unroll 1
       for (int wb = w0 + static_cast<int>(blockIdx.x) * U; wb < w1; wb += static_cast<int>(gridDim.x) * U) {
-        float4 g[U][W];
-        bool vec[U];
+        float4 g[U][W], th[U], sa[U], sb[U];
+        bool vec[U], on[U];
         const int e = threadIdx.x * 4;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          vec[u] = false;
+          vec[u] = false; on[u] = false;
+          sa[u] = make_float4(0.f, 0.f, 0.f, 0.f); sb[u] = sa[u]; th[u] = sa[u];
           if (wb + u < w1) {
             const OptWork& wk = p.work[wb + u];
             const long long off = wk.off;
             const int cnt = wk.count;
             vec[u] = (off & 3) == 0 && (cnt & 3) == 0 &&
                      (wk.Wn == nullptr || ((wk.out_dim & 3) == 0 && ((off - wk.mat_off) & 3) == 0 && (wk.ld_out & 3) == 0));
-            if (vec[u] && e < cnt) {
+            on[u] = vec[u] && e < cnt;
+            if (on[u]) {
 #pragma unroll
               for (int q = 0; q < W; ++q)
                 if (q < p.world) g[u][q] = ld_peer_f4(reinterpret_cast<const float*>(pb[q] + p.grad_off) + off + e);
+              th[u] = *reinterpret_cast<const float4*>(theta + off + e);
+              if (use_s1) sa[u] = *reinterpret_cast<const float4*>(s1 + off + e);
+              if (use_s2) sb[u] = *reinterpret_cast<const float4*>(s2 + off + e);
             }
           }
         }
@@ -211,20 +219,17 @@ xchg_update_kernel(const XchgParams p) {
           const OptWork wk = p.work[wb + u];
           const long long shadow_rel = wk.Wn != nullptr ? reinterpret_cast<char*>(wk.Wn) - my_base : 0;
           if (vec[u]) {
-            if (e < wk.count) {
+            if (on[u]) {
               float4 acc = g[u][0];               // fixed rank order -> the same bits wherever a sum is computed
 #pragma unroll
               for (int q = 1; q < W; ++q)
                 if (q < p.world) { acc.x += g[u][q].x; acc.y += g[u][q].y; acc.z += g[u][q].z; acc.w += g[u][q].w; }
               const long long idx = wk.off + e;
-              const float4 th = *reinterpret_cast<const float4*>(theta + idx);
-              float4 a = use_s1 ? *reinterpret_cast<const float4*>(s1 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-              float4 b = use_s2 ? *reinterpret_cast<const float4*>(s2 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-              float4 t;
-              t.x = opt_update(p.hyper, lr_t, th.x, acc.x * gs, a.x, b.x);
-              t.y = opt_update(p.hyper, lr_t, th.y, acc.y * gs, a.y, b.y);
-              t.z = opt_update(p.hyper, lr_t, th.z, acc.z * gs, a.z, b.z);
-              t.w = opt_update(p.hyper, lr_t, th.w, acc.w * gs, a.w, b.w);
+              float4 a = sa[u], b = sb[u], t;
+              t.x = opt_update(p.hyper, lr_t, th[u].x, acc.x * gs, a.x, b.x);
+              t.y = opt_update(p.hyper, lr_t, th[u].y, acc.y * gs, a.y, b.y);
+              t.z = opt_update(p.hyper, lr_t, th[u].z, acc.z * gs, a.z, b.z);
+              t.w = opt_update(p.hyper, lr_t, th[u].w, acc.w * gs, a.w, b.w);
               *reinterpret_cast<float4*>(theta + idx) = t;
               // the owner keeps the reduced gradient of its runs (nobody else reads this part of my buffer): parity hook
               *reinterpret_cast<float4*>(my_grad + idx) = acc;
@@ -275,13 +280,17 @@ xchg_update_kernel(const XchgParams p) {
   }
   stamp_max(4);
   // ---- updated: my owned runs carry the new values (local stores only, so this fence does not wait for the fabric) ----
-  __threadfence_system();
+  // (ONE fence per block, behind the barrier that orders the block's stores before it: a fence per thread serialised the
+  // eight warps' MEMBAR.SYS and took 12-14 us on an SM that shares its memory pipeline with a GEMM CTA)
   __syncthreads();
-  if (threadIdx.x == 0) sh_last = (atomicAdd(&mine->blocks_done[sync], 1u) == gridDim.x - 1) ? 1u : 0u;
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    sh_last = (atomicAdd(&mine->blocks_done[sync], 1u) == gridDim.x - 1) ? 1u : 0u;
+  }
   __syncthreads();
   if (sh_last) {
-    if (threadIdx.x == 0) mine->blocks_done[sync] = 0;
-    __threadfence_system();
+    if (threadIdx.x == 0) { mine->blocks_done[sync] = 0; __threadfence_system(); }
+    __syncthreads();
     if (threadIdx.x < p.world)
       st_release_sys(&reinterpret_cast<P2PFlags*>(p.peers->base[threadIdx.x] + p.flags_off)->done[sync][p.rank], epoch);
   }
