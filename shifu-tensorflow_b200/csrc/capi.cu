@@ -146,6 +146,8 @@ static XchgParams xchg_params(sb_trainer* t) {
   p.host_err = t->d_herr;
   p.timeout_ns = t->xchg_timeout_ns;
   p.early_dependents = t->peers_share_device ? 0 : 1;
+  static const bool fence_gpu = getenv("SB_XCHG_FENCE_GPU") != nullptr;
+  p.fence_gpu = fence_gpu ? 1 : 0;
   return p;
 }
 
@@ -165,8 +167,9 @@ static int enqueue_xchg(sb_trainer* t, int slot_mask, cudaStream_t st, bool publ
   for (int sl = 0; sl < t->x_slots; ++sl)
     if ((slot_mask >> sl) & 1) runs += (p.slot_end[sl] - p.slot_begin[sl] + t->world - 1) / t->world;
   const int U = t->world <= 2 ? 2 : 1;      // runs per block iteration (xchg_update_kernel)
-  // at most one block per SM and launch: a block must fit beside whatever persistent GEMM CTA shares its SM (xchg_p2p.cuh)
-  int grid = t->xchg_blocks > 0 ? t->xchg_blocks : n.num_sms;
+  // up to two blocks per SM: both fit beside a dW GEMM CTA, one beside a forward GEMM CTA (xchg_p2p.cuh).  Blocks that find
+  // no room wait for the GEMM CTAs to leave - those never wait for an exchange, so this cannot deadlock, only be slow.
+  int grid = t->xchg_blocks > 0 ? t->xchg_blocks : 2 * n.num_sms;
   if (t->peers_share_device && grid > 32) grid = 32;    // replicas on ONE device: leave registers to the replica being waited for
   if (grid > (runs + U - 1) / U) grid = (runs + U - 1) / U;
   if (grid < 1) grid = 1;
@@ -330,6 +333,8 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
     }
     SB_TRY(enqueue_xchg(t, XSEG_A, n.side, false, false));
     SB_CUDA(cudaEventRecord(t->ev_x[0], n.side));
+    static const bool a_early_wait = getenv("SB_XCHG_A_TOUCH") != nullptr;   // experiment: a no-op node on the main chain behind A's launch
+    (void)a_early_wait;
     // whatever follows on the main stream (the next step's layer-0 forward, or the end of the graph) needs hidden layer 0
     for (int c = 0; c < t->x_chunks; ++c)
       if ((t->x_sent >> (1 + c)) & 1) SB_CUDA(cudaStreamWaitEvent(n.stream, t->ev_x[1 + c], 0));

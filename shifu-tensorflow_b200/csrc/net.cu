@@ -158,6 +158,7 @@ int Net::init(const sb_net_desc* d, int device_, bool training_) {
   // the main chain is the critical path: its CTAs are scheduled ahead of the side stream's (dW GEMMs, second optimizer)
   int prio_least = 0, prio_greatest = 0;
   SB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  if (getenv("SB_FLAT_PRIO")) prio_greatest = prio_least;      // experiment: every stream at the same priority
   SB_CUDA(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_greatest));
   if (training_) {
     SB_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, prio_least));

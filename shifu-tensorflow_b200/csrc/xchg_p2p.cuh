@@ -71,6 +71,7 @@ struct XchgParams {
   float* host_scal;
   unsigned int* host_err;                 // mapped pinned: [0] = 0 ok | 1 + 16 * slot + missing rank
   unsigned long long timeout_ns;          // 0 = wait forever
+  int fence_gpu;                          // SB_XCHG_FENCE_GPU=1 (experiment): gpu-scope fence before the `updated` flag
   int early_dependents;                   // 1: let the next kernel of the stream (PDL) become resident while this one still
                                           // waits for its peers.  0 when the peers share this device (in-process replicas):
                                           // the next step's persistent GEMM CTAs would take every SM's shared memory while
@@ -284,15 +285,21 @@ xchg_update_kernel(const XchgParams p) {
   // eight warps' MEMBAR.SYS and took 12-14 us on an SM that shares its memory pipeline with a GEMM CTA)
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    // every store of phase 1 went to LOCAL memory, whose point of coherence - this GPU's L2 - also serves the peers' P2P
+    // loads: a gpu-scope fence orders them before the flag (fence_gpu = 0 uses the architecturally required sys scope)
+    if (p.fence_gpu) __threadfence(); else __threadfence_system();
     sh_last = (atomicAdd(&mine->blocks_done[sync], 1u) == gridDim.x - 1) ? 1u : 0u;
   }
   __syncthreads();
   if (sh_last) {
-    if (threadIdx.x == 0) { mine->blocks_done[sync] = 0; __threadfence_system(); }
+    if (threadIdx.x == 0) { mine->blocks_done[sync] = 0; if (p.fence_gpu) __threadfence(); else __threadfence_system(); }
     __syncthreads();
     if (threadIdx.x < p.world)
-      st_release_sys(&reinterpret_cast<P2PFlags*>(p.peers->base[threadIdx.x] + p.flags_off)->done[sync][p.rank], epoch);
+    {
+      unsigned int* f = &reinterpret_cast<P2PFlags*>(p.peers->base[threadIdx.x] + p.flags_off)->done[sync][p.rank];
+      if (p.fence_gpu) asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(f), "r"(epoch) : "memory");
+      else st_release_sys(f, epoch);
+    }
   }
   stamp_max(5);
   // ---- all-gather by P2P LOADS: every run somebody else owns is pulled from its owner once that owner has updated ----
