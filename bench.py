@@ -491,7 +491,7 @@ def main():
 
     main_res = measure(args.config, True)
     second = None
-    if args.also and args.also != args.config:
+    if args.also and args.also != args.config and args.also in CONFIGS:
         second = measure(args.also, False)
     if sampler:
         sampler.stop()
