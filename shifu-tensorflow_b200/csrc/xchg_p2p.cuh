@@ -330,8 +330,9 @@ xchg_update_kernel(const XchgParams p) {
           const int j = i0 + u;
           if (j >= n_other) continue;
           const int w = sb + j + ((sb + j >= w0) ? (w1 - w0) : 0);
-          int q = 0;
-          while (q + 1 < p.world && w >= xchg_share(sb, se, q + 1, p.world)) ++q;     // owner of run w
+          int q = static_cast<int>((static_cast<long long>(w - sb) * p.world) / (se - sb));     // owner of run w: estimate, then fix up
+          while (q + 1 < p.world && w >= xchg_share(sb, se, q + 1, p.world)) ++q;
+          while (q > 0 && w < xchg_share(sb, se, q, p.world)) --q;
           const OptWork& wk = p.work[w];
           const bool vec = (wk.off & 3) == 0 && (wk.count & 3) == 0 &&
                            (wk.Wn == nullptr || ((wk.out_dim & 3) == 0 && ((wk.off - wk.mat_off) & 3) == 0 && (wk.ld_out & 3) == 0));
