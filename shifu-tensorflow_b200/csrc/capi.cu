@@ -151,6 +151,8 @@ static XchgParams xchg_params(sb_trainer* t) {
   return p;
 }
 
+static __global__ void touch_kernel() {}
+
 // reduce-scatter -> owner update -> all-gather of the operands for the given segments (xchg_p2p.cuh); `g` must be t->grad
 static int enqueue_xchg(sb_trainer* t, int slot_mask, cudaStream_t st, bool publish_scalars, bool pdl) {
   Net& n = t->net;
@@ -331,10 +333,20 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
     } else {
       SB_CUDA(cudaStreamWaitEvent(n.side, n.ev_da_done, 0));
     }
+    // When nothing on the main chain waits for slot A before the next step's layer-1 forward, the graph executor released
+    // the edge dW_1 -> A only after the main chain had passed its waits for B0 / B1 (A started 18 us after B1 ENDED,
+    // measured on 2 x B200, whichever stream carried it).  A one-thread kernel in front of A that the main chain waits for
+    // right away pins the edge where it belongs.
+    static const bool no_touch = getenv("SB_XCHG_NO_TOUCH") != nullptr;
+    const bool touch = defer_A && !last_in_graph && !no_touch;
+    if (touch) {
+      touch_kernel<<<1, 32, 0, n.side>>>();
+      SB_CUDA(cudaGetLastError());
+      SB_CUDA(cudaEventRecord(t->ev_c[SB_XCHG_SLOTS - 1], n.side));
+    }
     SB_TRY(enqueue_xchg(t, XSEG_A, n.side, false, false));
     SB_CUDA(cudaEventRecord(t->ev_x[0], n.side));
-    static const bool a_early_wait = getenv("SB_XCHG_A_TOUCH") != nullptr;   // experiment: a no-op node on the main chain behind A's launch
-    (void)a_early_wait;
+    if (touch) SB_CUDA(cudaStreamWaitEvent(n.stream, t->ev_c[SB_XCHG_SLOTS - 1], 0));
     // whatever follows on the main stream (the next step's layer-0 forward, or the end of the graph) needs hidden layer 0
     for (int c = 0; c < t->x_chunks; ++c)
       if ((t->x_sent >> (1 + c)) & 1) SB_CUDA(cudaStreamWaitEvent(n.stream, t->ev_x[1 + c], 0));
@@ -589,7 +601,7 @@ int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, 
     // on run borders when out % 8 == 0), the last chunk also carries b_0; everything else is slot 0
     int chunks = 2;
     if (const char* e = getenv("SB_XCHG_CHUNKS")) chunks = atoi(e);
-    if (chunks > SB_XCHG_SLOTS - 1) chunks = SB_XCHG_SLOTS - 1;
+    if (chunks > SB_XCHG_SLOTS - 2) chunks = SB_XCHG_SLOTS - 2;   // (ev_c[SLOTS - 1] is the touch event)
     const Layer& l0 = n.layers[0];
     if (chunks < 1 || !n.tc() || (l0.out % 8) != 0 || l0.in < 256 * chunks) chunks = 1;
     n.dw0_chunks = chunks;
