@@ -3,6 +3,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <memory>
 #include <random>
 #include "net.cuh"
@@ -165,15 +166,19 @@ static int enqueue_xchg(sb_trainer* t, int slot_mask, cudaStream_t st, bool publ
   else if ((slot_mask & (slot_mask - 1)) == 0) snprintf(nm, sizeof(nm), "xchg_B%d", __builtin_ctz(slot_mask) - 1);
   else snprintf(nm, sizeof(nm), "xchg");
   p.trace = n.next_trace(nm);
-  int runs = 0;      // owned runs of the launch (the largest share)
+  int runs = 0, all_runs = 0;      // owned runs of the launch (the largest share) / runs of the launch
   for (int sl = 0; sl < t->x_slots; ++sl)
-    if ((slot_mask >> sl) & 1) runs += (p.slot_end[sl] - p.slot_begin[sl] + t->world - 1) / t->world;
-  const int U = t->world <= 2 ? 2 : 1;      // runs per block iteration (xchg_update_kernel)
+    if ((slot_mask >> sl) & 1) {
+      runs += (p.slot_end[sl] - p.slot_begin[sl] + t->world - 1) / t->world;
+      all_runs += p.slot_end[sl] - p.slot_begin[sl];
+    }
+  const int U = t->world <= 2 ? 2 : 1;      // runs per block iteration of the update phase (xchg_update_kernel)
+  const int want = std::max((runs + U - 1) / U, (all_runs - runs + 3) / 4);   // ... and 4 per iteration of the gather phase
   // up to two blocks per SM: both fit beside a dW GEMM CTA, one beside a forward GEMM CTA (xchg_p2p.cuh).  Blocks that find
   // no room wait for the GEMM CTAs to leave - those never wait for an exchange, so this cannot deadlock, only be slow.
   int grid = t->xchg_blocks > 0 ? t->xchg_blocks : 2 * n.num_sms;
   if (t->peers_share_device && grid > 32) grid = 32;    // replicas on ONE device: leave registers to the replica being waited for
-  if (grid > (runs + U - 1) / U) grid = (runs + U - 1) / U;
+  if (grid > want) grid = want;
   if (grid < 1) grid = 1;
   const dim3 g(static_cast<unsigned>(grid)), b(256);
   if (t->world <= 2) SB_TRY(n.launch(xchg_update_kernel<2>, g, b, 0, st, pdl, p));
