@@ -147,12 +147,10 @@ static XchgParams xchg_params(sb_trainer* t) {
   p.host_err = t->d_herr;
   p.timeout_ns = t->xchg_timeout_ns;
   p.early_dependents = t->peers_share_device ? 0 : 1;
-  static const bool fence_gpu = getenv("SB_XCHG_FENCE_GPU") != nullptr;
-  p.fence_gpu = fence_gpu ? 1 : 0;
+  static const bool fence_sys = getenv("SB_XCHG_FENCE_SYS") != nullptr;
+  p.fence_gpu = fence_sys ? 0 : 1;
   return p;
 }
-
-static __global__ void touch_kernel() {}
 
 // reduce-scatter -> owner update -> all-gather of the operands for the given segments (xchg_p2p.cuh); `g` must be t->grad
 static int enqueue_xchg(sb_trainer* t, int slot_mask, cudaStream_t st, bool publish_scalars, bool pdl) {
@@ -174,9 +172,10 @@ static int enqueue_xchg(sb_trainer* t, int slot_mask, cudaStream_t st, bool publ
     }
   const int U = t->world <= 2 ? 2 : 1;      // runs per block iteration of the update phase (xchg_update_kernel)
   const int want = std::max((runs + U - 1) / U, (all_runs - runs + 3) / 4);   // ... and 4 per iteration of the gather phase
-  // up to two blocks per SM: both fit beside a dW GEMM CTA, one beside a forward GEMM CTA (xchg_p2p.cuh).  Blocks that find
-  // no room wait for the GEMM CTAs to leave - those never wait for an exchange, so this cannot deadlock, only be slow.
-  int grid = t->xchg_blocks > 0 ? t->xchg_blocks : 2 * n.num_sms;
+  // one block per SM and launch: it fits beside a forward GEMM CTA, and two launches fit beside a dW GEMM CTA (xchg_p2p.cuh;
+  // with two blocks per SM the chunk exchanges crowded dW_1 out: 15 -> 27 us, measured).  Blocks that find no room wait for
+  // GEMM CTAs to leave - those never wait for an exchange, so this cannot deadlock, only be slow.
+  int grid = t->xchg_blocks > 0 ? t->xchg_blocks : n.num_sms;
   if (t->peers_share_device && grid > 32) grid = 32;    // replicas on ONE device: leave registers to the replica being waited for
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
@@ -221,6 +220,7 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
     ~Scope() {
       n.from_resident = false; n.zero_buf = nullptr; n.dw0_on_main = n.defer_join = false; n.sparse_step = false;
       n.dw0_chunks = 1; n.dw1_last = false; n.on_dw0_chunk = nullptr; n.before_layer1 = nullptr; n.zero_layer = 0;
+      n.beside_prev_xchg = false;
     }
   } scope{n};
   n.from_resident = resident;
@@ -248,13 +248,8 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   const bool defer_A = xsched && resident && n.L >= 3 && !no_defer;
   if (xsched) {
     n.zero_layer = defer_A ? 1 : 0;
-    if (t->pending_xA) {
-      n.before_layer1 = [t]() -> int {
-        SB_CUDA(cudaStreamWaitEvent(t->net.stream, t->ev_x[0], 0));
-        t->pending_xA = false;
-        return SB_OK;
-      };
-    }
+    n.beside_prev_xchg = t->pending_xA;     // slot A's exchange of the previous step is the kernel in front of this step
+    t->pending_xA = false;
   }
   if (resident) {
     // no load kernel: the batch is read by TMA from the bf16 resident set; set_batch_kernel already published n_nz.
@@ -328,37 +323,37 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   n.on_layer_grads = nullptr;
   SB_TRY(bs);
   if (xsched) {
-    // slot A: every gradient but hidden layer 0's - complete behind the other layers' dW GEMMs (dW_1: main stream, or side
-    // stream with SB_XCHG_BESIDE; the rest: side stream) and the last dA GEMM (the last reader of their weight shadows).
-    // It is launched ON the side stream: as a node whose parents sit on several branches, the graph executor queued it
-    // behind the main chain's next kernels and it started 100 us late (measured).
-    if (n.dw1_last) {
-      SB_CUDA(cudaEventRecord(t->ev_c[0], n.stream));
-      SB_CUDA(cudaStreamWaitEvent(n.side, t->ev_c[0], 0));
+    // slot A: every gradient but hidden layer 0's - complete behind dW_1 (main stream), the other layers' dW GEMMs (side
+    // stream) and the last dA GEMM (the last reader of their weight shadows).
+    // Deferred (multi-step graphs): the launch goes ON the main stream, as dW_1's programmatic dependent.  It releases ITS
+    // dependents at its start, the next step's layer-0 forward GEMM skips its dependency wait (all it needs - B0, B1 - are
+    // full dependencies) and so runs beside the exchange; layer 1's forward is a plain in-stream launch behind both.
+    // (As a node on another stream that nothing on the main chain waited for, the graph executor started the exchange 18 us
+    // after B1 had ENDED - whichever stream carried it, with or without a waited-for marker kernel in front.)
+    const bool a_on_main = defer_A && n.dw1_last && !t->peers_share_device;
+    if (a_on_main) {
+      if (n.L > 2) {
+        SB_CUDA(cudaEventRecord(n.ev_join, n.side));
+        SB_CUDA(cudaStreamWaitEvent(n.stream, n.ev_join, 0));
+      }
+      SB_TRY(enqueue_xchg(t, XSEG_A, n.stream, false, n.use_pdl));
     } else {
-      SB_CUDA(cudaStreamWaitEvent(n.side, n.ev_da_done, 0));
+      if (n.dw1_last) {
+        SB_CUDA(cudaEventRecord(t->ev_c[0], n.stream));
+        SB_CUDA(cudaStreamWaitEvent(n.side, t->ev_c[0], 0));
+      } else {
+        SB_CUDA(cudaStreamWaitEvent(n.side, n.ev_da_done, 0));
+      }
+      SB_TRY(enqueue_xchg(t, XSEG_A, n.side, false, false));
+      SB_CUDA(cudaEventRecord(t->ev_x[0], n.side));
     }
-    // When nothing on the main chain waits for slot A before the next step's layer-1 forward, the graph executor released
-    // the edge dW_1 -> A only after the main chain had passed its waits for B0 / B1 (A started 18 us after B1 ENDED,
-    // measured on 2 x B200, whichever stream carried it).  A one-thread kernel in front of A that the main chain waits for
-    // right away pins the edge where it belongs.
-    static const bool no_touch = getenv("SB_XCHG_NO_TOUCH") != nullptr;
-    const bool touch = defer_A && !last_in_graph && !no_touch;
-    if (touch) {
-      touch_kernel<<<1, 32, 0, n.side>>>();
-      SB_CUDA(cudaGetLastError());
-      SB_CUDA(cudaEventRecord(t->ev_c[SB_XCHG_SLOTS - 1], n.side));
-    }
-    SB_TRY(enqueue_xchg(t, XSEG_A, n.side, false, false));
-    SB_CUDA(cudaEventRecord(t->ev_x[0], n.side));
-    if (touch) SB_CUDA(cudaStreamWaitEvent(n.stream, t->ev_c[SB_XCHG_SLOTS - 1], 0));
     // whatever follows on the main stream (the next step's layer-0 forward, or the end of the graph) needs hidden layer 0
     for (int c = 0; c < t->x_chunks; ++c)
       if ((t->x_sent >> (1 + c)) & 1) SB_CUDA(cudaStreamWaitEvent(n.stream, t->ev_x[1 + c], 0));
     // (a layer-0 dW that was not cut into the trainer's chunks - wide+deep steps - is exchanged here, behind everything)
     const int missing = (xseg_all(t) & ~XSEG_A) & ~t->x_sent;
     if (missing) SB_TRY(enqueue_xchg(t, missing, n.stream, true, false));
-    if (defer_A && !last_in_graph) t->pending_xA = true;
+    if (a_on_main) t->pending_xA = !last_in_graph;      // (the last step of a graph: whatever follows is ordered behind it)
     else SB_CUDA(cudaStreamWaitEvent(n.stream, t->ev_x[0], 0));
     return SB_OK;
   }

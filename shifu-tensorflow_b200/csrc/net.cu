@@ -446,7 +446,8 @@ int Net::enqueue_hidden_forward(int rows, float* grad, bool* fused_out) {
       p.trace = next_trace("fwd", l, rows, ly.out, k_in);
       if (nparts == 1 && p.addend == nullptr)      // plain bf16: the epilogue stores its tiles by TMA
         SB_TRY(make_tmap_bf16(&tm.o, A[l], rows, ly.out, ly.ld_out, 128));
-      SB_TRY((launch_gemm_tc<EPI_FWD, false, true>(pl, tm, p, stream, use_pdl)));
+      if (beside_prev_xchg && l == 0) p.no_dep_wait = 1;
+      SB_TRY((launch_gemm_tc<EPI_FWD, false, true>(pl, tm, p, stream, use_pdl && !(beside_prev_xchg && l == 1))));
     } else {
       GemmF32Params p = {};
       p.M = rows; p.N = ly.out; p.K = k_in;

@@ -40,6 +40,10 @@ struct Net {
   std::function<int(int /*chunk*/)> on_dw0_chunk;
   std::function<int()> before_layer1;
   int zero_layer = 0;
+  // the previous step's exchange of slot 0 sits in front of this step on the main stream and has released its programmatic
+  // dependents at its start: the layer-0 forward GEMM skips its dependency wait (it runs BESIDE that exchange), and layer 1's
+  // forward is launched without the programmatic attribute, i.e. behind everything the stream has seen
+  bool beside_prev_xchg = false;
   int dw0_chunk_rows() const {
     const int c = dw0_chunks > 1 ? dw0_chunks : 1;
     return ((layers[0].in + c - 1) / c + 127) / 128 * 128;

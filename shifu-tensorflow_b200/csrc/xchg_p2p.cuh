@@ -71,7 +71,7 @@ struct XchgParams {
   float* host_scal;
   unsigned int* host_err;                 // mapped pinned: [0] = 0 ok | 1 + 16 * slot + missing rank
   unsigned long long timeout_ns;          // 0 = wait forever
-  int fence_gpu;                          // SB_XCHG_FENCE_GPU=1 (experiment): gpu-scope fence before the `updated` flag
+  int fence_gpu;                          // 1 (default): gpu-scope fence before the `updated` flag; SB_XCHG_FENCE_SYS=1 -> 0
   int early_dependents;                   // 1: let the next kernel of the stream (PDL) become resident while this one still
                                           // waits for its peers.  0 when the peers share this device (in-process replicas):
                                           // the next step's persistent GEMM CTAs would take every SM's shared memory while
@@ -286,7 +286,9 @@ xchg_update_kernel(const XchgParams p) {
   __syncthreads();
   if (threadIdx.x == 0) {
     // every store of phase 1 went to LOCAL memory, whose point of coherence - this GPU's L2 - also serves the peers' P2P
-    // loads: a gpu-scope fence orders them before the flag (fence_gpu = 0 uses the architecturally required sys scope)
+    // loads, so a gpu-scope fence is enough to order them before the flag: 2 us instead of the 9-11 us MEMBAR.SYS took on an
+    // SM that shares its memory pipeline with a GEMM CTA (measured; replicas stay bit-identical, tests/test_multi_gpu.py).
+    // fence_gpu = 0 (SB_XCHG_FENCE_SYS=1) uses the sys scope the PTX memory model asks for between devices.
     if (p.fence_gpu) __threadfence(); else __threadfence_system();
     sh_last = (atomicAdd(&mine->blocks_done[sync], 1u) == gridDim.x - 1) ? 1u : 0u;
   }
