@@ -66,6 +66,8 @@ struct sb_trainer {
   int x_begin[SB_XCHG_SLOTS] = {}, x_end[SB_XCHG_SLOTS] = {};
   cudaEvent_t ev_x[SB_XCHG_SLOTS] = {};   // exchange of slot s complete (recorded on its comm stream)
   cudaEvent_t ev_c[SB_XCHG_SLOTS] = {};   // dW_0 chunk c complete on the main stream / tail of the main stream
+  bool ll_ready = false;           // the LL exchange (xchg_ll_kernel) is usable: plain bf16, world > 1, buffers in the arena
+  long long llg_off = 0, lls_off = 0;
   int x_sent = 0;                  // (while enqueueing a step) slots whose exchange the dW_0 chunk hook has launched
   bool pending_xA = false;         // (while capturing) slot 0's exchange of the previous step has not been joined yet
   // pipelined host-buffer steps (sb_trainer_step_async): second staging slot + copy stream, so the H2D of batch i+1
@@ -146,17 +148,21 @@ static XchgParams xchg_params(sb_trainer* t) {
   p.hyper = t->hyper;
   p.host_err = t->d_herr;
   p.timeout_ns = t->xchg_timeout_ns;
-  p.early_dependents = t->peers_share_device ? 0 : 1;
+  p.early_dependents = 0;
   static const bool fence_sys = getenv("SB_XCHG_FENCE_SYS") != nullptr;
   p.fence_gpu = fence_sys ? 0 : 1;
   return p;
 }
 
 // reduce-scatter -> owner update -> all-gather of the operands for the given segments (xchg_p2p.cuh); `g` must be t->grad
-static int enqueue_xchg(sb_trainer* t, int slot_mask, cudaStream_t st, bool publish_scalars, bool pdl) {
+// release_early: the launch lets its programmatic dependents start as soon as it has started itself (only for a launch whose
+// dependents need nothing it produces, see the deferred slot 0 in enqueue_step_body) - every other launch completes first,
+// also for dependents that were given the programmatic attribute
+static int enqueue_xchg(sb_trainer* t, int slot_mask, cudaStream_t st, bool publish_scalars, bool pdl, bool release_early = false) {
   Net& n = t->net;
   XchgParams p = xchg_params(t);
   p.slot_mask = slot_mask;
+  p.early_dependents = (release_early && !t->peers_share_device) ? 1 : 0;
   p.scal = publish_scalars ? n.scal : nullptr;
   p.host_scal = publish_scalars ? t->d_hscal : nullptr;
   char nm[24];
@@ -180,6 +186,14 @@ static int enqueue_xchg(sb_trainer* t, int slot_mask, cudaStream_t st, bool publ
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
   const dim3 g(static_cast<unsigned>(grid)), b(256);
+  if (t->ll_ready) {
+    LLParams lp;
+    lp.x = p; lp.llg_off = t->llg_off; lp.lls_off = t->lls_off; lp.n4 = t->xch_n4;
+    if (t->world <= 2) SB_TRY(n.launch(xchg_ll_kernel<2>, g, b, 0, st, pdl, lp));
+    else if (t->world <= 4) SB_TRY(n.launch(xchg_ll_kernel<4>, g, b, 0, st, pdl, lp));
+    else if (t->world <= 8) SB_TRY(n.launch(xchg_ll_kernel<8>, g, b, 0, st, pdl, lp));
+    else SB_TRY(n.launch(xchg_ll_kernel<16>, g, b, 0, st, pdl, lp));
+  } else
   if (t->world <= 2) SB_TRY(n.launch(xchg_update_kernel<2>, g, b, 0, st, pdl, p));
   else if (t->world <= 4) SB_TRY(n.launch(xchg_update_kernel<4>, g, b, 0, st, pdl, p));
   else if (t->world <= 8) SB_TRY(n.launch(xchg_update_kernel<8>, g, b, 0, st, pdl, p));
@@ -336,7 +350,7 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
         SB_CUDA(cudaEventRecord(n.ev_join, n.side));
         SB_CUDA(cudaStreamWaitEvent(n.stream, n.ev_join, 0));
       }
-      SB_TRY(enqueue_xchg(t, XSEG_A, n.stream, false, n.use_pdl));
+      SB_TRY(enqueue_xchg(t, XSEG_A, n.stream, false, n.use_pdl, !last_in_graph));
     } else {
       if (n.dw1_last) {
         SB_CUDA(cudaEventRecord(t->ev_c[0], n.stream));
@@ -571,6 +585,12 @@ int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, 
     for (int l = 0; l <= desc->n_hidden; ++l) { const int out = l < desc->n_hidden ? desc->hidden[l] : 1; np += static_cast<long long>(prev) * out + out; prev = out; }
     t->xch_n4 = (np + 3) / 4;
     t->net.arena_extra_bytes = static_cast<size_t>(t->xch_n4) * 16 + sizeof(P2PFlags);
+    // LL exchange buffers (xchg_p2p.cuh): gbuf = world regions, sbuf = one, of n4 entries x 32 bytes
+    static const bool no_ll = getenv("SB_XCHG_PULL") != nullptr;
+    if (world > 1 && desc->precision == SB_PREC_BF16 && !no_ll) {
+      t->ll_ready = true;
+      t->net.arena_extra_bytes += 256 + static_cast<size_t>(world + 1) * static_cast<size_t>(t->xch_n4) * 32;
+    }
   }
   int s = t->net.init(desc, device, true);
   if (s != SB_OK) { t->net.destroy(); return s; }
@@ -586,6 +606,15 @@ int sb_trainer_create(const sb_net_desc* desc, int device, const void* nccl_id, 
   t->flags_off = t->grad_off + t->xch_n4 * 16;
   t->grad = reinterpret_cast<float*>(n.arena + t->grad_off);
   t->flags = reinterpret_cast<P2PFlags*>(n.arena + t->flags_off);
+  if (t->ll_ready) {
+    t->llg_off = (t->flags_off + static_cast<long long>(sizeof(P2PFlags)) + 255) / 256 * 256;
+    t->lls_off = t->llg_off + static_cast<long long>(world) * t->xch_n4 * 32;
+    // entries carry the epoch of the exchange that wrote them; epochs start at 1
+    if (cudaMemset(n.arena + t->llg_off, 0, static_cast<size_t>(world + 1) * static_cast<size_t>(t->xch_n4) * 32) != cudaSuccess) {
+      n.destroy();
+      return set_error(SB_ERR_CUDA, "cudaMemset(exchange buffers) failed");
+    }
+  }
   t->s1 = n.s1; t->s2 = n.s2;
   if ((s = n.dalloc(&t->acc, n.n_params))) { n.destroy(); return s; }
   if (cudaHostAlloc(reinterpret_cast<void**>(&t->h_err), sizeof(unsigned int) * 4, cudaHostAllocMapped) != cudaSuccess ||
@@ -710,6 +739,10 @@ static int preload_exchange_kernels() {
   SB_CUDA(cudaFuncGetAttributes(&a, xchg_update_kernel<4>));
   SB_CUDA(cudaFuncGetAttributes(&a, xchg_update_kernel<8>));
   SB_CUDA(cudaFuncGetAttributes(&a, xchg_update_kernel<16>));
+  SB_CUDA(cudaFuncGetAttributes(&a, xchg_ll_kernel<2>));
+  SB_CUDA(cudaFuncGetAttributes(&a, xchg_ll_kernel<4>));
+  SB_CUDA(cudaFuncGetAttributes(&a, xchg_ll_kernel<8>));
+  SB_CUDA(cudaFuncGetAttributes(&a, xchg_ll_kernel<16>));
   SB_CUDA(cudaFuncGetAttributes(&a, gather_master_kernel));
   SB_CUDA(cudaFuncGetAttributes(&a, set_batch_kernel));
   SB_CUDA(cudaFuncGetAttributes(&a, scale_kernel));

@@ -387,6 +387,364 @@ xchg_update_kernel(const XchgParams p) {
   trace_end(p.trace);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The same exchange with the flags INSIDE the data ("LL" protocol, as in NCCL): no arrive / updated flag, no fence, no
+// load round trip - every transfer is a fire-and-forget P2P STORE of 16 bytes {d0, epoch, d1, epoch} (8 data bytes, each
+// 8-byte half self-validating), and the receiver polls ITS OWN memory until both halves carry the step's epoch:
+//
+//   push    my gradient of every run somebody else owns  ->  the owner's  gbuf[me][...]
+//   update  owned runs: own gradient + the peers' (polled from gbuf, summed in rank order), optimizer, local master /
+//           state / shadow, and the new operand pushed to every peer's  sbuf[...]  (bf16 shadow: one 16-byte store per 4
+//           parameters; runs without a shadow: fp32 theta, two stores)
+//   gather  runs others own: poll sbuf, unpack into my shadow / theta
+//
+// The chain is  store latency (2.7 us) + 2 x bytes / bandwidth, twice - about half of the flag-and-pull protocol above,
+// whose three fabric round trips cost ~27 us beside a GEMM however little data they moved (profiles/results_r02.md).
+// Buffers (arena, behind the flag block): gbuf = world x n4 entries, sbuf = n4 entries of 32 bytes, entry i = parameters
+// 4 i .. 4 i + 3 as four 8-byte units {value bits, epoch}; a shadow entry uses the first two units {2 x bf16, epoch}.
+// Reuse is safe without any handshake: a sender overwrites gbuf / sbuf of step k only after it has left step k's
+// exchange of that slot, which it can only do after the receiver has consumed the entry (the receiver's own pushes of
+// step k, which the sender waited for, came after it).
+struct LLParams {
+  XchgParams x;
+  long long llg_off, lls_off;     // byte offsets of gbuf / sbuf inside every arena
+  long long n4;                   // entries per rank in gbuf
+};
+
+__device__ __forceinline__ void ll_store2(char* dst, unsigned int d0, unsigned int d1, unsigned int ep) {
+  asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(d0), "r"(ep), "r"(d1), "r"(ep) : "memory");
+}
+__device__ __forceinline__ void ll_store1(char* dst, unsigned int d0, unsigned int ep) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(d0), "r"(ep) : "memory");
+}
+// poll one 16-byte LL pair until both halves carry `ep`; false after a timeout / failure elsewhere in the block
+__device__ __forceinline__ bool ll_poll2(const char* src, unsigned int ep, unsigned int& d0, unsigned int& d1, const XchgParams& p,
+                                         int slot, int from, unsigned int* sh_fail) {
+  unsigned int f0, f1, spins = 0;
+  unsigned long long t0 = 0;
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(f0), "=r"(d1), "=r"(f1) : "l"(src) : "memory");
+    if (f0 == ep && f1 == ep) return true;
+    if ((++spins & 0xFFFu) == 0) {
+      if (*reinterpret_cast<volatile unsigned int*>(sh_fail)) return false;
+      if (p.timeout_ns != 0) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > p.timeout_ns) {
+          if (p.host_err != nullptr) { atomicCAS(p.host_err, 0u, 1u + 16u * slot + from); __threadfence_system(); }
+          *sh_fail = 1u;
+          return false;
+        }
+      }
+    }
+  }
+}
+__device__ __forceinline__ bool ll_poll1(const char* src, unsigned int ep, unsigned int& d0, const XchgParams& p, int slot, int from,
+                                         unsigned int* sh_fail) {
+  unsigned int f0, spins = 0;
+  unsigned long long t0 = 0;
+  for (;;) {
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(d0), "=r"(f0) : "l"(src) : "memory");
+    if (f0 == ep) return true;
+    if ((++spins & 0xFFFu) == 0) {
+      if (*reinterpret_cast<volatile unsigned int*>(sh_fail)) return false;
+      if (p.timeout_ns != 0) {
+        const unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > p.timeout_ns) {
+          if (p.host_err != nullptr) { atomicCAS(p.host_err, 0u, 1u + 16u * slot + from); __threadfence_system(); }
+          *sh_fail = 1u;
+          return false;
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ bool run_is_vec(const OptWork& wk) {
+  return (wk.off & 3) == 0 && (wk.count & 3) == 0 &&
+         (wk.Wn == nullptr || ((wk.out_dim & 3) == 0 && ((wk.off - wk.mat_off) & 3) == 0 && (wk.ld_out & 3) == 0));
+}
+__device__ __forceinline__ int run_owner(int w, int sb, int se, int world) {
+  int q = static_cast<int>((static_cast<long long>(w - sb) * world) / (se - sb));
+  while (q + 1 < world && w >= xchg_share(sb, se, q + 1, world)) ++q;
+  while (q > 0 && w < xchg_share(sb, se, q, world)) --q;
+  return q;
+}
+
+// plain-bf16 nets only (one shadow part).  One block per SM at most: no block ever waits for another block of its own
+// grid, but it does wait for the peers' blocks, which must all be able to become resident beside whatever GEMM is running.
+template <int W>
+static __global__ void __launch_bounds__(256, W <= 8 ? 3 : 2)
+xchg_ll_kernel(const LLParams lp) {
+  const XchgParams& p = lp.x;
+  __shared__ unsigned int sh_fail;
+  if (threadIdx.x == 0) sh_fail = 0u;
+  trace_begin(p.trace, true);
+  pdl_wait();
+  if (p.early_dependents) pdl_launch_dependents();
+  trace_begin(p.trace, false);
+  __syncthreads();
+  const unsigned int ep = p.desc->epoch;
+  char* const my_base = p.peers->base[p.rank];
+  float* const theta = reinterpret_cast<float*>(my_base);
+  if (p.host_scal != nullptr && blockIdx.x == 0 && threadIdx.x < SCAL_COUNT) {
+    p.host_scal[threadIdx.x] = p.scal[threadIdx.x];
+    if (threadIdx.x == 0 && p.desc->hist != nullptr) *p.desc->hist = make_float2(p.scal[SCAL_LOSS_SUM], p.scal[SCAL_NNZ]);
+    __threadfence_system();
+  }
+  const float lr_t = p.desc->lr_t, gs = p.desc->gscale;
+  const bool use_s1 = p.hyper.kind != SB_OPT_SGD;
+  const bool use_s2 = p.hyper.kind == SB_OPT_ADAM || p.hyper.kind == SB_OPT_ADADELTA;
+  float* const s1 = reinterpret_cast<float*>(my_base + p.s1_off);
+  float* const s2 = reinterpret_cast<float*>(my_base + p.s2_off);
+  float* const my_grad = reinterpret_cast<float*>(my_base + p.grad_off);
+  const long long ent = 32;                                   // bytes per LL entry (4 parameters)
+  const long long g_stride = lp.n4 * ent;                     // one sender's region of gbuf
+  auto stamp_max = [&](int slot) { if (p.trace != nullptr && threadIdx.x == 0) atomicMax(p.trace + slot, static_cast<unsigned long long>(globaltimer_ns())); };
+  const int e = threadIdx.x * 4;
+
+  // ---- push: my gradient of the runs other ranks own ----
+#pragma unroll 1
+  for (int slot = 0; slot < p.n_slots; ++slot) {
+    if (!((p.slot_mask >> slot) & 1)) continue;
+    const int sb = p.slot_begin[slot], se = p.slot_end[slot];
+    const int w0 = xchg_share(sb, se, p.rank, p.world), w1 = xchg_share(sb, se, p.rank + 1, p.world);
+    const int n_other = (se - sb) - (w1 - w0);
+    constexpr int UP = 4;
+#pragma unroll 1
+    for (int i0 = static_cast<int>(blockIdx.x) * UP; i0 < n_other; i0 += static_cast<int>(gridDim.x) * UP) {
+      float4 g[UP];
+      char* dst[UP];
+#pragma unroll
+      for (int u = 0; u < UP; ++u) {
+        dst[u] = nullptr;
+        const int j = i0 + u;
+        if (j >= n_other) continue;
+        const int w = sb + j + ((sb + j >= w0) ? (w1 - w0) : 0);
+        const int q = run_owner(w, sb, se, p.world);
+        const OptWork& wk = p.work[w];
+        char* qb = p.peers->base[q] + lp.llg_off + p.rank * g_stride;
+        if (run_is_vec(wk)) {
+          if (e < wk.count) {
+            g[u] = *reinterpret_cast<const float4*>(my_grad + wk.off + e);
+            dst[u] = qb + ((wk.off + e) >> 2) * ent;
+          }
+        } else {
+          for (int i = 0; i < 4; ++i) {
+            const int es = threadIdx.x + 256 * i;
+            if (es < wk.count) {
+              const long long idx = wk.off + es;
+              ll_store1(qb + (idx >> 2) * ent + (idx & 3) * 8, __float_as_uint(my_grad[idx]), ep);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UP; ++u) {
+        if (dst[u] == nullptr) continue;
+        ll_store2(dst[u], __float_as_uint(g[u].x), __float_as_uint(g[u].y), ep);
+        ll_store2(dst[u] + 16, __float_as_uint(g[u].z), __float_as_uint(g[u].w), ep);
+      }
+    }
+  }
+  if (p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) p.trace[3] = globaltimer_ns();
+  stamp_max(7);
+
+  // ---- update: owned runs ----
+  bool alive = true;
+#pragma unroll 1
+  for (int slot = 0; slot < p.n_slots && alive; ++slot) {
+    if (!((p.slot_mask >> slot) & 1)) continue;
+    const int sb = p.slot_begin[slot], se = p.slot_end[slot];
+    const int w0 = xchg_share(sb, se, p.rank, p.world), w1 = xchg_share(sb, se, p.rank + 1, p.world);
+#pragma unroll 1
+    for (int w = w0 + static_cast<int>(blockIdx.x); w < w1 && alive; w += static_cast<int>(gridDim.x)) {
+      const OptWork wk = p.work[w];
+      const long long shadow_rel = wk.Wn != nullptr ? reinterpret_cast<char*>(wk.Wn) - my_base : 0;
+      if (run_is_vec(wk)) {
+        if (e < wk.count) {
+          const long long idx = wk.off + e;
+          const float4 own = *reinterpret_cast<const float4*>(my_grad + idx);
+          const float4 th = *reinterpret_cast<const float4*>(theta + idx);
+          float4 a = use_s1 ? *reinterpret_cast<const float4*>(s1 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 b = use_s2 ? *reinterpret_cast<const float4*>(s2 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          const char* src = my_base + lp.llg_off + (idx >> 2) * ent;
+          // the peers' entries are polled four ranks at a time with all loads of an attempt in flight together (one L2
+          // latency per attempt instead of one per rank), then added in rank order -> the same bits wherever a sum is computed
+#pragma unroll
+          for (int q0 = 0; q0 < W; q0 += 4) {
+            if (q0 >= p.world || !alive) break;
+            uint4 lo[4], hi[4];
+            unsigned int spins = 0;
+            unsigned long long t0 = 0;
+            for (;;) {
+              bool ok = true;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int q = q0 + k;
+                if (q < W && q < p.world && q != p.rank) {
+                  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo[k].x), "=r"(lo[k].y), "=r"(lo[k].z), "=r"(lo[k].w) : "l"(src + q * g_stride) : "memory");
+                  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(hi[k].x), "=r"(hi[k].y), "=r"(hi[k].z), "=r"(hi[k].w) : "l"(src + q * g_stride + 16) : "memory");
+                }
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int q = q0 + k;
+                if (q < W && q < p.world && q != p.rank) ok = ok && lo[k].y == ep && lo[k].w == ep && hi[k].y == ep && hi[k].w == ep;
+              }
+              if (ok) break;
+              if ((++spins & 0xFFFu) == 0) {
+                if (*reinterpret_cast<volatile unsigned int*>(&sh_fail)) { alive = false; break; }
+                if (p.timeout_ns != 0) {
+                  const unsigned long long now = globaltimer_ns();
+                  if (t0 == 0) t0 = now;
+                  else if (now - t0 > p.timeout_ns) {
+                    int missing = q0;
+                    for (int k = 0; k < 4; ++k) {
+                      const int q = q0 + k;
+                      if (q < W && q < p.world && q != p.rank && !(lo[k].y == ep && lo[k].w == ep && hi[k].y == ep && hi[k].w == ep)) { missing = q; break; }
+                    }
+                    if (p.host_err != nullptr) { atomicCAS(p.host_err, 0u, 1u + 16u * slot + missing); __threadfence_system(); }
+                    sh_fail = 1u;
+                    alive = false;
+                    break;
+                  }
+                }
+              }
+            }
+            if (!alive) break;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int q = q0 + k;
+              if (q >= W || q >= p.world) break;
+              const float4 v = (q == p.rank) ? own
+                                             : make_float4(__uint_as_float(lo[k].x), __uint_as_float(lo[k].z), __uint_as_float(hi[k].x), __uint_as_float(hi[k].z));
+              if (q == 0) acc = v; else { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+            }
+          }
+          if (alive) {
+            float4 t;
+            t.x = opt_update(p.hyper, lr_t, th.x, acc.x * gs, a.x, b.x);
+            t.y = opt_update(p.hyper, lr_t, th.y, acc.y * gs, a.y, b.y);
+            t.z = opt_update(p.hyper, lr_t, th.z, acc.z * gs, a.z, b.z);
+            t.w = opt_update(p.hyper, lr_t, th.w, acc.w * gs, a.w, b.w);
+            *reinterpret_cast<float4*>(theta + idx) = t;
+            *reinterpret_cast<float4*>(my_grad + idx) = acc;      // the owner keeps the reduced gradient of its runs (parity hook)
+            if (use_s1) *reinterpret_cast<float4*>(s1 + idx) = a;
+            if (use_s2) *reinterpret_cast<float4*>(s2 + idx) = b;
+            const long long sent = lp.lls_off + (idx >> 2) * ent;
+            if (wk.Wn != nullptr) {
+              const long long m = idx - wk.mat_off;
+              const long long r = m / wk.out_dim;
+              uint2 o;
+              o.x = pack_bf16x2(t.x, t.y);
+              o.y = pack_bf16x2(t.z, t.w);
+              *reinterpret_cast<uint2*>(my_base + shadow_rel + (r * wk.ld_out + (m - r * wk.out_dim)) * 2) = o;
+#pragma unroll
+              for (int q = 0; q < W; ++q)
+                if (q < p.world && q != p.rank) ll_store2(p.peers->base[q] + sent, o.x, o.y, ep);
+            } else {
+#pragma unroll
+              for (int q = 0; q < W; ++q)
+                if (q < p.world && q != p.rank) {
+                  ll_store2(p.peers->base[q] + sent, __float_as_uint(t.x), __float_as_uint(t.y), ep);
+                  ll_store2(p.peers->base[q] + sent + 16, __float_as_uint(t.z), __float_as_uint(t.w), ep);
+                }
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int i = 0; i < 4 && alive; ++i) {
+          const int es = threadIdx.x + 256 * i;
+          if (es >= wk.count) continue;
+          const long long idx = wk.off + es;
+          const long long uoff = (idx >> 2) * ent + (idx & 3) * 8;
+          float acc = 0.f;
+          for (int q = 0; q < p.world; ++q) {
+            float v = my_grad[idx];
+            if (q != p.rank) {
+              unsigned int d0;
+              if (!ll_poll1(my_base + lp.llg_off + q * g_stride + uoff, ep, d0, p, slot, q, &sh_fail)) { alive = false; break; }
+              v = __uint_as_float(d0);
+            }
+            acc = (q == 0) ? v : acc + v;
+          }
+          if (!alive) break;
+          float a = use_s1 ? s1[idx] : 0.f, b = use_s2 ? s2[idx] : 0.f;
+          const float t = opt_update(p.hyper, lr_t, theta[idx], acc * gs, a, b);
+          theta[idx] = t;
+          my_grad[idx] = acc;
+          if (use_s1) s1[idx] = a;
+          if (use_s2) s2[idx] = b;
+          unsigned int bits = __float_as_uint(t);
+          if (wk.Wn != nullptr) {
+            const long long m = idx - wk.mat_off;
+            const long long r = m / wk.out_dim;
+            const __nv_bfloat16 hv = __float2bfloat16_rn(t);
+            *reinterpret_cast<__nv_bfloat16*>(my_base + shadow_rel + (r * wk.ld_out + (m - r * wk.out_dim)) * 2) = hv;
+            bits = static_cast<unsigned int>(*reinterpret_cast<const unsigned short*>(&hv));
+          }
+          for (int q = 0; q < p.world; ++q)
+            if (q != p.rank) ll_store1(p.peers->base[q] + lp.lls_off + uoff, bits, ep);
+        }
+      }
+    }
+  }
+  stamp_max(4);
+
+  // ---- gather: runs other ranks own ----
+#pragma unroll 1
+  for (int slot = 0; slot < p.n_slots && alive; ++slot) {
+    if (!((p.slot_mask >> slot) & 1)) continue;
+    const int sb = p.slot_begin[slot], se = p.slot_end[slot];
+    const int w0 = xchg_share(sb, se, p.rank, p.world), w1 = xchg_share(sb, se, p.rank + 1, p.world);
+    const int n_other = (se - sb) - (w1 - w0);
+#pragma unroll 1
+    for (int j = static_cast<int>(blockIdx.x); j < n_other && alive; j += static_cast<int>(gridDim.x)) {
+      const int w = sb + j + ((sb + j >= w0) ? (w1 - w0) : 0);
+      const int q = run_owner(w, sb, se, p.world);
+      const OptWork wk = p.work[w];
+      const long long shadow_rel = wk.Wn != nullptr ? reinterpret_cast<char*>(wk.Wn) - my_base : 0;
+      if (run_is_vec(wk)) {
+        if (e < wk.count) {
+          const long long idx = wk.off + e;
+          const char* src = my_base + lp.lls_off + (idx >> 2) * ent;
+          unsigned int d0, d1, d2, d3;
+          if (!ll_poll2(src, ep, d0, d1, p, slot, q, &sh_fail)) { alive = false; break; }
+          if (wk.Wn != nullptr) {
+            const long long m = idx - wk.mat_off;
+            const long long r = m / wk.out_dim;
+            *reinterpret_cast<uint2*>(my_base + shadow_rel + (r * wk.ld_out + (m - r * wk.out_dim)) * 2) = make_uint2(d0, d1);
+          } else {
+            if (!ll_poll2(src + 16, ep, d2, d3, p, slot, q, &sh_fail)) { alive = false; break; }
+            *reinterpret_cast<float4*>(theta + idx) = make_float4(__uint_as_float(d0), __uint_as_float(d1), __uint_as_float(d2), __uint_as_float(d3));
+          }
+        }
+      } else {
+        for (int i = 0; i < 4 && alive; ++i) {
+          const int es = threadIdx.x + 256 * i;
+          if (es >= wk.count) continue;
+          const long long idx = wk.off + es;
+          unsigned int d0;
+          if (!ll_poll1(my_base + lp.lls_off + (idx >> 2) * ent + (idx & 3) * 8, ep, d0, p, slot, q, &sh_fail)) { alive = false; break; }
+          if (wk.Wn != nullptr) {
+            const long long m = idx - wk.mat_off;
+            const long long r = m / wk.out_dim;
+            *reinterpret_cast<unsigned short*>(my_base + shadow_rel + (r * wk.ld_out + (m - r * wk.out_dim)) * 2) = static_cast<unsigned short>(d0);
+          } else {
+            theta[idx] = __uint_as_float(d0);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  trace_end(p.trace);
+}
+
 // Refresh the stale parts of a non-owner's fp32 master and optimizer state from the owners (before the host reads them);
 // what = 1: the reduced gradient instead (each owner kept the sum of its runs).
 // Every run is pulled from its owner unless this rank owns it.  One block per work item.
