@@ -67,6 +67,65 @@ def test_two_gpu_data_parallel_matches_oracle(sb, tmp_path, precision, exchange)
     assert np.abs(r[0]["theta"] - ref.theta).max() <= tol
 
 
+RES_F, RES_HIDDEN, RES_B, RES_STEPS = 96, [64, 48, 32], 128, 14      # 3 graphs of 4 steps + 2 single steps
+
+
+def _resident_rank_main(rank, world, port, out_dir, precision):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch.distributed as dist
+    import shifu_tensorflow_b200 as sb
+    from shifu_tensorflow_b200 import dist_util as du
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    os.environ.setdefault("SB_XCHG_TIMEOUT_S", "60")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    acts = [so.ACT_RELU, so.ACT_TANH, so.ACT_RELU]
+    net = so.NetDesc(RES_F, RES_HIDDEN, acts)
+    desc = sb.make_desc(RES_F, RES_HIDDEN, acts, optimizer=so.OPT_MOMENTUM, learning_rate=0.05, max_batch=RES_B, precision=precision)
+    t = sb.Trainer(desc, device=rank, nccl_id=None, rank=rank, world=world)
+    du.enable_peer_exchange(dist, t, world)
+    t.set_params(so.flatten_params(so.xavier_init(net, 4)))
+    X, y, w = so.synth_batch(world * RES_B * RES_STEPS, RES_F, 31, weights="mixed")
+    mine = np.concatenate([np.arange(s * world * RES_B + rank, (s + 1) * world * RES_B, world) for s in range(RES_STEPS)])
+    t.load_dataset(X[mine], y[mine], w[mine])
+    t.run_resident([s * RES_B for s in range(RES_STEPS)], RES_B)
+    hist = t.loss_history(1, RES_STEPS)
+    theta, grads = t.get_params(), t.get_grads()
+    dist.barrier()
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), theta=theta, grads=grads, losses=np.array(hist))
+    t.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", [1, 2])
+def test_two_gpu_resident_run_matches_oracle(sb, tmp_path, precision):
+    """sb_trainer_run_resident on two REAL GPUs over CUDA-IPC peer memory (no NCCL communicator at all): multi-step graphs
+    with three hidden layers, i.e. the schedule bench.py times - dW_0 in chunks with their exchanges beside the next GEMMs,
+    slot 0's exchange beside the NEXT step's layer-0 forward (bf16: the LL kernel; fp32_tc: the flag-and-pull kernel)."""
+    if sb.capi.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    mp.spawn(_resident_rank_main, args=(world, port, str(tmp_path), precision), nprocs=world, join=True)
+    r = [np.load(str(tmp_path / ("r%d.npz" % i))) for i in range(world)]
+    np.testing.assert_array_equal(r[0]["theta"], r[1]["theta"])      # replicas stay bit-identical
+    np.testing.assert_array_equal(r[0]["grads"], r[1]["grads"])
+    acts = [so.ACT_RELU, so.ACT_TANH, so.ACT_RELU]
+    net = so.NetDesc(RES_F, RES_HIDDEN, acts)
+    ref = so.CleanTrainer(net, so.xavier_init(net, 4), so.OptConfig(kind=so.OPT_MOMENTUM, lr=0.05))
+    X, y, w = so.synth_batch(world * RES_B * RES_STEPS, RES_F, 31, weights="mixed")
+    for s in range(RES_STEPS):
+        rows = [np.arange(s * world * RES_B + k, (s + 1) * world * RES_B, world) for k in range(world)]
+        want = ref.step([(X[i], y[i], w[i]) for i in rows])
+        tol_l = 1e-4 if precision == 2 else 2e-2
+        for k in range(world):
+            assert abs(want[k] - r[k]["losses"][s]) <= tol_l, (s, k, want[k], r[k]["losses"][s])
+    # fp32_tc (3 x bf16 split, fp32 accumulate): the fp32 bound of the single-GPU parity tests; bf16: the bound of the NCCL test above
+    tol = 1e-4 if precision == 2 else 5e-3
+    assert np.abs(r[0]["theta"] - ref.theta).max() <= tol
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("schedule", ["batch", "sync_replicas"])
 def test_launcher_with_two_real_ranks(sb, tmp_path, schedule):
