@@ -158,7 +158,8 @@ static XchgParams xchg_params(sb_trainer* t) {
 // release_early: the launch lets its programmatic dependents start as soon as it has started itself (only for a launch whose
 // dependents need nothing it produces, see the deferred slot 0 in enqueue_step_body) - every other launch completes first,
 // also for dependents that were given the programmatic attribute
-static int enqueue_xchg(sb_trainer* t, int slot_mask, cudaStream_t st, bool publish_scalars, bool pdl, bool release_early = false) {
+static int enqueue_xchg(sb_trainer* t, int slot_mask, cudaStream_t st, bool publish_scalars, bool pdl, bool release_early = false,
+                        bool alone = false) {
   Net& n = t->net;
   XchgParams p = xchg_params(t);
   p.slot_mask = slot_mask;
@@ -181,12 +182,20 @@ static int enqueue_xchg(sb_trainer* t, int slot_mask, cudaStream_t st, bool publ
   // one block per SM and launch: it fits beside a forward GEMM CTA, and two launches fit beside a dW GEMM CTA (xchg_p2p.cuh;
   // with two blocks per SM the chunk exchanges crowded dW_1 out: 15 -> 27 us, measured).  Blocks that find no room wait for
   // GEMM CTAs to leave - those never wait for an exchange, so this cannot deadlock, only be slow.
-  int grid = t->xchg_blocks > 0 ? t->xchg_blocks : n.num_sms;
+  // (alone: nothing but other exchange launches runs beside this one - two blocks per SM, all loads of a phase in one round)
+  int grid = t->xchg_blocks > 0 ? t->xchg_blocks : (alone ? 2 : 1) * n.num_sms;
   if (t->peers_share_device && grid > 32) grid = 32;    // replicas on ONE device: leave registers to the replica being waited for
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
   const dim3 g(static_cast<unsigned>(grid)), b(256);
-  if (t->ll_ready) {
+  // SB_XCHG_LL = all | last (default) | none: which launches use the LL protocol (flags inside the data).  Beside a GEMM its
+  // polling and its doubled store traffic cost the GEMM ~10 us (measured: dW_0 chunk 19 -> 30 us), alone it is the shorter chain.
+  static const int ll_mode = [] {
+    const char* e = getenv("SB_XCHG_LL");
+    if (e == nullptr) return 1;
+    return strcmp(e, "all") == 0 ? 2 : (strcmp(e, "none") == 0 ? 0 : 1);
+  }();
+  if (t->ll_ready && (ll_mode == 2 || (ll_mode == 1 && alone))) {
     LLParams lp;
     lp.x = p; lp.llg_off = t->llg_off; lp.lls_off = t->lls_off; lp.n4 = t->xch_n4;
     if (t->world <= 2) SB_TRY(n.launch(xchg_ll_kernel<2>, g, b, 0, st, pdl, lp));
@@ -234,6 +243,7 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
     ~Scope() {
       n.from_resident = false; n.zero_buf = nullptr; n.dw0_on_main = n.defer_join = false; n.sparse_step = false;
       n.dw0_chunks = 1; n.dw1_last = false; n.on_dw0_chunk = nullptr; n.before_layer1 = nullptr; n.zero_layer = 0;
+      n.dw1_first = false; n.after_dw1 = nullptr;
       n.beside_prev_xchg = false;
     }
   } scope{n};
@@ -258,8 +268,12 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   // which reads nothing slot A writes: layer 1's forward waits for A, and - because peers may read this rank's gradient
   // buffer until then - the buffer is cleared by layer 1's forward GEMM instead of layer 0's.
   const bool xsched = split_tail && t->world > 1;
+  // SB_XCHG_ORDER: "first" (default) = dW_1 in front of dW_0: slot A and chunk 0 hide behind dW_0's chunks, the LAST chunk's
+  // exchange runs on an otherwise idle GPU - an exchange kernel beside a GEMM takes 40-47 us, alone ~25 (measured, 2 x B200);
+  // "last" = dW_1 behind dW_0 as cover for the last chunk, slot A beside the next step's layer-0 forward.
+  static const bool order_last = getenv("SB_XCHG_ORDER") != nullptr && strcmp(getenv("SB_XCHG_ORDER"), "last") == 0;
   static const bool no_defer = getenv("SB_XCHG_NO_DEFER") != nullptr;
-  const bool defer_A = xsched && resident && n.L >= 3 && !no_defer;
+  const bool defer_A = xsched && order_last && resident && n.L >= 3 && !no_defer;
   if (xsched) {
     n.zero_layer = defer_A ? 1 : 0;
     n.beside_prev_xchg = t->pending_xA;     // slot A's exchange of the previous step is the kernel in front of this step
@@ -320,14 +334,27 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
     // SMs with dW_1 - 31 + 19 us instead of 18 + 19 - and the last exchange has nothing to hide behind.)
     static const bool beside = getenv("SB_XCHG_BESIDE") != nullptr;
     n.dw0_chunks = t->x_chunks;
-    n.dw1_last = !beside;
+    n.dw1_last = !beside && order_last;
+    n.dw1_first = !beside && !order_last;
     t->x_sent = 0;
+    if (n.dw1_first) {
+      n.after_dw1 = [t]() -> int {       // slot A on the side stream, behind dW_1 (main) and the other layers' dW GEMMs (side)
+        Net& nn = t->net;
+        SB_CUDA(cudaEventRecord(t->ev_c[0], nn.stream));
+        SB_CUDA(cudaStreamWaitEvent(nn.side, t->ev_c[0], 0));
+        SB_TRY(enqueue_xchg(t, XSEG_A, nn.side, false, false));
+        SB_CUDA(cudaEventRecord(t->ev_x[0], nn.side));
+        t->x_sent |= XSEG_A;
+        return SB_OK;
+      };
+    }
     n.on_dw0_chunk = [t, comms](int c) -> int {
       Net& nn = t->net;
       cudaStream_t cs = comms[c & 1];
       SB_CUDA(cudaEventRecord(t->ev_c[1 + c], nn.stream));
       SB_CUDA(cudaStreamWaitEvent(cs, t->ev_c[1 + c], 0));
-      SB_TRY(enqueue_xchg(t, 1 << (1 + c), cs, c == t->x_chunks - 1, false));   // (the last chunk publishes the step scalars)
+      const bool last = c == t->x_chunks - 1;
+      SB_TRY(enqueue_xchg(t, 1 << (1 + c), cs, last, false, false, last && nn.dw1_first));   // (the last chunk publishes the step scalars)
       SB_CUDA(cudaEventRecord(t->ev_x[1 + c], cs));
       t->x_sent |= 1 << (1 + c);
       return SB_OK;
@@ -345,7 +372,9 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
     // (As a node on another stream that nothing on the main chain waited for, the graph executor started the exchange 18 us
     // after B1 had ENDED - whichever stream carried it, with or without a waited-for marker kernel in front.)
     const bool a_on_main = defer_A && n.dw1_last && !t->peers_share_device;
-    if (a_on_main) {
+    if (t->x_sent & XSEG_A) {
+      // (dW_1 first: launched by after_dw1)
+    } else if (a_on_main) {
       if (n.L > 2) {
         SB_CUDA(cudaEventRecord(n.ev_join, n.side));
         SB_CUDA(cudaStreamWaitEvent(n.stream, n.ev_join, 0));

@@ -514,7 +514,7 @@ int Net::enqueue_backward(int rows, float* grad) {
   // finishing after dW_0" against "dW_1 on a third of the SMs, dW_0 on the rest" and take the shorter.
   int dw_sms[2] = {gemm_sms, gemm_sms};
   static const bool no_budget = getenv("SB_NO_DW_BUDGET") != nullptr;
-  if (fork && dw0_on_main && L > 1 && !on_layer_grads && !no_budget && !dw1_last) {
+  if (fork && dw0_on_main && L > 1 && !on_layer_grads && !no_budget && !dw1_last && !dw1_first) {
     const int kx = round_up(rows, 64) * pairs_of(nparts);
     const GemmPlan n0 = plan_gemm(layers[0].in, layers[0].out, kx, gemm_sms, true);
     const GemmPlan n1 = plan_gemm(layers[1].in, layers[1].out, kx, gemm_sms, true);
@@ -592,8 +592,13 @@ int Net::enqueue_backward(int rows, float* grad) {
       // dW_l[in,out] += sum_rows A_{l-1}[rows,in] (MN-major A) * dZ_l[rows,out] (MN-major B), split-K over rows.
       // With a gradient exchange behind it, a big layer is cut into row chunks of W_l (each a contiguous slice of the
       // flat gradient) so that the all-reduce of chunk c overlaps the GEMM of chunk c+1.
-      if (!(dw1_last && l == 1 && L > 1)) SB_TRY(emit_dw_tc(l, false));
-      if (dw1_last && l == 0 && L > 1) SB_TRY(emit_dw_tc(1, true));   // behind dW_0 on the main stream (covers its last exchange)
+      const bool dw1_moved = (dw1_last || dw1_first) && L > 1;
+      if (dw1_first && l == 0 && L > 1) {         // in front of dW_0 on the main stream: dW_0's last exchange then runs on an idle GPU
+        SB_TRY(emit_dw_tc(1, true));
+        if (after_dw1) SB_TRY(after_dw1());
+      }
+      if (!(dw1_moved && l == 1)) SB_TRY(emit_dw_tc(l, false));
+      if (dw1_last && !dw1_first && l == 0 && L > 1) SB_TRY(emit_dw_tc(1, true));   // behind dW_0 on the main stream (covers its last exchange)
       if (l > 0) {
         // dZ_{l-1}[rows,in] = (dZ_l[rows,out] (K-major) x W_l[in,out] (K-major B: k = out contiguous)) .* act'(A_{l-1})
         Layer& pl = layers[l - 1];

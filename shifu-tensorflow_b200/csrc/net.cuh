@@ -37,6 +37,8 @@ struct Net {
   //   buffer while layer 0 runs).
   int dw0_chunks = 1;
   bool dw1_last = false;
+  bool dw1_first = false;                    // dW_1 on the main stream IN FRONT of dW_0 (then after_dw1 is called behind it)
+  std::function<int()> after_dw1;
   std::function<int(int /*chunk*/)> on_dw0_chunk;
   std::function<int()> before_layer1;
   int zero_layer = 0;

@@ -401,7 +401,8 @@ xchg_update_kernel(const XchgParams p) {
 // The chain is  store latency (2.7 us) + 2 x bytes / bandwidth, twice - about half of the flag-and-pull protocol above,
 // whose three fabric round trips cost ~27 us beside a GEMM however little data they moved (profiles/results_r02.md).
 // Buffers (arena, behind the flag block): gbuf = world x n4 entries, sbuf = n4 entries of 32 bytes, entry i = parameters
-// 4 i .. 4 i + 3 as four 8-byte units {value bits, epoch}; a shadow entry uses the first two units {2 x bf16, epoch}.
+// 4 i .. 4 i + 3 as four 8-byte units {value bits, epoch} (two 16-byte halves in two planes, see the kernel); a shadow
+// entry uses the first half {2 x bf16, epoch, 2 x bf16, epoch}.
 // Reuse is safe without any handshake: a sender overwrites gbuf / sbuf of step k only after it has left step k's
 // exchange of that slot, which it can only do after the receiver has consumed the entry (the receiver's own pushes of
 // step k, which the sender waited for, came after it).
@@ -425,6 +426,7 @@ __device__ __forceinline__ bool ll_poll2(const char* src, unsigned int ep, unsig
   for (;;) {
     asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(d0), "=r"(f0), "=r"(d1), "=r"(f1) : "l"(src) : "memory");
     if (f0 == ep && f1 == ep) return true;
+    __nanosleep(40);          // (a tight poll loop on every thread takes L2 bandwidth from the GEMM that shares the SM)
     if ((++spins & 0xFFFu) == 0) {
       if (*reinterpret_cast<volatile unsigned int*>(sh_fail)) return false;
       if (p.timeout_ns != 0) {
@@ -446,6 +448,7 @@ __device__ __forceinline__ bool ll_poll1(const char* src, unsigned int ep, unsig
   for (;;) {
     asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(d0), "=r"(f0) : "l"(src) : "memory");
     if (f0 == ep) return true;
+    __nanosleep(40);
     if ((++spins & 0xFFFu) == 0) {
       if (*reinterpret_cast<volatile unsigned int*>(sh_fail)) return false;
       if (p.timeout_ns != 0) {
@@ -499,8 +502,11 @@ xchg_ll_kernel(const LLParams lp) {
   float* const s1 = reinterpret_cast<float*>(my_base + p.s1_off);
   float* const s2 = reinterpret_cast<float*>(my_base + p.s2_off);
   float* const my_grad = reinterpret_cast<float*>(my_base + p.grad_off);
-  const long long ent = 32;                                   // bytes per LL entry (4 parameters)
-  const long long g_stride = lp.n4 * ent;                     // one sender's region of gbuf
+  // entry i (parameters 4 i .. 4 i + 3) = 16 bytes {p0, ep, p1, ep} at i * 16 in the low plane + 16 bytes {p2, ep, p3, ep} at the
+  // same offset in the high plane (n4 * 16 further): a warp's store instruction covers 512 contiguous bytes
+  const long long hi_plane = lp.n4 * 16;
+  const long long g_stride = lp.n4 * 32;                      // one sender's region of gbuf
+  auto unit_off = [&](long long idx) { return ((idx & 2) ? hi_plane : 0ll) + (idx >> 2) * 16 + (idx & 1) * 8; };
   auto stamp_max = [&](int slot) { if (p.trace != nullptr && threadIdx.x == 0) atomicMax(p.trace + slot, static_cast<unsigned long long>(globaltimer_ns())); };
   const int e = threadIdx.x * 4;
 
@@ -528,14 +534,14 @@ xchg_ll_kernel(const LLParams lp) {
         if (run_is_vec(wk)) {
           if (e < wk.count) {
             g[u] = *reinterpret_cast<const float4*>(my_grad + wk.off + e);
-            dst[u] = qb + ((wk.off + e) >> 2) * ent;
+            dst[u] = qb + ((wk.off + e) >> 2) * 16;
           }
         } else {
           for (int i = 0; i < 4; ++i) {
             const int es = threadIdx.x + 256 * i;
             if (es < wk.count) {
               const long long idx = wk.off + es;
-              ll_store1(qb + (idx >> 2) * ent + (idx & 3) * 8, __float_as_uint(my_grad[idx]), ep);
+              ll_store1(qb + unit_off(idx), __float_as_uint(my_grad[idx]), ep);
             }
           }
         }
@@ -544,7 +550,7 @@ xchg_ll_kernel(const LLParams lp) {
       for (int u = 0; u < UP; ++u) {
         if (dst[u] == nullptr) continue;
         ll_store2(dst[u], __float_as_uint(g[u].x), __float_as_uint(g[u].y), ep);
-        ll_store2(dst[u] + 16, __float_as_uint(g[u].z), __float_as_uint(g[u].w), ep);
+        ll_store2(dst[u] + hi_plane, __float_as_uint(g[u].z), __float_as_uint(g[u].w), ep);
       }
     }
   }
@@ -570,7 +576,7 @@ xchg_ll_kernel(const LLParams lp) {
           float4 a = use_s1 ? *reinterpret_cast<const float4*>(s1 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
           float4 b = use_s2 ? *reinterpret_cast<const float4*>(s2 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          const char* src = my_base + lp.llg_off + (idx >> 2) * ent;
+          const char* src = my_base + lp.llg_off + (idx >> 2) * 16;
           // the peers' entries are polled four ranks at a time with all loads of an attempt in flight together (one L2
           // latency per attempt instead of one per rank), then added in rank order -> the same bits wherever a sum is computed
 #pragma unroll
@@ -586,7 +592,7 @@ xchg_ll_kernel(const LLParams lp) {
                 const int q = q0 + k;
                 if (q < W && q < p.world && q != p.rank) {
                   asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo[k].x), "=r"(lo[k].y), "=r"(lo[k].z), "=r"(lo[k].w) : "l"(src + q * g_stride) : "memory");
-                  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(hi[k].x), "=r"(hi[k].y), "=r"(hi[k].z), "=r"(hi[k].w) : "l"(src + q * g_stride + 16) : "memory");
+                  asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(hi[k].x), "=r"(hi[k].y), "=r"(hi[k].z), "=r"(hi[k].w) : "l"(src + q * g_stride + hi_plane) : "memory");
                 }
               }
 #pragma unroll
@@ -595,6 +601,7 @@ xchg_ll_kernel(const LLParams lp) {
                 if (q < W && q < p.world && q != p.rank) ok = ok && lo[k].y == ep && lo[k].w == ep && hi[k].y == ep && hi[k].w == ep;
               }
               if (ok) break;
+              __nanosleep(40);
               if ((++spins & 0xFFFu) == 0) {
                 if (*reinterpret_cast<volatile unsigned int*>(&sh_fail)) { alive = false; break; }
                 if (p.timeout_ns != 0) {
@@ -634,7 +641,7 @@ xchg_ll_kernel(const LLParams lp) {
             *reinterpret_cast<float4*>(my_grad + idx) = acc;      // the owner keeps the reduced gradient of its runs (parity hook)
             if (use_s1) *reinterpret_cast<float4*>(s1 + idx) = a;
             if (use_s2) *reinterpret_cast<float4*>(s2 + idx) = b;
-            const long long sent = lp.lls_off + (idx >> 2) * ent;
+            const long long sent = lp.lls_off + (idx >> 2) * 16;
             if (wk.Wn != nullptr) {
               const long long m = idx - wk.mat_off;
               const long long r = m / wk.out_dim;
@@ -650,7 +657,7 @@ xchg_ll_kernel(const LLParams lp) {
               for (int q = 0; q < W; ++q)
                 if (q < p.world && q != p.rank) {
                   ll_store2(p.peers->base[q] + sent, __float_as_uint(t.x), __float_as_uint(t.y), ep);
-                  ll_store2(p.peers->base[q] + sent + 16, __float_as_uint(t.z), __float_as_uint(t.w), ep);
+                  ll_store2(p.peers->base[q] + sent + hi_plane, __float_as_uint(t.z), __float_as_uint(t.w), ep);
                 }
             }
           }
@@ -661,7 +668,7 @@ xchg_ll_kernel(const LLParams lp) {
           const int es = threadIdx.x + 256 * i;
           if (es >= wk.count) continue;
           const long long idx = wk.off + es;
-          const long long uoff = (idx >> 2) * ent + (idx & 3) * 8;
+          const long long uoff = unit_off(idx);
           float acc = 0.f;
           for (int q = 0; q < p.world; ++q) {
             float v = my_grad[idx];
@@ -711,7 +718,7 @@ xchg_ll_kernel(const LLParams lp) {
       if (run_is_vec(wk)) {
         if (e < wk.count) {
           const long long idx = wk.off + e;
-          const char* src = my_base + lp.lls_off + (idx >> 2) * ent;
+          const char* src = my_base + lp.lls_off + (idx >> 2) * 16;
           unsigned int d0, d1, d2, d3;
           if (!ll_poll2(src, ep, d0, d1, p, slot, q, &sh_fail)) { alive = false; break; }
           if (wk.Wn != nullptr) {
@@ -719,7 +726,7 @@ xchg_ll_kernel(const LLParams lp) {
             const long long r = m / wk.out_dim;
             *reinterpret_cast<uint2*>(my_base + shadow_rel + (r * wk.ld_out + (m - r * wk.out_dim)) * 2) = make_uint2(d0, d1);
           } else {
-            if (!ll_poll2(src + 16, ep, d2, d3, p, slot, q, &sh_fail)) { alive = false; break; }
+            if (!ll_poll2(src + hi_plane, ep, d2, d3, p, slot, q, &sh_fail)) { alive = false; break; }
             *reinterpret_cast<float4*>(theta + idx) = make_float4(__uint_as_float(d0), __uint_as_float(d1), __uint_as_float(d2), __uint_as_float(d3));
           }
         }
@@ -729,7 +736,7 @@ xchg_ll_kernel(const LLParams lp) {
           if (es >= wk.count) continue;
           const long long idx = wk.off + es;
           unsigned int d0;
-          if (!ll_poll1(my_base + lp.lls_off + (idx >> 2) * ent + (idx & 3) * 8, ep, d0, p, slot, q, &sh_fail)) { alive = false; break; }
+          if (!ll_poll1(my_base + lp.lls_off + unit_off(idx), ep, d0, p, slot, q, &sh_fail)) { alive = false; break; }
           if (wk.Wn != nullptr) {
             const long long m = idx - wk.mat_off;
             const long long r = m / wk.out_dim;
