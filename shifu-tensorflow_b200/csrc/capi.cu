@@ -188,12 +188,13 @@ static int enqueue_xchg(sb_trainer* t, int slot_mask, cudaStream_t st, bool publ
   if (grid > want) grid = want;
   if (grid < 1) grid = 1;
   const dim3 g(static_cast<unsigned>(grid)), b(256);
-  // SB_XCHG_LL = all | last (default) | none: which launches use the LL protocol (flags inside the data).  Beside a GEMM its
-  // polling and its doubled store traffic cost the GEMM ~10 us (measured: dW_0 chunk 19 -> 30 us), alone it is the shorter chain.
+  // SB_XCHG_LL = all (default) | last | none: which launches use the LL protocol (flags inside the data).  Measured on 2 x B200,
+  // cfg2: all 163.8 us/step, last (only the launch nothing runs beside) 168.2, none 171.4; an LL launch takes 21-28 us where
+  // the flag-and-pull kernel takes 32-47, at the price of 2-4 us on the GEMM beside it (polling, doubled store traffic).
   static const int ll_mode = [] {
     const char* e = getenv("SB_XCHG_LL");
-    if (e == nullptr) return 1;
-    return strcmp(e, "all") == 0 ? 2 : (strcmp(e, "none") == 0 ? 0 : 1);
+    if (e == nullptr) return 2;
+    return strcmp(e, "last") == 0 ? 1 : (strcmp(e, "none") == 0 ? 0 : 2);
   }();
   if (t->ll_ready && (ll_mode == 2 || (ll_mode == 1 && alone))) {
     LLParams lp;
@@ -271,7 +272,10 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   // SB_XCHG_ORDER: "first" (default) = dW_1 in front of dW_0: slot A and chunk 0 hide behind dW_0's chunks, the LAST chunk's
   // exchange runs on an otherwise idle GPU - an exchange kernel beside a GEMM takes 40-47 us, alone ~25 (measured, 2 x B200);
   // "last" = dW_1 behind dW_0 as cover for the last chunk, slot A beside the next step's layer-0 forward.
-  static const bool order_last = getenv("SB_XCHG_ORDER") != nullptr && strcmp(getenv("SB_XCHG_ORDER"), "last") == 0;
+  static const bool order_last_env = getenv("SB_XCHG_ORDER") != nullptr && strcmp(getenv("SB_XCHG_ORDER"), "last") == 0;
+  // (replicas that share ONE device - tests - keep the "last" order: with three exchange launches of both replicas waiting
+  // beside each other's persistent GEMMs the "first" order stopped making progress within the exchange timeout)
+  const bool order_last = order_last_env || t->peers_share_device;
   static const bool no_defer = getenv("SB_XCHG_NO_DEFER") != nullptr;
   const bool defer_A = xsched && order_last && resident && n.L >= 3 && !no_defer;
   if (xsched) {
