@@ -358,7 +358,8 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
       SB_CUDA(cudaEventRecord(t->ev_c[1 + c], nn.stream));
       SB_CUDA(cudaStreamWaitEvent(cs, t->ev_c[1 + c], 0));
       const bool last = c == t->x_chunks - 1;
-      SB_TRY(enqueue_xchg(t, 1 << (1 + c), cs, last, false, false, last && nn.dw1_first));   // (the last chunk publishes the step scalars)
+      SB_TRY(enqueue_xchg(t, 1 << (1 + c), cs, last, false, false, last && !nn.dw1_last));   // (the last chunk publishes the step scalars;
+                                                                                              //  no GEMM follows it unless dW_1 does)
       SB_CUDA(cudaEventRecord(t->ev_x[1 + c], cs));
       t->x_sent |= 1 << (1 + c);
       return SB_OK;
