@@ -1,8 +1,10 @@
 """Data-parallel parity on EXACTLY the multi-GPU path bench.py times, runnable on ONE GPU:
 
-    sb_trainer_load_dataset + sb_trainer_run_resident + the peer-memory exchange kernels (xchg_update_kernel: reduce-scatter
-    by P2P loads -> optimizer on the owned runs -> all-gather of the bf16 weight shadows by P2P stores, segment A on the
-    side stream / segment B PDL-chained behind dW_0)
+    sb_trainer_load_dataset + sb_trainer_run_resident + the peer-memory exchange kernels of csrc/xchg_p2p.cuh (bf16: the LL
+    kernel - gradients pushed to their owners with the flag inside the data, optimizer on the owned runs, new operands pushed
+    back; fp32 / split modes: arrive flag -> P2P loads -> update -> `updated` flag -> all-gather by P2P loads), launched per
+    slot from the multi-step graphs.  (Replicas that share a device keep the serial launch order, see enqueue_step_body; the
+    schedule bench.py times runs on two real GPUs in tests/test_multi_gpu.py::test_two_gpu_resident_run_matches_oracle.)
 
 W replicas (ranks) live in this process on the SAME device, each with its own streams and its own parameter arena; the
 peer table of every replica points at the others' arenas (sb_trainer_set_peer_pointers - the in-process twin of the
