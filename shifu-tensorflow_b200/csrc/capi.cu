@@ -244,7 +244,7 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
     ~Scope() {
       n.from_resident = false; n.zero_buf = nullptr; n.dw0_on_main = n.defer_join = false; n.sparse_step = false;
       n.dw0_chunks = 1; n.dw1_last = false; n.on_dw0_chunk = nullptr; n.before_layer1 = nullptr; n.zero_layer = 0;
-      n.dw1_first = false; n.after_dw1 = nullptr;
+      n.dw1_first = false; n.after_dw1 = nullptr; n.dw1_serial_auto = false;
       n.beside_prev_xchg = false;
     }
   } scope{n};
@@ -362,6 +362,17 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
                                                                                               //  no GEMM follows it unless dW_1 does)
       SB_CUDA(cudaEventRecord(t->ev_x[1 + c], cs));
       t->x_sent |= 1 << (1 + c);
+      return SB_OK;
+    };
+  }
+  static const bool dw1_beside_n1 = getenv("SB_DW1_BESIDE") != nullptr;
+  if (split_tail && !xsched && !dw1_beside_n1) {
+    // one GPU: dW_1 may move in front of dW_0 (Net::dw1_serial_auto); the side stream's optimizer launch then waits for it
+    n.dw1_serial_auto = true;
+    n.after_dw1 = [t]() -> int {
+      Net& nn = t->net;
+      SB_CUDA(cudaEventRecord(t->ev_c[0], nn.stream));
+      SB_CUDA(cudaStreamWaitEvent(nn.side, t->ev_c[0], 0));
       return SB_OK;
     };
   }

@@ -514,11 +514,17 @@ int Net::enqueue_backward(int rows, float* grad) {
   // finishing after dW_0" against "dW_1 on a third of the SMs, dW_0 on the rest" and take the shorter.
   int dw_sms[2] = {gemm_sms, gemm_sms};
   static const bool no_budget = getenv("SB_NO_DW_BUDGET") != nullptr;
+  // dw1_serial_auto (single-GPU tail): when the natural grids of dW_0 and dW_1 do not fit the machine together, dW_1 runs IN
+  // FRONT of dW_0 on the main stream instead of beside it - side by side the two persistent grids take turns on the SMs
+  // (cfg2: 47.9 us for both; alone 13.9 + 29.0 us, profiles/ncu_r02_cfg2_launches.txt); small layers (cfg1) stay side by side
+  bool dw1_front = dw1_first;
   if (fork && dw0_on_main && L > 1 && !on_layer_grads && !no_budget && !dw1_last && !dw1_first) {
     const int kx = round_up(rows, 64) * pairs_of(nparts);
     const GemmPlan n0 = plan_gemm(layers[0].in, layers[0].out, kx, gemm_sms, true);
     const GemmPlan n1 = plan_gemm(layers[1].in, layers[1].out, kx, gemm_sms, true);
-    if (n0.grid + n1.grid > gemm_sms) {
+    if (n0.grid + n1.grid > gemm_sms && dw1_serial_auto && n0.cg == 2) {      // (pair tiles = a GEMM of several waves, plan_gemm)
+      dw1_front = true;
+    } else if (n0.grid + n1.grid > gemm_sms) {
       const GemmPlan b1 = plan_gemm(layers[1].in, layers[1].out, kx, gemm_sms / 3, true);
       const GemmPlan b0 = plan_gemm(layers[0].in, layers[0].out, kx, gemm_sms - b1.grid, true);
       auto waves = [&](const GemmPlan& pl, int M, int N, int sms) {   // k-blocks one CTA works through
@@ -592,13 +598,13 @@ int Net::enqueue_backward(int rows, float* grad) {
       // dW_l[in,out] += sum_rows A_{l-1}[rows,in] (MN-major A) * dZ_l[rows,out] (MN-major B), split-K over rows.
       // With a gradient exchange behind it, a big layer is cut into row chunks of W_l (each a contiguous slice of the
       // flat gradient) so that the all-reduce of chunk c overlaps the GEMM of chunk c+1.
-      const bool dw1_moved = (dw1_last || dw1_first) && L > 1;
-      if (dw1_first && l == 0 && L > 1) {         // in front of dW_0 on the main stream: dW_0's last exchange then runs on an idle GPU
+      const bool dw1_moved = (dw1_last || dw1_front) && L > 1;
+      if (dw1_front && l == 0 && L > 1) {         // in front of dW_0 on the main stream: dW_0's last exchange then runs on an idle GPU
         SB_TRY(emit_dw_tc(1, true));
         if (after_dw1) SB_TRY(after_dw1());
       }
       if (!(dw1_moved && l == 1)) SB_TRY(emit_dw_tc(l, false));
-      if (dw1_last && !dw1_first && l == 0 && L > 1) SB_TRY(emit_dw_tc(1, true));   // behind dW_0 on the main stream (covers its last exchange)
+      if (dw1_last && !dw1_front && l == 0 && L > 1) SB_TRY(emit_dw_tc(1, true));   // behind dW_0 on the main stream (covers its last exchange)
       if (l > 0) {
         // dZ_{l-1}[rows,in] = (dZ_l[rows,out] (K-major) x W_l[in,out] (K-major B: k = out contiguous)) .* act'(A_{l-1})
         Layer& pl = layers[l - 1];

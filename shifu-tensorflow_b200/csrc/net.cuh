@@ -39,6 +39,7 @@ struct Net {
   bool dw1_last = false;
   bool dw1_first = false;                    // dW_1 on the main stream IN FRONT of dW_0 (then after_dw1 is called behind it)
   std::function<int()> after_dw1;
+  bool dw1_serial_auto = false;              // let enqueue_backward move dW_1 in front of dW_0 when their grids do not fit together
   std::function<int(int /*chunk*/)> on_dw0_chunk;
   std::function<int()> before_layer1;
   int zero_layer = 0;
