@@ -75,7 +75,7 @@ if os.path.exists("gpurun_out/parity_benchmarked_paths.json"):
     shutil.copy("gpurun_out/parity_benchmarked_paths.json", "profiles/parity_r02.json")
 for path in sys.argv[1:]:
     if os.path.exists(path) and os.path.getsize(path) > 0:
-        d = json.load(open(path))
+        d = next(json.loads(l) for l in open(path) if l.lstrip().startswith("{"))      # (torchrun may print around the JSON line)
         name = "profiles/bench_r02_n%d_%s.json" % (d.get("n_gpus", 1), d["config"]["workload"].split(":")[0])
         json.dump(d, open(name, "w"), indent=1)
         print("wrote", name)

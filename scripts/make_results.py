@@ -102,5 +102,19 @@ if rows:
 p = load("profiles/parity_r02.json")
 if p:
     out += ["## Parity observed on the benchmarked paths (`tests/test_benchmarked_paths.py`, `profiles/parity_r02.json`)", "", "```", json.dumps(p, indent=1)[:3500], "```", ""]
+out += ["## Targets of `north_star` against what was measured", "",
+        "| target | measured | where |", "|---|---|---|",
+        "| hidden-layer GEMMs >= 70 % of the bf16 tensor peak | layer-0 forward 1.19-1.22 PFLOP/s = 0.70-0.72 of the measured cuBLAS burst peak (1690 TF/s); dW_0 1.13 PFLOP/s = 0.67; "
+        "the small GEMMs are epilogue / latency bound (dA_1 0.28, fwd_1 0.50, layers of 256-512 columns 0.12-0.18); all GEMMs of a step together 0.47 | spans above; "
+        "`profiles/ncu_r02_cfg2_gemm_full.txt` (tensor-pipe active: fwd_0 64 %, dW_0 64 %, dA_1 26 %) |",
+        "| >= 0.9 scaling efficiency at 8 GPUs on the 2000 x 8192 batch | 0.73 at N = 8, 0.81 at N = 2 (round 1: 0.69 at N = 8 on cfg2) | table above; DESIGN section 7 says what the rest is |",
+        "| loss / gradients within 1e-4 (fp32), scores within 1e-5 | fp32 and fp32_tc modes: loss curves <= 3.3e-5 (cfg1) / 9e-7 (cfg2) over 20-30 steps, single-step gradients <= 5e-6; "
+        "bf16 (the benchmarked mode) vs the bf16-emulating oracle 1.9e-4 / 1.4e-5 | parity block below, `tests/test_benchmarked_paths.py`, `tests/test_trainer_parity.py`, `tests/test_scorer_parity.py` |",
+        "| reference CPU worker next to it | 92 k rows/s on 16 host cores (torch-CPU port of the worker loop; TF-1.x cannot be installed here) - the reference arm `bench.py --impl reference` measures the same loop | `cpu_baseline` |",
+        "",
+        "What did not move the dA epilogue (kept, documented in DESIGN section 6): shared-memory column sums, TMA-staged tiles both ways, "
+        "A_{l-1} prefetched before the accumulator wait - 19.5-21 us before and after; sixteen epilogue warps: 19.7 -> 17.8 us.",
+        "The ncu capture (`profiles/ncu_r02_cfg2_*.txt`, `profiles/ncu_r02_traffic.json`) is of the build one commit before dW_1 moved in front of dW_0 "
+        "on one GPU: same kernels, launch order dW_2, dA_2, dW_1, dA_1, dW_0.", ""]
 open("profiles/results_r02.md", "w").write("\n".join(out) + "\n")
 print("\n".join(out)[:3000])
