@@ -70,7 +70,7 @@ if n1:
     if a and a["roofline"].get("kernels"):
         out += ["cfg1 step:", "", "| kernel | begin | end | span | TF/s |", "|---|---|---|---|---|"] + [krow(k) for k in a["roofline"]["kernels"]] + [""]
 
-out += ["## Scaling (weak, cfg2, one NVSwitch node) — `profiles/bench_r02_n{1,2,8}_cfg2.json`", "",
+out += ["## Scaling (weak, cfg2, one NVSwitch node) — `profiles/bench_r02_n{1,2,4,8}_cfg2.json`", "",
         "| N | M rows/s | µs/step | efficiency vs N = 1 |", "|---|---|---|---|"]
 for n in (1, 2, 4, 8):
     if b[n] and n1:
