@@ -260,14 +260,15 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   static const bool one_xchg = getenv("SB_XCHG_ONE") != nullptr;    // experiment: one exchange launch for everything after a join
   const bool split_tail = !old_sched && kind == G_STEP && (t->world == 1 || (t->p2p_ready && !one_xchg)) && !pipelined &&
                           n.concurrent_bwd && !n.profiling && n.side != nullptr && n.tc() && n.L > 1;
-  // Peer exchange (world > 1): the chain  arrive -> P2P loads -> update -> P2P stores + fence -> done  costs ~17 us through
-  // NVSwitch however little data it moves (xchg_p2p.cuh), so every exchange launch gets a GEMM to hide behind:
-  //   main:  ... dA_1 -> dW_0 chunk 0 -> dW_0 chunk 1 -> dW_1        | next step: layer-0 forward -> layer-1 forward ...
-  //   comm:              xchg B0 ---------> xchg B1 ------>           |
-  //   side:  ... dW_2 ...                                   xchg A ---------------------------->|
-  // B0 runs beside dW_0's second chunk, B1 beside dW_1, A (every other layer) beside the NEXT step's layer-0 forward GEMM,
-  // which reads nothing slot A writes: layer 1's forward waits for A, and - because peers may read this rank's gradient
-  // buffer until then - the buffer is cleared by layer 1's forward GEMM instead of layer 0's.
+  // Peer exchange (world > 1): one exchange launch costs 20-30 us through NVSwitch however little data it moves (fabric latency,
+  // xchg_p2p.cuh) - hidden when a GEMM follows it, exposed in full behind the last GEMM.  Default order ("first"):
+  //   main:  ... dA_1 -> dW_1 -> dW_0 chunk 0 -> dW_0 chunk 1 | wait A, B0, B1 | next step
+  //   side:  ... dW_2 ...     A ------------->
+  //   comm:                             B0 ---------------->    B1 ------>
+  // A (every layer but hidden layer 0) and B0 run beside dW_0's chunks, only B1 - half of layer 0 - is exposed.
+  // Order "last" (SB_XCHG_ORDER=last, and replicas that share a device): dW_1 BEHIND dW_0 as cover for B1, and A beside the
+  // NEXT step's layer-0 forward GEMM, which reads nothing slot A writes: layer 1's forward waits for A, and - because peers
+  // may read this rank's gradient buffer until then - the buffer is cleared by layer 1's forward GEMM instead of layer 0's.
   const bool xsched = split_tail && t->world > 1;
   // SB_XCHG_ORDER: "first" (default) = dW_1 in front of dW_0: slot A and chunk 0 hide behind dW_0's chunks, the LAST chunk's
   // exchange runs on an otherwise idle GPU - an exchange kernel beside a GEMM takes 40-47 us, alone ~25 (measured, 2 x B200);
@@ -333,9 +334,9 @@ static int enqueue_step_body(sb_trainer* t, int rows, int kind, bool resident = 
   n.defer_join = split_tail;
   cudaStream_t comms[2] = {n.comm2, n.comm};
   if (xsched) {
-    // dW_1 runs BEHIND dW_0 on the main stream: it is the cover of the last chunk's exchange.  (SB_XCHG_BESIDE=1 keeps it
-    // beside dW_0 on the side stream like the single-GPU schedule; measured on 2 x B200: the chunks of dW_0 then share the
-    // SMs with dW_1 - 31 + 19 us instead of 18 + 19 - and the last exchange has nothing to hide behind.)
+    // dW_1 leaves the side stream: in front of dW_0 ("first") or behind it ("last").  (SB_XCHG_BESIDE=1 keeps it beside dW_0
+    // like the single-GPU schedule; measured on 2 x B200: the chunks of dW_0 then share the SMs with dW_1 - 31 + 19 us
+    // instead of 18 + 19.)
     static const bool beside = getenv("SB_XCHG_BESIDE") != nullptr;
     n.dw0_chunks = t->x_chunks;
     n.dw1_last = !beside && order_last;
